@@ -1,0 +1,107 @@
+// nearl_b200 -- standalone K3 (`aggregate`) and `summation`.
+//
+// nrl_aggregate_kernel streams a frame-major [F, G] series out of HBM exactly once: a CTA
+// owns W consecutive voxels, one elected warp stages the F row segments (W*4 bytes each)
+// into shared memory with 1-D bulk asynchronous copies (TMA engine, cp.async.bulk ->
+// UBLKCP) completing on one mbarrier, and W/4 threads reduce float4 columns with the
+// reducers of reducers.cuh.  W is chosen by the host so that two CTAs fit per SM: the
+// copies of one overlap the reduction of the other.
+// Replaces gridwise_aggregation_global + aggregate_host (/root/reference/src/gpuutils.cu:48-105),
+// which copies every series into a 2 KB per-thread local-memory array first.
+#pragma once
+#include "common.cuh"
+#include "reducers.cuh"
+
+__device__ __forceinline__ uint32_t nrl_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void nrl_mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nrl_smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void nrl_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nrl_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nrl_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   nrl_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(nrl_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void nrl_mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = nrl_smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
+#define NRL_AGG_NT 128
+
+// W: voxels per CTA (multiple of 4, <= 512).  bulk != 0 requires G % 4 == 0 and a 16-byte
+// aligned series pointer (checked by the host).
+__global__ void __launch_bounds__(NRL_AGG_NT) nrl_aggregate_kernel(const float *__restrict__ series, const int n,
+                                                                   const long long G, const int agg, const int W,
+                                                                   const int bulk, float *__restrict__ out) {
+  extern __shared__ __align__(16) unsigned char nrl_agg_smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  float4 *buf = reinterpret_cast<float4 *>(nrl_agg_smem);
+  const int tid = threadIdx.x;
+  const long long g0 = (long long)blockIdx.x * W;
+  const int w = (int)min((long long)W, G - g0);
+  const int W4 = W >> 2;
+  if (bulk) {
+    if (tid == 0) nrl_mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0) nrl_mbar_expect_tx(&s_bar, (uint32_t)n * (uint32_t)w * 4u);
+    if (tid < 32)
+      for (int i = tid; i < n; i += 32)
+        nrl_bulk_g2s(buf + (size_t)i * W4, series + (long long)i * G + g0, (uint32_t)w * 4u, &s_bar);
+    nrl_mbar_wait(&s_bar, 0);
+  } else {
+    float *fb = reinterpret_cast<float *>(buf);
+    for (int i = 0; i < n; ++i)
+      for (int v = tid; v < W; v += NRL_AGG_NT) fb[(size_t)i * W + v] = v < w ? series[(long long)i * G + g0 + v] : 0.0f;
+    __syncthreads();
+  }
+  for (int t4 = tid; t4 * 4 < w; t4 += NRL_AGG_NT) {
+    const float4 r = nrl_reduce4(buf + t4, W4, n, agg);
+    float *o = out + g0 + 4 * t4;
+    if (4 * t4 + 3 < w && bulk) {
+      *reinterpret_cast<float4 *>(o) = r;
+    } else {
+      if (4 * t4 + 0 < w) o[0] = r.x;
+      if (4 * t4 + 1 < w) o[1] = r.y;
+      if (4 * t4 + 2 < w) o[2] = r.z;
+      if (4 * t4 + 3 < w) o[3] = r.w;
+    }
+  }
+}
+
+// summation: the reference's 256-wide shared-memory tree per block, then a sequential sum of
+// the block partials (/root/reference/src/gpuutils.cu:9-31,107-134) -- kept on the device.
+__global__ void __launch_bounds__(256) nrl_block_sum_kernel(const float *__restrict__ in, float *__restrict__ partial,
+                                                            const long long n) {
+  __shared__ float sm[256];
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  sm[threadIdx.x] = idx < n ? in[idx] : 0.0f;
+  __syncthreads();
+  for (int stride = 128; stride > 0; stride >>= 1) {
+    if ((int)threadIdx.x < stride) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + stride];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+__global__ void nrl_final_sum_kernel(const float *__restrict__ partial, const int nblocks, float *__restrict__ out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int i = 0; i < nblocks; ++i) s = s + partial[i];
+    out[0] = s;
+  }
+}
+
+__global__ void nrl_buff_dim_kernel(const float cutoff, const float spacing, int *out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = nrl_buff_dim_device(cutoff, spacing);
+}

@@ -1,0 +1,560 @@
+// nearl_b200 -- C ABI (include/nearl_b200.h) over the sm_100a kernels.
+//
+// Replaces the pybind11 module /root/reference/src/actions_py.cpp and the CUDA host wrappers
+// voxelize_host / trajectory_voxelization_host (/root/reference/src/voxelize.cu:292-415),
+// marching_observer_host / observe_frame_host (/root/reference/src/marching_observers.cu:435-553),
+// aggregate_host / sum_reduction_host (/root/reference/src/gpuutils.cu:80-134).  Where those
+// allocate, copy, synchronise and free on every call, this layer keeps a per-device context
+// with grow-only workspaces, one stream, and checks every CUDA status.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/nearl_b200.h"
+#include "agg_kernels.cuh"
+#include "common.cuh"
+#include "pack_kernels.cuh"
+#include "tile_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return NRL_ERR_CUDA + (int)e;
+}
+#define NRL_CUDA(call)                                    \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+#define NRL_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != NRL_OK) return rc__; \
+  } while (0)
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return NRL_OK;
+    if (p) { NRL_CUDA(cudaFree(p)); p = nullptr; cap = 0; }
+    size_t want = std::max(bytes, (size_t)4096);
+    want = (want + (want >> 2) + 255) & ~(size_t)255;   // 25% slack: grow-only arena
+    NRL_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return NRL_OK;
+  }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Ctx {
+  int dev = -1;
+  int sms = 148;
+  size_t smem_optin = 227 * 1024;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  DevBuf coords, weights, perm, atoms, inv, off, cnt, out, tasks, flist, cand_scr, ser_scr, misc, series;
+  DevBuf xyz, wtabs, sels, resid, orders, crops, fcrop, fsrc, keep, resflags;
+  bool attr_set[32] = {false};
+};
+
+std::mutex g_ctx_mu;
+Ctx *g_ctx[64] = {nullptr};
+
+int get_ctx(Ctx **out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(NRL_ERR_NO_DEVICE, std::string("nearl_b200: no usable CUDA device (") + cudaGetErrorString(e) +
+                                       "); this library has no CPU fallback");
+  }
+  if (dev < 0 || dev >= 64) return fail(NRL_ERR_ARGUMENT, "device index out of range");
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (!g_ctx[dev]) {
+    cudaDeviceProp prop;
+    NRL_CUDA(cudaGetDeviceProperties(&prop, dev));
+    Ctx *c = new Ctx();
+    c->dev = dev;
+    c->sms = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    NRL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    g_ctx[dev] = c;
+  }
+  *out = g_ctx[dev];
+  return NRL_OK;
+}
+
+bool valid_obs(int t) {
+  static const int ok[] = {1, 2, 3, 11, 12, 13, 14, 15, 16};
+  for (int v : ok) if (v == t) return true;
+  return false;
+}
+bool valid_agg(int t) { return t >= 1 && t <= 8; }
+
+int check_dims(const int *dims, long long *G) {
+  if (!dims) return fail(NRL_ERR_ARGUMENT, "dims is NULL");
+  if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return fail(NRL_ERR_SHAPE, "grid dimensions must be positive");
+  const long long g = (long long)dims[0] * dims[1] * dims[2];
+  if (g >= (1ll << 31)) return fail(NRL_ERR_SHAPE, "grid has 2^31 voxels or more");
+  *G = g;
+  return NRL_OK;
+}
+
+// ---- tile launches ------------------------------------------------------------------------
+constexpr int kCandCap = 1024;        // candidates held in shared memory (16 KB)
+constexpr int kSerCapFloats = 8192;   // series floats held in shared memory (32 KB: 16 frames x 512 voxels)
+constexpr size_t kScratchBudget = (size_t)1 << 30;
+
+template <int MODE>
+int launch_tiles_mode(Ctx &c, const NrlTileParams &p, int grid, size_t smem, cudaStream_t st, int slot) {
+  if (!c.attr_set[slot]) {
+    NRL_CUDA(cudaFuncSetAttribute(nrl_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kCandCap * sizeof(float4) + kSerCapFloats * sizeof(float))));
+    c.attr_set[slot] = true;
+  }
+  nrl_tile_kernel<MODE><<<grid, NRL_NT, smem, st>>>(p);
+  g_launches.fetch_add(1);
+  NRL_CUDA(cudaGetLastError());
+  return NRL_OK;
+}
+
+int launch_tiles(Ctx &c, int mode, const NrlTileParams &p, int grid, size_t smem, cudaStream_t st) {
+  switch (mode) {
+    case NRL_MODE_VOXELIZE: return launch_tiles_mode<NRL_MODE_VOXELIZE>(c, p, grid, smem, st, 0);
+    case NRL_OBS_EXISTENCE: return launch_tiles_mode<NRL_OBS_EXISTENCE>(c, p, grid, smem, st, 1);
+    case NRL_OBS_DIRECT_COUNT: return launch_tiles_mode<NRL_OBS_DIRECT_COUNT>(c, p, grid, smem, st, 2);
+    case NRL_OBS_DISTINCT_COUNT: return launch_tiles_mode<NRL_OBS_DISTINCT_COUNT>(c, p, grid, smem, st, 3);
+    case NRL_OBS_MEAN_DISTANCE: return launch_tiles_mode<NRL_OBS_MEAN_DISTANCE>(c, p, grid, smem, st, 4);
+    case NRL_OBS_CUMULATIVE_WEIGHT: return launch_tiles_mode<NRL_OBS_CUMULATIVE_WEIGHT>(c, p, grid, smem, st, 5);
+    case NRL_OBS_DENSITY: return launch_tiles_mode<NRL_OBS_DENSITY>(c, p, grid, smem, st, 6);
+    case NRL_OBS_DISPERSION: return launch_tiles_mode<NRL_OBS_DISPERSION>(c, p, grid, smem, st, 7);
+    case NRL_OBS_ECCENTRICITY: return launch_tiles_mode<NRL_OBS_ECCENTRICITY>(c, p, grid, smem, st, 8);
+    case NRL_OBS_RADIUS_OF_GYRATION: return launch_tiles_mode<NRL_OBS_RADIUS_OF_GYRATION>(c, p, grid, smem, st, 9);
+    default: return fail(NRL_ERR_OBSERVABLE, "The observable type is not supported");
+  }
+}
+
+void fill_task_geometry(NrlTask &t, const int *dims, float spacing, float cutoff, float sigma) {
+  t.nx = dims[2]; t.ny = dims[1]; t.nz = dims[0];
+  t.ntx = (t.nx + NRL_TX - 1) / NRL_TX;
+  t.nty = (t.ny + NRL_TY - 1) / NRL_TY;
+  t.ntz = (t.nz + NRL_TZ - 1) / NRL_TZ;
+  t.spacing = spacing;
+  t.cutoff = cutoff;
+  t.sigma = sigma;
+  t.k2 = sigma != 0.0f ? (float)(-0.5 * 1.4426950408889634 / ((double)sigma * (double)sigma)) : 0.0f;
+  t.sphere_volume = (4.0 / 3.0) * M_PI * (double)cutoff * (double)cutoff * (double)cutoff;
+}
+
+// Runs `tasks` (device pointers already filled in) grouped by mode: one launch per mode present.
+// max_atoms_per_frame bounds the per-CTA overflow candidate list.
+int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, float *d_out, int max_atoms_per_frame,
+              cudaStream_t st) {
+  if (tasks.empty()) return NRL_OK;
+  std::vector<int> order(tasks.size());
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tasks[a].mode < tasks[b].mode; });
+  std::vector<NrlTask> sorted;
+  sorted.reserve(tasks.size());
+  for (int i : order) sorted.push_back(tasks[i]);
+
+  // per-mode ranges with their own tile prefix
+  struct Range { int mode, begin, end, n_work, max_frames; };
+  std::vector<Range> ranges;
+  for (size_t i = 0; i < sorted.size();) {
+    size_t j = i;
+    int work = 0, maxf = 1;
+    while (j < sorted.size() && sorted[j].mode == sorted[i].mode) {
+      sorted[j].tile_begin = work;
+      work += sorted[j].ntx * sorted[j].nty * sorted[j].ntz;
+      maxf = std::max(maxf, sorted[j].n_frames);
+      ++j;
+    }
+    ranges.push_back({sorted[i].mode, (int)i, (int)j, work, maxf});
+    i = j;
+  }
+  NRL_TRY(c.tasks.reserve(sorted.size() * sizeof(NrlTask)));
+  NRL_CUDA(cudaMemcpyAsync(c.tasks.p, sorted.data(), sorted.size() * sizeof(NrlTask), cudaMemcpyHostToDevice, st));
+
+  const size_t smem = kCandCap * sizeof(float4) + kSerCapFloats * sizeof(float);
+  const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (smem + 1024)));
+  for (const Range &r : ranges) {
+    int grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 8));
+    // overflow scratch (candidate lists longer than kCandCap, series longer than kSerCapFloats)
+    const size_t cand_per_cta = max_atoms_per_frame > kCandCap ? (size_t)max_atoms_per_frame : 0;
+    const size_t ser_per_cta = (size_t)r.max_frames * NRL_TILE_VOX > (size_t)kSerCapFloats
+                                   ? (size_t)r.max_frames * NRL_TILE_VOX : 0;
+    const size_t per_cta = cand_per_cta * sizeof(float4) + ser_per_cta * sizeof(float);
+    if (per_cta > 0) {
+      const int max_grid = (int)std::max<size_t>((size_t)c.sms, kScratchBudget / per_cta);
+      grid = std::max(1, std::min(grid, max_grid));
+    }
+    NRL_TRY(c.cand_scr.reserve(cand_per_cta * sizeof(float4) * grid));
+    NRL_TRY(c.ser_scr.reserve(ser_per_cta * sizeof(float) * grid));
+    NrlTileParams p;
+    p.tasks = c.tasks.as<NrlTask>() + r.begin;
+    p.n_tasks = r.end - r.begin;
+    p.n_work = r.n_work;
+    p.frames = frames;
+    p.out = d_out;
+    p.cand_scratch = c.cand_scr.as<float4>();
+    p.cand_scratch_stride = (long long)cand_per_cta;
+    p.ser_scratch = c.ser_scr.as<float>();
+    p.ser_scratch_stride = (long long)ser_per_cta;
+    p.cand_cap = kCandCap;
+    p.ser_cap = kSerCapFloats;
+    NRL_TRY(launch_tiles(c, r.mode, p, grid, smem, st));
+  }
+  return NRL_OK;
+}
+
+int launch_norm(Ctx &c, const NrlFrames &frames, const int *d_frame_list, int n_list, int capacity, const NrlTask &geom,
+                float *d_inv, cudaStream_t st) {
+  if (n_list <= 0 || capacity <= 0) return NRL_OK;
+  NrlNormParams np;
+  np.frames = frames;
+  np.frame_list = d_frame_list;
+  np.nx = geom.nx; np.ny = geom.ny; np.nz = geom.nz;
+  np.spacing = geom.spacing; np.cutoff = geom.cutoff; np.k2 = geom.k2;
+  np.inv_norm = d_inv;
+  const int warps_per_cta = 4;
+  for (int f0 = 0; f0 < n_list; f0 += 65535) {
+    const int ny = std::min(65535, n_list - f0);
+    NrlNormParams q = np;
+    q.frame_list = d_frame_list + f0;
+    dim3 grid((unsigned)std::min((capacity + warps_per_cta - 1) / warps_per_cta, 1 << 16), (unsigned)ny);
+    nrl_atom_norm_kernel<<<grid, warps_per_cta * 32, 0, st>>>(q, capacity);
+    g_launches.fetch_add(1);
+    NRL_CUDA(cudaGetLastError());
+  }
+  return NRL_OK;
+}
+
+// value order of every frame's weights for distinct_count: equal values adjacent, NaNs last
+void host_value_order(const float *w, int F, int N, std::vector<int> &perm) {
+  perm.resize((size_t)F * N);
+  for (int f = 0; f < F; ++f) {
+    int *p = perm.data() + (size_t)f * N;
+    const float *wf = w + (size_t)f * N;
+    std::iota(p, p + N, 0);
+    std::stable_sort(p, p + N, [wf](int a, int b) {
+      const float x = wf[a], y = wf[b];
+      const bool nx = x != x, ny = y != y;
+      if (nx || ny) return !nx && ny;
+      return x < y;
+    });
+  }
+}
+
+// ---- shared implementation of the four "reference layout" operations --------------------
+struct LegacyArgs {
+  const float *coords, *weights;
+  int F, N;
+  const int *dims;
+  float spacing, cutoff, sigma;
+  int mode, agg;       // agg 0: single frame
+  float *out;
+  bool on_device;      // pointers are device pointers, no sync
+  cudaStream_t user_stream;
+};
+
+int legacy_run(const LegacyArgs &a) {
+  long long G = 0;
+  NRL_TRY(check_dims(a.dims, &G));
+  if (a.F <= 0 || a.N < 0) return fail(NRL_ERR_SHAPE, "frame / atom counts must be positive");
+  if (!a.out) return fail(NRL_ERR_ARGUMENT, "out is NULL");
+  if (a.N > 0 && (!a.coords || !a.weights)) return fail(NRL_ERR_ARGUMENT, "coords / weights is NULL");
+  Ctx *cp = nullptr;
+  NRL_TRY(get_ctx(&cp));
+  Ctx &c = *cp;
+  std::lock_guard<std::mutex> lk(c.mu);
+  cudaStream_t st = a.on_device ? a.user_stream : c.stream;
+  const int nF = std::min(a.F, NRL_MAX_FRAMES);   // gpuutils.cu:88, voxelize.cu:403, marching_observers.cu:490
+  const size_t n_atoms = (size_t)nF * (size_t)a.N;
+
+  float *d_out = a.out;
+  if (!a.on_device) { NRL_TRY(c.out.reserve((size_t)G * sizeof(float))); d_out = c.out.as<float>(); }
+
+  if (a.mode == NRL_MODE_VOXELIZE && a.sigma == 0.0f) {
+    // gaussian_map_device returns 0 for sigma == 0 (gpuutils.cuh:312-313): every sum is 0, nothing is deposited
+    NRL_CUDA(cudaMemsetAsync(d_out, 0, (size_t)G * sizeof(float), st));
+  } else {
+    const float *d_coords = a.coords, *d_weights = a.weights;
+    std::vector<int> perm;
+    if (!a.on_device && n_atoms > 0) {
+      NRL_TRY(c.coords.reserve(n_atoms * 3 * sizeof(float)));
+      NRL_TRY(c.weights.reserve(n_atoms * sizeof(float)));
+      NRL_CUDA(cudaMemcpyAsync(c.coords.p, a.coords, n_atoms * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+      NRL_CUDA(cudaMemcpyAsync(c.weights.p, a.weights, n_atoms * sizeof(float), cudaMemcpyHostToDevice, st));
+      d_coords = c.coords.as<float>();
+      d_weights = c.weights.as<float>();
+    }
+    const int *d_perm = nullptr;
+    if (a.mode == NRL_OBS_DISTINCT_COUNT && n_atoms > 0) {
+      std::vector<float> hw;
+      const float *w_host = a.weights;
+      if (a.on_device) {
+        hw.resize(n_atoms);
+        NRL_CUDA(cudaMemcpyAsync(hw.data(), a.weights, n_atoms * sizeof(float), cudaMemcpyDeviceToHost, st));
+        NRL_CUDA(cudaStreamSynchronize(st));
+        w_host = hw.data();
+      }
+      host_value_order(w_host, nF, a.N, perm);
+      NRL_TRY(c.perm.reserve(n_atoms * sizeof(int)));
+      NRL_CUDA(cudaMemcpyAsync(c.perm.p, perm.data(), n_atoms * sizeof(int), cudaMemcpyHostToDevice, st));
+      d_perm = c.perm.as<int>();
+    }
+    NRL_TRY(c.atoms.reserve(std::max<size_t>(n_atoms, 1) * sizeof(float4)));
+    NRL_TRY(c.off.reserve((size_t)nF * sizeof(long long)));
+    NRL_TRY(c.cnt.reserve((size_t)nF * sizeof(int)));
+    {
+      const long long total = (long long)n_atoms;
+      const int grid = (int)std::min<long long>(std::max<long long>((std::max<long long>(total, nF) + 255) / 256, 1), 4096);
+      nrl_pack_legacy_kernel<<<grid, 256, 0, st>>>(d_coords, d_weights, d_perm, nF, a.N,
+                                                    a.mode == NRL_OBS_DISTINCT_COUNT ? 1 : 0, c.atoms.as<float4>(),
+                                                    c.off.as<long long>(), c.cnt.as<int>());
+      g_launches.fetch_add(1);
+      NRL_CUDA(cudaGetLastError());
+    }
+    NrlFrames frames{c.atoms.as<float4>(), c.off.as<long long>(), c.cnt.as<int>()};
+    NrlTask t;
+    memset(&t, 0, sizeof t);
+    fill_task_geometry(t, a.dims, a.spacing, a.cutoff, a.sigma);
+    t.n_frames = nF;
+    t.agg = a.agg;
+    t.mode = a.mode;
+    t.frame0 = 0;
+    t.out_off = 0;
+    t.wtab = d_weights;
+    t.inv_norm = nullptr;
+    if (a.mode == NRL_MODE_VOXELIZE) {
+      NRL_TRY(c.inv.reserve(std::max<size_t>(n_atoms, 1) * sizeof(float)));
+      NRL_TRY(c.flist.reserve((size_t)nF * sizeof(int)));
+      std::vector<int> fl(nF);
+      std::iota(fl.begin(), fl.end(), 0);
+      NRL_CUDA(cudaMemcpyAsync(c.flist.p, fl.data(), (size_t)nF * sizeof(int), cudaMemcpyHostToDevice, st));
+      NRL_TRY(launch_norm(c, frames, c.flist.as<int>(), nF, a.N, t, c.inv.as<float>(), st));
+      t.inv_norm = c.inv.as<float>();
+    }
+    std::vector<NrlTask> tasks{t};
+    NRL_TRY(run_tasks(c, tasks, frames, d_out, a.N, st));
+  }
+  if (!a.on_device) {
+    NRL_CUDA(cudaMemcpyAsync(a.out, d_out, (size_t)G * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NRL_CUDA(cudaStreamSynchronize(st));
+  }
+  return NRL_OK;
+}
+
+int aggregate_impl(const float *series, int F, long long G, int agg, float *out, bool on_device, cudaStream_t user) {
+  if (F <= 0 || G <= 0) return fail(NRL_ERR_SHAPE, "series must be [n_frames > 0, n_voxels > 0]");
+  if (!series || !out) return fail(NRL_ERR_ARGUMENT, "series / out is NULL");
+  Ctx *cp = nullptr;
+  NRL_TRY(get_ctx(&cp));
+  Ctx &c = *cp;
+  std::lock_guard<std::mutex> lk(c.mu);
+  cudaStream_t st = on_device ? user : c.stream;
+  const int n = std::min(F, NRL_MAX_FRAMES);                 // gpuutils.cu:88
+  const float *d_in = series;
+  float *d_out = out;
+  if (!on_device) {
+    NRL_TRY(c.series.reserve((size_t)n * G * sizeof(float)));
+    NRL_TRY(c.out.reserve((size_t)G * sizeof(float)));
+    NRL_CUDA(cudaMemcpyAsync(c.series.p, series, (size_t)n * G * sizeof(float), cudaMemcpyHostToDevice, st));
+    d_in = c.series.as<float>();
+    d_out = c.out.as<float>();
+  }
+  if (!valid_agg(agg)) {
+    NRL_CUDA(cudaMemsetAsync(d_out, 0, (size_t)G * sizeof(float), st));   // gpuutils.cu:73-76
+  } else {
+    // widest tile that still lets two CTAs share an SM
+    int W = 512;
+    while (W > 64 && (size_t)n * W * sizeof(float) > 100 * 1024) W >>= 1;
+    const size_t smem = (size_t)n * W * sizeof(float);
+    if (smem > c.smem_optin - 1024) return fail(NRL_ERR_FRAMES, "series too long for shared memory");
+    if (!c.attr_set[20]) {
+      NRL_CUDA(cudaFuncSetAttribute(nrl_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(c.smem_optin - 1024)));
+      c.attr_set[20] = true;
+    }
+    const int bulk = (G % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
+    const long long grid = (G + W - 1) / W;
+    nrl_aggregate_kernel<<<(unsigned)grid, NRL_AGG_NT, smem, st>>>(d_in, n, G, agg, W, bulk, d_out);
+    g_launches.fetch_add(1);
+    NRL_CUDA(cudaGetLastError());
+  }
+  if (!on_device) {
+    NRL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)G * sizeof(float), cudaMemcpyDeviceToHost, st));
+    NRL_CUDA(cudaStreamSynchronize(st));
+  }
+  return NRL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nrl_last_error(void) { return g_err.c_str(); }
+const char *nrl_version(void) { return "nearl_b200 0.1 (sm_100a)"; }
+long long nrl_kernel_launches(void) { return g_launches.load(); }
+
+int nrl_device_count(int *out) {
+  if (!out) return fail(NRL_ERR_ARGUMENT, "out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+  *out = n;
+  return NRL_OK;
+}
+int nrl_set_device(int device) { NRL_CUDA(cudaSetDevice(device)); return NRL_OK; }
+int nrl_synchronize(void) {
+  Ctx *c = nullptr;
+  NRL_TRY(get_ctx(&c));
+  NRL_CUDA(cudaStreamSynchronize(c->stream));
+  return NRL_OK;
+}
+int nrl_host_register(void *ptr, long long bytes) {
+  if (!ptr || bytes <= 0) return fail(NRL_ERR_ARGUMENT, "nothing to register");
+  NRL_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return NRL_OK;
+}
+int nrl_host_unregister(void *ptr) { NRL_CUDA(cudaHostUnregister(ptr)); return NRL_OK; }
+
+int nrl_buff_dim(float cutoff, float spacing, int *out) {
+  if (!out) return fail(NRL_ERR_ARGUMENT, "out is NULL");
+  Ctx *cp = nullptr;
+  NRL_TRY(get_ctx(&cp));
+  std::lock_guard<std::mutex> lk(cp->mu);
+  NRL_TRY(cp->misc.reserve(64));
+  nrl_buff_dim_kernel<<<1, 32, 0, cp->stream>>>(cutoff, spacing, cp->misc.as<int>());
+  g_launches.fetch_add(1);
+  NRL_CUDA(cudaGetLastError());
+  NRL_CUDA(cudaMemcpyAsync(out, cp->misc.p, sizeof(int), cudaMemcpyDeviceToHost, cp->stream));
+  NRL_CUDA(cudaStreamSynchronize(cp->stream));
+  return NRL_OK;
+}
+
+int nrl_frame_voxelize(float *coords, const float *weights, int n_atoms, const int *dims, float spacing, float cutoff,
+                       float sigma, int auto_translate, float *out) {
+  if (auto_translate && coords && dims && n_atoms > 0) {
+    // translate_coord, /root/reference/src/cpuutils.h:340-357 (host code in the reference too; mutates the input)
+    float cog[3] = {0.f, 0.f, 0.f};
+    for (int i = 0; i < n_atoms; ++i) { cog[0] += coords[i * 3]; cog[1] += coords[i * 3 + 1]; cog[2] += coords[i * 3 + 2]; }
+    cog[0] /= n_atoms; cog[1] /= n_atoms; cog[2] /= n_atoms;
+    const double sp = (double)spacing;
+    for (int i = 0; i < n_atoms; ++i) {
+      coords[i * 3] = (float)((coords[i * 3] - cog[0]) + (dims[0] * sp) / 2);
+      coords[i * 3 + 1] = (float)((coords[i * 3 + 1] - cog[1]) + (dims[1] * sp) / 2);
+      coords[i * 3 + 2] = (float)((coords[i * 3 + 2] - cog[2]) + (dims[2] * sp) / 2);
+    }
+  }
+  LegacyArgs a{coords, weights, 1, n_atoms, dims, spacing, cutoff, sigma, NRL_MODE_VOXELIZE, 0, out, false, nullptr};
+  return legacy_run(a);
+}
+int nrl_frame_voxelize_dev(const float *coords, const float *weights, int n_atoms, const int *dims, float spacing,
+                           float cutoff, float sigma, float *out, void *stream) {
+  LegacyArgs a{coords, weights, 1, n_atoms, dims, spacing, cutoff, sigma, NRL_MODE_VOXELIZE, 0, out, true, (cudaStream_t)stream};
+  return legacy_run(a);
+}
+
+int nrl_frame_observation(const float *coords, const float *weights, int n_atoms, const int *dims, float spacing,
+                          float cutoff, int type_obs, float *out) {
+  if (!valid_obs(type_obs)) {   // the reference does not validate here: unknown ids give zeros
+    long long G = 0;
+    NRL_TRY(check_dims(dims, &G));
+    if (!out) return fail(NRL_ERR_ARGUMENT, "out is NULL");
+    memset(out, 0, (size_t)G * sizeof(float));
+    return NRL_OK;
+  }
+  LegacyArgs a{coords, weights, 1, n_atoms, dims, spacing, cutoff, 0.0f, type_obs, 0, out, false, nullptr};
+  return legacy_run(a);
+}
+int nrl_frame_observation_dev(const float *coords, const float *weights, int n_atoms, const int *dims, float spacing,
+                              float cutoff, int type_obs, float *out, void *stream) {
+  if (!valid_obs(type_obs)) return fail(NRL_ERR_OBSERVABLE, "The observable type is not supported");
+  LegacyArgs a{coords, weights, 1, n_atoms, dims, spacing, cutoff, 0.0f, type_obs, 0, out, true, (cudaStream_t)stream};
+  return legacy_run(a);
+}
+
+int nrl_marching_observer(const float *coords, const float *weights, int n_frames, int n_atoms, const int *dims,
+                          float spacing, float cutoff, int type_obs, int type_agg, float *out) {
+  if (!valid_obs(type_obs)) return fail(NRL_ERR_OBSERVABLE, "The observable type is not supported");
+  if (!valid_agg(type_agg)) return fail(NRL_ERR_AGGREGATION, "The aggregation type is not supported");
+  if (n_frames > NRL_MAX_FRAMES)
+    return fail(NRL_ERR_FRAMES, "The number of frames " + std::to_string(n_frames) +
+                                    " exceeds the maximum number of frames allowed " + std::to_string(NRL_MAX_FRAMES) +
+                                    " frames.");
+  LegacyArgs a{coords, weights, n_frames, n_atoms, dims, spacing, cutoff, 0.0f, type_obs, type_agg, out, false, nullptr};
+  return legacy_run(a);
+}
+int nrl_marching_observer_dev(const float *coords, const float *weights, int n_frames, int n_atoms, const int *dims,
+                              float spacing, float cutoff, int type_obs, int type_agg, float *out, void *stream) {
+  if (!valid_obs(type_obs)) return fail(NRL_ERR_OBSERVABLE, "The observable type is not supported");
+  if (!valid_agg(type_agg)) return fail(NRL_ERR_AGGREGATION, "The aggregation type is not supported");
+  if (n_frames > NRL_MAX_FRAMES) return fail(NRL_ERR_FRAMES, "The number of frames exceeds the maximum number of frames allowed 512 frames.");
+  LegacyArgs a{coords, weights, n_frames, n_atoms, dims, spacing, cutoff, 0.0f, type_obs, type_agg, out, true, (cudaStream_t)stream};
+  return legacy_run(a);
+}
+
+int nrl_density_flow(const float *coords, const float *weights, int n_frames, int n_atoms, const int *dims,
+                     float spacing, float cutoff, float sigma, int type_agg, float *out) {
+  if (!valid_agg(type_agg)) return fail(NRL_ERR_AGGREGATION, "The aggregation type is not supported");
+  LegacyArgs a{coords, weights, n_frames, n_atoms, dims, spacing, cutoff, sigma, NRL_MODE_VOXELIZE, type_agg, out, false, nullptr};
+  return legacy_run(a);
+}
+int nrl_density_flow_dev(const float *coords, const float *weights, int n_frames, int n_atoms, const int *dims,
+                         float spacing, float cutoff, float sigma, int type_agg, float *out, void *stream) {
+  if (!valid_agg(type_agg)) return fail(NRL_ERR_AGGREGATION, "The aggregation type is not supported");
+  LegacyArgs a{coords, weights, n_frames, n_atoms, dims, spacing, cutoff, sigma, NRL_MODE_VOXELIZE, type_agg, out, true, (cudaStream_t)stream};
+  return legacy_run(a);
+}
+
+int nrl_aggregate(const float *series, int n_frames, long long n_voxels, int type_agg, float *out) {
+  return aggregate_impl(series, n_frames, n_voxels, type_agg, out, false, nullptr);
+}
+int nrl_aggregate_dev(const float *series, int n_frames, long long n_voxels, int type_agg, float *out, void *stream) {
+  return aggregate_impl(series, n_frames, n_voxels, type_agg, out, true, (cudaStream_t)stream);
+}
+
+int nrl_summation(const float *arr, long long n, float *out) {
+  if (!out) return fail(NRL_ERR_ARGUMENT, "out is NULL");
+  if (n < 0 || (n > 0 && !arr)) return fail(NRL_ERR_ARGUMENT, "arr is NULL");
+  if (n == 0) { *out = 0.0f; return NRL_OK; }
+  Ctx *cp = nullptr;
+  NRL_TRY(get_ctx(&cp));
+  Ctx &c = *cp;
+  std::lock_guard<std::mutex> lk(c.mu);
+  const long long nblocks = (n + 255) / 256;
+  if (nblocks >= (1ll << 31)) return fail(NRL_ERR_SHAPE, "array too long");
+  NRL_TRY(c.series.reserve((size_t)n * sizeof(float)));
+  NRL_TRY(c.misc.reserve((size_t)(nblocks + 16) * sizeof(float)));
+  NRL_CUDA(cudaMemcpyAsync(c.series.p, arr, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+  float *partial = c.misc.as<float>() + 16;
+  nrl_block_sum_kernel<<<(unsigned)nblocks, 256, 0, c.stream>>>(c.series.as<float>(), partial, n);
+  nrl_final_sum_kernel<<<1, 32, 0, c.stream>>>(partial, (int)nblocks, c.misc.as<float>());
+  g_launches.fetch_add(2);
+  NRL_CUDA(cudaGetLastError());
+  NRL_CUDA(cudaMemcpyAsync(out, c.misc.p, sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+  NRL_CUDA(cudaStreamSynchronize(c.stream));
+  return NRL_OK;
+}
+
+#include "batch_api.inc"
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// nearl_b200 -- data-layout kernels in front of the gather kernels:
+//   nrl_pack_legacy_kernel  [F,N,3] + [F*N] arrays of the reference's FFI -> packed float4
+//   nrl_crop_pack_kernel    focus-box transform + crop + (by-residue) + selection + order-
+//                           preserving compaction of raw trajectory frames, ON THE DEVICE
+//                           (replaces the numpy host code of Feature.query / crop,
+//                           /root/reference/nearl/features.py:92-123,426-483,1329-1368)
+//   nrl_atom_norm_kernel    per-atom normalisation sum of the voxeliser (the first pass of
+//                           frame_interp_global, /root/reference/src/voxelize.cu:79-108)
+#pragma once
+#include "common.cuh"
+#include <float.h>
+
+// ---- legacy layout ------------------------------------------------------------------
+// perm (optional): for every frame a permutation of [0,N) that orders the frame's atoms by
+// weight value (needed by distinct_count); hide_placeholder_weights: atoms whose weight is
+// 99999.0f can never be counted by distinct_count (marching_observers.cu:118-138), they
+// are moved out of every tile's reach.
+__global__ void nrl_pack_legacy_kernel(const float *__restrict__ coords, const float *__restrict__ weights,
+                                       const int *__restrict__ perm, const int F, const int N,
+                                       const int hide_placeholder_weights, float4 *__restrict__ atoms,
+                                       long long *__restrict__ off, int *__restrict__ cnt) {
+  const long long total = (long long)F * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / N);
+    const int j = (int)(i - (long long)f * N);
+    const long long src = (long long)f * N + (perm ? perm[i] : j);
+    float x = coords[src * 3], y = coords[src * 3 + 1], z = coords[src * 3 + 2];
+    if (hide_placeholder_weights && weights[src] == NRL_PLACEHOLDER) x = FLT_MAX;
+    atoms[i] = make_float4(x, y, z, __int_as_float((int)src));
+    if (j == 0) { off[f] = (long long)f * N; cnt[f] = N; }
+  }
+  if (N == 0)
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) { off[f] = 0; cnt[f] = 0; }
+}
+
+// ---- device-side focus box -----------------------------------------------------------
+struct NrlCropDev {
+  float focal[3];           // FOCALPOINTS entry (float32, featurizer.py:352)
+  float center[3];          // Feature.center (float32, features.py:312)
+  float half_f32;           // float32(spacing/2): numpy weak-scalar rule for float32 coordinates
+  double half_f64;          // spacing/2 for float64 coordinates
+  double lo[3], hi[3];      // keep iff lo < x' < hi (features.py:113-122), thresholds as numpy compares them
+  int byres;                // features.py:471-475
+  int selection;            // row of the selection-mask table, -1: all atoms
+  int max_atoms;            // DynamicFeature.MAX_ALLOWED_ATOMS (features.py:1279,1353-1359), 0: no cap
+  int sort_table;           // row of the value-order permutation table, -1: topology order
+};
+
+struct NrlCropParams {
+  const void *xyz;              // [F_all, N_all, 3] float32 or float64
+  int n_atoms;
+  const NrlCropDev *crops;
+  const int *frame_crop;        // per output frame: crop index
+  const int *frame_src;         // per output frame: trajectory frame index
+  const unsigned char *sel;     // [n_sel, N_all]
+  const int *resid;             // [N_all] dense residue index
+  int n_res_words;
+  const int *perms;             // [n_tabs, N_all]
+  float4 *atoms;                // output, frame fd starts at fd * n_atoms
+  long long *off;
+  int *cnt;
+  unsigned char *keep;          // scratch [n_frames_out, N_all]
+  unsigned int *resflags;       // scratch [n_frames_out, n_res_words], zero-initialised
+};
+
+template <typename T> struct NrlXform;
+template <> struct NrlXform<float> {
+  // numpy: ((x - focal) + center) - float32(spacing/2), every step rounded to float32
+  static __device__ __forceinline__ float apply(float x, float f, float c, const NrlCropDev &cr) {
+    return ((x - f) + c) - cr.half_f32;
+  }
+};
+template <> struct NrlXform<double> {
+  // numpy: float64 coordinates promote the float32 focal point and centre exactly
+  static __device__ __forceinline__ double apply(double x, float f, float c, const NrlCropDev &cr) {
+    return ((x - (double)f) + (double)c) - cr.half_f64;
+  }
+};
+
+#define NRL_CROP_NT 256
+#define NRL_CROP_NW (NRL_CROP_NT / 32)
+
+template <typename T>
+__global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCropParams p) {
+  __shared__ int s_wcnt[NRL_CROP_NW];
+  const int fd = blockIdx.x;
+  const NrlCropDev &cr = p.crops[p.frame_crop[fd]];
+  const int N = p.n_atoms;
+  const T *xyz = reinterpret_cast<const T *>(p.xyz) + (long long)p.frame_src[fd] * N * 3;
+  unsigned char *keep = p.keep + (long long)fd * N;
+  unsigned int *resflags = p.resflags + (long long)fd * p.n_res_words;
+  const unsigned char *sel = cr.selection >= 0 ? p.sel + (long long)cr.selection * N : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // phase A: transform + strict two-sided crop per axis, in the coordinate dtype
+  for (int a = tid; a < N; a += NRL_CROP_NT) {
+    const T x = NrlXform<T>::apply(xyz[3 * a], cr.focal[0], cr.center[0], cr);
+    const T y = NrlXform<T>::apply(xyz[3 * a + 1], cr.focal[1], cr.center[1], cr);
+    const T z = NrlXform<T>::apply(xyz[3 * a + 2], cr.focal[2], cr.center[2], cr);
+    const bool in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
+                    ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
+    keep[a] = in ? 1 : 0;
+    if (cr.byres && in) {
+      const int r = p.resid[a];
+      atomicOr(&resflags[r >> 5], 1u << (r & 31));
+    }
+  }
+  __syncthreads();
+  if (cr.byres || sel) {
+    for (int a = tid; a < N; a += NRL_CROP_NT) {
+      bool k = keep[a] != 0;
+      if (cr.byres) { const int r = p.resid[a]; k = (resflags[r >> 5] >> (r & 31)) & 1u; }
+      if (sel) k = k && (sel[a] != 0);
+      keep[a] = k ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  const int *perm = cr.sort_table >= 0 ? p.perms + (long long)cr.sort_table * N : nullptr;
+  if (perm && cr.max_atoms > 0) {
+    // the cap keeps the first max_atoms atoms in TOPOLOGY order; resolve it before the
+    // value-ordered emission.  One warp, sequential chunks: this path is rare.
+    if (warp == 0) {
+      int seen = 0;
+      for (int a0 = 0; a0 < N; a0 += 32) {
+        const int a = a0 + lane;
+        const bool k = (a < N) && keep[a];
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (k && seen + __popc(m & ((1u << lane) - 1u)) >= cr.max_atoms) keep[a] = 0;
+        seen += __popc(m);
+      }
+    }
+    __syncthreads();
+  }
+
+  // phase B: order-preserving compaction in emission order, warp-contiguous segments
+  const int seg = ((N + NRL_CROP_NW - 1) / NRL_CROP_NW + 31) & ~31;
+  const int e_begin = min(warp * seg, N), e_end = min(e_begin + seg, N);
+  int mycnt = 0;
+  for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+    const int e = e0 + lane;
+    bool k = false;
+    if (e < e_end) k = keep[perm ? perm[e] : e] != 0;
+    mycnt += __popc(__ballot_sync(0xffffffffu, k));
+  }
+  if (lane == 0) s_wcnt[warp] = mycnt;
+  __syncthreads();
+  int base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < NRL_CROP_NW; ++w) { const int c = s_wcnt[w]; if (w < warp) base += c; total += c; }
+  const int cap = (cr.max_atoms > 0 && !perm) ? cr.max_atoms : 0x7fffffff;
+  float4 *out = p.atoms + (long long)fd * N;
+  for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+    const int e = e0 + lane;
+    bool k = false;
+    int a = 0;
+    if (e < e_end) { a = perm ? perm[e] : e; k = keep[a] != 0; }
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    const int pos = base + __popc(m & ((1u << lane) - 1u));
+    if (k && pos < cap) {
+      const T x = NrlXform<T>::apply(xyz[3 * a], cr.focal[0], cr.center[0], cr);
+      const T y = NrlXform<T>::apply(xyz[3 * a + 1], cr.focal[1], cr.center[1], cr);
+      const T z = NrlXform<T>::apply(xyz[3 * a + 2], cr.focal[2], cr.center[2], cr);
+      out[pos] = make_float4((float)x, (float)y, (float)z, __int_as_float(a));   // commands.*: astype(float32)
+    }
+    base += __popc(m);
+  }
+  if (tid == 0) { p.off[fd] = (long long)fd * N; p.cnt[fd] = min(total, cap); }
+}
+
+// ---- per-atom normalisation of the voxeliser -------------------------------------------
+// S_a = sum of the (unnormalised) Gaussian over the lattice points of the BUFFERED grid
+// [-b, n+b-1]^3 strictly inside the cutoff (voxelize.cu:79-96); the 1/(sigma*sqrt(2pi))
+// prefactor of gaussian_map_device cancels in G/S and is dropped.  One warp per packed atom,
+// lanes over the flattened bounding cube, partial sums in double.  Writes 1/S (0 when the
+// reference skips the atom: S == 0, voxelize.cu:109).
+struct NrlNormParams {
+  NrlFrames frames;
+  const int *frame_list;     // frames to process
+  int nx, ny, nz;
+  float spacing, cutoff, k2;
+  float *inv_norm;           // parallel to frames.atoms
+};
+
+__global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams p, const int capacity) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int fd = p.frame_list[blockIdx.y];
+  const int n = min(p.frames.cnt[fd], capacity);
+  const long long off = p.frames.off[fd];
+  const float s = p.spacing, c = p.cutoff, c2 = c * c, k2 = p.k2;
+  const int b = nrl_buff_dim_device(c, s);
+  for (int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_cta) {
+    const float4 a = __ldg(p.frames.atoms + off + i);
+    double sum = 0.0;
+    if (isfinite(a.x) && isfinite(a.y) && isfinite(a.z)) {
+      const int x_lo = (int)fmaxf(floorf((a.x - c) / s) - 1.0f, (float)(-b));
+      const int x_hi = (int)fminf(floorf((a.x + c) / s) + 1.0f, (float)(p.nx + b - 1));
+      const int y_lo = (int)fmaxf(floorf((a.y - c) / s) - 1.0f, (float)(-b));
+      const int y_hi = (int)fminf(floorf((a.y + c) / s) + 1.0f, (float)(p.ny + b - 1));
+      const int z_lo = (int)fmaxf(floorf((a.z - c) / s) - 1.0f, (float)(-b));
+      const int z_hi = (int)fminf(floorf((a.z + c) / s) + 1.0f, (float)(p.nz + b - 1));
+      const int ex = x_hi - x_lo + 1, ey = y_hi - y_lo + 1, ez = z_hi - z_lo + 1;
+      if (ex > 0 && ey > 0 && ez > 0) {
+        const int plane = ey * ez;
+        const float rcp_ez = 1.0f / (float)ez;
+        for (int xi = 0; xi < ex; ++xi) {
+          const float gx = (float)(x_lo + xi) * s;
+          const float dx = a.x - gx;
+          const float dx2 = dx * dx;
+          if (!(dx2 < c2)) continue;
+          for (int q = lane; q < plane; q += 32) {
+            const int yi = __float2int_rd(((float)q + 0.5f) * rcp_ez);
+            const int zi = q - yi * ez;
+            const float gy = (float)(y_lo + yi) * s, gz = (float)(z_lo + zi) * s;
+            const float dy = a.y - gy, dz = a.z - gz;
+            const float d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));        // voxelize.cu:92-94 as compiled
+            if (d2 < c2) sum += (double)nrl_ex2_approx(d2 * k2);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) p.inv_norm[off + i] = sum > 0.0 ? (float)(1.0 / sum) : 0.0f;
+  }
+}

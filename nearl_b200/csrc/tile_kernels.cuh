@@ -1,0 +1,359 @@
+// nearl_b200 -- the gather kernels of the hot path (K1 voxeliser, K2 observers, fused K3).
+//
+// One CTA owns an 8x8x8 tile of voxels of one task and walks the frames of the task's
+// window.  Per frame it (1) scans the frame's packed atoms with coalesced float4 loads
+// and compacts, ORDER-PRESERVING, the atoms whose cutoff sphere can touch the tile into
+// a shared-memory candidate list, (2) lets every thread sweep that list for its four
+// z-consecutive voxels with the reference's exact squared-distance arithmetic, and
+// (3) parks the per-frame value in a shared-memory time series.  After the last frame
+// the series is reduced in place by the reference's reducer (K3) and one float per voxel
+// is written.  No global atomics, no [F,G] intermediate in HBM, no per-frame launch.
+//
+// Replaces: frame_interp_global      /root/reference/src/voxelize.cu:38-130 (deposit half)
+//           marching_observer_global /root/reference/src/marching_observers.cu:405-429
+//           the nine observables     /root/reference/src/marching_observers.cu:30-355
+//           gridwise_aggregation_global /root/reference/src/gpuutils.cu:48-77 (fused)
+#pragma once
+#include "common.cuh"
+#include "reducers.cuh"
+
+// ---- squared distances, exactly as the reference binary evaluates them -------------
+// voxeliser (src/voxelize.cu:121-123): d = atom - gridpoint, fma(dz,dz, fma(dx,dx, dy*dy))
+__device__ __forceinline__ float nrl_vox_partial(float ax, float ay, float gx, float gy) {
+  const float dx = ax - gx, dy = ay - gy;
+  return fmaf(dx, dx, dy * dy);
+}
+// observers (src/gpuutils.cuh:338-345): d = observer - atom, fma(dz,dz, fma(dy,dy, dx*dx))
+__device__ __forceinline__ float nrl_obs_partial(float ox, float oy, float ax, float ay) {
+  const float dx = ox - ax, dy = oy - ay;
+  return fmaf(dy, dy, dx * dx);
+}
+__device__ __forceinline__ float nrl_obs_d2(float ox, float oy, float oz, float ax, float ay, float az) {
+  const float dz = oz - az;
+  return fmaf(dz, dz, nrl_obs_partial(ox, oy, ax, ay));
+}
+
+template <int MODE> struct NrlModeTraits {
+  static constexpr bool kNeedsWeight = (MODE != NRL_OBS_EXISTENCE && MODE != NRL_OBS_DIRECT_COUNT);
+};
+
+// ---- per-frame sweep of the candidate list for the 4 voxels of one thread ----------
+template <int MODE, typename CandPtr>
+__device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const NrlTask &t, const float c2,
+                                          const float px, const float py, const float (&pz)[NRL_VPT],
+                                          float (&val)[NRL_VPT]) {
+  if constexpr (MODE == NRL_MODE_VOXELIZE) {
+    float acc[NRL_VPT];
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) acc[k] = 0.0f;
+    const float k2 = t.k2;
+#pragma unroll 2
+    for (int c = 0; c < ncand; ++c) {
+      const float4 a = cand[c];
+      const float part = nrl_vox_partial(a.x, a.y, px, py);
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {
+        const float dz = a.z - pz[k];
+        const float d2 = fmaf(dz, dz, part);
+        if (d2 < c2) acc[k] = acc[k] + nrl_ex2_approx(d2 * k2) * a.w;   // voxelize.cu:125-127
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) val[k] = acc[k];
+  } else if constexpr (MODE == NRL_OBS_EXISTENCE || MODE == NRL_OBS_DIRECT_COUNT) {
+    float acc[NRL_VPT];
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) acc[k] = 0.0f;
+#pragma unroll 2
+    for (int c = 0; c < ncand; ++c) {
+      const float4 a = cand[c];
+      const float part = nrl_obs_partial(px, py, a.x, a.y);
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {
+        const float dz = pz[k] - a.z;
+        const float d2 = fmaf(dz, dz, part);
+        if (!(d2 > c2)) {                                               // marching_observers.cu:40,77
+          if constexpr (MODE == NRL_OBS_EXISTENCE) acc[k] = 1.0f; else acc[k] = acc[k] + 1.0f;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) val[k] = acc[k];
+  } else if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) {
+    // candidates arrive sorted by weight value (the pack stage orders atoms by value and
+    // the compaction preserves order), so "distinct" is "differs from the last in-range
+    // value"; the reference's 1000-slot table (marching_observers.cu:118-140) caps the
+    // count at 1000 whatever the visiting order.
+    float cnt[NRL_VPT], last[NRL_VPT];
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) { cnt[k] = 0.0f; last[k] = __int_as_float(0x7fc00000); }
+#pragma unroll 2
+    for (int c = 0; c < ncand; ++c) {
+      const float4 a = cand[c];
+      const float part = nrl_obs_partial(px, py, a.x, a.y);
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {
+        const float dz = pz[k] - a.z;
+        const float d2 = fmaf(dz, dz, part);
+        if (!(d2 > c2)) {
+          if (a.w != last[k]) cnt[k] = cnt[k] + 1.0f;
+          last[k] = a.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) val[k] = fminf(cnt[k], NRL_DISTINCT_LIMIT);
+  } else if constexpr (MODE == NRL_OBS_MEAN_DISTANCE) {
+    float r[NRL_VPT], ws[NRL_VPT];
+    int n[NRL_VPT];
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) { r[k] = 0.0f; ws[k] = 0.0f; n[k] = 0; }
+#pragma unroll 2
+    for (int c = 0; c < ncand; ++c) {
+      const float4 a = cand[c];
+      const float part = nrl_obs_partial(px, py, a.x, a.y);
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {
+        const float dz = pz[k] - a.z;
+        const float d2 = fmaf(dz, dz, part);
+        if (!(d2 > c2)) {                                               // :160-167
+          r[k] = fmaf(nrl_sqrt_approx(d2), a.w, r[k]);
+          ws[k] = ws[k] + a.w;
+          n[k] += 1;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) val[k] = n[k] > 0 ? nrl_div_approx(r[k], ws[k]) : 0.0f;
+  } else if constexpr (MODE == NRL_OBS_CUMULATIVE_WEIGHT || MODE == NRL_OBS_DENSITY) {
+    float ws[NRL_VPT];
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) ws[k] = 0.0f;
+#pragma unroll 2
+    for (int c = 0; c < ncand; ++c) {
+      const float4 a = cand[c];
+      const float part = nrl_obs_partial(px, py, a.x, a.y);
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {
+        const float dz = pz[k] - a.z;
+        const float d2 = fmaf(dz, dz, part);
+        if (!(d2 > c2)) ws[k] = ws[k] + a.w;                            // :183-189
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) {
+      if constexpr (MODE == NRL_OBS_DENSITY) val[k] = (float)((double)ws[k] / t.sphere_volume);  // :199-201
+      else val[k] = ws[k];
+    }
+  } else if constexpr (MODE == NRL_OBS_ECCENTRICITY || MODE == NRL_OBS_RADIUS_OF_GYRATION) {
+    float cx[NRL_VPT], cy[NRL_VPT], cz[NRL_VPT], ws[NRL_VPT];
+    int n[NRL_VPT];
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) { cx[k] = cy[k] = cz[k] = ws[k] = 0.0f; n[k] = 0; }
+    for (int c = 0; c < ncand; ++c) {
+      const float4 a = cand[c];
+      const float part = nrl_obs_partial(px, py, a.x, a.y);
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {
+        const float dz = pz[k] - a.z;
+        const float d2 = fmaf(dz, dz, part);
+        if (!(d2 > c2)) {                                               // :279-287, :322-332
+          n[k] += 1;
+          cx[k] = fmaf(a.w, a.x, cx[k]);
+          cy[k] = fmaf(a.w, a.y, cy[k]);
+          cz[k] = fmaf(a.w, a.z, cz[k]);
+          ws[k] = ws[k] + a.w;
+        }
+      }
+    }
+    if constexpr (MODE == NRL_OBS_ECCENTRICITY) {
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {
+        if (n[k] > 0 && ws[k] != 0.0f) {                                // :289-298
+          const float m0 = nrl_div_approx(cx[k], ws[k]), m1 = nrl_div_approx(cy[k], ws[k]),
+                      m2 = nrl_div_approx(cz[k], ws[k]);
+          val[k] = nrl_sqrt_approx(nrl_obs_d2(px, py, pz[k], m0, m1, m2));
+        } else {
+          val[k] = t.cutoff;
+        }
+      }
+    } else {
+      float m0[NRL_VPT], m1[NRL_VPT], m2[NRL_VPT], r[NRL_VPT];
+      bool live[NRL_VPT];
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {                               // :334-343
+        live[k] = (n[k] > 1) && (ws[k] != 0.0f);
+        m0[k] = nrl_div_approx(cx[k], ws[k]);
+        m1[k] = nrl_div_approx(cy[k], ws[k]);
+        m2[k] = nrl_div_approx(cz[k], ws[k]);
+        r[k] = 0.0f;
+      }
+      for (int c = 0; c < ncand; ++c) {                                 // :347-353
+        const float4 a = cand[c];
+        const float part = nrl_obs_partial(px, py, a.x, a.y);
+#pragma unroll
+        for (int k = 0; k < NRL_VPT; ++k) {
+          const float dz = pz[k] - a.z;
+          const float d2 = fmaf(dz, dz, part);
+          if (!(d2 > c2)) r[k] = fmaf(a.w, nrl_obs_d2(m0[k], m1[k], m2[k], a.x, a.y, a.z), r[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k)
+        val[k] = live[k] ? nrl_sqrt_approx(nrl_div_approx(r[k], ws[k])) : 0.0f;
+    }
+  } else if constexpr (MODE == NRL_OBS_DISPERSION) {
+    // pairs (j<k) of in-range atoms in candidate (= atom) order, marching_observers.cu:228-243
+#pragma unroll 1
+    for (int v = 0; v < NRL_VPT; ++v) {
+      float r = 0.0f, ws = 0.0f;
+      for (int j = 0; j < ncand; ++j) {
+        const float4 a = cand[j];
+        if (nrl_obs_d2(px, py, pz[v], a.x, a.y, a.z) > c2) continue;
+        for (int m = j + 1; m < ncand; ++m) {
+          const float4 b = cand[m];
+          if (nrl_obs_d2(px, py, pz[v], b.x, b.y, b.z) > c2) continue;
+          const float d2 = nrl_obs_d2(a.x, a.y, a.z, b.x, b.y, b.z);
+          const float ww = a.w * b.w;
+          r = fmaf(ww, nrl_sqrt_approx(d2), r);
+          ws = ws + ww;
+        }
+      }
+      val[v] = (ws == 0.0f) ? 0.0f : nrl_div_approx(r, ws);             // :244-248
+    }
+  }
+}
+
+// ---- the tile kernel ---------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p) {
+  extern __shared__ __align__(16) unsigned char nrl_smem[];
+  float4 *s_cand = reinterpret_cast<float4 *>(nrl_smem);
+  float4 *s_ser = reinterpret_cast<float4 *>(nrl_smem + (size_t)p.cand_cap * sizeof(float4));
+  __shared__ int s_wcnt[NRL_NW];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lzq = tid & 1, ly = (tid >> 1) & 7, lx = tid >> 4;
+  float4 *g_cand = p.cand_scratch + (long long)blockIdx.x * p.cand_scratch_stride;
+  float4 *g_ser = reinterpret_cast<float4 *>(p.ser_scratch + (long long)blockIdx.x * p.ser_scratch_stride);
+
+  for (int work = blockIdx.x; work < p.n_work; work += gridDim.x) {
+    int lo = 0, hi = p.n_tasks - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&p.tasks[mid].tile_begin) <= work) lo = mid; else hi = mid - 1;
+    }
+    const NrlTask &t = p.tasks[lo];
+    const int tile = work - t.tile_begin;
+    const int nx = t.nx, ny = t.ny, nz = t.nz;
+    const int tzi = tile % t.ntz, tyi = (tile / t.ntz) % t.nty, txi = tile / (t.ntz * t.nty);
+    const int x0 = txi * NRL_TX, y0 = tyi * NRL_TY, z0 = tzi * NRL_TZ;
+    const float s = t.spacing, c = t.cutoff;
+    const float c2 = c * c;
+    const int nF = t.n_frames;
+
+    // conservative bounding box of the tile's voxels grown by the cutoff
+    const float cm = c * 1.0001f + 1e-30f;
+    const float bx0 = (float)x0 * s - cm, bx1 = (float)min(x0 + NRL_TX - 1, nx - 1) * s + cm;
+    const float by0 = (float)y0 * s - cm, by1 = (float)min(y0 + NRL_TY - 1, ny - 1) * s + cm;
+    const float bz0 = (float)z0 * s - cm, bz1 = (float)min(z0 + NRL_TZ - 1, nz - 1) * s + cm;
+
+    const int ix = x0 + lx, iy = y0 + ly, iz = z0 + lzq * NRL_VPT;
+    const float px = (float)ix * s, py = (float)iy * s;
+    float pz[NRL_VPT];
+#pragma unroll
+    for (int k = 0; k < NRL_VPT; ++k) pz[k] = (float)(iz + k) * s;
+
+    const bool ser_in_smem = (long long)nF * NRL_TILE_VOX <= (long long)p.ser_cap;
+    float4 *ser = ser_in_smem ? s_ser : g_ser;
+
+    for (int f = 0; f < nF; ++f) {
+      const long long aoff = p.frames.off[t.frame0 + f];
+      const int n = p.frames.cnt[t.frame0 + f];
+      const float4 *atoms = p.frames.atoms + aoff;
+      const float *inv = (MODE == NRL_MODE_VOXELIZE) ? t.inv_norm + aoff : nullptr;
+
+      // ---- pass 1: each warp counts the survivors of its contiguous atom segment
+      const int seg = ((n + NRL_NW - 1) / NRL_NW + 31) & ~31;
+      const int a_begin = min(warp * seg, n), a_end = min(a_begin + seg, n);
+      int mycnt = 0;
+      for (int i0 = a_begin; i0 < a_end; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        if (i < a_end) {
+          const float4 a = __ldg(atoms + i);
+          if constexpr (MODE == NRL_MODE_VOXELIZE)
+            keep = (a.x >= bx0) && (a.x <= bx1) && (a.y >= by0) && (a.y <= by1) && (a.z >= bz0) && (a.z <= bz1);
+          else   // NaN coordinates are "in range" for the observers (d2 > c2 is false)
+            keep = !(a.x < bx0) && !(a.x > bx1) && !(a.y < by0) && !(a.y > by1) && !(a.z < bz0) && !(a.z > bz1);
+        }
+        mycnt += __popc(__ballot_sync(0xffffffffu, keep));
+      }
+      if (lane == 0) s_wcnt[warp] = mycnt;
+      __syncthreads();
+      int base = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < NRL_NW; ++w) {
+        const int cw = s_wcnt[w];
+        if (w < warp) base += cw;
+        total += cw;
+      }
+      const bool cand_in_smem = total <= p.cand_cap;
+      float4 *cand = cand_in_smem ? s_cand : g_cand;
+
+      // ---- pass 2: order-preserving compaction, weight resolved through the payload
+      for (int i0 = a_begin; i0 < a_end; i0 += 32) {
+        const int i = i0 + lane;
+        bool keep = false;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < a_end) {
+          a = __ldg(atoms + i);
+          if constexpr (MODE == NRL_MODE_VOXELIZE)
+            keep = (a.x >= bx0) && (a.x <= bx1) && (a.y >= by0) && (a.y <= by1) && (a.z >= bz0) && (a.z <= bz1);
+          else
+            keep = !(a.x < bx0) && !(a.x > bx1) && !(a.y < by0) && !(a.y > by1) && !(a.z < bz0) && !(a.z > bz1);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+          float w = 0.0f;
+          if constexpr (NrlModeTraits<MODE>::kNeedsWeight) w = __ldg(t.wtab + __float_as_int(a.w));
+          if constexpr (MODE == NRL_MODE_VOXELIZE) w = w * __ldg(inv + i);
+          if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) w = w + 0.0f;   // -0.0 == +0.0 in the reference's float compare
+          a.w = w;
+          cand[base + __popc(m & ((1u << lane) - 1u))] = a;
+        }
+        base += __popc(m);
+      }
+      __syncthreads();
+
+      // ---- sweep
+      float val[NRL_VPT];
+      if (cand_in_smem) nrl_sweep<MODE>(s_cand, total, t, c2, px, py, pz, val);
+      else nrl_sweep<MODE>(static_cast<const float4 *>(g_cand), total, t, c2, px, py, pz, val);
+
+      if (t.agg == 0) {
+        if (ix < nx && iy < ny) {
+          float *o = p.out + t.out_off + ((long long)ix * ny + iy) * nz;
+#pragma unroll
+          for (int k = 0; k < NRL_VPT; ++k)
+            if (iz + k < nz) o[iz + k] = val[k];
+        }
+      } else {
+        ser[f * NRL_NT + tid] = make_float4(val[0], val[1], val[2], val[3]);
+      }
+      __syncthreads();   // candidate list is rebuilt by the next frame
+    }
+
+    if (t.agg != 0) {
+      // K3 fused: every thread reduces the series of its own four voxels (it wrote them)
+      const float4 r = nrl_reduce4(ser + tid, NRL_NT, nF, t.agg);
+      if (ix < nx && iy < ny) {
+        float *o = p.out + t.out_off + ((long long)ix * ny + iy) * nz;
+        if (iz + 0 < nz) o[iz + 0] = r.x;
+        if (iz + 1 < nz) o[iz + 1] = r.y;
+        if (iz + 2 < nz) o[iz + 2] = r.z;
+        if (iz + 3 < nz) o[iz + 3] = r.w;
+      }
+    }
+  }
+}

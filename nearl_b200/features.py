@@ -1,0 +1,527 @@
+"""Feature classes of the hot path, with the reference's plug-in protocol.
+
+Every feature is ``hook(featurizer)`` -> ``cache(trajectory)`` -> ``query(topology, frames,
+focal)`` -> ``run(*queried)`` -> ``dump(result)`` exactly as in the reference
+(/root/reference/nearl/features.py:144-186), so user subclasses written against Nearl keep
+working through the per-task host protocol.  The built-in classes additionally describe
+themselves to the featuriser (``_native_spec``) so that their focus-box crop, frame slicing,
+voxelisation / observation and time aggregation run batched on the device
+(``nrl_featurize_batch``) instead of one host round trip per task.
+
+In scope: ``Feature``, ``AtomicNumber``, ``Mass``, ``HeavyAtom``,
+``Selection``, ``Backbone``, ``AtomType``, ``Electronegativity``, ``Hydrophobicity``,
+``DynamicFeature``, ``DensityFlow``, ``MarchingObservers``, ``crop``, ``cache_properties``.
+The chemistry-perception features (OpenBabel / RDKit / ChargeFW2) and label features are not
+part of this path.
+"""
+import logging
+
+import numpy as np
+
+from . import commands, constants, utils
+from . import printit, config
+from .io import Trajectory
+
+logger = logging.getLogger(__name__)
+
+__all__ = [
+  "Feature", "AtomicNumber", "Mass", "HeavyAtom", "Selection", "Backbone", "AtomType", "Electronegativity",
+  "Hydrophobicity", "DynamicFeature", "DensityFlow", "MarchingObservers", "cache_properties", "crop",
+  "SUPPORTED_FEATURES", "SUPPORTED_AGGREGATION", "SUPPORTED_OBSERVATION",
+]
+
+# ids are API: they are the integers the native layer dispatches on
+# (features.py:56-89, src/constants.h:15-48)
+SUPPORTED_FEATURES = {
+  "atomic_id": 1, "residue_id": 2, "atomic_number": 3, "hybridization": 4,
+  "mass": 11, "radius": 12, "electronegativity": 13, "hydrophobicity": 14, "partial_charge": 15, "uniformed": 16,
+  "heavy_atom": 21, "aromaticity": 22, "ring": 23, "hbond_donor": 24, "hbond_acceptor": 25,
+  "backboneness": 26, "sidechainness": 27, "atom_type": 28,
+}
+SUPPORTED_AGGREGATION = {
+  "mean": 1, "standard_deviation": 2, "median": 3, "variance": 4, "max": 5, "min": 6,
+  "information_entropy": 7, "drift": 8,
+}
+SUPPORTED_OBSERVATION = {
+  "existence": 1, "direct_count": 2, "distinct_count": 3, "mean_distance": 11, "cumulative_weight": 12,
+  "density": 13, "dispersion": 14, "eccentricity": 15, "radius_of_gyration": 16,
+}
+
+_NUMBER_TYPES = (int, float, np.integer, np.floating)
+
+
+def crop(points, upperbound, padding, spacing):
+  """Boolean mask of the points strictly inside the padded box, shifted by half a voxel
+  (features.py:92-123): ``-padding - spacing/2 < p < upperbound + padding - spacing/2``."""
+  inside = np.ones(len(points), dtype=bool)
+  for axis in range(3):
+    inside &= points[:, axis] < upperbound[axis] + padding - spacing / 2
+    inside &= points[:, axis] > 0 - padding - spacing / 2
+  return inside
+
+
+class Feature:
+  """Base class: a per-atom weight voxelised with a Gaussian around a focal point."""
+
+  _native_kind = "static"
+
+  def __init__(self, dims=None, spacing=None, outfile=None, outkey=None, cutoff=None, sigma=None, padding=None,
+               byres=None, outshape=None, force_recache=None, selection=None, translate="origin", frame_offset=None,
+               **kwargs):
+    self._dims = None
+    self._spacing = None
+    self._center = None
+    self._lengths = None
+    self._padding = None
+    self._frame_offset = frame_offset
+    if dims is not None:
+      self.dims = dims
+    if spacing is not None:
+      self.spacing = spacing
+    if padding is not None:
+      self.padding = padding
+    self.cutoff = cutoff
+    self.sigma = sigma
+    self.outfile = outfile
+    self.outkey = outkey
+    self.outshape = outshape
+    self.byres = byres
+    self.selection = selection
+    self.selected = None
+    self.cached_array = None
+    self.resids = None
+    self.atomic_numbers = None
+    self.classname = self.__class__.__name__
+    self.force_recache = force_recache is not None
+    self.translate = translate       # accepted and reported only, as in the reference (features.py:229-235)
+    if translate not in ("origin", "center"):
+      logger.warning(f"{self.classname}: The translate parameter is not recognized. ")
+    self.hdf_compress_level = kwargs.get("hdf_compress_level", 0)
+    self.hdf_dump_opts = {}
+    self.PARAMSPACE = {
+      "dims": self.dims, "spacing": self.spacing, "cutoff": self.cutoff, "sigma": self.sigma, "outfile": self.outfile,
+      "padding": self.padding, "byres": self.byres, "selection": self.selection, "translate": self.translate,
+      "force_recache": self.force_recache, "outshape": self.outshape, "HDF_OPTS": self.hdf_dump_opts,
+    }
+
+  def __str__(self):
+    return (f"{self.classname} <dims:{self.dims}|lengths:{self._lengths}|spacing:{self.spacing}|cutoff:{self.cutoff}"
+            f"|sigma:{self.sigma}|selection:{self.selection}>")
+
+  # ---- geometry -------------------------------------------------------------------------------
+  @property
+  def params(self):
+    return self.PARAMSPACE
+
+  @property
+  def dims(self):
+    return self._dims
+
+  @dims.setter
+  def dims(self, value):
+    if isinstance(value, _NUMBER_TYPES):
+      self._dims = np.array([int(value)] * 3)
+    elif isinstance(value, (list, tuple, np.ndarray)) and np.ndim(value) == 1:
+      self._dims = np.array([int(i) for i in value][:3])
+    elif isinstance(value, np.ndarray) and np.ndim(value) == 0:
+      self._dims = np.array([int(value)] * 3)      # Featurizer({"dimensions": 32}) hands over a 0-d array
+    else:
+      logger.warning(f"{self.classname} The dimension should be a number, list, tuple or a numpy array, not {type(value)}")
+      self._dims = None
+    self._refresh_geometry()
+
+  @property
+  def spacing(self):
+    return self._spacing
+
+  @spacing.setter
+  def spacing(self, value):
+    if isinstance(value, _NUMBER_TYPES):
+      self._spacing = float(value)
+    else:
+      logger.warning(f"{self.classname}: The spacing is not a valid number, setting to None")
+      self._spacing = None
+    self._refresh_geometry()
+
+  def _refresh_geometry(self):
+    if self._dims is not None and self._spacing is not None:
+      self._center = np.array(self._dims * self._spacing, dtype=np.float32) / 2      # features.py:312
+      self._lengths = self._dims * self._spacing                                       # float64
+
+  @property
+  def center(self):
+    return self._center
+
+  @property
+  def lengths(self):
+    return self._lengths
+
+  @property
+  def padding(self):
+    return self._padding
+
+  @padding.setter
+  def padding(self, value):
+    self._padding = float(value)
+
+  @property
+  def frame_offset(self):
+    return self._frame_offset
+
+  @frame_offset.setter
+  def frame_offset(self, value):
+    self._frame_offset = int(value)
+
+  # ---- protocol -------------------------------------------------------------------------------
+  def hook(self, featurizer):
+    """Inherit unset parameters from the featuriser (features.py:349-394)."""
+    if config.verbose():
+      printit(f"{self}: Hooking feature ({self}) to the featurizer. ")
+    if self.dims is None and featurizer.dims is not None:
+      self.dims = featurizer.dims
+    if self.spacing is None and featurizer.spacing is not None:
+      self.spacing = featurizer.spacing
+    for key in constants.COMMON_FEATURE_PARMS:
+      if getattr(self, key, None) is None:
+        inherited = featurizer.FEATURE_PARMS.get(key, None)
+        if inherited is not None:
+          setattr(self, key, inherited)
+          self.PARAMSPACE[key] = inherited
+    if self.padding is None and self.cutoff is not None:
+      self.padding = self.cutoff
+    if self.frame_offset is None:
+      self.frame_offset = 0
+    if getattr(self, "hdf_compress_level", 0):
+      self.hdf_dump_opts["compression_opts"] = self.hdf_compress_level
+      self.hdf_dump_opts["compression"] = "gzip"
+      self.PARAMSPACE["HDF_OPTS"] = dict(self.hdf_dump_opts)
+
+  def cache(self, trajectory):
+    """Per-trajectory atom tables and the selection mask (features.py:397-423)."""
+    atoms = list(trajectory.top.atoms)
+    self.resids = np.array([a.resid for a in atoms], dtype=int)
+    self.atomic_numbers = np.array([a.atomic_number for a in atoms], dtype=int)
+    n = len(atoms)
+    if self.selection is None:
+      self.selected = np.full(n, True, dtype=bool)
+    elif isinstance(self.selection, str):
+      self.selected = np.full(n, False, dtype=bool)
+      self.selected[trajectory.top.select(self.selection)] = True
+    elif isinstance(self.selection, (list, tuple, np.ndarray)):
+      if len(self.selection) != n:
+        logger.warning(f"{self.classname}: The length of selection array does not match the number of atoms {n} in the topology. ")
+      self.selected = np.full(n, False, dtype=bool)
+      self.selected[np.array(self.selection)] = True
+
+  def query(self, topology, frame_coords, focal_point):
+    """Host protocol: translate to the focus box, crop, apply by-residue and selection
+    (features.py:426-483).  Returns (mask over all atoms, coordinates of the kept atoms)."""
+    focal_point = np.asarray(focal_point)
+    assert focal_point.ndim == 1, f"The focal point should be a 1D array with length 3, rather than the given {focal_point.shape}"
+    if self.resids is None or len(self.resids) != topology.n_atoms or self.force_recache:
+      coords = np.asarray(frame_coords)
+      self.cache(Trajectory(coords if coords.ndim == 3 else coords[None], topology))
+    if self.center is None or self.lengths is None or self.padding is None:
+      logger.warning(f"{self} Skipping the coordinates cropping due to the missing center, lengths or padding information")
+      return np.full(topology.n_atoms, True, dtype=bool), frame_coords
+    frame_coords = frame_coords - focal_point + self.center - self.spacing / 2
+    mask = crop(frame_coords, self.lengths, self.padding, self.spacing)
+    if self.byres:
+      final_mask = np.isin(self.resids, np.unique(self.resids[mask]))
+    else:
+      final_mask = mask
+    if self.selection is not None:
+      final_mask = final_mask * self.selected
+    return final_mask, np.ascontiguousarray(frame_coords[final_mask])
+
+  def run(self, coords, weights):
+    """Host protocol: Gaussian voxelisation of the queried atoms (features.py:485-508)."""
+    if len(coords) == 0:
+      logger.warning(f"{self.classname}: The coordinates from query method are empty, returning an all-zero array")
+      return np.zeros(self.dims, dtype=np.float32)
+    return commands.frame_voxelize(coords, weights, self.dims, self.spacing, self.cutoff, self.sigma)
+
+  def dump(self, result):
+    """NaN -> 0, then append one row to dataset ``outkey`` of ``outfile`` (features.py:510-534)."""
+    if self.outfile is None or self.outkey is None or len(self.outfile) == 0:
+      logger.warning(f"{self.classname}: The outfile and/or outkey are not set, the result is not dumped into file. ")
+      return
+    result = np.asarray(result)
+    if np.isnan(result).any():
+      logger.warning(f"{self.classname}: Found {np.isnan(result).sum()} NaN values in the result array")
+      result = np.nan_to_num(result).astype(result.dtype)
+    row = np.array([result], dtype=np.float32)
+    if self.outshape is not None:
+      utils.append_hdf_data(self.outfile, self.outkey, row, dtype=np.float32, maxshape=self.outshape, chunks=True,
+                            compression="gzip", compression_opts=self.hdf_compress_level)
+    elif len(self.dims) == 3:
+      opts = dict(self.hdf_dump_opts) if self.hdf_compress_level else {}
+      utils.append_hdf_data(self.outfile, self.outkey, row, dtype=np.float32, maxshape=(None, *self.dims),
+                            chunks=(1, *self.dims), **opts)
+
+  # ---- device fast path -------------------------------------------------------------------------
+  def _is_builtin(self, *methods):
+    """True when none of `methods` was overridden outside this module (a user subclass that
+    customises query/run must go through the host protocol)."""
+    return all(getattr(type(self), m).__module__ == __name__ for m in methods)
+
+  def _native_spec(self):
+    """Description of this feature for nrl_featurize_batch, or None for the host protocol."""
+    if self._native_kind != "static" or not self._is_builtin("query", "run"):
+      return None
+    if self.cached_array is None or self.center is None or self.padding is None or self.cutoff is None or self.sigma is None:
+      return None
+    return {
+      "kind": "static", "mode": 0, "agg": 0, "weights": np.asarray(self.cached_array, dtype=np.float32),
+      "frame_offset": int(self.frame_offset or 0), "max_atoms": 0, "sigma": float(self.sigma),
+    }
+
+
+class _PerAtomWeight(Feature):
+  """Static features: one cached weight per atom, first frame (``frame_offset``) of the window."""
+
+  def _weights(self, trajectory):
+    raise NotImplementedError
+
+  def cache(self, trajectory):
+    super().cache(trajectory)
+    self.cached_array = np.asarray(self._weights(trajectory), dtype=np.float32)
+
+  def query(self, topology, frame_coords, focal_point):
+    frame_coords = np.asarray(frame_coords)
+    if frame_coords.ndim == 3:
+      frame_coords = frame_coords[self.frame_offset]
+    mask, coords = super().query(topology, frame_coords, focal_point)
+    return coords, self.cached_array[mask]
+
+
+class AtomicNumber(_PerAtomWeight):
+  """features.py:538-560"""
+  def _weights(self, trajectory):
+    return self.atomic_numbers
+
+
+class Mass(_PerAtomWeight):
+  """features.py:563-605"""
+  def _weights(self, trajectory):
+    return [constants.ATOMICMASS[z] for z in self.atomic_numbers]
+
+
+class HeavyAtom(_PerAtomWeight):
+  """features.py:608-637"""
+  def __init__(self, default_weight=1, **kwargs):
+    super().__init__(**kwargs)
+    self.default_weight = default_weight
+
+  def _weights(self, trajectory):
+    return np.where(self.atomic_numbers > 1, self.default_weight, 0)
+
+
+class Selection(_PerAtomWeight):
+  """features.py:724-754: `default_value` on the selected atoms; unselected atoms are dropped."""
+  def __init__(self, default_value=1, **kwargs):
+    if "selection" not in kwargs:
+      raise ValueError("Selection: The selection parameter should be set")
+    super().__init__(**kwargs)
+    self.default_value = default_value
+
+  def _weights(self, trajectory):
+    return np.where(self.selected, self.default_value, 0)
+
+
+class Backbone(_PerAtomWeight):
+  """features.py:826-857"""
+  def __init__(self, reverse=False, **kwargs):
+    super().__init__(**kwargs)
+    self.reverse = reverse
+
+  def _weights(self, trajectory):
+    bb = np.array([a.name in constants.BACKBONE_ATOM_NAMES for a in trajectory.top.atoms])
+    return (~bb if self.reverse else bb).astype(np.float32)
+
+
+class AtomType(_PerAtomWeight):
+  """features.py:860-892"""
+  def __init__(self, focus_element, **kwargs):
+    super().__init__(**kwargs)
+    self.focus_element = int(focus_element)
+
+  def __str__(self):
+    return f"{self.classname} <focus:{constants.ATOMICNR2SYMBOL.get(self.focus_element, self.focus_element)}>"
+
+  def _weights(self, trajectory):
+    return (self.atomic_numbers == self.focus_element).astype(np.float32)
+
+
+class Electronegativity(_PerAtomWeight):
+  """features.py:1033-1046"""
+  def _weights(self, trajectory):
+    return [constants.ELECNEG[z] for z in self.atomic_numbers]
+
+
+class Hydrophobicity(_PerAtomWeight):
+  """features.py:1049-1067: |EN - EN(carbon)| evaluated in float32"""
+  def _weights(self, trajectory):
+    en = np.array([constants.ELECNEG[z] for z in self.atomic_numbers], dtype=np.float32)
+    return np.abs(en - constants.ELECNEG[6])
+
+
+def cache_properties(trajectory, property_type, **kwargs):
+  """Per-atom weights of the dynamic features by id (features.py:1073-1230).  The ids whose
+  reference implementation depends on OpenBabel / RDKit / ChargeFW2 or is broken in the
+  reference snapshot (4, 12, 15, 22-25) raise NotImplementedError."""
+  atoms = list(trajectory.top.atoms)
+  z = np.array([a.atomic_number for a in atoms], dtype=int)
+  names = [a.name for a in atoms]
+  if property_type == 1:
+    arr = [a.index for a in atoms]
+  elif property_type == 2:
+    arr = [a.resid for a in atoms]
+  elif property_type == 3:
+    arr = z
+  elif property_type == 11:
+    arr = [constants.ATOMICMASS[i] for i in z]
+  elif property_type == 13:
+    arr = [constants.ELECNEG[i] for i in z]
+  elif property_type == 14:
+    en = np.array([constants.ELECNEG[i] for i in z], dtype=np.float32)
+    arr = np.abs(en - constants.ELECNEG[6])
+  elif property_type == 16:
+    arr = np.full(len(z), kwargs.get("manual_weight", 1), dtype=np.float32)
+  elif property_type == 21:
+    arr = (z > 1)
+  elif property_type in (26, 27):
+    # 26 "backboneness" yields the side-chain indicator in the reference too (features.py:1212-1215)
+    arr = [0 if n in constants.BACKBONE_ATOM_NAMES else 1 for n in names]
+  elif property_type == 28:
+    if "element_type" not in kwargs:
+      raise ValueError("The focus element should be set for the atom type")
+    arr = (z == kwargs["element_type"])
+  elif property_type in (4, 12, 15, 22, 23, 24, 25):
+    raise NotImplementedError(f"weight type {property_type} needs chemistry perception that is outside this path")
+  else:
+    raise ValueError(f"The weight type is not recognized {property_type}")
+  return np.array(arr, dtype=np.float32)
+
+
+class DynamicFeature(Feature):
+  """Base of the frame-window features (features.py:1233-1374)."""
+
+  _native_kind = None
+
+  def __init__(self, agg="mean", weight_type="mass", **kwargs):
+    super().__init__(**kwargs)
+    self._agg_type = agg
+    self._weight_type = weight_type
+    self.feature_args = kwargs
+    self.MAX_ALLOWED_ATOMS = 9999
+    self.DEFAULT_COORD = 99999.0
+
+  def __str__(self):
+    return f"{self.classname} <agg:{self._agg_type}|weight:{self._weight_type}|cutoff:{self.cutoff}>"
+
+  @property
+  def agg(self):
+    if self._agg_type in SUPPORTED_AGGREGATION:
+      return SUPPORTED_AGGREGATION[self._agg_type]
+    raise ValueError("The aggregation type is not recognized")
+
+  @agg.setter
+  def agg(self, value):
+    assert isinstance(value, str), "The aggregation type should be a string"
+    self._agg_type = value
+
+  @property
+  def weight_type(self):
+    if self._weight_type in SUPPORTED_FEATURES:
+      return SUPPORTED_FEATURES[self._weight_type]
+    raise ValueError(f"The weight type is not recognized {self._weight_type}; Available types are {SUPPORTED_FEATURES.keys()}")
+
+  @weight_type.setter
+  def weight_type(self, value):
+    assert isinstance(value, str), "The weight type should be a string"
+    self._weight_type = value
+
+  def cache(self, trajectory):
+    super().cache(trajectory)
+    self.cached_array = cache_properties(trajectory, self.weight_type, **self.feature_args)
+
+  def query(self, topology, frame_coords, focal_point):
+    """Host protocol: per-frame crop packed into [F, max_n, 3] padded with 99999 and weights
+    padded with 0, truncated to the first MAX_ALLOWED_ATOMS atoms (features.py:1329-1368)."""
+    frame_coords = np.asarray(frame_coords)
+    assert frame_coords.ndim == 3, f"{self.classname}: The coordinates should follow the convention (frames, atoms, 3); "
+    F = len(frame_coords)
+    coords = np.full((F, self.MAX_ALLOWED_ATOMS, 3), self.DEFAULT_COORD, dtype=np.float32)
+    weights = np.full((F, self.MAX_ALLOWED_ATOMS), 0.0, dtype=np.float32)
+    max_n = 0
+    for idx, frame in enumerate(frame_coords):
+      mask, inbox = Feature.query(self, topology, frame, focal_point)
+      n = np.count_nonzero(mask)
+      if n > self.MAX_ALLOWED_ATOMS:
+        logger.warning(f"{self.classname}: The maximum allowed atom slice is {self.MAX_ALLOWED_ATOMS} but the maximum atom number is {n}")
+      n = min(n, self.MAX_ALLOWED_ATOMS)
+      coords[idx, :n] = inbox[:n]
+      weights[idx, :n] = self.cached_array[mask][:n]
+      max_n = max(max_n, n)
+    return (np.ascontiguousarray(coords[:, :max_n], dtype=np.float32),
+            np.ascontiguousarray(weights[:, :max_n].flatten(), dtype=np.float32))
+
+  def run(self, frames, weights):
+    raise NotImplementedError("The run function should be implemented in the child class")
+
+  def _dynamic_spec(self, mode, sigma):
+    if not self._is_builtin("query", "run"):
+      return None
+    if self.cached_array is None or self.center is None or self.padding is None or self.cutoff is None:
+      return None
+    return {
+      "kind": "dynamic", "mode": int(mode), "agg": int(self.agg), "weights": np.asarray(self.cached_array, dtype=np.float32),
+      "frame_offset": 0, "max_atoms": int(self.MAX_ALLOWED_ATOMS), "sigma": float(sigma),
+    }
+
+
+class DensityFlow(DynamicFeature):
+  """Per-frame Gaussian voxelisation reduced over the window (features.py:1377-1421)."""
+
+  def __str__(self):
+    return f"{self.classname} <agg:{self._agg_type}|weight:{self._weight_type}|cutoff:{self.cutoff}|sigma:{self.sigma}>"
+
+  def run(self, frames, weights):
+    ret = commands.density_flow(frames, weights, self.dims, self.spacing, self.cutoff, self.sigma, self.agg)
+    return ret.reshape(self.dims)
+
+  def _native_spec(self):
+    if self.sigma is None:
+      return None
+    return self._dynamic_spec(0, self.sigma)
+
+
+class MarchingObservers(DynamicFeature):
+  """Every voxel observes the atoms within `cutoff` per frame, reduced over the window
+  (features.py:1424-1523)."""
+
+  def __init__(self, obs="existence", **kwargs):
+    super().__init__(**kwargs)
+    self._obs_type = obs
+
+  def __str__(self):
+    return f"{self.classname} <obs:{self._obs_type}|type:{self._weight_type}|agg:{self._agg_type}|cutoff:{self.cutoff}>"
+
+  @property
+  def obs(self):
+    if self._obs_type in SUPPORTED_OBSERVATION:
+      return SUPPORTED_OBSERVATION[self._obs_type]
+    raise ValueError(f"The observation type is not recognized {self._obs_type}; Available types are {SUPPORTED_OBSERVATION.keys()}")
+
+  @obs.setter
+  def obs(self, value):
+    assert isinstance(value, str), "The observation type should be a string"
+    self._obs_type = value
+
+  def run(self, coords, weights):
+    ret = commands.marching_observer(coords, weights, self.dims, self.spacing, self.cutoff, self.obs, self.agg)
+    return ret.reshape(self.dims)
+
+  def _native_spec(self):
+    return self._dynamic_spec(self.obs, 0.0)

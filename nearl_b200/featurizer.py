@@ -1,0 +1,376 @@
+"""``Featurizer``: trajectory -> frame window -> focal point -> feature loop of the reference
+(/root/reference/nearl/featurizer.py:29-469) with the same registration API, attributes and
+output order, where the inner three loops of every trajectory are lowered to ONE batched
+native call (``nrl_featurize_batch``): focus-box transform, crop and frame slicing happen on
+the device and no per-task host round trip remains.  Features the batch cannot describe
+(user subclasses overriding ``query``/``run``) still run through the host protocol, task by
+task, interleaved in the reference's order.
+"""
+import ctypes
+import json
+import logging
+import time
+
+import numpy as np
+
+from . import _lib, constants, utils
+from . import printit, config
+from .io import pinned_empty
+
+__all__ = ["Featurizer"]
+
+logger = logging.getLogger(__name__)
+
+_NUMBER_TYPES = (int, float, np.integer, np.floating)
+
+
+def _as3(value, dtype):
+  if isinstance(value, _NUMBER_TYPES) or np.ndim(value) == 0:
+    return np.array([value] * 3, dtype=dtype)
+  arr = np.array(value, dtype=dtype).reshape(-1)
+  assert len(arr) == 3, "length should be 3"
+  return arr
+
+
+class Featurizer:
+  """Automates the featurisation of many features over a batch of trajectories.
+
+  Parameters (featurizer.py:92-162): ``dimensions`` (int or 3 ints), ``lengths`` or ``spacing``,
+  ``time_window`` (default 1) and the parameters features inherit
+  (``constants.COMMON_FEATURE_PARMS``).  With an ``outfile`` the parameter set is written to
+  the group ``featurizer_parms`` immediately.
+  """
+
+  def __init__(self, parms={}, **kwargs):
+    self._dims = None
+    self._lengths = None
+    self._spacing = None
+    if parms.get("dimensions", None) is not None:
+      self._dims = _as3(parms["dimensions"], int)
+    if "lengths" in parms:
+      self._lengths = _as3(parms.get("lengths", 16), float)
+      if self._dims is not None:
+        self._spacing = float(np.mean(self._lengths / self._dims))
+    elif "spacing" in parms:
+      self._spacing = float(parms.get("spacing", 1.0))
+      if self._dims is not None:
+        self._lengths = self._dims * self._spacing
+    self.time_window = int(parms.get("time_window", 1))
+
+    self.FEATURE_PARMS = {}
+    for key in constants.COMMON_FEATURE_PARMS:
+      self.FEATURE_PARMS[key] = parms[key] if key in parms else kwargs.get(key, None)
+    self.OTHER_PARMS = {k: v for k, v in parms.items() if k not in constants.COMMON_FEATURE_PARMS}
+    self.OTHER_PARMS.update({k: v for k, v in kwargs.items() if k not in constants.COMMON_FEATURE_PARMS})
+
+    self._traj = None
+    self.frame_slice = None
+    self.FRAMENUMBER = 0
+    self.SLICENUMBER = 0
+    self.FRAMESLICENUMBER = 0
+    self.FRAMESLICES = []
+    self.FEATURESPACE = []
+    self.FEATURENUMBER = 0
+    self.FOCALPOINTS = []
+    self.FOCALPOINTS_PROTOTYPE = None
+    self.FOCALPOINTS_TYPE = None
+    self.FOCALNUMBER = 0
+    self.TRAJLOADER = None
+    self.TRAJECTORYNUMBER = 0
+    self.classname = self.__class__.__name__
+    # nearl_b200: set False to force every feature through the per-task host protocol
+    self.use_native_batch = True
+    self.last_run_stats = {}
+    if config.verbose():
+      printit(f"{self.classname}: Featurizer is initialized successfully with dimensions: {self.dims} and lengths: {self.lengths}")
+    if "outfile" in parms:
+      printit(f"{self.classname}: Dumping the parameters to {parms['outfile']} : {self.parms}")
+      utils.dump_dict(parms["outfile"], "featurizer_parms", self.parms)
+
+  def __str__(self):
+    return f"Feature Number: {self.FEATURENUMBER}; \n" + "".join(f"Feature: {feat}\n" for feat in self.FEATURESPACE)
+
+  # ---- parameters ---------------------------------------------------------------------------
+  @property
+  def parms(self):
+    """All parameters with None replaced by 0 (featurizer.py:170-175)."""
+    return {k: (v if v is not None else 0) for k, v in {**self.FEATURE_PARMS, **self.OTHER_PARMS}.items()}
+
+  @property
+  def dims(self):
+    return np.array(self._dims) if self._dims is not None else None
+
+  @dims.setter
+  def dims(self, newdims):
+    self._dims = _as3(newdims, int)
+    if self._lengths is not None:
+      self._spacing = float(np.mean(self._lengths / self._dims))
+
+  @property
+  def lengths(self):
+    return self._lengths
+
+  @lengths.setter
+  def lengths(self, new_length):
+    self._lengths = _as3(new_length, float)
+    if self._dims is not None:
+      self._spacing = float(np.mean(self._lengths / self._dims))
+
+  @property
+  def spacing(self):
+    return self._spacing
+
+  @property
+  def traj(self):
+    return self._traj
+
+  @traj.setter
+  def traj(self, the_traj):
+    """Frame windows of the active trajectory (featurizer.py:229-241)."""
+    self._traj = the_traj
+    self.FRAMENUMBER = the_traj.n_frames
+    self.SLICENUMBER = self.FRAMENUMBER // self.time_window
+    self.FRAMESLICENUMBER = self.SLICENUMBER
+    if self.SLICENUMBER == 0:
+      logger.warning(f"{self.classname}: No frame slice is available. The trajectory have {self.FRAMENUMBER} frames and the time window is {self.time_window}.")
+    if self.FRAMENUMBER % self.time_window != 0 and self.FRAMENUMBER != 1:
+      logger.warning(f"{self.classname}: the number of frames ({self.FRAMENUMBER}) is not divisible by the time window ({self.time_window}). The last few frames will be ignored.")
+    self.FRAMESLICES = [np.s_[i * self.time_window:(i + 1) * self.time_window] for i in range(self.SLICENUMBER)]
+
+  @property
+  def top(self):
+    return self.traj.top
+
+  # ---- registration -------------------------------------------------------------------------
+  def register_feature(self, feature):
+    feature.hook(self)
+    self.FEATURESPACE.append(feature)
+    self.FEATURENUMBER = len(self.FEATURESPACE)
+    keys = [f.outkey for f in self.FEATURESPACE]
+    if len(set(keys)) != len(keys):
+      raise ValueError("The output keys for the features should be unique.")
+
+  def register_features(self, features):
+    if isinstance(features, dict):
+      features = list(features.values())
+    for feature in features:
+      self.register_feature(feature)
+
+  def register_trajloader(self, trajloader):
+    self.TRAJLOADER = trajloader
+    self.TRAJECTORYNUMBER = len(trajloader)
+    printit(f"{self.classname}: Registered {self.TRAJECTORYNUMBER} trajectories")
+
+  def register_focus(self, focus, format):
+    """``mask`` (Amber masks), ``index`` (lists of atom indices), ``absolute`` ([P,3] points) or
+    ``json`` (file: trajectory identity -> atom indices); featurizer.py:299-343."""
+    if format == "absolute":
+      focus = np.asarray(focus)
+      assert focus.ndim == 2 and focus.shape[1] == 3, "The focus should be a 2D array with 3 columns"
+      self.FOCALPOINTS = focus
+    elif format in ("mask", "index", "json"):
+      self.FOCALPOINTS = None
+    else:
+      raise ValueError(f"Unexpected focus format: {format}. Please choose from 'mask', 'absolute', 'index', 'function'")
+    self.FOCALPOINTS_PROTOTYPE = focus
+    self.FOCALPOINTS_TYPE = format
+
+  def parse_focus(self):
+    """Focal points [slice, focus, 3] in float32 for the active trajectory: the centre of
+    geometry of the selection in the FIRST frame of every window (featurizer.py:345-397).
+    Computed with numpy on the host trajectory, as the reference does; O(S*P*n_sel)."""
+    proto = self.FOCALPOINTS_PROTOTYPE
+    if self.FOCALPOINTS_TYPE == "json":
+      with open(proto, "r") as fh:
+        table = json.load(fh)
+      key = self.traj.identity if self.traj.identity in table else str(self.traj.identity)[:4]
+      proto = [np.array(table[key], dtype=int)]
+    self.FOCALNUMBER = len(proto)
+    self.FOCALPOINTS = np.full((self.SLICENUMBER, self.FOCALNUMBER, 3), 99999, dtype=np.float32)
+    for midx, item in enumerate(proto):
+      if self.FOCALPOINTS_TYPE == "mask":
+        selection = self.traj.top.select(item)
+        if len(selection) == 0:
+          printit(f"{self.classname} Warning: The trajectory {self.traj.identity} does not have any atoms in the selection {item}")
+          return False
+      elif self.FOCALPOINTS_TYPE in ("index", "json"):
+        selection = np.asarray(item, dtype=int)
+      else:
+        assert len(item) == 3, "The focus should be a 3D coordinate"
+        self.FOCALPOINTS[:, midx] = item
+        continue
+      for fidx in range(self.SLICENUMBER):
+        frame = self.traj.xyz[fidx * self.time_window]
+        self.FOCALPOINTS[fidx, midx] = np.mean(frame[selection], axis=0)
+    return 1
+
+  # ---- the loop -----------------------------------------------------------------------------
+  def run(self, *_ignored, trajectory_indices=None):
+    """Featurise every registered trajectory (featurizer.py:399-469).  Positional arguments
+    (the worker counts some scripts pass) are accepted and ignored.  `trajectory_indices`
+    restricts the loop to a shard (multi-GPU: one process per GPU, see nearl_b200.sharding)."""
+    indices = range(self.TRAJECTORYNUMBER) if trajectory_indices is None else trajectory_indices
+    stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "frames": 0, "seconds": 0.0}
+    t_run = time.perf_counter()
+    for tid in indices:
+      self.traj = self.TRAJLOADER[tid]
+      printit(f"{self.classname}: Processing the trajectory {tid + 1} ({self.traj.identity}) with {self.SLICENUMBER} frame slices")
+      st = time.perf_counter()
+      focal_registered = self.FOCALPOINTS_PROTOTYPE is not None
+      if focal_registered:
+        if not self.parse_focus():
+          printit(f"{self.classname} Warning: Skipping the trajectory {self.traj.identity}(index {tid + 1}) because focal points parsing is failed. ")
+          continue
+      else:
+        self.FOCALNUMBER = 0
+      for feat in self.FEATURESPACE:
+        feat.cache(self.traj)
+
+      # task list in the reference's order: window -> focal point -> feature
+      n_focal = self.FOCALNUMBER if self.FOCALNUMBER > 0 else 1
+      task_keys = [(bid, pid, fidx) for bid in range(self.SLICENUMBER) for pid in range(n_focal)
+                   for fidx in range(self.FEATURENUMBER)]
+      specs = [feat._native_spec() if (self.use_native_batch and hasattr(feat, "_native_spec")) else None
+               for feat in self.FEATURESPACE]
+      results = [None] * len(task_keys)
+      native_ids = [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is not None]
+      if native_ids:
+        batch_out = self._run_native_batch([task_keys[i] for i in native_ids], specs)
+        for i, arr in zip(native_ids, batch_out):
+          results[i] = arr
+      frames_cache = {}
+      for i, (bid, pid, fidx) in enumerate(task_keys):
+        if results[i] is not None:
+          continue
+        self.frame_slice = self.FRAMESLICES[bid]
+        if bid not in frames_cache:
+          frames_cache = {bid: self.traj.xyz[self.FRAMESLICES[bid]]}
+        focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else np.zeros(3, dtype=np.float32)
+        feat = self.FEATURESPACE[fidx]
+        results[i] = feat.run(*feat.query(self.top, frames_cache[bid], focal))
+      printit(f"{self.classname}: Trajectory {tid + 1} yields {len(task_keys)} frame-slices (tasks) for the featurization. ")
+
+      with utils.batched_output():
+        for (bid, pid, fidx), result in zip(task_keys, results):
+          self.FEATURESPACE[fidx].dump(result)
+      stats["trajectories"] += 1
+      stats["tasks"] += len(task_keys)
+      stats["native_tasks"] += len(native_ids)
+      stats["frames"] += self.SLICENUMBER * self.time_window
+      printit(f"{self.classname}: Finished the trajectory {tid + 1} / {self.TRAJECTORYNUMBER} with {len(task_keys)} tasks in {time.perf_counter() - st:.6f} seconds")
+    stats["seconds"] = time.perf_counter() - t_run
+    self.last_run_stats = stats
+    printit(f"{self.classname}: All trajectories and tasks are finished. \n")
+    return stats
+
+  def main_loop(self, *args, **kwargs):
+    """Name used by the README / older scripts for the same loop."""
+    return self.run(*args, **kwargs)
+
+  # ---- lowering to nrl_featurize_batch --------------------------------------------------------
+  def _run_native_batch(self, keys, specs):
+    traj = self.traj
+    xyz = traj.xyz
+    if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
+      xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
+    is_f64 = xyz.dtype == np.float64
+    n_atoms = xyz.shape[1]
+
+    wtabs, wtab_ids = [], {}
+    sels, sel_ids = [], {}
+    order_needed = set()
+
+    def table_id(arr):
+      key = id(arr)
+      if key not in wtab_ids:
+        wtab_ids[key] = len(wtabs)
+        wtabs.append(np.ascontiguousarray(arr, dtype=np.float32))
+      return wtab_ids[key]
+
+    def selection_id(feat):
+      if feat.selection is None:
+        return -1
+      key = id(feat.selected)
+      if key not in sel_ids:
+        sel_ids[key] = len(sels)
+        sels.append(np.ascontiguousarray(feat.selected, dtype=np.uint8))
+      return sel_ids[key]
+
+    crops, crop_ids = [], {}
+    tasks = []
+    any_byres = False
+    for (bid, pid, fidx) in keys:
+      feat, spec = self.FEATURESPACE[fidx], specs[fidx]
+      wid = table_id(spec["weights"])
+      sid = selection_id(feat)
+      sort_table = wid if spec["mode"] == 3 else -1
+      if sort_table >= 0:
+        order_needed.add(wid)
+      start = bid * self.time_window
+      if spec["kind"] == "static":
+        start, n_frames = start + spec["frame_offset"], 1
+      else:
+        n_frames = self.time_window
+      focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else np.zeros(3, dtype=np.float32)
+      half = feat.spacing / 2
+      lo = 0 - feat.padding - half                                    # python float: numpy compares it as float32 ...
+      lo_cmp = float(np.float32(lo)) if not is_f64 else lo             # ... against float32 coordinates (weak scalar)
+      hi = [float(feat.lengths[k] + feat.padding - half) for k in range(3)]   # np.float64: compared in double
+      ckey = (start, n_frames, focal.tobytes(), feat.center.tobytes(), half, lo_cmp, tuple(hi), bool(feat.byres), sid,
+              spec["max_atoms"], sort_table)
+      if ckey not in crop_ids:
+        crop_ids[ckey] = len(crops)
+        c = _lib.CropStruct()
+        c.frame_start, c.n_frames = start, n_frames
+        c.focal[:] = [float(v) for v in focal]
+        c.center[:] = [float(v) for v in feat.center]
+        c.half_spacing_f32 = float(np.float32(half))
+        c.half_spacing_f64 = float(half)
+        c.lo[:] = [lo_cmp] * 3
+        c.hi[:] = hi
+        c.byres = 1 if feat.byres else 0
+        c.selection = sid
+        c.max_atoms = spec["max_atoms"]
+        c.sort_table = sort_table
+        any_byres |= bool(feat.byres)
+        crops.append(c)
+      t = _lib.TaskStruct()
+      t.crop, t.mode, t.agg, t.weight_table = crop_ids[ckey], spec["mode"], spec["agg"], wid
+      t.dims[:] = [int(v) for v in feat.dims]
+      t.spacing, t.cutoff, t.sigma = float(feat.spacing), float(feat.cutoff), float(spec["sigma"])
+      tasks.append(t)
+
+    wt = np.stack(wtabs) if wtabs else np.zeros((0, n_atoms), dtype=np.float32)
+    orders = None
+    if order_needed:
+      # value order: equal weights adjacent, NaN last (stable argsort), -0.0 == +0.0
+      orders = np.zeros((len(wtabs), n_atoms), dtype=np.int32)
+      for wid in order_needed:
+        orders[wid] = np.argsort(wtabs[wid] + np.float32(0.0), kind="stable").astype(np.int32)
+    sel_arr = np.stack(sels) if sels else None
+    resid_dense, n_res = None, 0
+    if any_byres:
+      uniq, inverse = np.unique(self.FEATURESPACE[keys[0][2]].resids, return_inverse=True)
+      resid_dense, n_res = np.ascontiguousarray(inverse, dtype=np.int32), len(uniq)
+
+    sizes = [int(np.prod(self.FEATURESPACE[fidx].dims)) for (_, _, fidx) in keys]
+    out = pinned_empty((int(np.sum(sizes)),), np.float32)
+    crop_arr = (_lib.CropStruct * len(crops))(*crops)
+    task_arr = (_lib.TaskStruct * len(tasks))(*tasks)
+    b = _lib.BatchStruct()
+    b.xyz, b.xyz_is_f64, b.xyz_on_device = _lib.ptr(xyz), int(is_f64), 0
+    b.n_frames_total, b.n_atoms = xyz.shape[0], n_atoms
+    b.weight_tables, b.n_weight_tables = _lib.ptr(wt), len(wtabs)
+    b.selections, b.n_selections = (_lib.ptr(sel_arr) if sel_arr is not None else None), len(sels)
+    b.residue_index, b.n_residues = (_lib.ptr(resid_dense) if resid_dense is not None else None), n_res
+    b.value_orders = _lib.ptr(orders) if orders is not None else None
+    b.crops, b.n_crops = crop_arr, len(crops)
+    b.tasks, b.n_tasks = task_arr, len(tasks)
+    b.out, b.out_on_device = _lib.ptr(out), 0
+    b.atom_counts = None
+    _lib.check(_lib.lib().nrl_featurize_batch(ctypes.byref(b)))
+    results, pos = [], 0
+    for (_, _, fidx), size in zip(keys, sizes):
+      results.append(out[pos:pos + size].reshape(self.FEATURESPACE[fidx].dims).copy())
+      pos += size
+    return results

@@ -1,0 +1,244 @@
+"""Trajectory / topology duck types and the synthetic systems of the benchmark.
+
+The featuriser only needs, from a trajectory, what ``Featurizer.run`` touches in the
+reference (/root/reference/nearl/featurizer.py:229-241,345-397,399-469 and
+/root/reference/nearl/features.py:397-423,846,1133-1230): ``n_frames``, ``xyz`` as an
+``[F, N, 3]`` array, ``identity``, and a topology with ``n_atoms``, ``atoms`` (items with
+``index``, ``name``, ``resid``, ``resname``, ``atomic_number``) and ``select(mask)``.
+pytraj objects satisfy this; so do the light classes here, which exist because pytraj (the
+reference's trajectory back-end, /root/reference/nearl/io/traj.py:17) is not part of this
+path and not installed.  Any sequence of such objects is a valid "trajloader"
+(featurizer.py:295,405 only use ``len`` and ``[]``).
+"""
+import re
+
+import numpy as np
+
+from . import constants
+
+__all__ = ["Atom", "Topology", "Trajectory", "synthetic_trajectory", "synthetic_complex", "pinned_empty"]
+
+
+def pinned_empty(shape, dtype):
+  """Page-locked host array (torch is used for the allocation only) so that host<->device copies
+  inside the C ABI run as DMA; falls back to ordinary memory without a CUDA device."""
+  try:
+    import torch
+    if torch.cuda.is_available():
+      tdtype = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
+      return torch.empty(tuple(int(s) for s in shape), dtype=tdtype, pin_memory=True).numpy()
+  except Exception:
+    pass
+  return np.empty(shape, dtype=dtype)
+
+
+class Atom:
+  __slots__ = ("index", "name", "resid", "resname", "atomic_number")
+
+  def __init__(self, index, name, resid, resname, atomic_number):
+    self.index = int(index)
+    self.name = name
+    self.resid = int(resid)
+    self.resname = resname
+    self.atomic_number = int(atomic_number)
+
+
+class Topology:
+  """Column-store topology with an Amber-mask subset (``select``)."""
+
+  def __init__(self, names, resids, resnames, atomic_numbers):
+    self.names = np.asarray(names, dtype=object)
+    self.resids = np.asarray(resids, dtype=np.int64)
+    self.resnames = np.asarray(resnames, dtype=object)
+    self.atomic_numbers = np.asarray(atomic_numbers, dtype=np.int64)
+    n = len(self.names)
+    assert len(self.resids) == n and len(self.resnames) == n and len(self.atomic_numbers) == n
+    self._atoms = None
+
+  @property
+  def n_atoms(self):
+    return len(self.names)
+
+  @property
+  def atoms(self):
+    if self._atoms is None:
+      self._atoms = [Atom(i, self.names[i], self.resids[i], self.resnames[i], self.atomic_numbers[i])
+                     for i in range(self.n_atoms)]
+    return self._atoms
+
+  @property
+  def residues(self):
+    seen = {}
+    for rid, rname in zip(self.resids.tolist(), self.resnames.tolist()):
+      seen.setdefault(rid, rname)
+    return list(seen.items())
+
+  def __getitem__(self, key):
+    idx = np.arange(self.n_atoms)[key]
+    return Topology(self.names[idx], self.resids[idx], self.resnames[idx], self.atomic_numbers[idx])
+
+  # ---- Amber mask subset: ':RES', ':1-10', ':A,B', ':*', '@NAME', '@1-5', ':RES@NAME', '@/El', '!', '&', '|', '()'
+  def select(self, mask):
+    mask = mask.strip()
+    tokens = re.findall(r"[()!&|]|[:@][^()!&|:@\s]+", mask)
+    if "".join(tokens) != re.sub(r"\s+", "", mask) or any(
+        t[0] in ":@" and not re.fullmatch(r"[:@][A-Za-z0-9*,\-+'/_]+", t) for t in tokens):
+      raise ValueError(f"unsupported Amber mask: {mask!r}")
+    pos = [0]
+
+    def peek():
+      return tokens[pos[0]] if pos[0] < len(tokens) else None
+
+    def take():
+      pos[0] += 1
+      return tokens[pos[0] - 1]
+
+    def primary():
+      tok = peek()
+      if tok == "(":
+        take()
+        val = expr()
+        if take() != ")":
+          raise ValueError(f"unbalanced parentheses in mask {mask!r}")
+        return val
+      if tok == "!":
+        take()
+        return ~primary()
+      if tok is None or tok in ")&|":
+        raise ValueError(f"malformed mask {mask!r}")
+      val = self._spec(take())
+      while peek() is not None and peek()[0] in ":@":   # ':RES@CA' is an implicit AND
+        val = val & self._spec(take())
+      return val
+
+    def conj():
+      val = primary()
+      while peek() == "&":
+        take()
+        val = val & primary()
+      return val
+
+    def expr():
+      val = conj()
+      while peek() == "|":
+        take()
+        val = val | conj()
+      return val
+
+    result = expr()
+    if pos[0] != len(tokens):
+      raise ValueError(f"malformed mask {mask!r}")
+    return np.flatnonzero(result)
+
+  def _spec(self, tok):
+    kind, body = tok[0], tok[1:]
+    out = np.zeros(self.n_atoms, dtype=bool)
+    if kind == ":":
+      order = {rid: i + 1 for i, rid in enumerate(dict.fromkeys(self.resids.tolist()))}
+      resnum = np.array([order[r] for r in self.resids.tolist()], dtype=np.int64)   # 1-based residue number
+      for part in body.split(","):
+        if part == "*":
+          out[:] = True
+        elif re.fullmatch(r"\d+(-\d+)?", part):
+          lo, _, hi = part.partition("-")
+          out |= (resnum >= int(lo)) & (resnum <= int(hi or lo))
+        else:
+          out |= self.resnames == part
+    else:
+      if body.startswith("/"):
+        for sym in body[1:].split(","):
+          out |= self.atomic_numbers == constants.SYMBOL2ATOMICNR.get(sym, -1)
+        return out
+      for part in body.split(","):
+        if part == "*":
+          out[:] = True
+        elif re.fullmatch(r"\d+(-\d+)?", part):
+          lo, _, hi = part.partition("-")
+          idx = np.arange(1, self.n_atoms + 1)
+          out |= (idx >= int(lo)) & (idx <= int(hi or lo))
+        else:
+          out |= self.names == part
+    return out
+
+
+class Trajectory:
+  """Coordinates ``xyz [F, N, 3]`` (float32 or float64) + topology + identity."""
+
+  def __init__(self, xyz, top, identity="traj"):
+    xyz = np.asarray(xyz)
+    if xyz.ndim == 2:
+      xyz = xyz[None]
+    assert xyz.ndim == 3 and xyz.shape[2] == 3 and xyz.shape[1] == top.n_atoms
+    self.xyz = xyz
+    self.top = top
+    self.identity = identity
+
+  @property
+  def n_frames(self):
+    return self.xyz.shape[0]
+
+  @property
+  def n_atoms(self):
+    return self.xyz.shape[1]
+
+  def __len__(self):
+    return self.n_frames
+
+
+_ELEMENTS = np.array([1, 6, 7, 8, 16])
+_ELEMENT_P = np.array([0.50, 0.32, 0.085, 0.09, 0.005])
+
+
+def _synthetic_topology(rng, n_atoms, ligand_atoms=0):
+  """Consecutive 16-atom residues named cyclically over the 20 amino acids; the first four atoms
+  of a residue are N, CA, C, O.  Optional trailing residue LIG."""
+  n_prot = n_atoms - ligand_atoms
+  z = rng.choice(_ELEMENTS, size=n_atoms, p=_ELEMENT_P)
+  resid = np.arange(n_prot) // 16
+  names = np.empty(n_atoms, dtype=object)
+  resnames = np.empty(n_atoms, dtype=object)
+  sym = constants.ATOMICNR2SYMBOL
+  within = np.arange(n_prot) % 16
+  backbone = {0: ("N", 7), 1: ("CA", 6), 2: ("C", 6), 3: ("O", 8)}
+  for i in range(n_prot):
+    if within[i] in backbone:
+      names[i], z[i] = backbone[within[i]]
+    else:
+      names[i] = f"{sym[int(z[i])]}{within[i]}"
+    resnames[i] = constants.RES[resid[i] % 20]
+  resids = np.empty(n_atoms, dtype=np.int64)
+  resids[:n_prot] = resid
+  if ligand_atoms:
+    last = (resid[-1] + 1) if n_prot else 0
+    for i in range(n_prot, n_atoms):
+      names[i] = f"{sym[int(z[i])]}{i - n_prot + 1}"
+      resnames[i] = "LIG"
+      resids[i] = last
+  return Topology(names, resids, resnames, z)
+
+
+def synthetic_trajectory(n_atoms, n_frames, seed, dtype=np.float32, identity=None, pin=True, step=0.3):
+  """Uniform-density (0.1 atoms/A^3) cube, random-walk dynamics of `step` A per frame."""
+  rng = np.random.default_rng(seed)
+  top = _synthetic_topology(rng, n_atoms)
+  side = (n_atoms / 0.1) ** (1.0 / 3.0)
+  xyz = pinned_empty((n_frames, n_atoms, 3), dtype) if pin else np.empty((n_frames, n_atoms, 3), dtype=dtype)
+  frame = rng.uniform(0.0, side, size=(n_atoms, 3))
+  for t in range(n_frames):
+    if t:
+      frame = frame + rng.normal(0.0, step, size=(n_atoms, 3))
+    xyz[t] = frame.astype(dtype)
+  return Trajectory(xyz, top, identity or f"synthetic_{n_atoms}x{n_frames}_{seed}")
+
+
+def synthetic_complex(n_atoms, seed, ligand_atoms=30, dtype=np.float32, identity=None, pin=False):
+  """Single-frame protein + 30-atom ligand (residue LIG) at the cube centre (PDBBind-style)."""
+  rng = np.random.default_rng(seed)
+  top = _synthetic_topology(rng, n_atoms, ligand_atoms=ligand_atoms)
+  side = (n_atoms / 0.1) ** (1.0 / 3.0)
+  frame = rng.uniform(0.0, side, size=(n_atoms, 3))
+  frame[n_atoms - ligand_atoms:] = side / 2 + rng.normal(0.0, 2.0, size=(ligand_atoms, 3))
+  xyz = pinned_empty((1, n_atoms, 3), dtype) if pin else np.empty((1, n_atoms, 3), dtype=dtype)
+  xyz[0] = frame.astype(dtype)
+  return Trajectory(xyz, top, identity or f"complex_{n_atoms}_{seed}")

@@ -1,0 +1,116 @@
+"""numpy restatement of the HOST half of the reference's hot path, feeding the C oracle.
+
+TEST INFRASTRUCTURE ONLY (see oracle/nearl_oracle.c).  It restates, independently of
+``nearl_b200.features`` / ``nearl_b200.featurizer``, what the reference does between a
+trajectory and the native calls:
+
+  focal points      /root/reference/nearl/featurizer.py:345-397  (parse_focus)
+  frame windows     /root/reference/nearl/featurizer.py:229-241
+  loop order        /root/reference/nearl/featurizer.py:429-441  (window -> focal -> feature)
+  translate + crop  /root/reference/nearl/features.py:92-123,426-483
+  static query/run  /root/reference/nearl/features.py:485-508,599-605
+  dynamic query     /root/reference/nearl/features.py:1329-1368 (9999-atom padded layout)
+  NaN -> 0 at dump  /root/reference/nearl/features.py:521-523
+
+Parity status: the reference's Python layers cannot be imported on this image (they need
+h5py and pytraj at module import), so this file is pinned only by reading the cited lines;
+the kernels it calls are pinned as described in nearl_oracle.c.
+"""
+import numpy as np
+
+from . import oracle as orc
+
+MAX_ALLOWED_ATOMS = 9999        # features.py:1279
+DEFAULT_COORD = 99999.0         # features.py:1280
+
+
+def focal_points_from_selections(xyz, selections, time_window):
+  """[S, P, 3] float32: mean position of each selection in the first frame of each window."""
+  n_slices = xyz.shape[0] // time_window
+  focal = np.full((n_slices, len(selections), 3), 99999, dtype=np.float32)
+  for midx, sel in enumerate(selections):
+    for fidx in range(n_slices):
+      frame = xyz[fidx * time_window]
+      focal[fidx, midx] = np.mean(frame[sel], axis=0)
+  return focal
+
+
+def crop_mask(points, upperbound, padding, spacing):
+  x0 = points[:, 0] < upperbound[0] + padding - spacing / 2
+  x1 = points[:, 0] > 0 - padding - spacing / 2
+  y0 = points[:, 1] < upperbound[1] + padding - spacing / 2
+  y1 = points[:, 1] > 0 - padding - spacing / 2
+  z0 = points[:, 2] < upperbound[2] + padding - spacing / 2
+  z1 = points[:, 2] > 0 - padding - spacing / 2
+  return np.array(x0 * x1 * y0 * y1 * z0 * z1, dtype=bool)
+
+
+def base_query(desc, resids, frame_coords, focal_point):
+  dims = np.array([int(i) for i in desc["dims"]])
+  spacing = float(desc["spacing"])
+  center = np.array(dims * spacing, dtype=np.float32) / 2
+  lengths = dims * spacing
+  padding = float(desc["padding"] if desc.get("padding") is not None else desc["cutoff"])
+  coords = frame_coords - focal_point + center - spacing / 2
+  mask = crop_mask(coords, lengths, padding, spacing)
+  if desc.get("byres"):
+    res_inbox = np.unique(resids[mask])
+    final = np.full(len(resids), False)
+    for res in res_inbox:
+      final[np.where(resids == res)] = True
+  else:
+    final = mask
+  if desc.get("selection") is not None:
+    final = final * desc["selection"]
+  return final, np.ascontiguousarray(coords[final])
+
+
+def run_task(desc, resids, frames, focal_point, buff_dim=-1):
+  """One (feature, window, focal point) task -> [dims] float32, before the NaN scrub.
+  `buff_dim`: -1 (IEEE evaluation), an int, or a callable (cutoff, spacing) -> int giving the
+  value the device computes (see nearl_oracle.c)."""
+  dims = np.array([int(i) for i in desc["dims"]])
+  spacing, cutoff = float(desc["spacing"]), float(desc["cutoff"])
+  if callable(buff_dim):
+    buff_dim = buff_dim(cutoff, spacing)
+  weights_all = np.asarray(desc["weights"], dtype=np.float32)
+  if desc["kind"] == "static":
+    frame = frames[int(desc.get("frame_offset") or 0)]
+    mask, coords = base_query(desc, resids, frame, focal_point)
+    if len(coords) == 0:
+      return np.zeros(dims, dtype=np.float32)
+    out = orc.frame_voxelize(coords.astype(np.float32), weights_all[mask], dims, spacing, cutoff, float(desc["sigma"]),
+                             buff_dim=buff_dim)
+    return out.reshape(dims)
+  F = len(frames)
+  coords = np.full((F, MAX_ALLOWED_ATOMS, 3), DEFAULT_COORD, dtype=np.float32)
+  weights = np.full((F, MAX_ALLOWED_ATOMS), 0.0, dtype=np.float32)
+  max_n = 0
+  for idx, frame in enumerate(frames):
+    mask, inbox = base_query(desc, resids, frame, focal_point)
+    n = min(np.count_nonzero(mask), MAX_ALLOWED_ATOMS)
+    coords[idx, :n] = inbox[:n]
+    weights[idx, :n] = weights_all[mask][:n]
+    max_n = max(max_n, n)
+  c = np.ascontiguousarray(coords[:, :max_n], dtype=np.float32)
+  w = np.ascontiguousarray(weights[:, :max_n].flatten(), dtype=np.float32)
+  if desc["kind"] == "density_flow":
+    out = orc.density_flow(c, w, dims, spacing, cutoff, float(desc["sigma"]), int(desc["agg"]), buff_dim=buff_dim)
+  else:
+    out = orc.marching_observer(c, w, dims, spacing, cutoff, int(desc["obs"]), int(desc["agg"]))
+  return out.reshape(dims)
+
+
+def featurize(xyz, resids, descs, focal, time_window, buff_dim=-1, scrub_nan=True):
+  """All tasks of one trajectory in the reference's order; returns {outkey: [rows...]}."""
+  n_slices = xyz.shape[0] // time_window
+  out = {d["outkey"]: [] for d in descs}
+  for bid in range(n_slices):
+    frames = xyz[bid * time_window:(bid + 1) * time_window]
+    for pid in range(focal.shape[1]):
+      for d in descs:
+        res = run_task(d, resids, frames, focal[bid, pid], buff_dim=buff_dim)
+        if scrub_nan and np.isnan(res).any():
+          res = np.nan_to_num(res).astype(res.dtype)
+        out[d["outkey"]].append(res)
+  return {k: np.array(v, dtype=np.float32) for k, v in out.items()}

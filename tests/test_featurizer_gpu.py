@@ -1,0 +1,134 @@
+"""End-to-end parity of Featurizer.run (device-side focus boxes + batched kernels) against the
+numpy restatement of the reference's host pipeline feeding the CPU oracle (oracle/host_ref.py),
+and against this package's own per-task host protocol."""
+import os
+
+import numpy as np
+import pytest
+
+import nearl_b200
+from nearl_b200 import _lib, features, featurizer, io, utils
+from oracle import host_ref
+
+pytestmark = pytest.mark.gpu
+nearl_b200.update_config(quiet=True)
+
+
+def rel_bad(new, ref, rtol=1e-5, atol=0.0):
+  ref = np.asarray(ref, dtype=np.float64); new = np.asarray(new, dtype=np.float64)
+  scale = np.maximum(np.abs(ref), 1e-5 * max(np.abs(ref).max(), 1e-30))
+  return int((np.abs(new - ref) > rtol * scale + atol).sum())
+
+
+def build(traj, tmp_path, feats, parms, focus=(":ARG",), native=True):
+  out = str(tmp_path / ("native.h5" if native else "host.h5"))
+  fz = featurizer.Featurizer({**parms, "outfile": out})
+  fz.use_native_batch = native
+  for f in feats():
+    fz.register_feature(f)
+  fz.register_focus(list(focus), "mask")
+  fz.register_trajloader([traj])
+  fz.main_loop()
+  with utils.open_hdf(out, "r") as h:
+    return {k: h[k][:] for k in h.keys() if k != "featurizer_parms"}, fz
+
+
+def descs_from(fz):
+  descs = []
+  for f in fz.FEATURESPACE:
+    d = {"outkey": f.outkey, "dims": f.dims, "spacing": f.spacing, "cutoff": f.cutoff, "sigma": f.sigma, "padding": f.padding,
+         "byres": f.byres, "selection": (f.selected if f.selection is not None else None), "weights": f.cached_array,
+         "frame_offset": f.frame_offset}
+    if isinstance(f, features.MarchingObservers):
+      d.update(kind="marching_observers", obs=f.obs, agg=f.agg)
+    elif isinstance(f, features.DensityFlow):
+      d.update(kind="density_flow", agg=f.agg)
+    else:
+      d.update(kind="static")
+    descs.append(d)
+  return descs
+
+
+def test_readme_quickstart_mass(tmp_path):
+  # README.rst:36-42 on a synthetic 5k-atom, 100-frame trajectory (BASELINE.json configs[0])
+  traj = io.synthetic_trajectory(5000, 100, seed=20240713 + 1)
+  parms = {"dimensions": 32, "lengths": 16, "time_window": 10}
+  feats = lambda: [features.Mass(outkey="mass", sigma=1.5, cutoff=5.0)]
+  got, fz = build(traj, tmp_path, feats, parms)
+  assert got["mass"].shape == (10, 32, 32, 32) and got["mass"].dtype == np.float32
+  ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 10,
+                           buff_dim=_lib.buff_dim)
+  assert rel_bad(got["mass"], ref["mass"]) == 0
+  host, _ = build(traj, tmp_path, feats, parms, native=False)
+  assert rel_bad(got["mass"], host["mass"]) == 0
+  with utils.open_hdf(str(tmp_path / "native.h5"), "r") as h:
+    assert list(h["featurizer_parms/dimensions"][()].reshape(-1)) in ([32], [32, 32, 32]) or h["featurizer_parms/dimensions"][()] == 32
+    assert h["mass"].chunks == (1, 32, 32, 32) and h["mass"].maxshape == (None, 32, 32, 32)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_mixed_static_dynamic_vs_host_pipeline(tmp_path, dtype):
+  traj = io.synthetic_trajectory(3000, 20, seed=7, dtype=dtype)
+  parms = {"dimensions": [24, 24, 24], "lengths": [12, 12, 12], "time_window": 5, "cutoff": 4.0, "sigma": 1.5}
+  def feats():
+    return [
+      features.Mass(outkey="mass"),
+      features.HeavyAtom(outkey="heavy", cutoff=2.5),
+      features.AtomType(focus_element=6, outkey="carbon", frame_offset=2),
+      features.Selection(selection=":ARG,LYS", outkey="sel", byres=True),
+      features.Hydrophobicity(outkey="hyd", padding=2.0),
+      features.MarchingObservers(obs="existence", agg="mean", outkey="obs_exist"),
+      features.MarchingObservers(obs="direct_count", agg="standard_deviation", weight_type="mass", outkey="obs_count"),
+      features.MarchingObservers(obs="distinct_count", agg="max", weight_type="atomic_number", outkey="obs_distinct"),
+      features.MarchingObservers(obs="distinct_count", agg="mean", weight_type="residue_id", outkey="obs_distinct_res"),
+      features.MarchingObservers(obs="mean_distance", agg="mean", weight_type="mass", outkey="obs_md"),
+      features.MarchingObservers(obs="radius_of_gyration", agg="median", weight_type="mass", outkey="obs_rg"),
+      features.DensityFlow(agg="mean", weight_type="mass", outkey="pdf_mean"),
+      features.DensityFlow(agg="standard_deviation", weight_type="electronegativity", outkey="pdf_std", selection="!:ARG"),
+    ]
+  got, fz = build(traj, tmp_path, feats, parms, focus=(":ARG", ":1-5"))
+  ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 5,
+                           buff_dim=_lib.buff_dim)
+  host, _ = build(traj, tmp_path, feats, parms, focus=(":ARG", ":1-5"), native=False)
+  for key in ref:
+    assert got[key].shape == (8, 24, 24, 24), key
+    if key in ("obs_exist", "obs_distinct", "obs_distinct_res"):
+      assert np.array_equal(got[key], ref[key]), key         # integer observables: bit-exact
+      assert np.array_equal(got[key], host[key]), key
+    elif key in ("obs_count", "pdf_std"):
+      scale = max(float(np.abs(ref[key]).max()), 1e-30)       # std cancels: tolerance relative to the grid scale
+      assert rel_bad(got[key], ref[key], atol=1e-5 * scale) == 0, key
+    else:
+      assert rel_bad(got[key], ref[key]) == 0, (key, np.abs(got[key] - ref[key]).max())
+      assert rel_bad(got[key], host[key]) == 0, key
+
+
+def test_empty_focus_box_and_missing_selection(tmp_path):
+  traj = io.synthetic_trajectory(800, 4, seed=3)
+  fz = featurizer.Featurizer({"dimensions": 8, "lengths": 4, "time_window": 2, "cutoff": 2.0, "sigma": 1.0,
+                              "outfile": str(tmp_path / "e.h5")})
+  fz.register_feature(features.Mass(outkey="mass"))
+  fz.register_feature(features.MarchingObservers(obs="eccentricity", agg="mean", outkey="ecc"))
+  fz.register_focus(np.array([[500.0, 500.0, 500.0]]), "absolute")     # nothing near this point
+  fz.register_trajloader([traj])
+  fz.run()
+  with utils.open_hdf(str(tmp_path / "e.h5"), "r") as h:
+    assert np.all(h["mass"][:] == 0) and h["mass"].shape == (2, 8, 8, 8)
+    assert np.all(h["ecc"][:] == np.float32(2.0))
+  fz2 = featurizer.Featurizer({"dimensions": 8, "lengths": 4, "time_window": 2, "cutoff": 2.0, "sigma": 1.0})
+  fz2.register_feature(features.Mass(outkey="mass", outfile=str(tmp_path / "f.h5")))
+  fz2.register_focus([":XYZ"], "mask")
+  fz2.register_trajloader([traj])
+  stats = fz2.run()
+  assert stats["trajectories"] == 0 and not os.path.exists(str(tmp_path / "f.h5"))
+
+
+def test_custom_feature_subclass_uses_host_protocol(tmp_path):
+  class Doubled(features.Mass):
+    def run(self, coords, weights):
+      return 2 * super().run(coords, weights)
+  traj = io.synthetic_trajectory(1500, 6, seed=11)
+  parms = {"dimensions": 16, "lengths": 8, "time_window": 3, "cutoff": 3.0, "sigma": 1.0}
+  got, fz = build(traj, tmp_path, lambda: [features.Mass(outkey="m"), Doubled(outkey="d")], parms)
+  assert fz.last_run_stats["native_tasks"] == 2 and fz.last_run_stats["tasks"] == 4
+  assert rel_bad(got["d"], 2 * got["m"]) == 0

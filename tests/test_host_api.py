@@ -1,0 +1,197 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, fails loudly
+without a device, the host-side mirror of the reference API behaves like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nearl_b200
+from nearl_b200 import _lib, constants, features, featurizer, io, utils
+
+nearl_b200.update_config(quiet=True)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  header = open(os.path.join(ROOT, "include", "nearl_b200.h")).read()
+  declared = set(re.findall(r"\b(nrl_[a-z0-9_]+)\s*\(", header))
+  assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
+  L = _lib.lib()
+  for name in declared:
+    assert hasattr(L, name), name
+  assert b"sm_100a" in L.nrl_version()
+
+
+def test_no_cpu_fallback():
+  if _lib.device_count() > 0:
+    pytest.skip("a CUDA device is present")
+  from nearl_b200 import all_actions
+  with pytest.raises(RuntimeError, match="no usable CUDA device"):
+    all_actions.aggregate(np.zeros((2, 8), dtype=np.float32), 1)
+  with pytest.raises(RuntimeError):
+    all_actions.frame_voxelize(np.zeros((4, 3), np.float32), np.ones(4, np.float32), [8, 8, 8], 1.0, 2.0, 1.0, 0)
+
+
+def test_product_never_imports_the_oracle():
+  for dirpath, _, files in os.walk(os.path.join(ROOT, "nearl_b200")):
+    for f in files:
+      if f.endswith((".py", ".cu", ".cuh", ".inc", ".h")):
+        text = open(os.path.join(dirpath, f)).read()
+        assert "import oracle" not in text and "from oracle" not in text and "nearl_oracle" not in text, f
+
+
+def test_validation_happens_before_any_device_work():
+  from nearl_b200 import all_actions
+  with pytest.raises(ValueError, match="3 dimensions"):
+    all_actions.marching_observer(np.zeros((5, 3), np.float32), np.ones(5, np.float32), [8, 8, 8], 1.0, 2.0, 1, 1)
+  L = _lib.lib()
+  dims = (ctypes.c_int * 3)(8, 8, 8)
+  buf = (ctypes.c_float * 512)()
+  assert L.nrl_marching_observer(buf, buf, 1, 1, dims, 1.0, 2.0, 7, 1, buf) == _lib.ERR_OBSERVABLE
+  assert L.nrl_marching_observer(buf, buf, 1, 1, dims, 1.0, 2.0, 1, 0, buf) == _lib.ERR_AGGREGATION
+  assert L.nrl_marching_observer(buf, buf, 513, 1, dims, 1.0, 2.0, 1, 1, buf) == _lib.ERR_FRAMES
+  assert b"exceeds the maximum number of frames allowed 512" in L.nrl_last_error()
+  assert L.nrl_density_flow(buf, buf, 1, 1, dims, 1.0, 2.0, 1.0, 9, buf) == _lib.ERR_AGGREGATION
+
+
+def test_constants_match_reference_tables():
+  ref = "/root/reference/nearl/constants.py"
+  assert constants.ATOMICMASS[6] == 12.011 and constants.ELECNEG[8] == 3.44 and len(constants.RES) == 20
+  if not os.path.exists(ref):
+    pytest.skip("reference tree not present")
+  import importlib.util
+  spec = importlib.util.spec_from_file_location("refconst", ref)
+  m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+  assert constants.ATOMICMASS == m.ATOMICMASS and constants.ELECNEG == m.ELECNEG
+  assert constants.COMMON_FEATURE_PARMS == m.COMMON_FEATURE_PARMS and constants.RES == m.RES
+
+
+def test_amber_mask_subset():
+  traj = io.synthetic_trajectory(320, 1, seed=0, pin=False)
+  top = traj.top
+  arg = top.select(":ARG")
+  assert len(arg) == 16 and all(top.resnames[i] == "ARG" for i in arg)
+  assert len(top.select("!:ARG")) == 304
+  assert len(top.select(":*")) == 320
+  assert np.array_equal(top.select(":1-2"), np.arange(32))
+  assert set(top.select(":ARG,LYS")) == set(top.select(":ARG")) | set(top.select(":LYS"))
+  assert set(top.select("!(:ARG,LYS)")) == set(range(320)) - set(top.select(":ARG,LYS"))
+  assert np.array_equal(top.select("@CA"), np.arange(1, 320, 16))
+  assert np.array_equal(top.select(":ARG@CA"), np.array([17]))
+  assert set(top.select(":ARG|@CA")) == set(arg) | set(range(1, 320, 16))
+  assert len(top.select(":XYZ")) == 0
+  with pytest.raises(ValueError):
+    top.select(":ARG<:5.0")
+
+
+def test_featurizer_parameters_and_hook():
+  fz = featurizer.Featurizer({"dimensions": 32, "lengths": 16, "time_window": 10, "cutoff": 5.0, "sigma": 1.5})
+  assert list(fz.dims) == [32, 32, 32] and fz.spacing == 0.5 and list(fz.lengths) == [16.0, 16.0, 16.0]
+  f = features.Mass(outkey="mass")
+  fz.register_feature(f)
+  assert f.cutoff == 5.0 and f.sigma == 1.5 and f.padding == 5.0 and f.frame_offset == 0
+  assert list(f.dims) == [32, 32, 32] and f.spacing == 0.5 and f.center.dtype == np.float32 and list(f.center) == [8, 8, 8]
+  g = features.Mass(outkey="mass")
+  with pytest.raises(ValueError, match="unique"):
+    fz.register_feature(g)
+  fz2 = featurizer.Featurizer({"dimensions": [24, 24, 24], "spacing": 0.75}, sigma=2.0)
+  assert list(fz2.lengths) == [18.0, 18.0, 18.0] and fz2.FEATURE_PARMS["sigma"] == 2.0
+  assert fz2.parms["cutoff"] == 0 and fz2.parms["spacing"] == 0.75
+  with pytest.raises(KeyError):
+    nearl_b200.update_config(nonsense=1)
+  mo = features.MarchingObservers(obs="distinct_count", agg="drift", weight_type="residue_id", outkey="x", cutoff=3.0)
+  assert (mo.obs, mo.agg, mo.weight_type) == (3, 8, 2)
+  with pytest.raises(ValueError):
+    features.MarchingObservers(obs="nope", outkey="y").obs
+
+
+def test_focus_parsing_and_frame_windows():
+  traj = io.synthetic_trajectory(640, 25, seed=1, pin=False)
+  fz = featurizer.Featurizer({"dimensions": 8, "lengths": 8, "time_window": 10})
+  fz.register_focus([":ARG", ":LYS"], "mask")
+  fz.traj = traj
+  assert fz.SLICENUMBER == 2 and fz.FRAMESLICES[1] == slice(10, 20)
+  assert fz.parse_focus() == 1 and fz.FOCALPOINTS.shape == (2, 2, 3) and fz.FOCALPOINTS.dtype == np.float32
+  sel = traj.top.select(":LYS")
+  assert np.array_equal(fz.FOCALPOINTS[1, 1], np.mean(traj.xyz[10][sel], axis=0).astype(np.float32))
+  fz.register_focus([[0, 1, 2]], "index")
+  assert fz.parse_focus() == 1 and np.allclose(fz.FOCALPOINTS[0, 0], traj.xyz[0][:3].mean(0))
+  fz.register_focus([":NOPE"], "mask")
+  assert not fz.parse_focus()
+
+
+def test_host_query_matches_independent_restatement():
+  from oracle import host_ref
+  traj = io.synthetic_trajectory(2000, 3, seed=5, pin=False)
+  fz = featurizer.Featurizer({"dimensions": 16, "lengths": 8, "time_window": 3, "cutoff": 3.0, "sigma": 1.0})
+  feats = [features.Mass(outkey="a"), features.Selection(selection=":ARG", outkey="b", byres=True, padding=1.0),
+           features.MarchingObservers(obs="direct_count", outkey="c", weight_type="atomic_id")]
+  for f in feats:
+    fz.register_feature(f)
+    f.cache(traj)
+  focal = np.mean(traj.xyz[0][traj.top.select(":GLY")], axis=0).astype(np.float32)
+  for f in feats:
+    desc = {"dims": f.dims, "spacing": f.spacing, "cutoff": f.cutoff, "padding": f.padding, "byres": f.byres,
+            "selection": f.selected if f.selection is not None else None}
+    if isinstance(f, features.DynamicFeature):
+      coords, weights = f.query(traj.top, traj.xyz, focal)
+      assert coords.shape[0] == 3 and coords.dtype == np.float32 and weights.shape == (3 * coords.shape[1],)
+      for i in range(3):
+        mask, inbox = host_ref.base_query(desc, f.resids, traj.xyz[i], focal)
+        n = len(inbox)
+        assert np.array_equal(coords[i, :n], inbox.astype(np.float32)) and np.all(coords[i, n:] == 99999.0)
+        assert np.array_equal(weights.reshape(3, -1)[i, :n], f.cached_array[mask])
+    else:
+      coords, weights = f.query(traj.top, traj.xyz, focal)
+      mask, inbox = host_ref.base_query(desc, f.resids, traj.xyz[0], focal)
+      assert np.array_equal(coords, inbox) and np.array_equal(weights, f.cached_array[mask])
+
+
+def test_weight_tables():
+  traj = io.synthetic_trajectory(160, 1, seed=2, pin=False)
+  z = traj.top.atomic_numbers
+  def w(f):
+    f.cache(traj); return f.cached_array
+  assert np.array_equal(w(features.Mass()), np.array([constants.ATOMICMASS[i] for i in z], dtype=np.float32))
+  assert np.array_equal(w(features.HeavyAtom(default_weight=3)), np.where(z > 1, 3, 0).astype(np.float32))
+  assert np.array_equal(w(features.AtomType(focus_element=8)), (z == 8).astype(np.float32))
+  bb = np.array([n in ("C", "O", "CA", "HA", "N", "HN") for n in traj.top.names])
+  assert np.array_equal(w(features.Backbone()), bb.astype(np.float32))
+  assert np.array_equal(w(features.Backbone(reverse=True)), (~bb).astype(np.float32))
+  assert np.array_equal(features.cache_properties(traj, 26), (~bb).astype(np.float32))     # inverted in the reference too
+  assert np.array_equal(features.cache_properties(traj, 27), (~bb).astype(np.float32))
+  assert np.array_equal(features.cache_properties(traj, 1), np.arange(160, dtype=np.float32))
+  assert np.array_equal(features.cache_properties(traj, 16, manual_weight=2.5), np.full(160, 2.5, np.float32))
+  en = np.array([constants.ELECNEG[i] for i in z], dtype=np.float32)
+  assert np.array_equal(w(features.Hydrophobicity()), np.abs(en - constants.ELECNEG[6]))
+  with pytest.raises(NotImplementedError):
+    features.cache_properties(traj, 22)
+
+
+def test_hdf5_layout_roundtrip(tmp_path):
+  path = str(tmp_path / "o.h5")
+  utils.dump_dict(path, "featurizer_parms", {"outfile": path, "cutoff": 5.0, "dimensions": [4, 4, 4], "time_window": 10, "byres": 0})
+  rows = np.random.default_rng(0).random((70, 4, 4, 4)).astype(np.float32)
+  for i in range(0, 70, 7):
+    utils.append_hdf_data(path, "mass", rows[i:i + 7], dtype=np.float32, maxshape=(None, 4, 4, 4), chunks=(1, 4, 4, 4))
+  with utils.batched_output():
+    for i in range(70):
+      utils.append_hdf_data(path, "gz", rows[i:i + 1], dtype=np.float32, maxshape=(None, 4, 4, 4), chunks=(1, 4, 4, 4),
+                            compression="gzip", compression_opts=4)
+  utils.dump_dict(path, "featurizer_parms", {"cutoff": 2.5, "name": "x"})     # recreated, not merged (utils.py:564-568)
+  with utils.open_hdf(path, "r") as h:
+    assert set(h.keys()) == {"featurizer_parms", "mass", "gz"}
+    assert h["mass"].shape == (70, 4, 4, 4) and h["mass"].dtype == np.float32
+    assert h["mass"].maxshape == (None, 4, 4, 4) and h["mass"].chunks == (1, 4, 4, 4)
+    assert np.array_equal(h["mass"][:], rows) and np.array_equal(h["gz"][:], rows)
+    assert np.array_equal(h["mass"][65], rows[65]) and np.array_equal(h["gz"][10:20], rows[10:20])
+    assert set(h["featurizer_parms"].keys()) == {"cutoff", "name"}
+    assert h["featurizer_parms/cutoff"][()] == 2.5 and h["featurizer_parms/name"][()] in ("x", b"x")
+  if utils.hdf_backend() == "hdf5_lite":
+    raw = open(path, "rb").read(16)
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n" and raw[8] == 2
+    from nearl_b200 import hdf5_lite
+    assert hdf5_lite.lookup3(b"") == 0xDEADBEEF
+    assert hdf5_lite.lookup3(b"Four score and seven years ago") == 0x17770551     # lookup3.c self-test vector
