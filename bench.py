@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the Nearl featurisation hot path on B200 (contract: see DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+A step = featurise ONE synthetic trajectory of BASELINE.json configs[1]: 20 000 atoms x 100
+frames, 32^3 grid at 0.5 A, window 10, focus ':ARG', four dynamic features (existence,
+distinct_count(atomic_number), mean_distance(mass), density_flow(mass); mean over the window)
+= 40 (feature, window, focus) tasks consuming 100 frames.  metric = featurised frames / s.
+
+  value : nrl_featurize_batch with the trajectory already resident in HBM and the results left in
+          HBM (CUDA events on the launching stream, max over ranks).
+  e2e   : Featurizer.run() on host trajectories in pinned memory -- host lowering, H2D of the
+          frames, kernels, D2H of the 40 grids -- nothing cached between steps.
+Eight different trajectories per rank are cycled (8 x 24 MB of coordinates > L2).
+
+--impl reference runs the reference's own CUDA kernels (compiled unmodified from
+/root/reference/src into oracle/_ref by oracle/build_ref.sh) behind a numpy restatement of the
+reference's per-task host pipeline (oracle/host_ref.py), i.e. "Nearl as shipped" on the same
+GPU; when that module is unavailable it falls back to the CPU oracle port on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "featurised frames/sec"
+UNIT = "frames/s"
+N_ROTATE = 8
+WORKLOAD = ("configs[1]: dynamic marching-observer features (existence, distinct_count, mean_distance) + density_flow, "
+            "32^3 @0.5A, time_window=10, cutoff 5.0, sigma 1.5, focus ':ARG', synthetic 20k-atom x 100-frame trajectory")
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+  FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+            "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.index = index
+    self.proc = None
+    self.lines = []
+
+  def __enter__(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                    "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+      threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+    except Exception:
+      self.proc = None
+    return self
+
+  def __exit__(self, *exc):
+    if self.proc is not None:
+      time.sleep(0.25)
+      self.proc.terminate()
+      try:
+        self.proc.wait(timeout=2)
+      except Exception:
+        pass
+
+  def summary(self):
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(",")]
+      if len(parts) < 8:
+        continue
+      try:
+        sm.append(float(parts[0])); mx.append(float(parts[1]))
+      except ValueError:
+        continue
+      for name, val in zip(names, parts[4:8]):
+        if val.lower().startswith("active"):
+          reasons.add(name)
+    if not sm:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+  return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def run_native(args):
+  import torch
+  import torch.distributed as dist
+  import nearl_b200
+  from nearl_b200 import _lib, workloads
+  rank, local_rank, world = dist_env()
+  nearl_b200.update_config(quiet=True)
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py: no CUDA device -- the native arm has no CPU fallback")
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+  stream = torch.cuda.current_stream()
+  _lib.check(_lib.lib().nrl_set_device(local_rank))
+  _lib.set_stream(stream.cuda_stream, True)
+
+  # every rank featurises its own trajectories: weak scaling, no data-path collective
+  fz, trajs = workloads.dynamic_observers(n_traj=N_ROTATE, seed_offset=rank * N_ROTATE)
+  fz.keep_results = True
+  n_frames = trajs[0].n_frames
+  n_tasks = fz.FEATURENUMBER * (n_frames // fz.time_window)
+
+  # ---- device-resident arm: lowered batches + trajectories in HBM -------------------------------
+  lowered, dev_xyz = [], []
+  for tid, traj in enumerate(trajs):
+    fz.traj = traj
+    assert fz.parse_focus()
+    for feat in fz.FEATURESPACE:
+      feat.cache(traj)
+    specs = [f._native_spec() for f in fz.FEATURESPACE]
+    keys = [(b, 0, f) for b in range(fz.SLICENUMBER) for f in range(fz.FEATURENUMBER)]
+    lowered.append(fz.lower_batch(keys, specs, traj.n_atoms, False))
+    dev_xyz.append(torch.from_numpy(traj.xyz).cuda())
+  dev_out = torch.empty(lowered[0].out_floats, dtype=torch.float32, device="cuda")
+
+  def step_device(i):
+    k = i % N_ROTATE
+    lowered[k].execute(dev_xyz[k].data_ptr(), n_frames, dev_out.data_ptr(), xyz_on_device=True, out_on_device=True,
+                       no_sync=True)
+
+  def step_e2e(i):
+    fz.RESULTS.clear()
+    fz.run(trajectory_indices=[i % N_ROTATE])
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(step, steps, warmup, profile=False):
+    for i in range(warmup):
+      step(i)
+    barrier()
+    if profile:
+      _lib.profile(True)
+      _lib.profile_read(reset=True)
+    launches0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+      e0.record(stream)
+      for i in range(steps):
+        step(warmup + i)
+      e1.record(stream)
+      barrier()
+    ms = e0.elapsed_time(e1)
+    prof = _lib.profile_read(reset=True) if profile else {}
+    if profile:
+      _lib.profile(False)
+    launches = _lib.kernel_launches() - launches0
+    if world > 1:
+      t = torch.tensor([ms], device="cuda")
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms, launches, prof, clk.summary()
+
+  ms_dev, launches, prof, clocks = timed(step_device, args.steps, args.warmup, profile=True)
+  ms_e2e, _, _, clocks_e2e = timed(step_e2e, args.steps, args.warmup)
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+  frames_total = n_frames * world * args.steps
+  value = frames_total / (ms_dev * 1e-3)
+  e2e = frames_total / (ms_e2e * 1e-3)
+
+  # ---- roofline of the dominant kernel (per-launch CUDA-event times collected over the timed region)
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+  except Exception:
+    pass
+  hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+  peak_kind = "measured (MEASURED_PEAKS.json, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+  kernels = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": v[0] / max(v[1], 1)} for k, v in prof.items()}
+  top = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+  roof = None
+  # atoms inside the focus box, from the same crop the kernels saw
+  fz.traj = trajs[0]
+  fz.parse_focus()
+  f0 = fz.FEATURESPACE[0]
+  f0.cache(trajs[0])
+  n_in = int(np.mean([f0.query(trajs[0].top, trajs[0].xyz[i * 10:i * 10 + 1], fz.FOCALPOINTS[i, 0])[0].shape[1] for i in range(3)]))
+  G = 32 ** 3
+  if top is not None:
+    t_launch = kernels[top]["ms_per_launch"] * 1e-3
+    windows = n_frames // fz.time_window
+    # algorithmic bytes of one (feature, window) task = F*N*16 (packed atoms read) + 4*G (grid written);
+    # one launch of a tile kernel covers the `windows` tasks of its mode
+    alg_bytes = windows * (fz.time_window * n_in * 16 + 4 * G)
+    achieved = alg_bytes / t_launch / 1e9
+    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
+            "launch_ms": kernels[top]["ms_per_launch"],
+            "note": "the gather kernels are FP32-issue bound, not HBM bound: see roofline_compute"}
+    # compute side: voxel x candidate pair tests per second against the FP32 issue rate
+    sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    pair_tests = windows * fz.time_window * G * n_in     # upper bound actually swept: every voxel x in-box atom would be brute force
+    roof_c = {"bound": "fp32-issue", "kernel": top, "brute_force_pairs_per_launch": pair_tests,
+              "brute_force_pairs_per_s": pair_tests / t_launch, "sm_mhz": sm_mhz,
+              "fp32_lane_ops_per_s_peak": 148 * 128 * sm_mhz * 1e6}
+  else:
+    roof_c = None
+
+  # ---- CPU baseline: oracle port on the host cores, bounded sample of the same workload -----------
+  cpu = cpu_baseline_sample(fz, trajs[0])
+
+  line = {
+    "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "dtype": "f32", "data": "synthetic",
+    "config": {"workload": WORKLOAD, "tasks_per_step": n_tasks, "frames_per_step": n_frames, "atoms": trajs[0].n_atoms,
+               "atoms_in_focus_box": n_in, "grid": [32, 32, 32], "l2": f"inputs larger than L2: {N_ROTATE} trajectories x 24 MB cycled",
+               "sharding": "one process per GPU, trajectories sharded by rank, no collective on the data path"},
+    "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+            "h2d_bytes_per_step": int(n_frames * trajs[0].n_atoms * 12 + 4 * trajs[0].n_atoms * 4),
+            "d2h_bytes_per_step": int(n_tasks * G * 4),
+            "api": "nearl_b200.featurizer.Featurizer.run() on pinned host trajectories -> host result grids"},
+    "gpu_launches": int(launches),
+    "clocks": clocks, "clocks_e2e": clocks_e2e,
+    "roofline": roof, "roofline_compute": roof_c, "kernels": kernels,
+    "cpu_baseline": cpu,
+  }
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def cpu_baseline_sample(fz, traj, max_slices=1):
+  """Oracle port (CPU restatement of the reference kernels + numpy host pipeline) on the host
+  cores for `max_slices` windows of the workload."""
+  from nearl_b200 import workloads
+  from oracle import host_ref
+  cores = os.cpu_count() or 1
+  os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+  fz.traj = traj
+  fz.parse_focus()
+  for f in fz.FEATURESPACE:
+    f.cache(traj)
+  descs = workloads.describe(fz)
+  t0 = time.perf_counter()
+  host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs, fz.FOCALPOINTS, fz.time_window, max_slices=max_slices)
+  dt = time.perf_counter() - t0
+  frames = max_slices * fz.time_window
+  return {"value": frames / dt, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"{max_slices} window(s) x {fz.FEATURENUMBER} features ({frames} frames) of the same workload, "
+                    f"brute-force oracle (oracle/nearl_oracle.c, OpenMP over voxels) in {dt:.2f} s"}
+
+
+def run_reference(args):
+  rank, local_rank, world = dist_env()
+  if rank != 0:
+    return
+  import nearl_b200
+  from nearl_b200 import workloads
+  from oracle import host_ref
+  nearl_b200.update_config(quiet=True)
+  fz, trajs = workloads.dynamic_observers(n_traj=min(N_ROTATE, max(1, args.steps)))
+  kernels, kind, device = None, "port", f"{os.cpu_count()} host cores (CPU oracle port)"
+  try:
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import all_actions as ref_actions
+    probe = ref_actions.frame_voxelize(np.full((4, 3), 4.0, dtype=np.float32), np.ones(4, dtype=np.float32),
+                                       np.array([8, 8, 8]), 1.0, 2.0, 1.0, 0)
+    if np.any(probe):     # without a GPU the reference silently returns zeros
+      kernels, kind = host_ref.ModuleKernels(ref_actions), "reference"
+      device = "reference CUDA kernels (unmodified /root/reference/src, sm_100 build) on GPU 0 + 1 host thread for its per-task numpy pipeline"
+  except Exception as exc:
+    device += f" [oracle/_ref unavailable: {exc}]"
+  n_frames = trajs[0].n_frames
+  per_traj = []
+  for traj in trajs:
+    fz.traj = traj
+    fz.parse_focus()
+    for f in fz.FEATURESPACE:
+      f.cache(traj)
+    per_traj.append((traj, fz.FOCALPOINTS.copy(), workloads.describe(fz), fz.FEATURESPACE[0].resids))
+  # the CPU port is ~100x slower: bound its sample to one window per step
+  max_slices = None if kind == "reference" else 1
+
+  def step(i):
+    traj, focal, descs, resids = per_traj[i % len(per_traj)]
+    host_ref.featurize(traj.xyz, resids, descs, focal, fz.time_window, kernels=kernels, max_slices=max_slices)
+
+  for i in range(args.warmup):
+    step(i)
+  t0 = time.perf_counter()
+  for i in range(args.steps):
+    step(args.warmup + i)
+  dt = time.perf_counter() - t0
+  frames = (n_frames if max_slices is None else max_slices * fz.time_window) * args.steps
+  value = frames / dt
+  line = {
+    "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+    "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    "config": {"workload": WORKLOAD, "device": device},
+    "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1 if kind == "reference" else (os.cpu_count() or 1), "kind": kind,
+                     "sample": ("whole trajectory (40 tasks) per step" if max_slices is None else "1 window (4 tasks) per step")},
+    "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="native", choices=["native", "reference"])
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_native(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -144,7 +144,10 @@ typedef struct {
   float *out;                    /* host (pinned for speed) or device: task results back to back, task order */
   int out_on_device;
   int *atom_counts;              /* optional host [total crop frames]: atoms kept per crop frame */
+  int flags;                     /* NRL_BATCH_* */
 } nrl_batch_t;
+
+#define NRL_BATCH_NO_SYNC 1      /* return without synchronising (device-resident in/out only) */
 
 int nrl_featurize_batch(const nrl_batch_t *batch);
 
@@ -154,6 +157,15 @@ int nrl_buff_dim(float cutoff, float spacing, int *out);
 int nrl_device_count(int *out);
 int nrl_set_device(int device);
 int nrl_synchronize(void);
+/* enable != 0: enqueue all work of the host entry points and of nrl_featurize_batch on `stream`
+ * (a cudaStream_t, e.g. torch's current stream) instead of the library's own stream */
+int nrl_set_stream(void *stream, int enable);
+/* per-kernel device timing: CUDA events around every launch of this library, accumulated per
+ * category; nrl_profile_read synchronises and copies NRL_PROFILE_CATEGORIES totals (ms, launches) */
+#define NRL_PROFILE_CATEGORIES 16
+int nrl_profile(int enable);
+int nrl_profile_read(double *ms, long long *counts, int reset);
+const char *nrl_profile_name(int category);
 /* page-lock / unlock caller memory so that the copies inside the host entry points run as DMA */
 int nrl_host_register(void *ptr, long long bytes);
 int nrl_host_unregister(void *ptr);

@@ -19,7 +19,7 @@ EXPORTED = [
   "nrl_frame_voxelize", "nrl_frame_observation", "nrl_marching_observer", "nrl_density_flow", "nrl_aggregate",
   "nrl_summation", "nrl_frame_voxelize_dev", "nrl_frame_observation_dev", "nrl_marching_observer_dev",
   "nrl_density_flow_dev", "nrl_aggregate_dev", "nrl_featurize_batch", "nrl_buff_dim", "nrl_device_count",
-  "nrl_set_device", "nrl_synchronize", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
+  "nrl_set_device", "nrl_synchronize", "nrl_set_stream", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
   "nrl_last_error", "nrl_version",
 ]
 
@@ -55,6 +55,7 @@ class BatchStruct(ctypes.Structure):
     ("tasks", ctypes.POINTER(TaskStruct)), ("n_tasks", c_int),
     ("out", c_void_p), ("out_on_device", c_int),
     ("atom_counts", c_void_p),
+    ("flags", c_int),
   ]
 
 
@@ -92,9 +93,14 @@ def lib():
   L.nrl_set_device.argtypes = [c_int]
   L.nrl_host_register.argtypes = [p, c_ll]
   L.nrl_host_unregister.argtypes = [p]
+  L.nrl_set_stream.argtypes = [p, c_int]
+  L.nrl_profile.argtypes = [c_int]
+  L.nrl_profile_read.argtypes = [p, p, c_int]
+  L.nrl_profile_name.argtypes = [c_int]
+  L.nrl_profile_name.restype = ctypes.c_char_p
   for name in EXPORTED:
     fn = getattr(L, name)
-    if fn.restype is c_int and name not in ("nrl_last_error", "nrl_version", "nrl_kernel_launches"):
+    if fn.restype is c_int and name not in ("nrl_last_error", "nrl_version", "nrl_kernel_launches", "nrl_profile_name"):
       fn.restype = c_int
   _lib = L
   return L
@@ -127,6 +133,26 @@ def device_count():
 
 def kernel_launches():
   return int(lib().nrl_kernel_launches())
+
+
+PROFILE_CATEGORIES = 16
+
+
+def set_stream(stream_ptr, enable=True):
+  check(lib().nrl_set_stream(c_void_p(stream_ptr), 1 if enable else 0))
+
+
+def profile(enable=True):
+  check(lib().nrl_profile(1 if enable else 0))
+
+
+def profile_read(reset=True):
+  """{category name: (total ms, launches)} of the kernels timed since the last reset."""
+  ms = (c_double * PROFILE_CATEGORIES)()
+  cnt = (c_ll * PROFILE_CATEGORIES)()
+  check(lib().nrl_profile_read(ms, cnt, 1 if reset else 0))
+  L = lib()
+  return {L.nrl_profile_name(i).decode(): (ms[i], int(cnt[i])) for i in range(PROFILE_CATEGORIES) if cnt[i]}
 
 
 def buff_dim(cutoff, spacing):

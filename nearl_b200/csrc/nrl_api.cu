@@ -70,7 +70,52 @@ struct Ctx {
   DevBuf coords, weights, perm, atoms, inv, off, cnt, out, tasks, flist, cand_scr, ser_scr, misc, series;
   DevBuf xyz, wtabs, sels, resid, orders, crops, fcrop, fsrc, keep, resflags;
   bool attr_set[32] = {false};
+  cudaStream_t user_stream = nullptr;   // nrl_set_stream: run on the caller's stream instead of our own
+  bool use_user_stream = false;
+  // optional per-kernel timing (nrl_profile): CUDA events around every launch, resolved at the next sync
+  bool prof_on = false;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[NRL_PROFILE_CATEGORIES] = {0};
+  long long prof_cnt[NRL_PROFILE_CATEGORIES] = {0};
+  cudaStream_t work_stream() const { return use_user_stream ? user_stream : stream; }
 };
+
+enum { CAT_PACK_LEGACY = 0, CAT_CROP_PACK = 1, CAT_ATOM_NORM = 2, CAT_TILE0 = 3, CAT_AGGREGATE = 13, CAT_SUMMATION = 14, CAT_MISC = 15 };
+const char *kCatNames[NRL_PROFILE_CATEGORIES] = {
+    "pack_legacy", "crop_pack", "atom_norm", "tile_voxelize", "tile_existence", "tile_direct_count", "tile_distinct_count",
+    "tile_mean_distance", "tile_cumulative_weight", "tile_density", "tile_dispersion", "tile_eccentricity",
+    "tile_radius_of_gyration", "aggregate", "summation", "misc"};
+
+struct ScopedProf {
+  Ctx &c; cudaStream_t st; int cat; cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t get(Ctx &c) {
+    if (!c.prof_pool.empty()) { cudaEvent_t e = c.prof_pool.back(); c.prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ScopedProf(Ctx &c_, cudaStream_t st_, int cat_) : c(c_), st(st_), cat(cat_) {
+    if (c.prof_on) { a = get(c); b = get(c); cudaEventRecord(a, st); }
+  }
+  ~ScopedProf() {
+    if (a) { cudaEventRecord(b, st); c.prof_pending.push_back({cat, a, b}); }
+  }
+};
+void prof_collect(Ctx &c) {
+  for (auto &r : c.prof_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      c.prof_ms[r.cat] += ms;
+      c.prof_cnt[r.cat] += 1;
+    }
+    c.prof_pool.push_back(r.a);
+    c.prof_pool.push_back(r.b);
+  }
+  c.prof_pending.clear();
+  cudaGetLastError();
+}
 
 std::mutex g_ctx_mu;
 Ctx *g_ctx[64] = {nullptr};
@@ -127,7 +172,10 @@ int launch_tiles_mode(Ctx &c, const NrlTileParams &p, int grid, size_t smem, cud
                                   (int)(kCandCap * sizeof(float4) + kSerCapFloats * sizeof(float))));
     c.attr_set[slot] = true;
   }
-  nrl_tile_kernel<MODE><<<grid, NRL_NT, smem, st>>>(p);
+  {
+    ScopedProf sp(c, st, CAT_TILE0 + slot);
+    nrl_tile_kernel<MODE><<<grid, NRL_NT, smem, st>>>(p);
+  }
   g_launches.fetch_add(1);
   NRL_CUDA(cudaGetLastError());
   return NRL_OK;
@@ -238,7 +286,10 @@ int launch_norm(Ctx &c, const NrlFrames &frames, const int *d_frame_list, int n_
     NrlNormParams q = np;
     q.frame_list = d_frame_list + f0;
     dim3 grid((unsigned)std::min((capacity + warps_per_cta - 1) / warps_per_cta, 1 << 16), (unsigned)ny);
-    nrl_atom_norm_kernel<<<grid, warps_per_cta * 32, 0, st>>>(q, capacity);
+    {
+      ScopedProf sp(c, st, CAT_ATOM_NORM);
+      nrl_atom_norm_kernel<<<grid, warps_per_cta * 32, 0, st>>>(q, capacity);
+    }
     g_launches.fetch_add(1);
     NRL_CUDA(cudaGetLastError());
   }
@@ -283,7 +334,7 @@ int legacy_run(const LegacyArgs &a) {
   NRL_TRY(get_ctx(&cp));
   Ctx &c = *cp;
   std::lock_guard<std::mutex> lk(c.mu);
-  cudaStream_t st = a.on_device ? a.user_stream : c.stream;
+  cudaStream_t st = a.on_device ? a.user_stream : c.work_stream();
   const int nF = std::min(a.F, NRL_MAX_FRAMES);   // gpuutils.cu:88, voxelize.cu:403, marching_observers.cu:490
   const size_t n_atoms = (size_t)nF * (size_t)a.N;
 
@@ -325,9 +376,12 @@ int legacy_run(const LegacyArgs &a) {
     {
       const long long total = (long long)n_atoms;
       const int grid = (int)std::min<long long>(std::max<long long>((std::max<long long>(total, nF) + 255) / 256, 1), 4096);
-      nrl_pack_legacy_kernel<<<grid, 256, 0, st>>>(d_coords, d_weights, d_perm, nF, a.N,
-                                                    a.mode == NRL_OBS_DISTINCT_COUNT ? 1 : 0, c.atoms.as<float4>(),
-                                                    c.off.as<long long>(), c.cnt.as<int>());
+      {
+        ScopedProf sp(c, st, CAT_PACK_LEGACY);
+        nrl_pack_legacy_kernel<<<grid, 256, 0, st>>>(d_coords, d_weights, d_perm, nF, a.N,
+                                                      a.mode == NRL_OBS_DISTINCT_COUNT ? 1 : 0, c.atoms.as<float4>(),
+                                                      c.off.as<long long>(), c.cnt.as<int>());
+      }
       g_launches.fetch_add(1);
       NRL_CUDA(cudaGetLastError());
     }
@@ -357,6 +411,7 @@ int legacy_run(const LegacyArgs &a) {
   if (!a.on_device) {
     NRL_CUDA(cudaMemcpyAsync(a.out, d_out, (size_t)G * sizeof(float), cudaMemcpyDeviceToHost, st));
     NRL_CUDA(cudaStreamSynchronize(st));
+    prof_collect(c);
   }
   return NRL_OK;
 }
@@ -368,7 +423,7 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
   NRL_TRY(get_ctx(&cp));
   Ctx &c = *cp;
   std::lock_guard<std::mutex> lk(c.mu);
-  cudaStream_t st = on_device ? user : c.stream;
+  cudaStream_t st = on_device ? user : c.work_stream();
   const int n = std::min(F, NRL_MAX_FRAMES);                 // gpuutils.cu:88
   const float *d_in = series;
   float *d_out = out;
@@ -395,13 +450,17 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
     const int bulk = (G % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
     const long long grid = (G + W - 1) / W;
-    nrl_aggregate_kernel<<<(unsigned)grid, NRL_AGG_NT, smem, st>>>(d_in, n, G, agg, W, bulk, d_out);
+    {
+      ScopedProf sp(c, st, CAT_AGGREGATE);
+      nrl_aggregate_kernel<<<(unsigned)grid, NRL_AGG_NT, smem, st>>>(d_in, n, G, agg, W, bulk, d_out);
+    }
     g_launches.fetch_add(1);
     NRL_CUDA(cudaGetLastError());
   }
   if (!on_device) {
     NRL_CUDA(cudaMemcpyAsync(out, d_out, (size_t)G * sizeof(float), cudaMemcpyDeviceToHost, st));
     NRL_CUDA(cudaStreamSynchronize(st));
+    prof_collect(c);
   }
   return NRL_OK;
 }
@@ -426,8 +485,42 @@ int nrl_set_device(int device) { NRL_CUDA(cudaSetDevice(device)); return NRL_OK;
 int nrl_synchronize(void) {
   Ctx *c = nullptr;
   NRL_TRY(get_ctx(&c));
-  NRL_CUDA(cudaStreamSynchronize(c->stream));
+  std::lock_guard<std::mutex> lk(c->mu);
+  NRL_CUDA(cudaStreamSynchronize(c->work_stream()));
+  prof_collect(*c);
   return NRL_OK;
+}
+int nrl_set_stream(void *stream, int enable) {
+  Ctx *c = nullptr;
+  NRL_TRY(get_ctx(&c));
+  std::lock_guard<std::mutex> lk(c->mu);
+  NRL_CUDA(cudaStreamSynchronize(c->work_stream()));
+  c->user_stream = (cudaStream_t)stream;
+  c->use_user_stream = enable != 0;
+  return NRL_OK;
+}
+int nrl_profile(int enable) {
+  Ctx *c = nullptr;
+  NRL_TRY(get_ctx(&c));
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->prof_on = enable != 0;
+  return NRL_OK;
+}
+int nrl_profile_read(double *ms, long long *counts, int reset) {
+  Ctx *c = nullptr;
+  NRL_TRY(get_ctx(&c));
+  std::lock_guard<std::mutex> lk(c->mu);
+  NRL_CUDA(cudaStreamSynchronize(c->work_stream()));
+  prof_collect(*c);
+  for (int i = 0; i < NRL_PROFILE_CATEGORIES; ++i) {
+    if (ms) ms[i] = c->prof_ms[i];
+    if (counts) counts[i] = c->prof_cnt[i];
+    if (reset) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+  }
+  return NRL_OK;
+}
+const char *nrl_profile_name(int category) {
+  return (category >= 0 && category < NRL_PROFILE_CATEGORIES) ? kCatNames[category] : "";
 }
 int nrl_host_register(void *ptr, long long bytes) {
   if (!ptr || bytes <= 0) return fail(NRL_ERR_ARGUMENT, "nothing to register");

@@ -80,6 +80,9 @@ class Featurizer:
     self.classname = self.__class__.__name__
     # nearl_b200: set False to force every feature through the per-task host protocol
     self.use_native_batch = True
+    # nearl_b200: collect results in self.RESULTS[outkey] (list of arrays) besides / instead of dumping
+    self.keep_results = False
+    self.RESULTS = {}
     self.last_run_stats = {}
     if config.verbose():
       printit(f"{self.classname}: Featurizer is initialized successfully with dimensions: {self.dims} and lengths: {self.lengths}")
@@ -252,7 +255,11 @@ class Featurizer:
 
       with utils.batched_output():
         for (bid, pid, fidx), result in zip(task_keys, results):
-          self.FEATURESPACE[fidx].dump(result)
+          feat = self.FEATURESPACE[fidx]
+          if self.keep_results:
+            self.RESULTS.setdefault(feat.outkey, []).append(result)
+          if feat.outfile or not self.keep_results:
+            feat.dump(result)
       stats["trajectories"] += 1
       stats["tasks"] += len(task_keys)
       stats["native_tasks"] += len(native_ids)
@@ -269,35 +276,37 @@ class Featurizer:
 
   # ---- lowering to nrl_featurize_batch --------------------------------------------------------
   def _run_native_batch(self, keys, specs):
-    traj = self.traj
-    xyz = traj.xyz
+    xyz = self.traj.xyz
     if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
       xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
-    is_f64 = xyz.dtype == np.float64
-    n_atoms = xyz.shape[1]
+    batch = self.lower_batch(keys, specs, xyz.shape[1], xyz.dtype == np.float64)
+    out = pinned_empty((batch.out_floats,), np.float32)
+    batch.execute(_lib.ptr(xyz), xyz.shape[0], _lib.ptr(out))
+    return batch.split(out)
 
+  def lower_batch(self, keys, specs, n_atoms, is_f64):
+    """Translate tasks (window, focal point, feature) of the active trajectory into the crop and
+    task tables of the C ABI.  Crops are shared by every feature that looks at the same frames
+    through the same box (same padding / by-residue / selection / cap / emission order)."""
     wtabs, wtab_ids = [], {}
     sels, sel_ids = [], {}
     order_needed = set()
 
     def table_id(arr):
-      key = id(arr)
-      if key not in wtab_ids:
-        wtab_ids[key] = len(wtabs)
+      if id(arr) not in wtab_ids:
+        wtab_ids[id(arr)] = len(wtabs)
         wtabs.append(np.ascontiguousarray(arr, dtype=np.float32))
-      return wtab_ids[key]
+      return wtab_ids[id(arr)]
 
     def selection_id(feat):
       if feat.selection is None:
         return -1
-      key = id(feat.selected)
-      if key not in sel_ids:
-        sel_ids[key] = len(sels)
+      if id(feat.selected) not in sel_ids:
+        sel_ids[id(feat.selected)] = len(sels)
         sels.append(np.ascontiguousarray(feat.selected, dtype=np.uint8))
-      return sel_ids[key]
+      return sel_ids[id(feat.selected)]
 
-    crops, crop_ids = [], {}
-    tasks = []
+    crops, crop_ids, tasks, shapes = [], {}, [], []
     any_byres = False
     for (bid, pid, fidx) in keys:
       feat, spec = self.FEATURESPACE[fidx], specs[fidx]
@@ -315,8 +324,8 @@ class Featurizer:
       half = feat.spacing / 2
       lo = 0 - feat.padding - half                                    # python float: numpy compares it as float32 ...
       lo_cmp = float(np.float32(lo)) if not is_f64 else lo             # ... against float32 coordinates (weak scalar)
-      hi = [float(feat.lengths[k] + feat.padding - half) for k in range(3)]   # np.float64: compared in double
-      ckey = (start, n_frames, focal.tobytes(), feat.center.tobytes(), half, lo_cmp, tuple(hi), bool(feat.byres), sid,
+      hi = tuple(float(feat.lengths[k] + feat.padding - half) for k in range(3))   # np.float64: compared in double
+      ckey = (start, n_frames, focal.tobytes(), feat.center.tobytes(), half, lo_cmp, hi, bool(feat.byres), sid,
               spec["max_atoms"], sort_table)
       if ckey not in crop_ids:
         crop_ids[ckey] = len(crops)
@@ -339,38 +348,53 @@ class Featurizer:
       t.dims[:] = [int(v) for v in feat.dims]
       t.spacing, t.cutoff, t.sigma = float(feat.spacing), float(feat.cutoff), float(spec["sigma"])
       tasks.append(t)
+      shapes.append(tuple(int(v) for v in feat.dims))
 
-    wt = np.stack(wtabs) if wtabs else np.zeros((0, n_atoms), dtype=np.float32)
-    orders = None
+    batch = LoweredBatch()
+    batch.n_atoms, batch.is_f64 = n_atoms, bool(is_f64)
+    batch.weight_tables = np.stack(wtabs) if wtabs else np.zeros((0, n_atoms), dtype=np.float32)
+    batch.value_orders = None
     if order_needed:
       # value order: equal weights adjacent, NaN last (stable argsort), -0.0 == +0.0
-      orders = np.zeros((len(wtabs), n_atoms), dtype=np.int32)
+      batch.value_orders = np.zeros((len(wtabs), n_atoms), dtype=np.int32)
       for wid in order_needed:
-        orders[wid] = np.argsort(wtabs[wid] + np.float32(0.0), kind="stable").astype(np.int32)
-    sel_arr = np.stack(sels) if sels else None
-    resid_dense, n_res = None, 0
+        batch.value_orders[wid] = np.argsort(wtabs[wid] + np.float32(0.0), kind="stable").astype(np.int32)
+    batch.selections = np.stack(sels) if sels else None
+    batch.residue_index, batch.n_residues = None, 0
     if any_byres:
       uniq, inverse = np.unique(self.FEATURESPACE[keys[0][2]].resids, return_inverse=True)
-      resid_dense, n_res = np.ascontiguousarray(inverse, dtype=np.int32), len(uniq)
+      batch.residue_index, batch.n_residues = np.ascontiguousarray(inverse, dtype=np.int32), len(uniq)
+    batch.crops = (_lib.CropStruct * len(crops))(*crops)
+    batch.tasks = (_lib.TaskStruct * len(tasks))(*tasks)
+    batch.shapes = shapes
+    batch.out_floats = int(sum(int(np.prod(sh)) for sh in shapes))
+    return batch
 
-    sizes = [int(np.prod(self.FEATURESPACE[fidx].dims)) for (_, _, fidx) in keys]
-    out = pinned_empty((int(np.sum(sizes)),), np.float32)
-    crop_arr = (_lib.CropStruct * len(crops))(*crops)
-    task_arr = (_lib.TaskStruct * len(tasks))(*tasks)
+
+class LoweredBatch:
+  """Crop / task tables of one trajectory, ready for nrl_featurize_batch."""
+
+  def execute(self, xyz_ptr, n_frames_total, out_ptr, xyz_on_device=False, out_on_device=False, no_sync=False):
     b = _lib.BatchStruct()
-    b.xyz, b.xyz_is_f64, b.xyz_on_device = _lib.ptr(xyz), int(is_f64), 0
-    b.n_frames_total, b.n_atoms = xyz.shape[0], n_atoms
-    b.weight_tables, b.n_weight_tables = _lib.ptr(wt), len(wtabs)
-    b.selections, b.n_selections = (_lib.ptr(sel_arr) if sel_arr is not None else None), len(sels)
-    b.residue_index, b.n_residues = (_lib.ptr(resid_dense) if resid_dense is not None else None), n_res
-    b.value_orders = _lib.ptr(orders) if orders is not None else None
-    b.crops, b.n_crops = crop_arr, len(crops)
-    b.tasks, b.n_tasks = task_arr, len(tasks)
-    b.out, b.out_on_device = _lib.ptr(out), 0
+    b.xyz, b.xyz_is_f64, b.xyz_on_device = xyz_ptr, int(self.is_f64), int(xyz_on_device)
+    b.n_frames_total, b.n_atoms = int(n_frames_total), int(self.n_atoms)
+    b.weight_tables, b.n_weight_tables = _lib.ptr(self.weight_tables), len(self.weight_tables)
+    b.selections = _lib.ptr(self.selections) if self.selections is not None else None
+    b.n_selections = len(self.selections) if self.selections is not None else 0
+    b.residue_index = _lib.ptr(self.residue_index) if self.residue_index is not None else None
+    b.n_residues = self.n_residues
+    b.value_orders = _lib.ptr(self.value_orders) if self.value_orders is not None else None
+    b.crops, b.n_crops = self.crops, len(self.crops)
+    b.tasks, b.n_tasks = self.tasks, len(self.tasks)
+    b.out, b.out_on_device = out_ptr, int(out_on_device)
     b.atom_counts = None
+    b.flags = 1 if no_sync else 0
     _lib.check(_lib.lib().nrl_featurize_batch(ctypes.byref(b)))
+
+  def split(self, out):
     results, pos = [], 0
-    for (_, _, fidx), size in zip(keys, sizes):
-      results.append(out[pos:pos + size].reshape(self.FEATURESPACE[fidx].dims).copy())
+    for shape in self.shapes:
+      size = int(np.prod(shape))
+      results.append(out[pos:pos + size].reshape(shape).copy())
       pos += size
     return results

@@ -65,22 +65,55 @@ def base_query(desc, resids, frame_coords, focal_point):
   return final, np.ascontiguousarray(coords[final])
 
 
-def run_task(desc, resids, frames, focal_point, buff_dim=-1):
+class OracleKernels:
+  """Kernel back-end of run_task: the C restatement (default)."""
+  def __init__(self, buff_dim=-1):
+    self.buff_dim = buff_dim
+
+  def _b(self, cutoff, spacing):
+    return self.buff_dim(cutoff, spacing) if callable(self.buff_dim) else self.buff_dim
+
+  def frame_voxelize(self, coords, weights, dims, spacing, cutoff, sigma):
+    return orc.frame_voxelize(coords, weights, dims, spacing, cutoff, sigma, buff_dim=self._b(cutoff, spacing))
+
+  def density_flow(self, coords, weights, dims, spacing, cutoff, sigma, agg):
+    return orc.density_flow(coords, weights, dims, spacing, cutoff, sigma, agg, buff_dim=self._b(cutoff, spacing))
+
+  def marching_observer(self, coords, weights, dims, spacing, cutoff, obs, agg):
+    return orc.marching_observer(coords, weights, dims, spacing, cutoff, obs, agg)
+
+
+class ModuleKernels:
+  """Kernel back-end that calls an `all_actions`-compatible module exactly as
+  /root/reference/nearl/commands.py:56-66,136-142,177-190 does (used with the reference's own
+  compiled kernels from oracle/_ref on the GPU box)."""
+  def __init__(self, module):
+    self.m = module
+
+  def frame_voxelize(self, coords, weights, dims, spacing, cutoff, sigma):
+    return self.m.frame_voxelize(coords, weights, np.array(dims, dtype=int), float(spacing), float(cutoff), float(sigma), 0)
+
+  def density_flow(self, coords, weights, dims, spacing, cutoff, sigma, agg):
+    return self.m.density_flow(coords, weights, np.array(dims, dtype=int), float(spacing), float(cutoff), float(sigma), int(agg))
+
+  def marching_observer(self, coords, weights, dims, spacing, cutoff, obs, agg):
+    return self.m.marching_observer(coords, weights, np.asarray(dims, dtype=int), spacing, cutoff, obs, agg)
+
+
+def run_task(desc, resids, frames, focal_point, buff_dim=-1, kernels=None):
   """One (feature, window, focal point) task -> [dims] float32, before the NaN scrub.
   `buff_dim`: -1 (IEEE evaluation), an int, or a callable (cutoff, spacing) -> int giving the
   value the device computes (see nearl_oracle.c)."""
   dims = np.array([int(i) for i in desc["dims"]])
   spacing, cutoff = float(desc["spacing"]), float(desc["cutoff"])
-  if callable(buff_dim):
-    buff_dim = buff_dim(cutoff, spacing)
+  k = kernels if kernels is not None else OracleKernels(buff_dim)
   weights_all = np.asarray(desc["weights"], dtype=np.float32)
   if desc["kind"] == "static":
     frame = frames[int(desc.get("frame_offset") or 0)]
     mask, coords = base_query(desc, resids, frame, focal_point)
     if len(coords) == 0:
       return np.zeros(dims, dtype=np.float32)
-    out = orc.frame_voxelize(coords.astype(np.float32), weights_all[mask], dims, spacing, cutoff, float(desc["sigma"]),
-                             buff_dim=buff_dim)
+    out = k.frame_voxelize(coords.astype(np.float32), weights_all[mask], dims, spacing, cutoff, float(desc["sigma"]))
     return out.reshape(dims)
   F = len(frames)
   coords = np.full((F, MAX_ALLOWED_ATOMS, 3), DEFAULT_COORD, dtype=np.float32)
@@ -95,21 +128,23 @@ def run_task(desc, resids, frames, focal_point, buff_dim=-1):
   c = np.ascontiguousarray(coords[:, :max_n], dtype=np.float32)
   w = np.ascontiguousarray(weights[:, :max_n].flatten(), dtype=np.float32)
   if desc["kind"] == "density_flow":
-    out = orc.density_flow(c, w, dims, spacing, cutoff, float(desc["sigma"]), int(desc["agg"]), buff_dim=buff_dim)
+    out = k.density_flow(c, w, dims, spacing, cutoff, float(desc["sigma"]), int(desc["agg"]))
   else:
-    out = orc.marching_observer(c, w, dims, spacing, cutoff, int(desc["obs"]), int(desc["agg"]))
+    out = k.marching_observer(c, w, dims, spacing, cutoff, int(desc["obs"]), int(desc["agg"]))
   return out.reshape(dims)
 
 
-def featurize(xyz, resids, descs, focal, time_window, buff_dim=-1, scrub_nan=True):
+def featurize(xyz, resids, descs, focal, time_window, buff_dim=-1, scrub_nan=True, kernels=None, max_slices=None):
   """All tasks of one trajectory in the reference's order; returns {outkey: [rows...]}."""
   n_slices = xyz.shape[0] // time_window
+  if max_slices is not None:
+    n_slices = min(n_slices, max_slices)
   out = {d["outkey"]: [] for d in descs}
   for bid in range(n_slices):
     frames = xyz[bid * time_window:(bid + 1) * time_window]
     for pid in range(focal.shape[1]):
       for d in descs:
-        res = run_task(d, resids, frames, focal[bid, pid], buff_dim=buff_dim)
+        res = run_task(d, resids, frames, focal[bid, pid], buff_dim=buff_dim, kernels=kernels)
         if scrub_nan and np.isnan(res).any():
           res = np.nan_to_num(res).astype(res.dtype)
         out[d["outkey"]].append(res)
