@@ -239,14 +239,16 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
   NRL_TRY(c.tasks.reserve(sorted.size() * sizeof(NrlTask)));
   NRL_CUDA(cudaMemcpyAsync(c.tasks.p, sorted.data(), sorted.size() * sizeof(NrlTask), cudaMemcpyHostToDevice, st));
 
-  const size_t smem = kCandCap * sizeof(float4) + kSerCapFloats * sizeof(float);
-  const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (smem + 1024)));
   for (const Range &r : ranges) {
-    int grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 8));
+    // shared memory: the candidate list plus the time series when it fits (else per-CTA global scratch)
+    const size_t ser_need = (size_t)r.max_frames * NRL_TILE_VOX;
+    const int ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
+    const size_t smem = kCandCap * sizeof(float4) + (size_t)ser_cap * sizeof(float);
+    const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (smem + 1024)));
+    int grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 12));
     // overflow scratch (candidate lists longer than kCandCap, series longer than kSerCapFloats)
     const size_t cand_per_cta = max_atoms_per_frame > kCandCap ? (size_t)max_atoms_per_frame : 0;
-    const size_t ser_per_cta = (size_t)r.max_frames * NRL_TILE_VOX > (size_t)kSerCapFloats
-                                   ? (size_t)r.max_frames * NRL_TILE_VOX : 0;
+    const size_t ser_per_cta = ser_cap == 0 ? ser_need : 0;
     const size_t per_cta = cand_per_cta * sizeof(float4) + ser_per_cta * sizeof(float);
     if (per_cta > 0) {
       const int max_grid = (int)std::max<size_t>((size_t)c.sms, kScratchBudget / per_cta);
@@ -265,7 +267,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
     p.ser_scratch = c.ser_scr.as<float>();
     p.ser_scratch_stride = (long long)ser_per_cta;
     p.cand_cap = kCandCap;
-    p.ser_cap = kSerCapFloats;
+    p.ser_cap = ser_cap;
     NRL_TRY(launch_tiles(c, r.mode, p, grid, smem, st));
   }
   return NRL_OK;
@@ -285,7 +287,8 @@ int launch_norm(Ctx &c, const NrlFrames &frames, const int *d_frame_list, int n_
     const int ny = std::min(65535, n_list - f0);
     NrlNormParams q = np;
     q.frame_list = d_frame_list + f0;
-    dim3 grid((unsigned)std::min((capacity + warps_per_cta - 1) / warps_per_cta, 1 << 16), (unsigned)ny);
+    // warps stride over the atoms of their frame: 48 CTAs x 4 warps per frame keep short frames cheap
+    dim3 grid((unsigned)std::max(1, std::min((capacity + warps_per_cta - 1) / warps_per_cta, 48)), (unsigned)ny);
     {
       ScopedProf sp(c, st, CAT_ATOM_NORM);
       nrl_atom_norm_kernel<<<grid, warps_per_cta * 32, 0, st>>>(q, capacity);

@@ -78,7 +78,7 @@ template <> struct NrlXform<double> {
   }
 };
 
-#define NRL_CROP_NT 256
+#define NRL_CROP_NT 1024
 #define NRL_CROP_NW (NRL_CROP_NT / 32)
 
 template <typename T>
@@ -87,13 +87,14 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
   const int fd = blockIdx.x;
   const NrlCropDev &cr = p.crops[p.frame_crop[fd]];
   const int N = p.n_atoms;
-  const T *xyz = reinterpret_cast<const T *>(p.xyz) + (long long)p.frame_src[fd] * N * 3;
-  unsigned char *keep = p.keep + (long long)fd * N;
-  unsigned int *resflags = p.resflags + (long long)fd * p.n_res_words;
-  const unsigned char *sel = cr.selection >= 0 ? p.sel + (long long)cr.selection * N : nullptr;
+  const T *__restrict__ xyz = reinterpret_cast<const T *>(p.xyz) + (long long)p.frame_src[fd] * N * 3;
+  unsigned char *__restrict__ keep = p.keep + (long long)fd * N;
+  unsigned int *__restrict__ resflags = p.resflags + (long long)fd * p.n_res_words;
+  const unsigned char *__restrict__ sel = cr.selection >= 0 ? p.sel + (long long)cr.selection * N : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   // phase A: transform + strict two-sided crop per axis, in the coordinate dtype
+#pragma unroll 4
   for (int a = tid; a < N; a += NRL_CROP_NT) {
     const T x = NrlXform<T>::apply(xyz[3 * a], cr.focal[0], cr.center[0], cr);
     const T y = NrlXform<T>::apply(xyz[3 * a + 1], cr.focal[1], cr.center[1], cr);
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
     }
     __syncthreads();
   }
-  const int *perm = cr.sort_table >= 0 ? p.perms + (long long)cr.sort_table * N : nullptr;
+  const int *__restrict__ perm = cr.sort_table >= 0 ? p.perms + (long long)cr.sort_table * N : nullptr;
   if (perm && cr.max_atoms > 0) {
     // the cap keeps the first max_atoms atoms in TOPOLOGY order; resolve it before the
     // value-ordered emission.  One warp, sequential chunks: this path is rare.
@@ -182,15 +183,25 @@ struct NrlNormParams {
   float *inv_norm;           // parallel to frames.atoms
 };
 
+#define NRL_NORM_MAXZ 96     // lattice points along z inside one cutoff sphere handled by the fast path
+
+// in-cutoff predicate of the reference, bit for bit (voxelize.cu:92-95 as compiled)
+__device__ __forceinline__ bool nrl_norm_in(const float az, const int z, const float s, const float t2, const float c2) {
+  const float dz = az - (float)z * s;
+  return fmaf(dz, dz, t2) < c2;
+}
+
 __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams p, const int capacity) {
-  const int lane = threadIdx.x & 31;
+  __shared__ double s_prefix[4][NRL_NORM_MAXZ + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const int fd = p.frame_list[blockIdx.y];
   const int n = min(p.frames.cnt[fd], capacity);
   const long long off = p.frames.off[fd];
   const float s = p.spacing, c = p.cutoff, c2 = c * c, k2 = p.k2;
   const int b = nrl_buff_dim_device(c, s);
-  for (int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_cta) {
+  double *P = s_prefix[wid];
+  for (int i = blockIdx.x * warps_per_cta + wid; i < n; i += gridDim.x * warps_per_cta) {
     const float4 a = __ldg(p.frames.atoms + off + i);
     double sum = 0.0;
     if (isfinite(a.x) && isfinite(a.y) && isfinite(a.z)) {
@@ -201,19 +212,55 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
       const int z_lo = (int)fmaxf(floorf((a.z - c) / s) - 1.0f, (float)(-b));
       const int z_hi = (int)fminf(floorf((a.z + c) / s) + 1.0f, (float)(p.nz + b - 1));
       const int ex = x_hi - x_lo + 1, ey = y_hi - y_lo + 1, ez = z_hi - z_lo + 1;
-      if (ex > 0 && ey > 0 && ez > 0) {
+      if (ex > 0 && ey > 0 && ez > 0 && ez <= NRL_NORM_MAXZ) {
+        // Separable form.  exp(-(dx^2+dy^2+dz^2)/2s^2) = E_xy * E_z, and along z the lattice points
+        // that pass the reference's float predicate form ONE interval (the predicate is monotone in
+        // |dz|), so a row contributes E_xy * (prefix[z_last+1] - prefix[z_first]).
+        __syncwarp();
+        double carry = 0.0;
+        for (int j0 = 0; j0 < ez; j0 += 32) {
+          const int j = j0 + lane;
+          double v = 0.0;
+          if (j < ez) { const float dz = a.z - (float)(z_lo + j) * s; v = (double)nrl_ex2_approx(dz * dz * k2); }
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+          if (j < ez) P[j + 1] = carry + v;
+          carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) P[0] = 0.0;
+        __syncwarp();
+        const int rows = ex * ey;
+        const float rcp_ey = 1.0f / (float)ey;
+        const float inv_s = 1.0f / s, zc = a.z * inv_s;
+        for (int q = lane; q < rows; q += 32) {
+          const int xi = __float2int_rd(((float)q + 0.5f) * rcp_ey);
+          const int yi = q - xi * ey;
+          const float dx = a.x - (float)(x_lo + xi) * s, dy = a.y - (float)(y_lo + yi) * s;
+          const float t2 = fmaf(dx, dx, dy * dy);
+          if (!(t2 < c2)) continue;
+          const float r = nrl_sqrt_approx(c2 - t2) * inv_s;    // only an estimate: settled exactly below
+          int jl = (int)ceilf(zc - r), jh = (int)floorf(zc + r);
+          jl = max(jl, z_lo - 1); jh = min(jh, z_hi + 1);
+          // settle the two ends on the exact predicate (the estimate is off by at most a point or two)
+          int guard = 0;
+          while (jl > z_lo && nrl_norm_in(a.z, jl - 1, s, t2, c2) && guard < 8) { --jl; ++guard; }
+          while (jl <= jh && !nrl_norm_in(a.z, jl, s, t2, c2) && guard < 16) { ++jl; ++guard; }
+          while (jh < z_hi && nrl_norm_in(a.z, jh + 1, s, t2, c2) && guard < 24) { ++jh; ++guard; }
+          while (jh >= jl && !nrl_norm_in(a.z, jh, s, t2, c2) && guard < 32) { --jh; ++guard; }
+          jl = max(jl, z_lo); jh = min(jh, z_hi);
+          if (jl <= jh) sum += (double)nrl_ex2_approx(t2 * k2) * (P[jh - z_lo + 1] - P[jl - z_lo]);
+        }
+      } else if (ex > 0 && ey > 0 && ez > 0) {
+        // very fine lattices: plain sweep of the bounding cube
         const int plane = ey * ez;
         const float rcp_ez = 1.0f / (float)ez;
         for (int xi = 0; xi < ex; ++xi) {
-          const float gx = (float)(x_lo + xi) * s;
-          const float dx = a.x - gx;
-          const float dx2 = dx * dx;
-          if (!(dx2 < c2)) continue;
+          const float dx = a.x - (float)(x_lo + xi) * s;
+          if (!(dx * dx < c2)) continue;
           for (int q = lane; q < plane; q += 32) {
             const int yi = __float2int_rd(((float)q + 0.5f) * rcp_ez);
             const int zi = q - yi * ez;
-            const float gy = (float)(y_lo + yi) * s, gz = (float)(z_lo + zi) * s;
-            const float dy = a.y - gy, dz = a.z - gz;
+            const float dy = a.y - (float)(y_lo + yi) * s, dz = a.z - (float)(z_lo + zi) * s;
             const float d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));        // voxelize.cu:92-94 as compiled
             if (d2 < c2) sum += (double)nrl_ex2_approx(d2 * k2);
           }

@@ -33,6 +33,20 @@ __device__ __forceinline__ float nrl_obs_d2(float ox, float oy, float oz, float 
   return fmaf(dz, dz, nrl_obs_partial(ox, oy, ax, ay));
 }
 
+#define NRL_SCAN_ILP 4
+#define NRL_FAR 3.0e38f
+
+// tile bounding-box test of the candidate scan.  NaN coordinates are "in range" for the
+// observers (d2 > c2 is false, marching_observers.cu:40) and never in range for the voxeliser
+// (d2 < c2 is false, voxelize.cu:125).
+template <int MODE>
+__device__ __forceinline__ bool nrl_in_box(const float4 a, float bx0, float bx1, float by0, float by1, float bz0, float bz1) {
+  if constexpr (MODE == NRL_MODE_VOXELIZE)
+    return (a.x >= bx0) && (a.x <= bx1) && (a.y >= by0) && (a.y <= by1) && (a.z >= bz0) && (a.z <= bz1);
+  else
+    return !(a.x < bx0) && !(a.x > bx1) && !(a.y < by0) && !(a.y > by1) && !(a.z < bz0) && !(a.z > bz1);
+}
+
 template <int MODE> struct NrlModeTraits {
   static constexpr bool kNeedsWeight = (MODE != NRL_OBS_EXISTENCE && MODE != NRL_OBS_DIRECT_COUNT);
 };
@@ -273,21 +287,21 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
       const float4 *atoms = p.frames.atoms + aoff;
       const float *inv = (MODE == NRL_MODE_VOXELIZE) ? t.inv_norm + aoff : nullptr;
 
-      // ---- pass 1: each warp counts the survivors of its contiguous atom segment
+      // ---- pass 1: each warp counts the survivors of its contiguous atom segment.  Four
+      // independent coalesced float4 loads are in flight per lane (the scan is latency bound).
       const int seg = ((n + NRL_NW - 1) / NRL_NW + 31) & ~31;
       const int a_begin = min(warp * seg, n), a_end = min(a_begin + seg, n);
       int mycnt = 0;
-      for (int i0 = a_begin; i0 < a_end; i0 += 32) {
-        const int i = i0 + lane;
-        bool keep = false;
-        if (i < a_end) {
-          const float4 a = __ldg(atoms + i);
-          if constexpr (MODE == NRL_MODE_VOXELIZE)
-            keep = (a.x >= bx0) && (a.x <= bx1) && (a.y >= by0) && (a.y <= by1) && (a.z >= bz0) && (a.z <= bz1);
-          else   // NaN coordinates are "in range" for the observers (d2 > c2 is false)
-            keep = !(a.x < bx0) && !(a.x > bx1) && !(a.y < by0) && !(a.y > by1) && !(a.z < bz0) && !(a.z > bz1);
+      for (int i0 = a_begin; i0 < a_end; i0 += 32 * NRL_SCAN_ILP) {
+        float4 a[NRL_SCAN_ILP];
+#pragma unroll
+        for (int u = 0; u < NRL_SCAN_ILP; ++u) {
+          const int i = i0 + u * 32 + lane;
+          a[u] = i < a_end ? __ldg(atoms + i) : make_float4(NRL_FAR, NRL_FAR, NRL_FAR, 0.f);
         }
-        mycnt += __popc(__ballot_sync(0xffffffffu, keep));
+#pragma unroll
+        for (int u = 0; u < NRL_SCAN_ILP; ++u)
+          mycnt += __popc(__ballot_sync(0xffffffffu, nrl_in_box<MODE>(a[u], bx0, bx1, by0, by1, bz0, bz1)));
       }
       if (lane == 0) s_wcnt[warp] = mycnt;
       __syncthreads();
@@ -302,27 +316,34 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
       float4 *cand = cand_in_smem ? s_cand : g_cand;
 
       // ---- pass 2: order-preserving compaction, weight resolved through the payload
-      for (int i0 = a_begin; i0 < a_end; i0 += 32) {
-        const int i = i0 + lane;
-        bool keep = false;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < a_end) {
-          a = __ldg(atoms + i);
-          if constexpr (MODE == NRL_MODE_VOXELIZE)
-            keep = (a.x >= bx0) && (a.x <= bx1) && (a.y >= by0) && (a.y <= by1) && (a.z >= bz0) && (a.z <= bz1);
-          else
-            keep = !(a.x < bx0) && !(a.x > bx1) && !(a.y < by0) && !(a.y > by1) && !(a.z < bz0) && !(a.z > bz1);
+      for (int i0 = a_begin; i0 < a_end; i0 += 32 * NRL_SCAN_ILP) {
+        float4 a[NRL_SCAN_ILP];
+        bool keep[NRL_SCAN_ILP];
+#pragma unroll
+        for (int u = 0; u < NRL_SCAN_ILP; ++u) {
+          const int i = i0 + u * 32 + lane;
+          a[u] = i < a_end ? __ldg(atoms + i) : make_float4(NRL_FAR, NRL_FAR, NRL_FAR, 0.f);
+          keep[u] = nrl_in_box<MODE>(a[u], bx0, bx1, by0, by1, bz0, bz1);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-          float w = 0.0f;
-          if constexpr (NrlModeTraits<MODE>::kNeedsWeight) w = __ldg(t.wtab + __float_as_int(a.w));
-          if constexpr (MODE == NRL_MODE_VOXELIZE) w = w * __ldg(inv + i);
-          if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) w = w + 0.0f;   // -0.0 == +0.0 in the reference's float compare
-          a.w = w;
-          cand[base + __popc(m & ((1u << lane) - 1u))] = a;
+        float w[NRL_SCAN_ILP];
+#pragma unroll
+        for (int u = 0; u < NRL_SCAN_ILP; ++u) {
+          w[u] = 0.0f;
+          if (keep[u]) {
+            if constexpr (NrlModeTraits<MODE>::kNeedsWeight) w[u] = __ldg(t.wtab + __float_as_int(a[u].w));
+            if constexpr (MODE == NRL_MODE_VOXELIZE) w[u] = w[u] * __ldg(inv + i0 + u * 32 + lane);
+            if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) w[u] = w[u] + 0.0f;   // -0.0 == +0.0 in the reference's float compare
+          }
         }
-        base += __popc(m);
+#pragma unroll
+        for (int u = 0; u < NRL_SCAN_ILP; ++u) {
+          const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
+          if (keep[u]) {
+            a[u].w = w[u];
+            cand[base + __popc(m & ((1u << lane) - 1u))] = a[u];
+          }
+          base += __popc(m);
+        }
       }
       __syncthreads();
 

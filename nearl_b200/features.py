@@ -50,6 +50,48 @@ SUPPORTED_OBSERVATION = {
 _NUMBER_TYPES = (int, float, np.integer, np.floating)
 
 
+def _lut(table):
+  arr = np.full(max(table) + 1, np.nan, dtype=np.float64)
+  for z, v in table.items():
+    arr[z] = v
+  return arr
+
+
+_MASS_LUT = _lut(constants.ATOMICMASS)
+_ELECNEG_LUT = _lut(constants.ELECNEG)
+
+
+def _lookup(lut, table, z):
+  """`np.array([table[i] for i in z], float32)` without the Python loop (KeyError preserved)."""
+  z = np.asarray(z, dtype=int)
+  if len(z) and (z.min() < 0 or z.max() >= len(lut) or np.isnan(lut[z]).any()):
+    return np.array([table[i] for i in z], dtype=np.float32)     # raises the reference's KeyError
+  return lut[z].astype(np.float32)
+
+
+def atom_table(top):
+  """(index, resid, atomic_number, name) columns of a topology, memoised on the topology object.
+  Uses column arrays when the topology has them (nearl_b200.io.Topology), else iterates
+  ``top.atoms`` like the reference (features.py:405-407,1133-1134)."""
+  cached = getattr(top, "_nearl_atom_table", None)
+  if cached is not None:
+    return cached
+  if all(hasattr(top, a) for a in ("resids", "atomic_numbers", "names")):
+    table = {"index": np.arange(top.n_atoms), "resid": np.asarray(top.resids, dtype=int),
+             "atomic_number": np.asarray(top.atomic_numbers, dtype=int), "name": np.asarray(top.names, dtype=object)}
+  else:
+    atoms = list(top.atoms)
+    table = {"index": np.array([a.index for a in atoms], dtype=int), "resid": np.array([a.resid for a in atoms], dtype=int),
+             "atomic_number": np.array([a.atomic_number for a in atoms], dtype=int),
+             "name": np.array([a.name for a in atoms], dtype=object)}
+  table["is_backbone"] = np.isin(table["name"], constants.BACKBONE_ATOM_NAMES)
+  try:
+    top._nearl_atom_table = table
+  except Exception:
+    pass
+  return table
+
+
 def crop(points, upperbound, padding, spacing):
   """Boolean mask of the points strictly inside the padded box, shifted by half a voxel
   (features.py:92-123): ``-padding - spacing/2 < p < upperbound + padding - spacing/2``."""
@@ -198,10 +240,10 @@ class Feature:
 
   def cache(self, trajectory):
     """Per-trajectory atom tables and the selection mask (features.py:397-423)."""
-    atoms = list(trajectory.top.atoms)
-    self.resids = np.array([a.resid for a in atoms], dtype=int)
-    self.atomic_numbers = np.array([a.atomic_number for a in atoms], dtype=int)
-    n = len(atoms)
+    table = atom_table(trajectory.top)
+    self.resids = table["resid"]
+    self.atomic_numbers = table["atomic_number"]
+    n = len(self.resids)
     if self.selection is None:
       self.selected = np.full(n, True, dtype=bool)
     elif isinstance(self.selection, str):
@@ -284,8 +326,11 @@ class _PerAtomWeight(Feature):
     raise NotImplementedError
 
   def cache(self, trajectory):
+    if trajectory.top is getattr(self, "_cached_top", None) and not self.force_recache:
+      return                                   # same topology object: the per-atom weights cannot have changed
     super().cache(trajectory)
     self.cached_array = np.asarray(self._weights(trajectory), dtype=np.float32)
+    self._cached_top = trajectory.top
 
   def query(self, topology, frame_coords, focal_point):
     frame_coords = np.asarray(frame_coords)
@@ -304,7 +349,7 @@ class AtomicNumber(_PerAtomWeight):
 class Mass(_PerAtomWeight):
   """features.py:563-605"""
   def _weights(self, trajectory):
-    return [constants.ATOMICMASS[z] for z in self.atomic_numbers]
+    return _lookup(_MASS_LUT, constants.ATOMICMASS, self.atomic_numbers)
 
 
 class HeavyAtom(_PerAtomWeight):
@@ -336,7 +381,7 @@ class Backbone(_PerAtomWeight):
     self.reverse = reverse
 
   def _weights(self, trajectory):
-    bb = np.array([a.name in constants.BACKBONE_ATOM_NAMES for a in trajectory.top.atoms])
+    bb = atom_table(trajectory.top)["is_backbone"]
     return (~bb if self.reverse else bb).astype(np.float32)
 
 
@@ -356,13 +401,13 @@ class AtomType(_PerAtomWeight):
 class Electronegativity(_PerAtomWeight):
   """features.py:1033-1046"""
   def _weights(self, trajectory):
-    return [constants.ELECNEG[z] for z in self.atomic_numbers]
+    return _lookup(_ELECNEG_LUT, constants.ELECNEG, self.atomic_numbers)
 
 
 class Hydrophobicity(_PerAtomWeight):
   """features.py:1049-1067: |EN - EN(carbon)| evaluated in float32"""
   def _weights(self, trajectory):
-    en = np.array([constants.ELECNEG[z] for z in self.atomic_numbers], dtype=np.float32)
+    en = _lookup(_ELECNEG_LUT, constants.ELECNEG, self.atomic_numbers)
     return np.abs(en - constants.ELECNEG[6])
 
 
@@ -370,29 +415,27 @@ def cache_properties(trajectory, property_type, **kwargs):
   """Per-atom weights of the dynamic features by id (features.py:1073-1230).  The ids whose
   reference implementation depends on OpenBabel / RDKit / ChargeFW2 or is broken in the
   reference snapshot (4, 12, 15, 22-25) raise NotImplementedError."""
-  atoms = list(trajectory.top.atoms)
-  z = np.array([a.atomic_number for a in atoms], dtype=int)
-  names = [a.name for a in atoms]
+  table = atom_table(trajectory.top)
+  z = table["atomic_number"]
   if property_type == 1:
-    arr = [a.index for a in atoms]
+    arr = table["index"]
   elif property_type == 2:
-    arr = [a.resid for a in atoms]
+    arr = table["resid"]
   elif property_type == 3:
     arr = z
   elif property_type == 11:
-    arr = [constants.ATOMICMASS[i] for i in z]
+    arr = _lookup(_MASS_LUT, constants.ATOMICMASS, z)
   elif property_type == 13:
-    arr = [constants.ELECNEG[i] for i in z]
+    arr = _lookup(_ELECNEG_LUT, constants.ELECNEG, z)
   elif property_type == 14:
-    en = np.array([constants.ELECNEG[i] for i in z], dtype=np.float32)
-    arr = np.abs(en - constants.ELECNEG[6])
+    arr = np.abs(_lookup(_ELECNEG_LUT, constants.ELECNEG, z) - constants.ELECNEG[6])
   elif property_type == 16:
     arr = np.full(len(z), kwargs.get("manual_weight", 1), dtype=np.float32)
   elif property_type == 21:
     arr = (z > 1)
   elif property_type in (26, 27):
     # 26 "backboneness" yields the side-chain indicator in the reference too (features.py:1212-1215)
-    arr = [0 if n in constants.BACKBONE_ATOM_NAMES else 1 for n in names]
+    arr = ~table["is_backbone"]
   elif property_type == 28:
     if "element_type" not in kwargs:
       raise ValueError("The focus element should be set for the atom type")
@@ -443,8 +486,11 @@ class DynamicFeature(Feature):
     self._weight_type = value
 
   def cache(self, trajectory):
+    if trajectory.top is getattr(self, "_cached_top", None) and not self.force_recache:
+      return
     super().cache(trajectory)
     self.cached_array = cache_properties(trajectory, self.weight_type, **self.feature_args)
+    self._cached_top = trajectory.top
 
   def query(self, topology, frame_coords, focal_point):
     """Host protocol: per-frame crop packed into [F, max_n, 3] padded with 99999 and weights

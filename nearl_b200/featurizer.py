@@ -280,7 +280,9 @@ class Featurizer:
     if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
       xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
     batch = self.lower_batch(keys, specs, xyz.shape[1], xyz.dtype == np.float64)
-    out = pinned_empty((batch.out_floats,), np.float32)
+    if getattr(self, "_out_buffer", None) is None or self._out_buffer.size < batch.out_floats:
+      self._out_buffer = pinned_empty((batch.out_floats,), np.float32)      # page-locked, reused across trajectories
+    out = self._out_buffer[:batch.out_floats]
     batch.execute(_lib.ptr(xyz), xyz.shape[0], _lib.ptr(out))
     return batch.split(out)
 
@@ -392,9 +394,10 @@ class LoweredBatch:
     _lib.check(_lib.lib().nrl_featurize_batch(ctypes.byref(b)))
 
   def split(self, out):
+    flat = np.array(out[:self.out_floats])        # one copy out of the reused pinned buffer
     results, pos = [], 0
     for shape in self.shapes:
-      size = int(np.prod(shape))
-      results.append(out[pos:pos + size].reshape(shape).copy())
+      size = shape[0] * shape[1] * shape[2]
+      results.append(flat[pos:pos + size].reshape(shape))
       pos += size
     return results

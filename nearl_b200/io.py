@@ -80,6 +80,12 @@ class Topology:
 
   # ---- Amber mask subset: ':RES', ':1-10', ':A,B', ':*', '@NAME', '@1-5', ':RES@NAME', '@/El', '!', '&', '|', '()'
   def select(self, mask):
+    cache = self.__dict__.setdefault("_select_cache", {})
+    if mask not in cache:
+      cache[mask] = self._select(mask)
+    return cache[mask].copy()
+
+  def _select(self, mask):
     mask = mask.strip()
     tokens = re.findall(r"[()!&|]|[:@][^()!&|:@\s]+", mask)
     if "".join(tokens) != re.sub(r"\s+", "", mask) or any(
@@ -135,8 +141,8 @@ class Topology:
     kind, body = tok[0], tok[1:]
     out = np.zeros(self.n_atoms, dtype=bool)
     if kind == ":":
-      order = {rid: i + 1 for i, rid in enumerate(dict.fromkeys(self.resids.tolist()))}
-      resnum = np.array([order[r] for r in self.resids.tolist()], dtype=np.int64)   # 1-based residue number
+      _, first, inverse = np.unique(self.resids, return_index=True, return_inverse=True)
+      resnum = np.argsort(np.argsort(first))[inverse] + 1     # 1-based residue number in order of appearance
       for part in body.split(","):
         if part == "*":
           out[:] = True
@@ -196,25 +202,21 @@ def _synthetic_topology(rng, n_atoms, ligand_atoms=0):
   n_prot = n_atoms - ligand_atoms
   z = rng.choice(_ELEMENTS, size=n_atoms, p=_ELEMENT_P)
   resid = np.arange(n_prot) // 16
-  names = np.empty(n_atoms, dtype=object)
-  resnames = np.empty(n_atoms, dtype=object)
-  sym = constants.ATOMICNR2SYMBOL
   within = np.arange(n_prot) % 16
-  backbone = {0: ("N", 7), 1: ("CA", 6), 2: ("C", 6), 3: ("O", 8)}
-  for i in range(n_prot):
-    if within[i] in backbone:
-      names[i], z[i] = backbone[within[i]]
-    else:
-      names[i] = f"{sym[int(z[i])]}{within[i]}"
-    resnames[i] = constants.RES[resid[i] % 20]
+  for slot, (_, zz) in enumerate((("N", 7), ("CA", 6), ("C", 6), ("O", 8))):
+    z[:n_prot][within == slot] = zz
+  sym_lut = np.array([constants.ATOMICNR2SYMBOL.get(i, "X") for i in range(0, 119)], dtype=object)
+  suffix = np.concatenate([within, np.arange(1, ligand_atoms + 1)]).astype(str).astype(object)
+  names = sym_lut[z] + suffix
+  for slot, nm in enumerate(("N", "CA", "C", "O")):
+    names[:n_prot][within == slot] = nm
+  resnames = np.empty(n_atoms, dtype=object)
+  resnames[:n_prot] = np.array(constants.RES, dtype=object)[resid % 20]
   resids = np.empty(n_atoms, dtype=np.int64)
   resids[:n_prot] = resid
   if ligand_atoms:
-    last = (resid[-1] + 1) if n_prot else 0
-    for i in range(n_prot, n_atoms):
-      names[i] = f"{sym[int(z[i])]}{i - n_prot + 1}"
-      resnames[i] = "LIG"
-      resids[i] = last
+    resnames[n_prot:] = "LIG"
+    resids[n_prot:] = (resid[-1] + 1) if n_prot else 0
   return Topology(names, resids, resnames, z)
 
 
