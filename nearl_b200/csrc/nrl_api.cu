@@ -161,7 +161,7 @@ int check_dims(const int *dims, long long *G) {
 }
 
 // ---- tile launches ------------------------------------------------------------------------
-constexpr int kCandCap = 1024;        // candidates held in shared memory (16 KB)
+constexpr int kCandCap = 512;         // candidates held in shared memory (8 KB; 24 KB for the voxeliser's records)
 constexpr int kSerCapFloats = 8192;   // series floats held in shared memory (32 KB: 16 frames x 512 voxels)
 constexpr size_t kScratchBudget = (size_t)1 << 30;
 
@@ -169,7 +169,7 @@ template <int MODE>
 int launch_tiles_mode(Ctx &c, const NrlTileParams &p, int grid, size_t smem, cudaStream_t st, int slot) {
   if (!c.attr_set[slot]) {
     NRL_CUDA(cudaFuncSetAttribute(nrl_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kCandCap * sizeof(float4) + kSerCapFloats * sizeof(float))));
+                                  (int)(kCandCap * 3 * sizeof(float4) + kSerCapFloats * sizeof(float))));
     c.attr_set[slot] = true;
   }
   {
@@ -243,18 +243,19 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
     // shared memory: the candidate list plus the time series when it fits (else per-CTA global scratch)
     const size_t ser_need = (size_t)r.max_frames * NRL_TILE_VOX;
     const int ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
-    const size_t smem = kCandCap * sizeof(float4) + (size_t)ser_cap * sizeof(float);
+    const size_t cand_rec = (r.mode == NRL_MODE_VOXELIZE ? 3 : 1) * sizeof(float4);
+    const size_t smem = kCandCap * cand_rec + (size_t)ser_cap * sizeof(float);
     const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (smem + 1024)));
     int grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 12));
     // overflow scratch (candidate lists longer than kCandCap, series longer than kSerCapFloats)
     const size_t cand_per_cta = max_atoms_per_frame > kCandCap ? (size_t)max_atoms_per_frame : 0;
     const size_t ser_per_cta = ser_cap == 0 ? ser_need : 0;
-    const size_t per_cta = cand_per_cta * sizeof(float4) + ser_per_cta * sizeof(float);
+    const size_t per_cta = cand_per_cta * cand_rec + ser_per_cta * sizeof(float);
     if (per_cta > 0) {
       const int max_grid = (int)std::max<size_t>((size_t)c.sms, kScratchBudget / per_cta);
       grid = std::max(1, std::min(grid, max_grid));
     }
-    NRL_TRY(c.cand_scr.reserve(cand_per_cta * sizeof(float4) * grid));
+    NRL_TRY(c.cand_scr.reserve(cand_per_cta * cand_rec * grid));
     NRL_TRY(c.ser_scr.reserve(ser_per_cta * sizeof(float) * grid));
     NrlTileParams p;
     p.tasks = c.tasks.as<NrlTask>() + r.begin;
@@ -263,7 +264,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
     p.frames = frames;
     p.out = d_out;
     p.cand_scratch = c.cand_scr.as<float4>();
-    p.cand_scratch_stride = (long long)cand_per_cta;
+    p.cand_scratch_stride = (long long)(cand_per_cta * cand_rec / sizeof(float4));
     p.ser_scratch = c.ser_scr.as<float>();
     p.ser_scratch_stride = (long long)ser_per_cta;
     p.cand_cap = kCandCap;

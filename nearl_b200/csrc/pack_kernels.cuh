@@ -205,12 +205,16 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
     const float4 a = __ldg(p.frames.atoms + off + i);
     double sum = 0.0;
     if (isfinite(a.x) && isfinite(a.y) && isfinite(a.z)) {
-      const int x_lo = (int)fmaxf(floorf((a.x - c) / s) - 1.0f, (float)(-b));
-      const int x_hi = (int)fminf(floorf((a.x + c) / s) + 1.0f, (float)(p.nx + b - 1));
-      const int y_lo = (int)fmaxf(floorf((a.y - c) / s) - 1.0f, (float)(-b));
-      const int y_hi = (int)fminf(floorf((a.y + c) / s) + 1.0f, (float)(p.ny + b - 1));
-      const int z_lo = (int)fmaxf(floorf((a.z - c) / s) - 1.0f, (float)(-b));
-      const int z_hi = (int)fminf(floorf((a.z + c) / s) + 1.0f, (float)(p.nz + b - 1));
+      // lattice planes that can hold a point inside the cutoff, with a margin far above the float
+      // rounding of the exact predicates that decide membership below
+      const float is = 1.0f / s, cr = c * is;
+      const float mx = 2e-3f + 2e-6f * fabsf(a.x * is), my = 2e-3f + 2e-6f * fabsf(a.y * is), mz = 2e-3f + 2e-6f * fabsf(a.z * is);
+      const int x_lo = (int)fmaxf(ceilf(a.x * is - cr - mx), (float)(-b));
+      const int x_hi = (int)fminf(floorf(a.x * is + cr + mx), (float)(p.nx + b - 1));
+      const int y_lo = (int)fmaxf(ceilf(a.y * is - cr - my), (float)(-b));
+      const int y_hi = (int)fminf(floorf(a.y * is + cr + my), (float)(p.ny + b - 1));
+      const int z_lo = (int)fmaxf(ceilf(a.z * is - cr - mz), (float)(-b));
+      const int z_hi = (int)fminf(floorf(a.z * is + cr + mz), (float)(p.nz + b - 1));
       const int ex = x_hi - x_lo + 1, ey = y_hi - y_lo + 1, ez = z_hi - z_lo + 1;
       if (ex > 0 && ey > 0 && ez > 0 && ez <= NRL_NORM_MAXZ) {
         // Separable form.  exp(-(dx^2+dy^2+dz^2)/2s^2) = E_xy * E_z, and along z the lattice points
@@ -238,15 +242,24 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
           const float dx = a.x - (float)(x_lo + xi) * s, dy = a.y - (float)(y_lo + yi) * s;
           const float t2 = fmaf(dx, dx, dy * dy);
           if (!(t2 < c2)) continue;
-          const float r = nrl_sqrt_approx(c2 - t2) * inv_s;    // only an estimate: settled exactly below
-          int jl = (int)ceilf(zc - r), jh = (int)floorf(zc + r);
-          jl = max(jl, z_lo - 1); jh = min(jh, z_hi + 1);
-          // settle the two ends on the exact predicate (the estimate is off by at most a point or two)
-          int guard = 0;
-          while (jl > z_lo && nrl_norm_in(a.z, jl - 1, s, t2, c2) && guard < 8) { --jl; ++guard; }
-          while (jl <= jh && !nrl_norm_in(a.z, jl, s, t2, c2) && guard < 16) { ++jl; ++guard; }
-          while (jh < z_hi && nrl_norm_in(a.z, jh + 1, s, t2, c2) && guard < 24) { ++jh; ++guard; }
-          while (jh >= jl && !nrl_norm_in(a.z, jh, s, t2, c2) && guard < 32) { --jh; ++guard; }
+          const float gap = c2 - t2;
+          const float r = nrl_sqrt_approx(gap) * inv_s;        // half-width of the interval in lattice units
+          const float ul = zc - r, uh = zc + r;
+          const float fl = ceilf(ul), fh = floorf(uh);
+          int jl = (int)fl, jh = (int)fh;
+          // The float predicate can only disagree with this real-number estimate when an end falls
+          // within rounding reach of a lattice plane, or when the row is nearly tangent to the sphere
+          // (gap of a few ulp).  Only then are the two ends settled on the exact predicate.
+          const float el = fl - ul, eh = uh - fh;                // distances of the ends to the planes beside them
+          const bool fragile = (el < 4e-3f) || (el > 0.996f) || (eh < 4e-3f) || (eh > 0.996f) || (r < 0.25f) || (fabsf(zc) > 1000.0f);
+          if (fragile) {
+            jl = max(jl, z_lo - 1); jh = min(jh, z_hi + 1);
+            int guard = 0;
+            while (jl > z_lo && nrl_norm_in(a.z, jl - 1, s, t2, c2) && guard < 8) { --jl; ++guard; }
+            while (jl <= jh && !nrl_norm_in(a.z, jl, s, t2, c2) && guard < 16) { ++jl; ++guard; }
+            while (jh < z_hi && nrl_norm_in(a.z, jh + 1, s, t2, c2) && guard < 24) { ++jh; ++guard; }
+            while (jh >= jl && !nrl_norm_in(a.z, jh, s, t2, c2) && guard < 32) { --jh; ++guard; }
+          }
           jl = max(jl, z_lo); jh = min(jh, z_hi);
           if (jl <= jh) sum += (double)nrl_ex2_approx(t2 * k2) * (P[jh - z_lo + 1] - P[jl - z_lo]);
         }

@@ -99,7 +99,7 @@ __device__ __noinline__ float4 nrl_reduce4(float4 *col, const int stride, const 
             const int cnt = (int)((h[q][b >> 2] >> ((b & 3) * 16)) & 0xffffull);
             if (cnt > 0) {
               const float pr = nrl_div_approx((float)cnt, fn);
-              e = e - pr * nrl_lg2_approx(pr);
+              e = fmaf(-pr, nrl_lg2_approx(pr), e);      // ptxas fuses the reference's mul+sub into FFMA
             }
           }
         }
@@ -107,8 +107,8 @@ __device__ __noinline__ float4 nrl_reduce4(float4 *col, const int stride, const 
       });
     }
   } else if (agg == 8) {
-    // slope_device :190-205; op order of the reference PTX: two products and a subtraction,
-    // no contraction, then div.approx
+    // slope_device :190-205; op order of the reference SASS: one product, one fused
+    // multiply-subtract (ptxas contracts the unrounded mul/sub pair), then rcp * numerator
     if (n > 1) {
       float sx = 0.0f, sx2 = 0.0f;
       float sy[4] = {0.f, 0.f, 0.f, 0.f}, sxy[4] = {0.f, 0.f, 0.f, 0.f};
@@ -119,8 +119,8 @@ __device__ __noinline__ float4 nrl_reduce4(float4 *col, const int stride, const 
         NRL4({ sy[q] = sy[q] + x[q]; sxy[q] = fmaf(x[q], fi, sxy[q]); });
         sx2 = sx2 + (float)(i * i);
       }
-      const float denom = sx2 * fn - sx * sx;
-      if (denom != 0.0f) { NRL4(out[q] = nrl_div_approx(sxy[q] * fn - sy[q] * sx, denom)); }
+      const float denom = fmaf(fn, sx2, -(sx * sx));
+      if (denom != 0.0f) { NRL4(out[q] = nrl_div_approx(fmaf(fn, sxy[q], -(sy[q] * sx)), denom)); }
     }
   }
   return make_float4(out[0], out[1], out[2], out[3]);

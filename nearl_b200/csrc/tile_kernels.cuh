@@ -36,16 +36,22 @@ __device__ __forceinline__ float nrl_obs_d2(float ox, float oy, float oz, float 
 #define NRL_SCAN_ILP 4
 #define NRL_FAR 3.0e38f
 
-// tile bounding-box test of the candidate scan.  NaN coordinates are "in range" for the
-// observers (d2 > c2 is false, marching_observers.cu:40) and never in range for the voxeliser
-// (d2 < c2 is false, voxelize.cu:125).
-template <int MODE>
-__device__ __forceinline__ bool nrl_in_box(const float4 a, float bx0, float bx1, float by0, float by1, float bz0, float bz1) {
-  if constexpr (MODE == NRL_MODE_VOXELIZE)
-    return (a.x >= bx0) && (a.x <= bx1) && (a.y >= by0) && (a.y <= by1) && (a.z >= bz0) && (a.z <= bz1);
-  else
-    return !(a.x < bx0) && !(a.x > bx1) && !(a.y < by0) && !(a.y > by1) && !(a.z < bz0) && !(a.z > bz1);
+// Candidate test of the scan: squared distance from the atom to the box spanned by the tile's
+// voxel centres against a slightly inflated cutoff.  Conservative for the exact float predicates
+// of the sweep (the margin dwarfs their rounding), ~30 % tighter than box-plus-cutoff on every
+// axis.  fmaxf drops NaNs, so a NaN coordinate survives the scan: the observers count it as in
+// range (d2 > c2 is false, marching_observers.cu:40), the voxeliser's d2 < c2 rejects it later.
+struct NrlTileBox { float x0, x1, y0, y1, z0, z1, r2; };
+__device__ __forceinline__ bool nrl_near_box(const float4 a, const NrlTileBox &b) {
+  const float dx = fmaxf(fmaxf(b.x0 - a.x, a.x - b.x1), 0.0f);
+  const float dy = fmaxf(fmaxf(b.y0 - a.y, a.y - b.y1), 0.0f);
+  const float dz = fmaxf(fmaxf(b.z0 - a.z, a.z - b.z1), 0.0f);
+  return !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > b.r2);
 }
+
+// shared-memory record per candidate: the atom (x, y, z, weight) and, for the voxeliser, the
+// eight per-plane factors exp(-(z_atom - z_plane)^2 / 2 sigma^2) of the tile's z planes
+template <int MODE> struct NrlCandStride { static constexpr int value = (MODE == NRL_MODE_VOXELIZE) ? 3 : 1; };
 
 template <int MODE> struct NrlModeTraits {
   static constexpr bool kNeedsWeight = (MODE != NRL_OBS_EXISTENCE && MODE != NRL_OBS_DIRECT_COUNT);
@@ -57,19 +63,26 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
                                           const float px, const float py, const float (&pz)[NRL_VPT],
                                           float (&val)[NRL_VPT]) {
   if constexpr (MODE == NRL_MODE_VOXELIZE) {
+    // Gaussian in separable form: exp(-d2/2s^2) = E_xy * E_z; E_z of the tile's z planes was
+    // tabulated per candidate by the scan, so one exponential per (candidate, thread) remains.
+    // The in/out decision still uses the reference's exact d2 (voxelize.cu:121-125).
     float acc[NRL_VPT];
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) acc[k] = 0.0f;
     const float k2 = t.k2;
+    const int zq = 1 + (threadIdx.x & 1);
 #pragma unroll 2
     for (int c = 0; c < ncand; ++c) {
-      const float4 a = cand[c];
+      const float4 a = cand[c * 3];
+      const float4 ezq = cand[c * 3 + zq];
       const float part = nrl_vox_partial(a.x, a.y, px, py);
+      const float wxy = nrl_ex2_approx(part * k2) * a.w;
+      const float ez[NRL_VPT] = {ezq.x, ezq.y, ezq.z, ezq.w};
 #pragma unroll
       for (int k = 0; k < NRL_VPT; ++k) {
         const float dz = a.z - pz[k];
         const float d2 = fmaf(dz, dz, part);
-        if (d2 < c2) acc[k] = acc[k] + nrl_ex2_approx(d2 * k2) * a.w;   // voxelize.cu:125-127
+        if (d2 < c2) acc[k] = fmaf(wxy, ez[k], acc[k]);
       }
     }
 #pragma unroll
@@ -243,7 +256,7 @@ template <int MODE>
 __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p) {
   extern __shared__ __align__(16) unsigned char nrl_smem[];
   float4 *s_cand = reinterpret_cast<float4 *>(nrl_smem);
-  float4 *s_ser = reinterpret_cast<float4 *>(nrl_smem + (size_t)p.cand_cap * sizeof(float4));
+  float4 *s_ser = reinterpret_cast<float4 *>(nrl_smem + (size_t)p.cand_cap * NrlCandStride<MODE>::value * sizeof(float4));
   __shared__ int s_wcnt[NRL_NW];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -266,11 +279,12 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
     const float c2 = c * c;
     const int nF = t.n_frames;
 
-    // conservative bounding box of the tile's voxels grown by the cutoff
-    const float cm = c * 1.0001f + 1e-30f;
-    const float bx0 = (float)x0 * s - cm, bx1 = (float)min(x0 + NRL_TX - 1, nx - 1) * s + cm;
-    const float by0 = (float)y0 * s - cm, by1 = (float)min(y0 + NRL_TY - 1, ny - 1) * s + cm;
-    const float bz0 = (float)z0 * s - cm, bz1 = (float)min(z0 + NRL_TZ - 1, nz - 1) * s + cm;
+    // box spanned by the centres of the tile's voxels, and the inflated squared cutoff of the scan
+    NrlTileBox box;
+    box.x0 = (float)x0 * s; box.x1 = (float)min(x0 + NRL_TX - 1, nx - 1) * s;
+    box.y0 = (float)y0 * s; box.y1 = (float)min(y0 + NRL_TY - 1, ny - 1) * s;
+    box.z0 = (float)z0 * s; box.z1 = (float)min(z0 + NRL_TZ - 1, nz - 1) * s;
+    box.r2 = c2 * 1.0005f + 1e-30f;
 
     const int ix = x0 + lx, iy = y0 + ly, iz = z0 + lzq * NRL_VPT;
     const float px = (float)ix * s, py = (float)iy * s;
@@ -301,7 +315,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
         }
 #pragma unroll
         for (int u = 0; u < NRL_SCAN_ILP; ++u)
-          mycnt += __popc(__ballot_sync(0xffffffffu, nrl_in_box<MODE>(a[u], bx0, bx1, by0, by1, bz0, bz1)));
+          mycnt += __popc(__ballot_sync(0xffffffffu, nrl_near_box(a[u], box)));
       }
       if (lane == 0) s_wcnt[warp] = mycnt;
       __syncthreads();
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
         if (w < warp) base += cw;
         total += cw;
       }
-      const bool cand_in_smem = total <= p.cand_cap;
+      const bool cand_in_smem = total <= p.cand_cap;      // p.cand_cap counts candidates, whatever their record size
       float4 *cand = cand_in_smem ? s_cand : g_cand;
 
       // ---- pass 2: order-preserving compaction, weight resolved through the payload
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
         for (int u = 0; u < NRL_SCAN_ILP; ++u) {
           const int i = i0 + u * 32 + lane;
           a[u] = i < a_end ? __ldg(atoms + i) : make_float4(NRL_FAR, NRL_FAR, NRL_FAR, 0.f);
-          keep[u] = nrl_in_box<MODE>(a[u], bx0, bx1, by0, by1, bz0, bz1);
+          keep[u] = nrl_near_box(a[u], box);
         }
         float w[NRL_SCAN_ILP];
 #pragma unroll
@@ -340,7 +354,15 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
           const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
           if (keep[u]) {
             a[u].w = w[u];
-            cand[base + __popc(m & ((1u << lane) - 1u))] = a[u];
+            float4 *slot = cand + (size_t)(base + __popc(m & ((1u << lane) - 1u))) * NrlCandStride<MODE>::value;
+            slot[0] = a[u];
+            if constexpr (MODE == NRL_MODE_VOXELIZE) {
+              float e[NRL_TZ];
+#pragma unroll
+              for (int k = 0; k < NRL_TZ; ++k) { const float dz = a[u].z - (float)(z0 + k) * s; e[k] = nrl_ex2_approx(dz * dz * t.k2); }
+              slot[1] = make_float4(e[0], e[1], e[2], e[3]);
+              slot[2] = make_float4(e[4], e[5], e[6], e[7]);
+            }
           }
           base += __popc(m);
         }

@@ -385,12 +385,11 @@ static float orc_reduce(float *a, int n, int type_agg) {
       for (int i = 0; i < ORC_ENTROPY_BINS; ++i)
         if (hist[i] > 0) {
           volatile float p = (float)hist[i] / (float)n;
-          volatile float t = p * log2f(p);
-          e = e - t;
+          e = fmaf(-p, log2f(p), e);          /* FFMA in the reference SASS */
         }
       return e;
     }
-    case 8: {                                              /* :190-205, op order from the PTX */
+    case 8: {                                              /* :190-205, op order from the SASS */
       if (n <= 1) return 0.0f;
       volatile float sx = 0, sy = 0, sxy = 0, sx2 = 0;
       for (int i = 0; i < n; ++i) {
@@ -399,11 +398,11 @@ static float orc_reduce(float *a, int n, int type_agg) {
         sxy = fmaf(a[i], (float)i, sxy);
         sx2 = sx2 + (float)(i * i);
       }
-      volatile float t1 = sx2 * (float)n, t2 = sx * sx;
-      const float denom = t1 - t2;
+      volatile float t2 = sx * sx;
+      const float denom = fmaf((float)n, sx2, -t2);   /* FMUL + FFMA in the reference SASS */
       if (denom == 0) return 0.0f;
-      volatile float u1 = sxy * (float)n, u2 = sy * sx;
-      return (u1 - u2) / denom;
+      volatile float u2 = sy * sx;
+      return fmaf((float)n, sxy, -u2) / denom;
     }
     default: return 0.0f;                                  /* gpuutils.cu:73-76 */
   }
