@@ -145,9 +145,12 @@ typedef struct {
   int out_on_device;
   int *atom_counts;              /* optional host [total crop frames]: atoms kept per crop frame */
   int flags;                     /* NRL_BATCH_* */
+  int lane;                      /* 0 .. NRL_MAX_LANES-1: independent stream + workspace (see nrl_lane_synchronize) */
 } nrl_batch_t;
 
-#define NRL_BATCH_NO_SYNC 1      /* return without synchronising (device-resident in/out only) */
+#define NRL_BATCH_NO_SYNC 1      /* enqueue only: results are valid after nrl_lane_synchronize(lane); host buffers
+                                    (xyz, out) must be page-locked and stay alive until then */
+#define NRL_MAX_LANES 4
 
 int nrl_featurize_batch(const nrl_batch_t *batch);
 
@@ -157,6 +160,9 @@ int nrl_buff_dim(float cutoff, float spacing, int *out);
 int nrl_device_count(int *out);
 int nrl_set_device(int device);
 int nrl_synchronize(void);
+/* wait for everything enqueued on `lane` (batches submitted with NRL_BATCH_NO_SYNC); batches on
+ * different lanes overlap, e.g. the upload of one trajectory under the kernels of the previous one */
+int nrl_lane_synchronize(int lane);
 /* enable != 0: enqueue all work of the host entry points and of nrl_featurize_batch on `stream`
  * (a cudaStream_t, e.g. torch's current stream) instead of the library's own stream */
 int nrl_set_stream(void *stream, int enable);

@@ -19,7 +19,7 @@ EXPORTED = [
   "nrl_frame_voxelize", "nrl_frame_observation", "nrl_marching_observer", "nrl_density_flow", "nrl_aggregate",
   "nrl_summation", "nrl_frame_voxelize_dev", "nrl_frame_observation_dev", "nrl_marching_observer_dev",
   "nrl_density_flow_dev", "nrl_aggregate_dev", "nrl_featurize_batch", "nrl_buff_dim", "nrl_device_count",
-  "nrl_set_device", "nrl_synchronize", "nrl_set_stream", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
+  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_set_stream", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
   "nrl_last_error", "nrl_version",
 ]
 
@@ -56,6 +56,7 @@ class BatchStruct(ctypes.Structure):
     ("out", c_void_p), ("out_on_device", c_int),
     ("atom_counts", c_void_p),
     ("flags", c_int),
+    ("lane", c_int),
   ]
 
 
@@ -94,6 +95,7 @@ def lib():
   L.nrl_host_register.argtypes = [p, c_ll]
   L.nrl_host_unregister.argtypes = [p]
   L.nrl_set_stream.argtypes = [p, c_int]
+  L.nrl_lane_synchronize.argtypes = [c_int]
   L.nrl_profile.argtypes = [c_int]
   L.nrl_profile_read.argtypes = [p, p, c_int]
   L.nrl_profile_name.argtypes = [c_int]

@@ -118,9 +118,13 @@ void prof_collect(Ctx &c) {
 }
 
 std::mutex g_ctx_mu;
-Ctx *g_ctx[64] = {nullptr};
+Ctx *g_ctx[64][NRL_MAX_LANES] = {{nullptr}};
 
-int get_ctx(Ctx **out) {
+// A lane is an independent (stream, workspace) pair on a device: work submitted on different lanes
+// may overlap (upload of one trajectory under the kernels of another).  Lane 0 serves the twins of
+// the reference FFI.
+int get_ctx(Ctx **out, int lane = 0) {
+  if (lane < 0 || lane >= NRL_MAX_LANES) return fail(NRL_ERR_ARGUMENT, "lane out of range");
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) {
@@ -130,7 +134,7 @@ int get_ctx(Ctx **out) {
   }
   if (dev < 0 || dev >= 64) return fail(NRL_ERR_ARGUMENT, "device index out of range");
   std::lock_guard<std::mutex> lk(g_ctx_mu);
-  if (!g_ctx[dev]) {
+  if (!g_ctx[dev][lane]) {
     cudaDeviceProp prop;
     NRL_CUDA(cudaGetDeviceProperties(&prop, dev));
     Ctx *c = new Ctx();
@@ -138,9 +142,9 @@ int get_ctx(Ctx **out) {
     c->sms = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     NRL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    g_ctx[dev] = c;
+    g_ctx[dev][lane] = c;
   }
-  *out = g_ctx[dev];
+  *out = g_ctx[dev][lane];
   return NRL_OK;
 }
 
@@ -489,6 +493,14 @@ int nrl_set_device(int device) { NRL_CUDA(cudaSetDevice(device)); return NRL_OK;
 int nrl_synchronize(void) {
   Ctx *c = nullptr;
   NRL_TRY(get_ctx(&c));
+  std::lock_guard<std::mutex> lk(c->mu);
+  NRL_CUDA(cudaStreamSynchronize(c->work_stream()));
+  prof_collect(*c);
+  return NRL_OK;
+}
+int nrl_lane_synchronize(int lane) {
+  Ctx *c = nullptr;
+  NRL_TRY(get_ctx(&c, lane));
   std::lock_guard<std::mutex> lk(c->mu);
   NRL_CUDA(cudaStreamSynchronize(c->work_stream()));
   prof_collect(*c);

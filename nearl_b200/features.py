@@ -302,6 +302,38 @@ class Feature:
                             chunks=(1, *self.dims), **opts)
 
   # ---- device fast path -------------------------------------------------------------------------
+  # per-topology memo of everything cache() derives (a loader cycling over a few topologies pays once each)
+  def _remember(self, top):
+    memo = self.__dict__.setdefault("_top_memo", {})
+    if len(memo) >= 64:
+      memo.clear()
+    memo[id(top)] = (top, self.resids, self.atomic_numbers, self.selected, self.cached_array,
+                     getattr(self, "_value_order_memo", None))
+
+  def _recall(self, top):
+    if self.force_recache:
+      return False
+    hit = self.__dict__.get("_top_memo", {}).get(id(top))
+    if hit is None or hit[0] is not top:
+      return False
+    _, self.resids, self.atomic_numbers, self.selected, self.cached_array, order = hit
+    if order is not None:
+      self._value_order_memo = order
+    return True
+
+  def value_order(self):
+    """Stable argsort of the cached weights (equal values adjacent, NaN last, -0.0 == +0.0): the
+    emission order of the crop kernel for distinct_count.  Memoised per weight array."""
+    memo = getattr(self, "_value_order_memo", None)
+    if memo is None or memo[0] is not self.cached_array:
+      order = np.argsort(np.asarray(self.cached_array, dtype=np.float32) + np.float32(0.0), kind="stable").astype(np.int32)
+      self._value_order_memo = memo = (self.cached_array, order)
+      hit = self.__dict__.get("_top_memo", {})
+      for k, v in list(hit.items()):
+        if v[4] is self.cached_array:
+          hit[k] = v[:5] + (memo,)
+    return memo[1]
+
   def _is_builtin(self, *methods):
     """True when none of `methods` was overridden outside this module (a user subclass that
     customises query/run must go through the host protocol)."""
@@ -326,11 +358,11 @@ class _PerAtomWeight(Feature):
     raise NotImplementedError
 
   def cache(self, trajectory):
-    if trajectory.top is getattr(self, "_cached_top", None) and not self.force_recache:
+    if self._recall(trajectory.top):
       return                                   # same topology object: the per-atom weights cannot have changed
     super().cache(trajectory)
     self.cached_array = np.asarray(self._weights(trajectory), dtype=np.float32)
-    self._cached_top = trajectory.top
+    self._remember(trajectory.top)
 
   def query(self, topology, frame_coords, focal_point):
     frame_coords = np.asarray(frame_coords)
@@ -486,11 +518,11 @@ class DynamicFeature(Feature):
     self._weight_type = value
 
   def cache(self, trajectory):
-    if trajectory.top is getattr(self, "_cached_top", None) and not self.force_recache:
+    if self._recall(trajectory.top):
       return
     super().cache(trajectory)
     self.cached_array = cache_properties(trajectory, self.weight_type, **self.feature_args)
-    self._cached_top = trajectory.top
+    self._remember(trajectory.top)
 
   def query(self, topology, frame_coords, focal_point):
     """Host protocol: per-frame crop packed into [F, max_n, 3] padded with 99999 and weights

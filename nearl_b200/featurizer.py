@@ -83,6 +83,10 @@ class Featurizer:
     # nearl_b200: collect results in self.RESULTS[outkey] (list of arrays) besides / instead of dumping
     self.keep_results = False
     self.RESULTS = {}
+    # nearl_b200: callable(outkey, trajectory_index, window, focal_index, grid) invoked for every result in
+    # the reference's order instead of (or, with an outfile, besides) Feature.dump; grids are views into a
+    # re-used page-locked buffer and must be consumed inside the call
+    self.result_sink = None
     self.last_run_stats = {}
     if config.verbose():
       printit(f"{self.classname}: Featurizer is initialized successfully with dimensions: {self.dims} and lengths: {self.lengths}")
@@ -211,60 +215,28 @@ class Featurizer:
   def run(self, *_ignored, trajectory_indices=None):
     """Featurise every registered trajectory (featurizer.py:399-469).  Positional arguments
     (the worker counts some scripts pass) are accepted and ignored.  `trajectory_indices`
-    restricts the loop to a shard (multi-GPU: one process per GPU, see nearl_b200.sharding)."""
+    restricts the loop to a shard (multi-GPU: one process per GPU, see nearl_b200.sharding).
+
+    Trajectories are software-pipelined over two lanes of the native library: while the
+    kernels of trajectory i run, the host lowers trajectory i+1 and its frames upload; results
+    are dumped in trajectory order."""
     indices = range(self.TRAJECTORYNUMBER) if trajectory_indices is None else trajectory_indices
     stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "frames": 0, "seconds": 0.0}
     t_run = time.perf_counter()
-    for tid in indices:
-      self.traj = self.TRAJLOADER[tid]
-      printit(f"{self.classname}: Processing the trajectory {tid + 1} ({self.traj.identity}) with {self.SLICENUMBER} frame slices")
-      st = time.perf_counter()
-      focal_registered = self.FOCALPOINTS_PROTOTYPE is not None
-      if focal_registered:
-        if not self.parse_focus():
-          printit(f"{self.classname} Warning: Skipping the trajectory {self.traj.identity}(index {tid + 1}) because focal points parsing is failed. ")
-          continue
+    pending = None
+    for count, tid in enumerate(indices):
+      job = self._submit(tid, lane=count % 2)
+      if pending is not None:
+        self._finish(pending, stats)
+        pending = None
+      if job is None:
+        continue
+      if job["generic_ids"]:
+        self._finish(job, stats)        # host-protocol features read self.traj: no overlap with the next trajectory
       else:
-        self.FOCALNUMBER = 0
-      for feat in self.FEATURESPACE:
-        feat.cache(self.traj)
-
-      # task list in the reference's order: window -> focal point -> feature
-      n_focal = self.FOCALNUMBER if self.FOCALNUMBER > 0 else 1
-      task_keys = [(bid, pid, fidx) for bid in range(self.SLICENUMBER) for pid in range(n_focal)
-                   for fidx in range(self.FEATURENUMBER)]
-      specs = [feat._native_spec() if (self.use_native_batch and hasattr(feat, "_native_spec")) else None
-               for feat in self.FEATURESPACE]
-      results = [None] * len(task_keys)
-      native_ids = [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is not None]
-      if native_ids:
-        batch_out = self._run_native_batch([task_keys[i] for i in native_ids], specs)
-        for i, arr in zip(native_ids, batch_out):
-          results[i] = arr
-      frames_cache = {}
-      for i, (bid, pid, fidx) in enumerate(task_keys):
-        if results[i] is not None:
-          continue
-        self.frame_slice = self.FRAMESLICES[bid]
-        if bid not in frames_cache:
-          frames_cache = {bid: self.traj.xyz[self.FRAMESLICES[bid]]}
-        focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else np.zeros(3, dtype=np.float32)
-        feat = self.FEATURESPACE[fidx]
-        results[i] = feat.run(*feat.query(self.top, frames_cache[bid], focal))
-      printit(f"{self.classname}: Trajectory {tid + 1} yields {len(task_keys)} frame-slices (tasks) for the featurization. ")
-
-      with utils.batched_output():
-        for (bid, pid, fidx), result in zip(task_keys, results):
-          feat = self.FEATURESPACE[fidx]
-          if self.keep_results:
-            self.RESULTS.setdefault(feat.outkey, []).append(result)
-          if feat.outfile or not self.keep_results:
-            feat.dump(result)
-      stats["trajectories"] += 1
-      stats["tasks"] += len(task_keys)
-      stats["native_tasks"] += len(native_ids)
-      stats["frames"] += self.SLICENUMBER * self.time_window
-      printit(f"{self.classname}: Finished the trajectory {tid + 1} / {self.TRAJECTORYNUMBER} with {len(task_keys)} tasks in {time.perf_counter() - st:.6f} seconds")
+        pending = job
+    if pending is not None:
+      self._finish(pending, stats)
     stats["seconds"] = time.perf_counter() - t_run
     self.last_run_stats = stats
     printit(f"{self.classname}: All trajectories and tasks are finished. \n")
@@ -274,109 +246,178 @@ class Featurizer:
     """Name used by the README / older scripts for the same loop."""
     return self.run(*args, **kwargs)
 
-  # ---- lowering to nrl_featurize_batch --------------------------------------------------------
-  def _run_native_batch(self, keys, specs):
-    xyz = self.traj.xyz
-    if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
-      xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
-    batch = self.lower_batch(keys, specs, xyz.shape[1], xyz.dtype == np.float64)
-    if getattr(self, "_out_buffer", None) is None or self._out_buffer.size < batch.out_floats:
-      self._out_buffer = pinned_empty((batch.out_floats,), np.float32)      # page-locked, reused across trajectories
-    out = self._out_buffer[:batch.out_floats]
-    batch.execute(_lib.ptr(xyz), xyz.shape[0], _lib.ptr(out))
-    return batch.split(out)
+  def _submit(self, tid, lane=0):
+    """Everything up to and including the asynchronous native call for trajectory `tid`."""
+    self.traj = self.TRAJLOADER[tid]
+    printit(f"{self.classname}: Processing the trajectory {tid + 1} ({self.traj.identity}) with {self.SLICENUMBER} frame slices")
+    st = time.perf_counter()
+    if self.FOCALPOINTS_PROTOTYPE is not None:
+      if not self.parse_focus():
+        printit(f"{self.classname} Warning: Skipping the trajectory {self.traj.identity}(index {tid + 1}) because focal points parsing is failed. ")
+        return None
+    else:
+      self.FOCALNUMBER = 0
+    for feat in self.FEATURESPACE:
+      feat.cache(self.traj)
+    # task list in the reference's order: window -> focal point -> feature
+    n_focal = self.FOCALNUMBER if self.FOCALNUMBER > 0 else 1
+    task_keys = [(bid, pid, fidx) for bid in range(self.SLICENUMBER) for pid in range(n_focal)
+                 for fidx in range(self.FEATURENUMBER)]
+    specs = [feat._native_spec() if (self.use_native_batch and hasattr(feat, "_native_spec")) else None
+             for feat in self.FEATURESPACE]
+    native_feats = [f for f in range(self.FEATURENUMBER) if specs[f] is not None]
+    native_ids = [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is not None]
+    job = {"tid": tid, "traj": self.traj, "task_keys": task_keys, "native_ids": native_ids, "lane": lane, "start": st,
+           "generic_ids": [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is None], "batch": None}
+    if native_ids:
+      xyz = self.traj.xyz
+      if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
+      batch = self.lower_batch(native_feats, specs, xyz.shape[1], xyz.dtype == np.float64)
+      buffers = self.__dict__.setdefault("_out_buffers", {})
+      if lane not in buffers or buffers[lane].size < batch.out_floats:
+        buffers[lane] = pinned_empty((batch.out_floats,), np.float32)     # page-locked, reused across trajectories
+      out = buffers[lane][:batch.out_floats]
+      batch.execute(_lib.ptr(xyz), xyz.shape[0], _lib.ptr(out), no_sync=True, lane=lane)
+      job.update(batch=batch, out=out, xyz=xyz)
+    return job
 
-  def lower_batch(self, keys, specs, n_atoms, is_f64):
-    """Translate tasks (window, focal point, feature) of the active trajectory into the crop and
-    task tables of the C ABI.  Crops are shared by every feature that looks at the same frames
-    through the same box (same padding / by-residue / selection / cap / emission order)."""
-    wtabs, wtab_ids = [], {}
-    sels, sel_ids = [], {}
-    order_needed = set()
-
-    def table_id(arr):
-      if id(arr) not in wtab_ids:
-        wtab_ids[id(arr)] = len(wtabs)
-        wtabs.append(np.ascontiguousarray(arr, dtype=np.float32))
-      return wtab_ids[id(arr)]
-
-    def selection_id(feat):
-      if feat.selection is None:
-        return -1
-      if id(feat.selected) not in sel_ids:
-        sel_ids[id(feat.selected)] = len(sels)
-        sels.append(np.ascontiguousarray(feat.selected, dtype=np.uint8))
-      return sel_ids[id(feat.selected)]
-
-    crops, crop_ids, tasks, shapes = [], {}, [], []
-    any_byres = False
-    for (bid, pid, fidx) in keys:
-      feat, spec = self.FEATURESPACE[fidx], specs[fidx]
-      wid = table_id(spec["weights"])
-      sid = selection_id(feat)
-      sort_table = wid if spec["mode"] == 3 else -1
-      if sort_table >= 0:
-        order_needed.add(wid)
-      start = bid * self.time_window
-      if spec["kind"] == "static":
-        start, n_frames = start + spec["frame_offset"], 1
-      else:
-        n_frames = self.time_window
+  def _finish(self, job, stats):
+    """Wait for the native results of `job`, run its host-protocol tasks, dump in order."""
+    task_keys = job["task_keys"]
+    results = [None] * len(task_keys)
+    if job["batch"] is not None:
+      _lib.check(_lib.lib().nrl_lane_synchronize(job["lane"]))
+      for i, arr in zip(job["native_ids"], job["batch"].split(job["out"], copy=self.keep_results)):
+        results[i] = arr
+    frames_cache = {}
+    for i in job["generic_ids"]:
+      bid, pid, fidx = task_keys[i]
+      self.frame_slice = self.FRAMESLICES[bid]
+      if bid not in frames_cache:
+        frames_cache = {bid: self.traj.xyz[self.FRAMESLICES[bid]]}
       focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else np.zeros(3, dtype=np.float32)
-      half = feat.spacing / 2
-      lo = 0 - feat.padding - half                                    # python float: numpy compares it as float32 ...
-      lo_cmp = float(np.float32(lo)) if not is_f64 else lo             # ... against float32 coordinates (weak scalar)
-      hi = tuple(float(feat.lengths[k] + feat.padding - half) for k in range(3))   # np.float64: compared in double
-      ckey = (start, n_frames, focal.tobytes(), feat.center.tobytes(), half, lo_cmp, hi, bool(feat.byres), sid,
-              spec["max_atoms"], sort_table)
-      if ckey not in crop_ids:
-        crop_ids[ckey] = len(crops)
-        c = _lib.CropStruct()
-        c.frame_start, c.n_frames = start, n_frames
-        c.focal[:] = [float(v) for v in focal]
-        c.center[:] = [float(v) for v in feat.center]
-        c.half_spacing_f32 = float(np.float32(half))
-        c.half_spacing_f64 = float(half)
-        c.lo[:] = [lo_cmp] * 3
-        c.hi[:] = hi
-        c.byres = 1 if feat.byres else 0
-        c.selection = sid
-        c.max_atoms = spec["max_atoms"]
-        c.sort_table = sort_table
-        any_byres |= bool(feat.byres)
-        crops.append(c)
-      t = _lib.TaskStruct()
-      t.crop, t.mode, t.agg, t.weight_table = crop_ids[ckey], spec["mode"], spec["agg"], wid
-      t.dims[:] = [int(v) for v in feat.dims]
-      t.spacing, t.cutoff, t.sigma = float(feat.spacing), float(feat.cutoff), float(spec["sigma"])
-      tasks.append(t)
-      shapes.append(tuple(int(v) for v in feat.dims))
+      feat = self.FEATURESPACE[fidx]
+      results[i] = feat.run(*feat.query(self.top, frames_cache[bid], focal))
+    tid = job["tid"]
+    printit(f"{self.classname}: Trajectory {tid + 1} yields {len(task_keys)} frame-slices (tasks) for the featurization. ")
+    with utils.batched_output():
+      for (bid, pid, fidx), result in zip(task_keys, results):
+        feat = self.FEATURESPACE[fidx]
+        if self.result_sink is not None:
+          self.result_sink(feat.outkey, tid, bid, pid, result)
+        if self.keep_results:
+          self.RESULTS.setdefault(feat.outkey, []).append(result)
+        if feat.outfile or (self.result_sink is None and not self.keep_results):
+          feat.dump(result)
+    stats["trajectories"] += 1
+    stats["tasks"] += len(task_keys)
+    stats["native_tasks"] += len(job["native_ids"])
+    stats["frames"] += job["traj"].n_frames // self.time_window * self.time_window
+    printit(f"{self.classname}: Finished the trajectory {tid + 1} / {self.TRAJECTORYNUMBER} with {len(task_keys)} tasks in {time.perf_counter() - job['start']:.6f} seconds")
 
+  # ---- lowering to nrl_featurize_batch --------------------------------------------------------
+  def _template(self, native_feats, specs, n_atoms, is_f64):
+    """Crop / task tables for the current (features, windows, focal points) structure.  Only the
+    focal points, weights and selections change from one trajectory to the next, so the tables
+    are built once and re-used.  Crops are shared by every feature that looks at the same frames
+    through the same box (same padding / by-residue / selection / cap / emission order)."""
+    n_focal = self.FOCALNUMBER if self.FOCALNUMBER > 0 else 1
+
+    def fingerprint(fidx):
+      f, sp = self.FEATURESPACE[fidx], specs[fidx]
+      return (fidx, tuple(int(v) for v in f.dims), float(f.spacing), float(f.cutoff), float(sp["sigma"]), float(f.padding),
+              bool(f.byres), f.selection is not None, sp["kind"], sp["mode"], sp["agg"], sp["frame_offset"], sp["max_atoms"])
+
+    key = (tuple(fingerprint(f) for f in native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64))
+    cache = self.__dict__.setdefault("_template_cache", {})
+    if key in cache:
+      return cache[key]
+    table_of = {f: i for i, f in enumerate(native_feats)}
+    sel_feats = [f for f in native_feats if self.FEATURESPACE[f].selection is not None]
+    sel_of = {f: i for i, f in enumerate(sel_feats)}
+    crops, crop_ids, crop_slots, tasks, shapes = [], {}, [], [], []
+    order_feats, any_byres = [], False
+    for bid in range(self.SLICENUMBER):
+      for pid in range(n_focal):
+        for fidx in native_feats:
+          feat, spec = self.FEATURESPACE[fidx], specs[fidx]
+          wid = table_of[fidx]
+          sid = sel_of.get(fidx, -1)
+          sort_table = wid if spec["mode"] == 3 else -1
+          if sort_table >= 0 and fidx not in order_feats:
+            order_feats.append(fidx)
+          start = bid * self.time_window
+          if spec["kind"] == "static":
+            start, n_frames = start + spec["frame_offset"], 1
+          else:
+            n_frames = self.time_window
+          half = feat.spacing / 2
+          lo = 0 - feat.padding - half                                    # python float: numpy compares it as float32 ...
+          lo_cmp = float(np.float32(lo)) if not is_f64 else lo             # ... against float32 coordinates (weak scalar)
+          hi = tuple(float(feat.lengths[k] + feat.padding - half) for k in range(3))   # np.float64: compared in double
+          ckey = (bid, pid, start, n_frames, feat.center.tobytes(), half, lo_cmp, hi, bool(feat.byres), sid,
+                  spec["max_atoms"], sort_table)
+          if ckey not in crop_ids:
+            crop_ids[ckey] = len(crops)
+            c = _lib.CropStruct()
+            c.frame_start, c.n_frames = start, n_frames
+            c.center[:] = [float(v) for v in feat.center]
+            c.half_spacing_f32 = float(np.float32(half))
+            c.half_spacing_f64 = float(half)
+            c.lo[:] = [lo_cmp] * 3
+            c.hi[:] = hi
+            c.byres = 1 if feat.byres else 0
+            c.selection = sid
+            c.max_atoms = spec["max_atoms"]
+            c.sort_table = sort_table
+            any_byres |= bool(feat.byres)
+            crops.append(c)
+            crop_slots.append((bid, pid))
+          t = _lib.TaskStruct()
+          t.crop, t.mode, t.agg, t.weight_table = crop_ids[ckey], spec["mode"], spec["agg"], wid
+          t.dims[:] = [int(v) for v in feat.dims]
+          t.spacing, t.cutoff, t.sigma = float(feat.spacing), float(feat.cutoff), float(spec["sigma"])
+          tasks.append(t)
+          shapes.append(tuple(int(v) for v in feat.dims))
+    tpl = {"crops": crops, "crop_slots": crop_slots, "tasks": (_lib.TaskStruct * len(tasks))(*tasks), "shapes": shapes,
+           "sel_feats": sel_feats, "order_feats": order_feats, "any_byres": any_byres,
+           "out_floats": int(sum(sh[0] * sh[1] * sh[2] for sh in shapes))}
+    cache[key] = tpl
+    return tpl
+
+  def lower_batch(self, native_feats, specs, n_atoms, is_f64):
+    """Crop and task tables of the C ABI for the active trajectory (tasks in the reference's
+    order window -> focal point -> feature, restricted to `native_feats`)."""
+    tpl = self._template(native_feats, specs, n_atoms, is_f64)
     batch = LoweredBatch()
     batch.n_atoms, batch.is_f64 = n_atoms, bool(is_f64)
-    batch.weight_tables = np.stack(wtabs) if wtabs else np.zeros((0, n_atoms), dtype=np.float32)
+    crops = (_lib.CropStruct * len(tpl["crops"]))(*tpl["crops"])     # copies: focal points are per trajectory
+    zero = np.zeros(3, dtype=np.float32)
+    for ci, (bid, pid) in enumerate(tpl["crop_slots"]):
+      focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else zero
+      crops[ci].focal[0], crops[ci].focal[1], crops[ci].focal[2] = float(focal[0]), float(focal[1]), float(focal[2])
+    batch.crops, batch.tasks, batch.shapes, batch.out_floats = crops, tpl["tasks"], tpl["shapes"], tpl["out_floats"]
+    batch.weight_tables = (np.stack([np.asarray(specs[f]["weights"], dtype=np.float32) for f in native_feats])
+                           if native_feats else np.zeros((0, n_atoms), dtype=np.float32))
+    batch.selections = (np.stack([np.asarray(self.FEATURESPACE[f].selected, dtype=np.uint8) for f in tpl["sel_feats"]])
+                        if tpl["sel_feats"] else None)
     batch.value_orders = None
-    if order_needed:
-      # value order: equal weights adjacent, NaN last (stable argsort), -0.0 == +0.0
-      batch.value_orders = np.zeros((len(wtabs), n_atoms), dtype=np.int32)
-      for wid in order_needed:
-        batch.value_orders[wid] = np.argsort(wtabs[wid] + np.float32(0.0), kind="stable").astype(np.int32)
-    batch.selections = np.stack(sels) if sels else None
+    if tpl["order_feats"]:
+      batch.value_orders = np.zeros((len(native_feats), n_atoms), dtype=np.int32)
+      for f in tpl["order_feats"]:
+        batch.value_orders[native_feats.index(f)] = self.FEATURESPACE[f].value_order()
     batch.residue_index, batch.n_residues = None, 0
-    if any_byres:
-      uniq, inverse = np.unique(self.FEATURESPACE[keys[0][2]].resids, return_inverse=True)
+    if tpl["any_byres"]:
+      uniq, inverse = np.unique(self.FEATURESPACE[native_feats[0]].resids, return_inverse=True)
       batch.residue_index, batch.n_residues = np.ascontiguousarray(inverse, dtype=np.int32), len(uniq)
-    batch.crops = (_lib.CropStruct * len(crops))(*crops)
-    batch.tasks = (_lib.TaskStruct * len(tasks))(*tasks)
-    batch.shapes = shapes
-    batch.out_floats = int(sum(int(np.prod(sh)) for sh in shapes))
     return batch
 
 
 class LoweredBatch:
   """Crop / task tables of one trajectory, ready for nrl_featurize_batch."""
 
-  def execute(self, xyz_ptr, n_frames_total, out_ptr, xyz_on_device=False, out_on_device=False, no_sync=False):
+  def execute(self, xyz_ptr, n_frames_total, out_ptr, xyz_on_device=False, out_on_device=False, no_sync=False, lane=0):
     b = _lib.BatchStruct()
     b.xyz, b.xyz_is_f64, b.xyz_on_device = xyz_ptr, int(self.is_f64), int(xyz_on_device)
     b.n_frames_total, b.n_atoms = int(n_frames_total), int(self.n_atoms)
@@ -391,10 +432,13 @@ class LoweredBatch:
     b.out, b.out_on_device = out_ptr, int(out_on_device)
     b.atom_counts = None
     b.flags = 1 if no_sync else 0
+    b.lane = int(lane)
     _lib.check(_lib.lib().nrl_featurize_batch(ctypes.byref(b)))
 
-  def split(self, out):
-    flat = np.array(out[:self.out_floats])        # one copy out of the reused pinned buffer
+  def split(self, out, copy=True):
+    """Per-task views of the flat result buffer (copied out of the re-used pinned buffer when the
+    caller keeps them)."""
+    flat = np.array(out[:self.out_floats]) if copy else out[:self.out_floats]
     results, pos = [], 0
     for shape in self.shapes:
       size = shape[0] * shape[1] * shape[2]

@@ -14,8 +14,7 @@ fz.parse_focus()
 for f in fz.FEATURESPACE:
   f.cache(traj)
 specs = [f._native_spec() for f in fz.FEATURESPACE]
-keys = [(b, 0, f) for b in range(fz.SLICENUMBER) for f in range(fz.FEATURENUMBER)]
-batch = fz.lower_batch(keys, specs, traj.n_atoms, False)
+batch = fz.lower_batch(list(range(fz.FEATURENUMBER)), specs, traj.n_atoms, False)
 xyz = torch.from_numpy(traj.xyz).cuda()
 out = torch.empty(batch.out_floats, dtype=torch.float32, device="cuda")
 for _ in range(steps):
