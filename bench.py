@@ -321,10 +321,11 @@ def run_reference(args):
   frames = (n_frames if max_slices is None else max_slices * fz.time_window) * args.steps
   value = frames / dt
   line = {
-    "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+    "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
     "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": WORKLOAD, "device": device},
+    "config": {"workload": WORKLOAD, "device": device,
+               "note": "the reference has no multi-GPU path: one process (rank 0) on one GPU whatever --gpus says"},
     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1 if kind == "reference" else (os.cpu_count() or 1), "kind": kind,
                      "sample": ("whole trajectory (40 tasks) per step" if max_slices is None else "1 window (4 tasks) per step")},
     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

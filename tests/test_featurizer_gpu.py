@@ -136,3 +136,32 @@ def test_custom_feature_subclass_uses_host_protocol(tmp_path):
   got, fz = build(traj, tmp_path, lambda: [features.Mass(outkey="m"), Doubled(outkey="d")], parms)
   assert fz.last_run_stats["native_tasks"] == 2 and fz.last_run_stats["tasks"] == 4
   assert rel_bad(got["d"], 2 * got["m"]) == 0
+
+
+def test_atom_cap_and_sorted_emission(tmp_path):
+  """More atoms in the focus box than DynamicFeature.MAX_ALLOWED_ATOMS: the reference keeps the
+  first N in topology order (features.py:1353-1359); the device crop must do the same, also when
+  it emits atoms in weight-value order for distinct_count."""
+  traj = io.synthetic_trajectory(6000, 4, seed=21)
+  parms = {"dimensions": 16, "lengths": 24, "time_window": 2, "cutoff": 3.0, "sigma": 1.5}
+  def feats():
+    fs = [features.MarchingObservers(obs="direct_count", agg="max", weight_type="mass", outkey="count"),
+          features.MarchingObservers(obs="distinct_count", agg="max", weight_type="residue_id", outkey="distinct"),
+          features.DensityFlow(agg="mean", weight_type="mass", outkey="flow")]
+    for f in fs:
+      f.MAX_ALLOWED_ATOMS = 700
+    return fs
+  got, fz = build(traj, tmp_path, feats, parms)
+  assert fz.last_run_stats["native_tasks"] == 6
+  from oracle import host_ref as hr
+  old = hr.MAX_ALLOWED_ATOMS
+  hr.MAX_ALLOWED_ATOMS = 700
+  try:
+    ref = hr.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 2, buff_dim=_lib.buff_dim)
+  finally:
+    hr.MAX_ALLOWED_ATOMS = old
+  assert np.array_equal(got["count"], ref["count"])
+  assert np.array_equal(got["distinct"], ref["distinct"])
+  assert rel_bad(got["flow"], ref["flow"]) == 0
+  uncapped = hr.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz)[:1], fz.FOCALPOINTS, 2)
+  assert not np.array_equal(uncapped["count"], ref["count"])      # the cap really bites on this system

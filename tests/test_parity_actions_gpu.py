@@ -254,3 +254,58 @@ def test_buff_dim_probe(ref_actions):
   with open("gpurun_out/buff_dim_probe.json", "w") as fh:
     json.dump(rows, fh, indent=1)
   assert all(abs(r["device"] - r["ieee"]) <= 1 for r in rows)
+
+
+# ---- overflow paths of the tile kernels ------------------------------------------------------------
+def test_long_window_series_in_global_scratch():
+  """40 frames x 512 voxels x 4 B = 80 KB per tile: the series leaves shared memory."""
+  rng = np.random.default_rng(10)
+  dims = np.array([16, 16, 16], dtype=np.int32)
+  F, N, s, c = 40, 300, 0.5, 3.0
+  coords = synth(rng, F, N, 8.0, c)
+  weights = rng.integers(1, 5, size=F * N).astype(np.float32)
+  for obs, agg in [(2, 1), (2, 3), (3, 5), (1, 7), (12, 2), (2, 8)]:
+    got = nb.marching_observer(coords, weights, dims, s, c, obs, agg)
+    ref = orc.marching_observer(coords, weights, dims, s, c, obs, agg)
+    if agg in (3, 5):
+      assert np.array_equal(got, ref), (obs, agg)
+    elif agg == 7:
+      assert np.count_nonzero(~np.isclose(got, ref, atol=1e-3)) < 3
+    else:
+      assert np.allclose(got, ref, rtol=1e-5, atol=1e-5), (obs, agg, np.abs(got - ref).max())
+  got = nb.density_flow(coords, weights, dims, s, c, 1.0, 1)
+  ref = orc.density_flow(coords, weights, dims, s, c, 1.0, 1, buff_dim=_lib.buff_dim(c, s))
+  assert rel_close(got, ref).sum() == 0
+
+
+def test_dense_system_candidates_in_global_scratch():
+  """More than 512 atoms within reach of one tile: the candidate list leaves shared memory."""
+  rng = np.random.default_rng(11)
+  dims = np.array([12, 12, 12], dtype=np.int32)
+  N, s, c = 3000, 0.5, 6.0
+  coords = rng.uniform(-2.0, 8.0, size=(2, N, 3)).astype(np.float32)
+  weights = rng.integers(1, 40, size=2 * N).astype(np.float32)
+  for obs in (2, 3):
+    got = nb.marching_observer(coords, weights, dims, s, c, obs, 5)
+    ref = orc.marching_observer(coords, weights, dims, s, c, obs, 5)
+    assert got.max() > 512 or obs == 3
+    assert np.array_equal(got, ref), obs
+  got = nb.frame_voxelize(coords[0], weights[:N], dims, s, c, 2.0, 0)
+  ref = orc.frame_voxelize(coords[0], weights[:N], dims, s, c, 2.0, buff_dim=_lib.buff_dim(c, s))
+  assert rel_close(got, ref).sum() == 0
+  got = nb.frame_observation(coords[0], weights[:N], dims, s, c, 11)
+  ref = orc.frame_observation(coords[0], weights[:N], dims, s, c, 11)
+  assert rel_close(got, ref).sum() == 0
+
+
+def test_max_frames_boundary():
+  rng = np.random.default_rng(12)
+  dims = np.array([8, 8, 8], dtype=np.int32)
+  coords = rng.uniform(0, 8, size=(512, 20, 3)).astype(np.float32)
+  w = np.ones(512 * 20, dtype=np.float32)
+  got = nb.marching_observer(coords, w, dims, 1.0, 2.0, 2, 1)          # exactly MAX_FRAME_NUMBER frames is allowed
+  ref = orc.marching_observer(coords, w, dims, 1.0, 2.0, 2, 1)
+  assert np.allclose(got, ref, rtol=1e-6, atol=1e-6)
+  big = np.concatenate([coords, coords[:8]], axis=0)                   # density_flow: frames beyond 512 are ignored
+  wb = np.ones(520 * 20, dtype=np.float32)
+  assert np.array_equal(nb.density_flow(big, wb, dims, 1.0, 2.0, 1.0, 5), nb.density_flow(coords, w, dims, 1.0, 2.0, 1.0, 5))
