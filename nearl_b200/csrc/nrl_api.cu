@@ -173,7 +173,8 @@ template <int MODE>
 int launch_tiles_mode(Ctx &c, const NrlTileParams &p, int grid, size_t smem, cudaStream_t st, int slot) {
   if (!c.attr_set[slot]) {
     NRL_CUDA(cudaFuncSetAttribute(nrl_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kCandCap * 3 * sizeof(float4) + kSerCapFloats * sizeof(float))));
+                                  (int)(kCandCap * 3 * sizeof(float4) + kSerCapFloats * sizeof(float) +
+                                        NRL_NW * kCandCap * sizeof(unsigned short))));
     c.attr_set[slot] = true;
   }
   {
@@ -247,12 +248,14 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
     // shared memory: the candidate list plus the time series when it fits (else per-CTA global scratch)
     const size_t ser_need = (size_t)r.max_frames * NRL_TILE_VOX;
     const int ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
+    // candidate records held in shared memory: 512 atoms, 384 of the voxeliser's 48-byte records
     const size_t cand_rec = (r.mode == NRL_MODE_VOXELIZE ? 3 : 1) * sizeof(float4);
-    const size_t smem = kCandCap * cand_rec + (size_t)ser_cap * sizeof(float);
+    const int cand_cap = r.mode == NRL_MODE_VOXELIZE ? 384 : kCandCap;
+    const size_t smem = cand_cap * cand_rec + (size_t)ser_cap * sizeof(float) + (size_t)NRL_NW * cand_cap * sizeof(unsigned short);
     const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (smem + 1024)));
     int grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 12));
     // overflow scratch (candidate lists longer than kCandCap, series longer than kSerCapFloats)
-    const size_t cand_per_cta = max_atoms_per_frame > kCandCap ? (size_t)max_atoms_per_frame : 0;
+    const size_t cand_per_cta = max_atoms_per_frame + 4 > cand_cap ? (size_t)max_atoms_per_frame : 0;
     const size_t ser_per_cta = ser_cap == 0 ? ser_need : 0;
     const size_t per_cta = cand_per_cta * cand_rec + ser_per_cta * sizeof(float);
     if (per_cta > 0) {
@@ -271,7 +274,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
     p.cand_scratch_stride = (long long)(cand_per_cta * cand_rec / sizeof(float4));
     p.ser_scratch = c.ser_scr.as<float>();
     p.ser_scratch_stride = (long long)ser_per_cta;
-    p.cand_cap = kCandCap;
+    p.cand_cap = cand_cap;
     p.ser_cap = ser_cap;
     NRL_TRY(launch_tiles(c, r.mode, p, grid, smem, st));
   }

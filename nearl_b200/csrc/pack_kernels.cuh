@@ -60,7 +60,7 @@ struct NrlCropParams {
   float4 *atoms;                // output, frame fd starts at fd * n_atoms
   long long *off;
   int *cnt;
-  unsigned char *keep;          // scratch [n_frames_out, N_all]
+  unsigned char *keep;          // unused (kept for ABI stability of the struct)
   unsigned int *resflags;       // scratch [n_frames_out, n_res_words], zero-initialised
 };
 
@@ -83,52 +83,69 @@ template <> struct NrlXform<double> {
 
 template <typename T>
 __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCropParams p) {
+  extern __shared__ unsigned int s_keep[];            // one bit per atom of the frame
   __shared__ int s_wcnt[NRL_CROP_NW];
   const int fd = blockIdx.x;
   const NrlCropDev &cr = p.crops[p.frame_crop[fd]];
   const int N = p.n_atoms;
   const T *__restrict__ xyz = reinterpret_cast<const T *>(p.xyz) + (long long)p.frame_src[fd] * N * 3;
-  unsigned char *__restrict__ keep = p.keep + (long long)fd * N;
   unsigned int *__restrict__ resflags = p.resflags + (long long)fd * p.n_res_words;
   const unsigned char *__restrict__ sel = cr.selection >= 0 ? p.sel + (long long)cr.selection * N : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_pad = (N + 31) & ~31;
 
-  // phase A: transform + strict two-sided crop per axis, in the coordinate dtype
+  // phase A: transform + strict two-sided crop per axis, in the coordinate dtype; a warp handles 32
+  // consecutive atoms (384 contiguous bytes of float32 coordinates) and ballots their flags into one word
 #pragma unroll 4
-  for (int a = tid; a < N; a += NRL_CROP_NT) {
-    const T x = NrlXform<T>::apply(xyz[3 * a], cr.focal[0], cr.center[0], cr);
-    const T y = NrlXform<T>::apply(xyz[3 * a + 1], cr.focal[1], cr.center[1], cr);
-    const T z = NrlXform<T>::apply(xyz[3 * a + 2], cr.focal[2], cr.center[2], cr);
-    const bool in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
-                    ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
-    keep[a] = in ? 1 : 0;
-    if (cr.byres && in) {
-      const int r = p.resid[a];
-      atomicOr(&resflags[r >> 5], 1u << (r & 31));
+  for (int a = tid; a < n_pad; a += NRL_CROP_NT) {
+    bool in = false;
+    if (a < N) {
+      const T x = NrlXform<T>::apply(xyz[3 * a], cr.focal[0], cr.center[0], cr);
+      const T y = NrlXform<T>::apply(xyz[3 * a + 1], cr.focal[1], cr.center[1], cr);
+      const T z = NrlXform<T>::apply(xyz[3 * a + 2], cr.focal[2], cr.center[2], cr);
+      in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
+           ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
+      if (cr.byres && in) {
+        const int r = p.resid[a];
+        atomicOr(&resflags[r >> 5], 1u << (r & 31));
+      }
+      if (!cr.byres && sel) in = in && (sel[a] != 0);
     }
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) s_keep[a >> 5] = m;
   }
   __syncthreads();
-  if (cr.byres || sel) {
-    for (int a = tid; a < N; a += NRL_CROP_NT) {
-      bool k = keep[a] != 0;
-      if (cr.byres) { const int r = p.resid[a]; k = (resflags[r >> 5] >> (r & 31)) & 1u; }
-      if (sel) k = k && (sel[a] != 0);
-      keep[a] = k ? 1 : 0;
+  if (cr.byres) {
+    // whole residues of any kept atom (features.py:471-475), then the selection mask
+    for (int a = tid; a < n_pad; a += NRL_CROP_NT) {
+      bool k = false;
+      if (a < N) {
+        const int r = p.resid[a];
+        k = (resflags[r >> 5] >> (r & 31)) & 1u;
+        if (sel) k = k && (sel[a] != 0);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, k);
+      if (lane == 0) s_keep[a >> 5] = m;
     }
     __syncthreads();
   }
   const int *__restrict__ perm = cr.sort_table >= 0 ? p.perms + (long long)cr.sort_table * N : nullptr;
   if (perm && cr.max_atoms > 0) {
     // the cap keeps the first max_atoms atoms in TOPOLOGY order; resolve it before the
-    // value-ordered emission.  One warp, sequential chunks: this path is rare.
+    // value-ordered emission.  One warp, sequential words: this path is rare.
     if (warp == 0) {
       int seen = 0;
-      for (int a0 = 0; a0 < N; a0 += 32) {
-        const int a = a0 + lane;
-        const bool k = (a < N) && keep[a];
-        const unsigned m = __ballot_sync(0xffffffffu, k);
-        if (k && seen + __popc(m & ((1u << lane) - 1u)) >= cr.max_atoms) keep[a] = 0;
-        seen += __popc(m);
+      for (int w0 = 0; w0 < (n_pad >> 5); w0 += 32) {
+        const int wi = w0 + lane;
+        unsigned m = wi < (n_pad >> 5) ? s_keep[wi] : 0u;
+        int c = __popc(m), incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        int before = seen + incl - c;
+        // drop the bits whose topology rank reaches the cap
+        while (m && before + __popc(m) > cr.max_atoms) m &= ~(0x80000000u >> __clz(m));
+        if (wi < (n_pad >> 5)) s_keep[wi] = m;
+        seen += __shfl_sync(0xffffffffu, incl, 31);
       }
     }
     __syncthreads();
@@ -138,11 +155,18 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
   const int seg = ((N + NRL_CROP_NW - 1) / NRL_CROP_NW + 31) & ~31;
   const int e_begin = min(warp * seg, N), e_end = min(e_begin + seg, N);
   int mycnt = 0;
-  for (int e0 = e_begin; e0 < e_end; e0 += 32) {
-    const int e = e0 + lane;
-    bool k = false;
-    if (e < e_end) k = keep[perm ? perm[e] : e] != 0;
-    mycnt += __popc(__ballot_sync(0xffffffffu, k));
+  if (!perm) {
+    if (e_begin < e_end)
+      for (int w0 = (e_begin >> 5) + lane; w0 < ((e_end + 31) >> 5); w0 += 32) mycnt += __popc(s_keep[w0]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mycnt += __shfl_xor_sync(0xffffffffu, mycnt, o);
+  } else {
+    for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+      const int e = e0 + lane;
+      bool k = false;
+      if (e < e_end) { const int a = perm[e]; k = (s_keep[a >> 5] >> (a & 31)) & 1u; }
+      mycnt += __popc(__ballot_sync(0xffffffffu, k));
+    }
   }
   if (lane == 0) s_wcnt[warp] = mycnt;
   __syncthreads();
@@ -155,8 +179,16 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
     const int e = e0 + lane;
     bool k = false;
     int a = 0;
-    if (e < e_end) { a = perm ? perm[e] : e; k = keep[a] != 0; }
-    const unsigned m = __ballot_sync(0xffffffffu, k);
+    unsigned m;
+    if (!perm) {
+      m = s_keep[e0 >> 5];                    // segments start on word boundaries
+      k = (m >> lane) & 1u;
+      a = e;
+    } else {
+      if (e < e_end) { a = perm[e]; k = (s_keep[a >> 5] >> (a & 31)) & 1u; }
+      m = __ballot_sync(0xffffffffu, k);
+    }
+    if (m == 0u) continue;
     const int pos = base + __popc(m & ((1u << lane) - 1u));
     if (k && pos < cap) {
       const T x = NrlXform<T>::apply(xyz[3 * a], cr.focal[0], cr.center[0], cr);
@@ -236,6 +268,9 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
         const int rows = ex * ey;
         const float rcp_ey = 1.0f / (float)ey;
         const float inv_s = 1.0f / s, zc = a.z * inv_s;
+        // reach of float rounding, in lattice units, on the position of an interval end: coordinate
+        // scaling (2 ulp of zc), the cancellation in c2 - t2 and the predicate's own last-bit fuzz
+        const float eps = 5e-4f + 4e-6f * fabsf(zc);
         for (int q = lane; q < rows; q += 32) {
           const int xi = __float2int_rd(((float)q + 0.5f) * rcp_ey);
           const int yi = q - xi * ey;
@@ -251,7 +286,7 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
           // within rounding reach of a lattice plane, or when the row is nearly tangent to the sphere
           // (gap of a few ulp).  Only then are the two ends settled on the exact predicate.
           const float el = fl - ul, eh = uh - fh;                // distances of the ends to the planes beside them
-          const bool fragile = (el < 4e-3f) || (el > 0.996f) || (eh < 4e-3f) || (eh > 0.996f) || (r < 0.25f) || (fabsf(zc) > 1000.0f);
+          const bool fragile = (el < eps) || (el > 1.0f - eps) || (eh < eps) || (eh > 1.0f - eps) || (r < 0.05f);
           if (fragile) {
             jl = max(jl, z_lo - 1); jh = min(jh, z_hi + 1);
             int guard = 0;

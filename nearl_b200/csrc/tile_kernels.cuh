@@ -57,9 +57,25 @@ template <int MODE> struct NrlModeTraits {
   static constexpr bool kNeedsWeight = (MODE != NRL_OBS_EXISTENCE && MODE != NRL_OBS_DIRECT_COUNT);
 };
 
+// Loop over the candidates of a sweep.  INDEXED: `idx` is the warp's sub-list of candidate numbers,
+// padded to a multiple of four with the number of a far-away sentinel record; four numbers come in
+// one 8-byte shared load and the four candidate records are fetched back to back (ILP over the
+// dependent index -> record loads).  Inside BODY the candidate number is `ci`.
+#define NRL_CAND_LOOP(...)                                                                     \
+  if constexpr (INDEXED) {                                                                     \
+    for (int c4 = 0; c4 < ncand; c4 += 4) {                                                    \
+      const ushort4 q4 = *reinterpret_cast<const ushort4 *>(idx + c4);                         \
+      const int ii[4] = {q4.x, q4.y, q4.z, q4.w};                                              \
+      _Pragma("unroll") for (int u = 0; u < 4; ++u) { const int ci = ii[u]; __VA_ARGS__ }      \
+    }                                                                                          \
+  } else {                                                                                     \
+    _Pragma("unroll 2") for (int ci = 0; ci < ncand; ++ci) { __VA_ARGS__ }                     \
+  }
+
 // ---- per-frame sweep of the candidate list for the 4 voxels of one thread ----------
-template <int MODE, typename CandPtr>
-__device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const NrlTask &t, const float c2,
+// `idx` (optional): the warp's own sub-list of candidate numbers, see the tile kernel
+template <int MODE, bool INDEXED, typename CandPtr>
+__device__ __forceinline__ void nrl_sweep(CandPtr cand, const unsigned short *idx, const int ncand, const NrlTask &t, const float c2,
                                           const float px, const float py, const float (&pz)[NRL_VPT],
                                           float (&val)[NRL_VPT]) {
   if constexpr (MODE == NRL_MODE_VOXELIZE) {
@@ -71,31 +87,29 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
     for (int k = 0; k < NRL_VPT; ++k) acc[k] = 0.0f;
     const float k2 = t.k2;
     const int zq = 1 + (threadIdx.x & 1);
-#pragma unroll 2
-    for (int c = 0; c < ncand; ++c) {
-      const float4 a = cand[c * 3];
-      const float4 ezq = cand[c * 3 + zq];
+    NRL_CAND_LOOP(
+      const float4 a = cand[ci * 3];
+      const float4 ezq = cand[ci * 3 + zq];
       const float part = nrl_vox_partial(a.x, a.y, px, py);
       const float wxy = nrl_ex2_approx(part * k2) * a.w;
       const float ez[NRL_VPT] = {ezq.x, ezq.y, ezq.z, ezq.w};
-#pragma unroll
+_Pragma("unroll")
       for (int k = 0; k < NRL_VPT; ++k) {
         const float dz = a.z - pz[k];
         const float d2 = fmaf(dz, dz, part);
         if (d2 < c2) acc[k] = fmaf(wxy, ez[k], acc[k]);
       }
-    }
+    )
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) val[k] = acc[k];
   } else if constexpr (MODE == NRL_OBS_EXISTENCE || MODE == NRL_OBS_DIRECT_COUNT) {
     float acc[NRL_VPT];
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) acc[k] = 0.0f;
-#pragma unroll 2
-    for (int c = 0; c < ncand; ++c) {
-      const float4 a = cand[c];
+    NRL_CAND_LOOP(
+      const float4 a = cand[ci];
       const float part = nrl_obs_partial(px, py, a.x, a.y);
-#pragma unroll
+_Pragma("unroll")
       for (int k = 0; k < NRL_VPT; ++k) {
         const float dz = pz[k] - a.z;
         const float d2 = fmaf(dz, dz, part);
@@ -103,7 +117,7 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
           if constexpr (MODE == NRL_OBS_EXISTENCE) acc[k] = 1.0f; else acc[k] = acc[k] + 1.0f;
         }
       }
-    }
+    )
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) val[k] = acc[k];
   } else if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) {
@@ -114,11 +128,10 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
     float cnt[NRL_VPT], last[NRL_VPT];
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) { cnt[k] = 0.0f; last[k] = __int_as_float(0x7fc00000); }
-#pragma unroll 2
-    for (int c = 0; c < ncand; ++c) {
-      const float4 a = cand[c];
+    NRL_CAND_LOOP(
+      const float4 a = cand[ci];
       const float part = nrl_obs_partial(px, py, a.x, a.y);
-#pragma unroll
+_Pragma("unroll")
       for (int k = 0; k < NRL_VPT; ++k) {
         const float dz = pz[k] - a.z;
         const float d2 = fmaf(dz, dz, part);
@@ -127,7 +140,7 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
           last[k] = a.w;
         }
       }
-    }
+    )
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) val[k] = fminf(cnt[k], NRL_DISTINCT_LIMIT);
   } else if constexpr (MODE == NRL_OBS_MEAN_DISTANCE) {
@@ -135,11 +148,10 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
     int n[NRL_VPT];
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) { r[k] = 0.0f; ws[k] = 0.0f; n[k] = 0; }
-#pragma unroll 2
-    for (int c = 0; c < ncand; ++c) {
-      const float4 a = cand[c];
+    NRL_CAND_LOOP(
+      const float4 a = cand[ci];
       const float part = nrl_obs_partial(px, py, a.x, a.y);
-#pragma unroll
+_Pragma("unroll")
       for (int k = 0; k < NRL_VPT; ++k) {
         const float dz = pz[k] - a.z;
         const float d2 = fmaf(dz, dz, part);
@@ -149,24 +161,23 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
           n[k] += 1;
         }
       }
-    }
+    )
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) val[k] = n[k] > 0 ? nrl_div_approx(r[k], ws[k]) : 0.0f;
   } else if constexpr (MODE == NRL_OBS_CUMULATIVE_WEIGHT || MODE == NRL_OBS_DENSITY) {
     float ws[NRL_VPT];
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) ws[k] = 0.0f;
-#pragma unroll 2
-    for (int c = 0; c < ncand; ++c) {
-      const float4 a = cand[c];
+    NRL_CAND_LOOP(
+      const float4 a = cand[ci];
       const float part = nrl_obs_partial(px, py, a.x, a.y);
-#pragma unroll
+_Pragma("unroll")
       for (int k = 0; k < NRL_VPT; ++k) {
         const float dz = pz[k] - a.z;
         const float d2 = fmaf(dz, dz, part);
         if (!(d2 > c2)) ws[k] = ws[k] + a.w;                            // :183-189
       }
-    }
+    )
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) {
       if constexpr (MODE == NRL_OBS_DENSITY) val[k] = (float)((double)ws[k] / t.sphere_volume);  // :199-201
@@ -177,10 +188,10 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
     int n[NRL_VPT];
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) { cx[k] = cy[k] = cz[k] = ws[k] = 0.0f; n[k] = 0; }
-    for (int c = 0; c < ncand; ++c) {
-      const float4 a = cand[c];
+    NRL_CAND_LOOP(
+      const float4 a = cand[ci];
       const float part = nrl_obs_partial(px, py, a.x, a.y);
-#pragma unroll
+_Pragma("unroll")
       for (int k = 0; k < NRL_VPT; ++k) {
         const float dz = pz[k] - a.z;
         const float d2 = fmaf(dz, dz, part);
@@ -192,7 +203,7 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
           ws[k] = ws[k] + a.w;
         }
       }
-    }
+    )
     if constexpr (MODE == NRL_OBS_ECCENTRICITY) {
 #pragma unroll
       for (int k = 0; k < NRL_VPT; ++k) {
@@ -215,16 +226,16 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
         m2[k] = nrl_div_approx(cz[k], ws[k]);
         r[k] = 0.0f;
       }
-      for (int c = 0; c < ncand; ++c) {                                 // :347-353
-        const float4 a = cand[c];
+      NRL_CAND_LOOP(
+        const float4 a = cand[ci];
         const float part = nrl_obs_partial(px, py, a.x, a.y);
-#pragma unroll
+_Pragma("unroll")
         for (int k = 0; k < NRL_VPT; ++k) {
           const float dz = pz[k] - a.z;
           const float d2 = fmaf(dz, dz, part);
           if (!(d2 > c2)) r[k] = fmaf(a.w, nrl_obs_d2(m0[k], m1[k], m2[k], a.x, a.y, a.z), r[k]);
         }
-      }
+      )
 #pragma unroll
       for (int k = 0; k < NRL_VPT; ++k)
         val[k] = live[k] ? nrl_sqrt_approx(nrl_div_approx(r[k], ws[k])) : 0.0f;
@@ -235,10 +246,10 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const int ncand, const N
     for (int v = 0; v < NRL_VPT; ++v) {
       float r = 0.0f, ws = 0.0f;
       for (int j = 0; j < ncand; ++j) {
-        const float4 a = cand[j];
+        const float4 a = cand[INDEXED ? (int)idx[j] : j];
         if (nrl_obs_d2(px, py, pz[v], a.x, a.y, a.z) > c2) continue;
         for (int m = j + 1; m < ncand; ++m) {
-          const float4 b = cand[m];
+          const float4 b = cand[INDEXED ? (int)idx[m] : m];
           if (nrl_obs_d2(px, py, pz[v], b.x, b.y, b.z) > c2) continue;
           const float d2 = nrl_obs_d2(a.x, a.y, a.z, b.x, b.y, b.z);
           const float ww = a.w * b.w;
@@ -258,9 +269,15 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
   float4 *s_cand = reinterpret_cast<float4 *>(nrl_smem);
   float4 *s_ser = reinterpret_cast<float4 *>(nrl_smem + (size_t)p.cand_cap * NrlCandStride<MODE>::value * sizeof(float4));
   __shared__ int s_wcnt[NRL_NW];
+  // per-warp sub-lists (candidate numbers) live behind the series in dynamic shared memory
+  unsigned short *s_idx = reinterpret_cast<unsigned short *>(
+      nrl_smem + (size_t)p.cand_cap * NrlCandStride<MODE>::value * sizeof(float4) + (size_t)p.ser_cap * sizeof(float));
 
+  // a warp owns a compact 4x4x8 block of the tile (32 lanes x 4 z-consecutive voxels): of all
+  // 128-voxel shapes it has the smallest cutoff-dilated volume, i.e. the shortest candidate list
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lzq = tid & 1, ly = (tid >> 1) & 7, lx = tid >> 4;
+  const int lzq = lane & 1, ly = ((lane >> 1) & 3) + 4 * (warp & 1), lx = ((lane >> 3) & 3) + 4 * (warp >> 1);
+  unsigned short *my_idx = s_idx + (size_t)warp * p.cand_cap;
   float4 *g_cand = p.cand_scratch + (long long)blockIdx.x * p.cand_scratch_stride;
   float4 *g_ser = reinterpret_cast<float4 *>(p.ser_scratch + (long long)blockIdx.x * p.ser_scratch_stride);
 
@@ -285,6 +302,9 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
     box.y0 = (float)y0 * s; box.y1 = (float)min(y0 + NRL_TY - 1, ny - 1) * s;
     box.z0 = (float)z0 * s; box.z1 = (float)min(z0 + NRL_TZ - 1, nz - 1) * s;
     box.r2 = c2 * 1.0005f + 1e-30f;
+    NrlTileBox wbox = box;      // the same test against the warp's own 4x4x8 block
+    wbox.x0 = (float)min(x0 + 4 * (warp >> 1), nx - 1) * s; wbox.x1 = (float)min(x0 + 4 * (warp >> 1) + 3, nx - 1) * s;
+    wbox.y0 = (float)min(y0 + 4 * (warp & 1), ny - 1) * s;  wbox.y1 = (float)min(y0 + 4 * (warp & 1) + 3, ny - 1) * s;
 
     const int ix = x0 + lx, iy = y0 + ly, iz = z0 + lzq * NRL_VPT;
     const float px = (float)ix * s, py = (float)iy * s;
@@ -326,7 +346,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
         if (w < warp) base += cw;
         total += cw;
       }
-      const bool cand_in_smem = total <= p.cand_cap;      // p.cand_cap counts candidates, whatever their record size
+      const bool cand_in_smem = total + 4 <= p.cand_cap;  // p.cand_cap counts candidates, whatever their record size; room for the sentinel
       float4 *cand = cand_in_smem ? s_cand : g_cand;
 
       // ---- pass 2: order-preserving compaction, weight resolved through the payload
@@ -367,12 +387,33 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
           base += __popc(m);
         }
       }
+      if (cand_in_smem && tid == 0) {
+        // far-away sentinel record behind the list: pads the warps' sub-lists to multiples of four
+#pragma unroll
+        for (int q = 0; q < NrlCandStride<MODE>::value; ++q)
+          s_cand[total * NrlCandStride<MODE>::value + q] =
+              q == 0 ? make_float4(NRL_FAR, NRL_FAR, NRL_FAR, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       __syncthreads();
 
       // ---- sweep
       float val[NRL_VPT];
-      if (cand_in_smem) nrl_sweep<MODE>(s_cand, total, t, c2, px, py, pz, val);
-      else nrl_sweep<MODE>(static_cast<const float4 *>(g_cand), total, t, c2, px, py, pz, val);
+      if (cand_in_smem) {
+        // second-level culling: each warp keeps (in order) only the candidates that can reach its block
+        int nsub = 0;
+        for (int c0 = 0; c0 < total; c0 += 32) {
+          const int ci = c0 + lane;
+          const bool k = ci < total && nrl_near_box(s_cand[ci * NrlCandStride<MODE>::value], wbox);
+          const unsigned m = __ballot_sync(0xffffffffu, k);
+          if (k) my_idx[nsub + __popc(m & ((1u << lane) - 1u))] = (unsigned short)ci;
+          nsub += __popc(m);
+        }
+        while (nsub & 3) { if (lane == 0) my_idx[nsub] = (unsigned short)total; ++nsub; }
+        __syncwarp();
+        nrl_sweep<MODE, true>(s_cand, my_idx, nsub, t, c2, px, py, pz, val);
+      } else {
+        nrl_sweep<MODE, false>(static_cast<const float4 *>(g_cand), nullptr, total, t, c2, px, py, pz, val);
+      }
 
       if (t.agg == 0) {
         if (ix < nx && iy < ny) {

@@ -165,3 +165,17 @@ def test_atom_cap_and_sorted_emission(tmp_path):
   assert rel_bad(got["flow"], ref["flow"]) == 0
   uncapped = hr.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz)[:1], fz.FOCALPOINTS, 2)
   assert not np.array_equal(uncapped["count"], ref["count"])      # the cap really bites on this system
+
+
+@pytest.mark.parametrize("n_atoms", [16, 33, 480, 1500, 4097])
+def test_ragged_atom_counts(tmp_path, n_atoms):
+  """Device crop / compaction at atom counts around warp, word and segment boundaries."""
+  traj = io.synthetic_trajectory(n_atoms, 4, seed=100 + n_atoms)
+  parms = {"dimensions": 8, "lengths": 8, "time_window": 2, "cutoff": 3.0, "sigma": 1.0}
+  feats = lambda: [features.Mass(outkey="m"),
+                   features.MarchingObservers(obs="direct_count", agg="max", outkey="n"),
+                   features.MarchingObservers(obs="distinct_count", agg="max", weight_type="residue_id", outkey="r", byres=True)]
+  got, fz = build(traj, tmp_path, feats, parms, focus=(":1",))
+  ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 2, buff_dim=_lib.buff_dim)
+  assert np.array_equal(got["n"], ref["n"]) and np.array_equal(got["r"], ref["r"])
+  assert rel_bad(got["m"], ref["m"]) == 0
