@@ -35,8 +35,28 @@ sys.path.insert(0, ROOT)
 METRIC = "featurised frames/sec"
 UNIT = "frames/s"
 N_ROTATE = 8
-WORKLOAD = ("configs[1]: dynamic marching-observer features (existence, distinct_count, mean_distance) + density_flow, "
-            "32^3 @0.5A, time_window=10, cutoff 5.0, sigma 1.5, focus ':ARG', synthetic 20k-atom x 100-frame trajectory")
+WORKLOADS = {
+  # the headline: BASELINE.json configs[1]
+  "dynamic": ("configs[1]: dynamic marching-observer features (existence, distinct_count, mean_distance) + density_flow, "
+              "32^3 @0.5A, time_window=10, cutoff 5.0, sigma 1.5, focus ':ARG', synthetic 20k-atom x 100-frame trajectory"),
+  # extra, for the record (profiles/): BASELINE.json configs[0] and configs[2]
+  "readme": ("configs[0]: README quick start, Mass, 32^3 @0.5A, time_window=10, sigma 1.5, cutoff 5.0, focus ':ARG', "
+             "synthetic 5k-atom x 100-frame trajectory"),
+  "pdbbind": ("configs[2]: PDBBind-style static featurisation, 8 atom-property channels at 24^3 over 20 A, cutoff 2.5, sigma 1.5, "
+              "focus ':LIG', synthetic 3k-atom complexes (one frame each; a step = one complex)"),
+}
+WORKLOAD = WORKLOADS["dynamic"]
+
+
+def make_workload(name, n_traj, seed_offset=0, pin=True):
+  from nearl_b200 import workloads
+  if name == "dynamic":
+    return workloads.dynamic_observers(n_traj=n_traj, seed_offset=seed_offset, pin=pin)
+  if name == "readme":
+    return workloads.readme_mass(n_traj=n_traj, seed_offset=seed_offset, pin=pin)
+  if name == "pdbbind":
+    return workloads.pdbbind_static(n_complex=n_traj * 8, seed_offset=seed_offset, pin=pin)
+  raise SystemExit(f"unknown workload {name}")
 
 
 class ClockSampler:
@@ -108,7 +128,9 @@ def run_native(args):
   _lib.set_stream(stream.cuda_stream, True)
 
   # every rank featurises its own trajectories: weak scaling, no data-path collective
-  fz, trajs = workloads.dynamic_observers(n_traj=N_ROTATE, seed_offset=rank * N_ROTATE)
+  global WORKLOAD
+  WORKLOAD = WORKLOADS[args.workload]
+  fz, trajs = make_workload(args.workload, N_ROTATE, seed_offset=rank * N_ROTATE)
   fz.keep_results = True
   n_frames = trajs[0].n_frames
   n_tasks = fz.FEATURENUMBER * (n_frames // fz.time_window)
@@ -125,8 +147,10 @@ def run_native(args):
     dev_xyz.append(torch.from_numpy(traj.xyz).cuda())
   dev_out = torch.empty(lowered[0].out_floats, dtype=torch.float32, device="cuda")
 
+  n_rot = len(trajs)
+
   def step_device(i):
-    k = i % N_ROTATE
+    k = i % n_rot
     lowered[k].execute(dev_xyz[k].data_ptr(), n_frames, dev_out.data_ptr(), xyz_on_device=True, out_on_device=True,
                        no_sync=True)
 
@@ -140,7 +164,7 @@ def run_native(args):
   fz.result_sink = sink
 
   def run_e2e(first, count):
-    fz.run(trajectory_indices=[(first + i) % N_ROTATE for i in range(count)])
+    fz.run(trajectory_indices=[(first + i) % n_rot for i in range(count)])
 
   def barrier():
     if world > 1:
@@ -209,8 +233,10 @@ def run_native(args):
   fz.parse_focus()
   f0 = fz.FEATURESPACE[0]
   f0.cache(trajs[0])
-  n_in = int(np.mean([f0.query(trajs[0].top, trajs[0].xyz[i * 10:i * 10 + 1], fz.FOCALPOINTS[i, 0])[0].shape[1] for i in range(3)]))
-  G = 32 ** 3
+  from nearl_b200 import features as _features
+  n_in = int(np.mean([np.count_nonzero(_features.Feature.query(f0, trajs[0].top, trajs[0].xyz[i * fz.time_window], fz.FOCALPOINTS[i, 0])[0])
+                      for i in range(min(3, fz.SLICENUMBER))]))
+  G = int(np.prod(f0.dims))
   if top is not None:
     t_launch = kernels[top]["ms_per_launch"] * 1e-3
     windows = n_frames // fz.time_window
@@ -239,7 +265,9 @@ def run_native(args):
     "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
     "dtype": "f32", "data": "synthetic",
     "config": {"workload": WORKLOAD, "tasks_per_step": n_tasks, "frames_per_step": n_frames, "atoms": trajs[0].n_atoms,
-               "atoms_in_focus_box": n_in, "grid": [32, 32, 32], "l2": f"inputs larger than L2: {N_ROTATE} trajectories x 24 MB cycled",
+               "atoms_in_focus_box": n_in, "grid": [int(v) for v in f0.dims],
+               "l2": f"inputs larger than L2: {n_rot} trajectories x {trajs[0].xyz.nbytes / 1e6:.1f} MB cycled"
+                     if n_rot * trajs[0].xyz.nbytes > 126e6 else f"{n_rot} trajectories x {trajs[0].xyz.nbytes / 1e6:.2f} MB cycled (fits L2; extra workload, not the headline)",
                "sharding": "one process per GPU, trajectories sharded by rank, no collective on the data path"},
     "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
             "h2d_bytes_per_step": int(n_frames * trajs[0].n_atoms * 12 + 4 * trajs[0].n_atoms * 4),
@@ -285,8 +313,25 @@ def run_reference(args):
   from nearl_b200 import workloads
   from oracle import host_ref
   nearl_b200.update_config(quiet=True)
-  fz, trajs = workloads.dynamic_observers(n_traj=min(N_ROTATE, max(1, args.steps)))
+  global WORKLOAD
+  WORKLOAD = WORKLOADS[args.workload]
+  # ordinary pageable trajectories, as a Nearl user has them: page-locked host memory in the process makes the
+  # reference's per-call cudaMalloc/cudaFree several times slower and would bias the comparison against it
+  fz, trajs = make_workload(args.workload, min(N_ROTATE, max(1, args.steps)), pin=False)
   kernels, kind, device = None, "port", f"{os.cpu_count()} host cores (CPU oracle port)"
+  warm_ctx = False
+  if not args.cold_context:
+    # A live torch allocation keeps the driver's sub-allocator warm: the reference cudaMalloc's and
+    # cudaFree's 4-6 buffers per call, which is ~10x cheaper in a context that already holds memory
+    # (a Nearl process that also trains) than in a bare one.  The favourable case is the default.
+    try:
+      import torch
+      if torch.cuda.is_available():
+        _keep = torch.zeros(1 << 20, device="cuda")
+        torch.cuda.synchronize()
+        warm_ctx = True
+    except Exception:
+      pass
   try:
     sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
     import all_actions as ref_actions
@@ -325,7 +370,8 @@ def run_reference(args):
     "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
     "config": {"workload": WORKLOAD, "device": device,
-               "note": "the reference has no multi-GPU path: one process (rank 0) on one GPU whatever --gpus says"},
+               "note": "the reference has no multi-GPU path: one process (rank 0) on one GPU whatever --gpus says",
+               "cuda_context": "warm (torch allocation alive: cheap cudaMalloc/cudaFree)" if warm_ctx else "bare (as a stand-alone Nearl process)"},
     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1 if kind == "reference" else (os.cpu_count() or 1), "kind": kind,
                      "sample": ("whole trajectory (40 tasks) per step" if max_slices is None else "1 window (4 tasks) per step")},
     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -339,6 +385,8 @@ def main():
   ap.add_argument("--steps", type=int, default=20)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
+  ap.add_argument("--workload", default="dynamic", choices=sorted(WORKLOADS), help="default: the headline configs[1]")
+  ap.add_argument("--cold-context", action="store_true", help="reference arm: do not pre-create a torch CUDA context")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
   if args.impl == "reference":
