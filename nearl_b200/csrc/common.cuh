@@ -23,6 +23,7 @@
 #define NRL_TZ 8
 #define NRL_TILE_VOX (NRL_TX * NRL_TY * NRL_TZ)
 #define NRL_VPT 4
+#define NRL_MAX_CH 4
 #define NRL_NT (NRL_TILE_VOX / NRL_VPT)   // 128 threads
 #define NRL_NW (NRL_NT / 32)
 
@@ -79,7 +80,14 @@ struct NrlTask {
   int ntx, nty, ntz;        // tiles per axis
   int tile_begin;           // first work item of this task in the launch
   int n_frames;             // frames observed (already clamped to NRL_MAX_FRAMES)
-  int agg;                  // 0: single frame written as is; 1..8 reducer id
+  // A work item produces up to NRL_MAX_CH output grids ("channels") from ONE sweep: several reducers
+  // of the same per-frame value, and -- voxeliser only -- up to NRL_MAX_CH weight tables deposited
+  // together (the geometry, the cutoff tests and the exponentials are shared).
+  int n_ch;                 // channels
+  int n_w;                  // weight slots (1 unless voxeliser with several weight tables)
+  int ch_agg[NRL_MAX_CH];   // per channel: 0 = single frame written as is, 1..8 reducer id
+  int ch_w[NRL_MAX_CH];     // per channel: weight slot whose per-frame values it reduces
+  long long ch_out[NRL_MAX_CH];   // per channel: first output float
   int mode;                 // NrlMode
   float spacing;
   float cutoff;
@@ -87,8 +95,7 @@ struct NrlTask {
   float sigma;
   double sphere_volume;     // density: (4/3) pi cutoff^3 in double (marching_observers.cu:200)
   long long frame0;         // first frame descriptor
-  long long out_off;        // first output float
-  const float *wtab;        // weight table addressed by the atom's index payload
+  const float *wtab[NRL_MAX_CH];   // per weight slot: table addressed by the atom's index payload
   const float *inv_norm;    // voxelize: 1/S per packed atom (parallel to atoms), else null
 };
 

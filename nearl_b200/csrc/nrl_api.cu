@@ -169,38 +169,43 @@ constexpr int kCandCap = 512;         // candidates held in shared memory (8 KB;
 constexpr int kSerCapFloats = 8192;   // series floats held in shared memory (32 KB: 16 frames x 512 voxels)
 constexpr size_t kScratchBudget = (size_t)1 << 30;
 
-template <int MODE>
+template <int MODE, int NWT>
 int launch_tiles_mode(Ctx &c, const NrlTileParams &p, int grid, size_t smem, cudaStream_t st, int slot) {
-  if (!c.attr_set[slot]) {
-    NRL_CUDA(cudaFuncSetAttribute(nrl_tile_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kCandCap * 3 * sizeof(float4) + kSerCapFloats * sizeof(float) +
-                                        NRL_NW * kCandCap * sizeof(unsigned short))));
-    c.attr_set[slot] = true;
+  const int attr = NWT > 1 ? 22 : slot;
+  if (!c.attr_set[attr]) {
+    NRL_CUDA(cudaFuncSetAttribute(nrl_tile_kernel<MODE, NWT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(c.smem_optin - 2048)));
+    c.attr_set[attr] = true;
   }
   {
     ScopedProf sp(c, st, CAT_TILE0 + slot);
-    nrl_tile_kernel<MODE><<<grid, NRL_NT, smem, st>>>(p);
+    nrl_tile_kernel<MODE, NWT><<<grid, NRL_NT, smem, st>>>(p);
   }
   g_launches.fetch_add(1);
   NRL_CUDA(cudaGetLastError());
   return NRL_OK;
 }
 
-int launch_tiles(Ctx &c, int mode, const NrlTileParams &p, int grid, size_t smem, cudaStream_t st) {
-  switch (mode) {
-    case NRL_MODE_VOXELIZE: return launch_tiles_mode<NRL_MODE_VOXELIZE>(c, p, grid, smem, st, 0);
-    case NRL_OBS_EXISTENCE: return launch_tiles_mode<NRL_OBS_EXISTENCE>(c, p, grid, smem, st, 1);
-    case NRL_OBS_DIRECT_COUNT: return launch_tiles_mode<NRL_OBS_DIRECT_COUNT>(c, p, grid, smem, st, 2);
-    case NRL_OBS_DISTINCT_COUNT: return launch_tiles_mode<NRL_OBS_DISTINCT_COUNT>(c, p, grid, smem, st, 3);
-    case NRL_OBS_MEAN_DISTANCE: return launch_tiles_mode<NRL_OBS_MEAN_DISTANCE>(c, p, grid, smem, st, 4);
-    case NRL_OBS_CUMULATIVE_WEIGHT: return launch_tiles_mode<NRL_OBS_CUMULATIVE_WEIGHT>(c, p, grid, smem, st, 5);
-    case NRL_OBS_DENSITY: return launch_tiles_mode<NRL_OBS_DENSITY>(c, p, grid, smem, st, 6);
-    case NRL_OBS_DISPERSION: return launch_tiles_mode<NRL_OBS_DISPERSION>(c, p, grid, smem, st, 7);
-    case NRL_OBS_ECCENTRICITY: return launch_tiles_mode<NRL_OBS_ECCENTRICITY>(c, p, grid, smem, st, 8);
-    case NRL_OBS_RADIUS_OF_GYRATION: return launch_tiles_mode<NRL_OBS_RADIUS_OF_GYRATION>(c, p, grid, smem, st, 9);
+// mode_key: observable id, NRL_MODE_VOXELIZE, or kVoxelizeMulti (voxeliser with several weight tables)
+constexpr int kVoxelizeMulti = -1;
+int launch_tiles(Ctx &c, int mode_key, const NrlTileParams &p, int grid, size_t smem, cudaStream_t st) {
+  switch (mode_key) {
+    case kVoxelizeMulti: return launch_tiles_mode<NRL_MODE_VOXELIZE, NRL_MAX_CH>(c, p, grid, smem, st, 0);
+    case NRL_MODE_VOXELIZE: return launch_tiles_mode<NRL_MODE_VOXELIZE, 1>(c, p, grid, smem, st, 0);
+    case NRL_OBS_EXISTENCE: return launch_tiles_mode<NRL_OBS_EXISTENCE, 1>(c, p, grid, smem, st, 1);
+    case NRL_OBS_DIRECT_COUNT: return launch_tiles_mode<NRL_OBS_DIRECT_COUNT, 1>(c, p, grid, smem, st, 2);
+    case NRL_OBS_DISTINCT_COUNT: return launch_tiles_mode<NRL_OBS_DISTINCT_COUNT, 1>(c, p, grid, smem, st, 3);
+    case NRL_OBS_MEAN_DISTANCE: return launch_tiles_mode<NRL_OBS_MEAN_DISTANCE, 1>(c, p, grid, smem, st, 4);
+    case NRL_OBS_CUMULATIVE_WEIGHT: return launch_tiles_mode<NRL_OBS_CUMULATIVE_WEIGHT, 1>(c, p, grid, smem, st, 5);
+    case NRL_OBS_DENSITY: return launch_tiles_mode<NRL_OBS_DENSITY, 1>(c, p, grid, smem, st, 6);
+    case NRL_OBS_DISPERSION: return launch_tiles_mode<NRL_OBS_DISPERSION, 1>(c, p, grid, smem, st, 7);
+    case NRL_OBS_ECCENTRICITY: return launch_tiles_mode<NRL_OBS_ECCENTRICITY, 1>(c, p, grid, smem, st, 8);
+    case NRL_OBS_RADIUS_OF_GYRATION: return launch_tiles_mode<NRL_OBS_RADIUS_OF_GYRATION, 1>(c, p, grid, smem, st, 9);
     default: return fail(NRL_ERR_OBSERVABLE, "The observable type is not supported");
   }
 }
+
+int mode_key_of(const NrlTask &t) { return (t.mode == NRL_MODE_VOXELIZE && t.n_w > 1) ? kVoxelizeMulti : t.mode; }
 
 void fill_task_geometry(NrlTask &t, const int *dims, float spacing, float cutoff, float sigma) {
   t.nx = dims[2]; t.ny = dims[1]; t.nz = dims[0];
@@ -221,7 +226,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
   if (tasks.empty()) return NRL_OK;
   std::vector<int> order(tasks.size());
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return tasks[a].mode < tasks[b].mode; });
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return mode_key_of(tasks[a]) < mode_key_of(tasks[b]); });
   std::vector<NrlTask> sorted;
   sorted.reserve(tasks.size());
   for (int i : order) sorted.push_back(tasks[i]);
@@ -232,13 +237,13 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
   for (size_t i = 0; i < sorted.size();) {
     size_t j = i;
     int work = 0, maxf = 1;
-    while (j < sorted.size() && sorted[j].mode == sorted[i].mode) {
+    while (j < sorted.size() && mode_key_of(sorted[j]) == mode_key_of(sorted[i])) {
       sorted[j].tile_begin = work;
       work += sorted[j].ntx * sorted[j].nty * sorted[j].ntz;
-      maxf = std::max(maxf, sorted[j].n_frames);
+      maxf = std::max(maxf, sorted[j].n_frames * sorted[j].n_w);     // series rows a tile keeps
       ++j;
     }
-    ranges.push_back({sorted[i].mode, (int)i, (int)j, work, maxf});
+    ranges.push_back({mode_key_of(sorted[i]), (int)i, (int)j, work, maxf});
     i = j;
   }
   NRL_TRY(c.tasks.reserve(sorted.size() * sizeof(NrlTask)));
@@ -249,8 +254,8 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
     const size_t ser_need = (size_t)r.max_frames * NRL_TILE_VOX;
     const int ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
     // candidate records held in shared memory: 512 atoms, 384 of the voxeliser's 48-byte records
-    const size_t cand_rec = (r.mode == NRL_MODE_VOXELIZE ? 3 : 1) * sizeof(float4);
-    const int cand_cap = r.mode == NRL_MODE_VOXELIZE ? 384 : kCandCap;
+    const size_t cand_rec = (r.mode == kVoxelizeMulti ? 4 : r.mode == NRL_MODE_VOXELIZE ? 3 : 1) * sizeof(float4);
+    const int cand_cap = (r.mode == NRL_MODE_VOXELIZE || r.mode == kVoxelizeMulti) ? 384 : kCandCap;
     const size_t smem = cand_cap * cand_rec + (size_t)ser_cap * sizeof(float) + (size_t)NRL_NW * cand_cap * sizeof(unsigned short);
     const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (smem + 1024)));
     int grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 12));
@@ -401,11 +406,14 @@ int legacy_run(const LegacyArgs &a) {
     memset(&t, 0, sizeof t);
     fill_task_geometry(t, a.dims, a.spacing, a.cutoff, a.sigma);
     t.n_frames = nF;
-    t.agg = a.agg;
+    t.n_ch = 1;
+    t.n_w = 1;
+    t.ch_agg[0] = a.agg;
+    t.ch_w[0] = 0;
+    t.ch_out[0] = 0;
     t.mode = a.mode;
     t.frame0 = 0;
-    t.out_off = 0;
-    t.wtab = d_weights;
+    t.wtab[0] = d_weights;
     t.inv_norm = nullptr;
     if (a.mode == NRL_MODE_VOXELIZE) {
       NRL_TRY(c.inv.reserve(std::max<size_t>(n_atoms, 1) * sizeof(float)));

@@ -51,7 +51,10 @@ __device__ __forceinline__ bool nrl_near_box(const float4 a, const NrlTileBox &b
 
 // shared-memory record per candidate: the atom (x, y, z, weight) and, for the voxeliser, the
 // eight per-plane factors exp(-(z_atom - z_plane)^2 / 2 sigma^2) of the tile's z planes
-template <int MODE> struct NrlCandStride { static constexpr int value = (MODE == NRL_MODE_VOXELIZE) ? 3 : 1; };
+// (+ one float4 of per-slot weights when several weight tables are deposited together)
+template <int MODE, int NWT> struct NrlCandStride {
+  static constexpr int value = (MODE == NRL_MODE_VOXELIZE) ? (NWT > 1 ? 4 : 3) : 1;
+};
 
 template <int MODE> struct NrlModeTraits {
   static constexpr bool kNeedsWeight = (MODE != NRL_OBS_EXISTENCE && MODE != NRL_OBS_DIRECT_COUNT);
@@ -74,11 +77,44 @@ template <int MODE> struct NrlModeTraits {
 
 // ---- per-frame sweep of the candidate list for the 4 voxels of one thread ----------
 // `idx` (optional): the warp's own sub-list of candidate numbers, see the tile kernel
-template <int MODE, bool INDEXED, typename CandPtr>
+template <int MODE, int NWT, bool INDEXED, typename CandPtr>
 __device__ __forceinline__ void nrl_sweep(CandPtr cand, const unsigned short *idx, const int ncand, const NrlTask &t, const float c2,
                                           const float px, const float py, const float (&pz)[NRL_VPT],
-                                          float (&val)[NRL_VPT]) {
-  if constexpr (MODE == NRL_MODE_VOXELIZE) {
+                                          float (&vals)[NWT][NRL_VPT]) {
+  float (&val)[NRL_VPT] = vals[0];
+  if constexpr (MODE == NRL_MODE_VOXELIZE && NWT > 1) {
+    // several weight tables at once: geometry, cutoff test and exponentials are shared
+    float acc[NWT][NRL_VPT];
+#pragma unroll
+    for (int w = 0; w < NWT; ++w)
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) acc[w][k] = 0.0f;
+    const float k2 = t.k2;
+    const int zq = 1 + (threadIdx.x & 1);
+    NRL_CAND_LOOP(
+      const float4 a = cand[ci * 4];
+      const float4 ezq = cand[ci * 4 + zq];
+      const float4 ww = cand[ci * 4 + 3];
+      const float part = nrl_vox_partial(a.x, a.y, px, py);
+      const float exy = nrl_ex2_approx(part * k2);
+      const float ez[NRL_VPT] = {ezq.x, ezq.y, ezq.z, ezq.w};
+      const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+_Pragma("unroll")
+      for (int k = 0; k < NRL_VPT; ++k) {
+        const float dz = a.z - pz[k];
+        const float d2 = fmaf(dz, dz, part);
+        if (d2 < c2) {
+          const float g = exy * ez[k];
+_Pragma("unroll")
+          for (int w = 0; w < NWT; ++w) acc[w][k] = fmaf(g, wv[w], acc[w][k]);
+        }
+      }
+    )
+#pragma unroll
+    for (int w = 0; w < NWT; ++w)
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) vals[w][k] = acc[w][k];
+  } else if constexpr (MODE == NRL_MODE_VOXELIZE) {
     // Gaussian in separable form: exp(-d2/2s^2) = E_xy * E_z; E_z of the tile's z planes was
     // tabulated per candidate by the scan, so one exponential per (candidate, thread) remains.
     // The in/out decision still uses the reference's exact d2 (voxelize.cu:121-125).
@@ -263,15 +299,15 @@ _Pragma("unroll")
 }
 
 // ---- the tile kernel ---------------------------------------------------------------
-template <int MODE>
+template <int MODE, int NWT>
 __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p) {
   extern __shared__ __align__(16) unsigned char nrl_smem[];
   float4 *s_cand = reinterpret_cast<float4 *>(nrl_smem);
-  float4 *s_ser = reinterpret_cast<float4 *>(nrl_smem + (size_t)p.cand_cap * NrlCandStride<MODE>::value * sizeof(float4));
+  float4 *s_ser = reinterpret_cast<float4 *>(nrl_smem + (size_t)p.cand_cap * NrlCandStride<MODE, NWT>::value * sizeof(float4));
   __shared__ int s_wcnt[NRL_NW];
   // per-warp sub-lists (candidate numbers) live behind the series in dynamic shared memory
   unsigned short *s_idx = reinterpret_cast<unsigned short *>(
-      nrl_smem + (size_t)p.cand_cap * NrlCandStride<MODE>::value * sizeof(float4) + (size_t)p.ser_cap * sizeof(float));
+      nrl_smem + (size_t)p.cand_cap * NrlCandStride<MODE, NWT>::value * sizeof(float4) + (size_t)p.ser_cap * sizeof(float));
 
   // a warp owns a compact 4x4x8 block of the tile (32 lanes x 4 z-consecutive voxels): of all
   // 128-voxel shapes it has the smallest cutoff-dilated volume, i.e. the shortest candidate list
@@ -312,7 +348,11 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) pz[k] = (float)(iz + k) * s;
 
-    const bool ser_in_smem = (long long)nF * NRL_TILE_VOX <= (long long)p.ser_cap;
+    const int n_w = t.n_w;
+    const float *wtabs[NWT];
+#pragma unroll
+    for (int q = 0; q < NWT; ++q) wtabs[q] = t.wtab[q];
+    const bool ser_in_smem = (long long)n_w * nF * NRL_TILE_VOX <= (long long)p.ser_cap;
     float4 *ser = ser_in_smem ? s_ser : g_ser;
 
     for (int f = 0; f < nF; ++f) {
@@ -359,22 +399,31 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
           a[u] = i < a_end ? __ldg(atoms + i) : make_float4(NRL_FAR, NRL_FAR, NRL_FAR, 0.f);
           keep[u] = nrl_near_box(a[u], box);
         }
-        float w[NRL_SCAN_ILP];
+        float w[NRL_SCAN_ILP][NWT];
 #pragma unroll
         for (int u = 0; u < NRL_SCAN_ILP; ++u) {
-          w[u] = 0.0f;
+#pragma unroll
+          for (int q = 0; q < NWT; ++q) w[u][q] = 0.0f;
           if (keep[u]) {
-            if constexpr (NrlModeTraits<MODE>::kNeedsWeight) w[u] = __ldg(t.wtab + __float_as_int(a[u].w));
-            if constexpr (MODE == NRL_MODE_VOXELIZE) w[u] = w[u] * __ldg(inv + i0 + u * 32 + lane);
-            if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) w[u] = w[u] + 0.0f;   // -0.0 == +0.0 in the reference's float compare
+            const int payload = __float_as_int(a[u].w);
+            if constexpr (NrlModeTraits<MODE>::kNeedsWeight) {
+#pragma unroll
+              for (int q = 0; q < NWT; ++q) if (q < n_w) w[u][q] = __ldg(wtabs[q] + payload);
+            }
+            if constexpr (MODE == NRL_MODE_VOXELIZE) {
+              const float iv = __ldg(inv + i0 + u * 32 + lane);
+#pragma unroll
+              for (int q = 0; q < NWT; ++q) w[u][q] = w[u][q] * iv;
+            }
+            if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) w[u][0] = w[u][0] + 0.0f;   // -0.0 == +0.0 in the reference's float compare
           }
         }
 #pragma unroll
         for (int u = 0; u < NRL_SCAN_ILP; ++u) {
           const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
           if (keep[u]) {
-            a[u].w = w[u];
-            float4 *slot = cand + (size_t)(base + __popc(m & ((1u << lane) - 1u))) * NrlCandStride<MODE>::value;
+            a[u].w = w[u][0];
+            float4 *slot = cand + (size_t)(base + __popc(m & ((1u << lane) - 1u))) * NrlCandStride<MODE, NWT>::value;
             slot[0] = a[u];
             if constexpr (MODE == NRL_MODE_VOXELIZE) {
               float e[NRL_TZ];
@@ -382,6 +431,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
               for (int k = 0; k < NRL_TZ; ++k) { const float dz = a[u].z - (float)(z0 + k) * s; e[k] = nrl_ex2_approx(dz * dz * t.k2); }
               slot[1] = make_float4(e[0], e[1], e[2], e[3]);
               slot[2] = make_float4(e[4], e[5], e[6], e[7]);
+              if constexpr (NWT > 1) slot[3] = make_float4(w[u][0], w[u][1 % NWT], w[u][2 % NWT], w[u][3 % NWT]);
             }
           }
           base += __popc(m);
@@ -390,54 +440,70 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
       if (cand_in_smem && tid == 0) {
         // far-away sentinel record behind the list: pads the warps' sub-lists to multiples of four
 #pragma unroll
-        for (int q = 0; q < NrlCandStride<MODE>::value; ++q)
-          s_cand[total * NrlCandStride<MODE>::value + q] =
+        for (int q = 0; q < NrlCandStride<MODE, NWT>::value; ++q)
+          s_cand[total * NrlCandStride<MODE, NWT>::value + q] =
               q == 0 ? make_float4(NRL_FAR, NRL_FAR, NRL_FAR, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       __syncthreads();
 
       // ---- sweep
-      float val[NRL_VPT];
+      float val[NWT][NRL_VPT];
       if (cand_in_smem) {
         // second-level culling: each warp keeps (in order) only the candidates that can reach its block
         int nsub = 0;
         for (int c0 = 0; c0 < total; c0 += 32) {
           const int ci = c0 + lane;
-          const bool k = ci < total && nrl_near_box(s_cand[ci * NrlCandStride<MODE>::value], wbox);
+          const bool k = ci < total && nrl_near_box(s_cand[ci * NrlCandStride<MODE, NWT>::value], wbox);
           const unsigned m = __ballot_sync(0xffffffffu, k);
           if (k) my_idx[nsub + __popc(m & ((1u << lane) - 1u))] = (unsigned short)ci;
           nsub += __popc(m);
         }
         while (nsub & 3) { if (lane == 0) my_idx[nsub] = (unsigned short)total; ++nsub; }
         __syncwarp();
-        nrl_sweep<MODE, true>(s_cand, my_idx, nsub, t, c2, px, py, pz, val);
+        nrl_sweep<MODE, NWT, true>(s_cand, my_idx, nsub, t, c2, px, py, pz, val);
       } else {
-        nrl_sweep<MODE, false>(static_cast<const float4 *>(g_cand), nullptr, total, t, c2, px, py, pz, val);
+        nrl_sweep<MODE, NWT, false>(static_cast<const float4 *>(g_cand), nullptr, total, t, c2, px, py, pz, val);
       }
 
-      if (t.agg == 0) {
+      if (t.ch_agg[0] == 0) {
+        // static channels: the single frame is the result
         if (ix < nx && iy < ny) {
-          float *o = p.out + t.out_off + ((long long)ix * ny + iy) * nz;
+          for (int ch = 0; ch < t.n_ch; ++ch) {
+            float *o = p.out + t.ch_out[ch] + ((long long)ix * ny + iy) * nz;
+            const int slot = NWT > 1 ? t.ch_w[ch] : 0;
 #pragma unroll
-          for (int k = 0; k < NRL_VPT; ++k)
-            if (iz + k < nz) o[iz + k] = val[k];
+            for (int q = 0; q < NWT; ++q)
+              if (q == slot) {
+#pragma unroll
+                for (int k = 0; k < NRL_VPT; ++k)
+                  if (iz + k < nz) o[iz + k] = val[q][k];
+              }
+          }
         }
       } else {
-        ser[f * NRL_NT + tid] = make_float4(val[0], val[1], val[2], val[3]);
+#pragma unroll
+        for (int q = 0; q < NWT; ++q)
+          if (q < n_w) ser[((size_t)q * nF + f) * NRL_NT + tid] = make_float4(val[q][0], val[q][1], val[q][2], val[q][3]);
       }
       __syncthreads();   // candidate list is rebuilt by the next frame
     }
 
-    if (t.agg != 0) {
-      // K3 fused: every thread reduces the series of its own four voxels (it wrote them)
-      const float4 r = nrl_reduce4(ser + tid, NRL_NT, nF, t.agg);
-      if (ix < nx && iy < ny) {
-        float *o = p.out + t.out_off + ((long long)ix * ny + iy) * nz;
-        if (iz + 0 < nz) o[iz + 0] = r.x;
-        if (iz + 1 < nz) o[iz + 1] = r.y;
-        if (iz + 2 < nz) o[iz + 2] = r.z;
-        if (iz + 3 < nz) o[iz + 3] = r.w;
-      }
+    if (t.ch_agg[0] != 0) {
+      // K3 fused: every thread reduces the series of its own four voxels (it wrote them), once per
+      // channel.  The median sorts its series in place, so channels that need it go last.
+      for (int pass = 0; pass < 2; ++pass)
+        for (int ch = 0; ch < t.n_ch; ++ch) {
+          const int agg = t.ch_agg[ch];
+          if ((agg == 3) != (pass == 1)) continue;
+          const float4 r = nrl_reduce4(ser + (size_t)t.ch_w[ch] * nF * NRL_NT + tid, NRL_NT, nF, agg);
+          if (ix < nx && iy < ny) {
+            float *o = p.out + t.ch_out[ch] + ((long long)ix * ny + iy) * nz;
+            if (iz + 0 < nz) o[iz + 0] = r.x;
+            if (iz + 1 < nz) o[iz + 1] = r.y;
+            if (iz + 2 < nz) o[iz + 2] = r.z;
+            if (iz + 3 < nz) o[iz + 3] = r.w;
+          }
+        }
     }
   }
 }

@@ -345,8 +345,17 @@ class Feature:
       return None
     if self.cached_array is None or self.center is None or self.padding is None or self.cutoff is None or self.sigma is None:
       return None
+    weights = np.asarray(self.cached_array, dtype=np.float32)
+    if self.selection is not None:
+      # For the voxeliser an unselected atom (dropped by query, features.py:479-480) and a zero-weight atom
+      # (skipped by the kernel, voxelize.cu:63) are the same thing: fold the selection into the weights so
+      # that the feature shares its focus box -- and its sweep -- with the other static channels.
+      memo = getattr(self, "_masked_weights", None)
+      if memo is None or memo[0] is not self.cached_array or memo[1] is not self.selected:
+        self._masked_weights = memo = (self.cached_array, self.selected, np.where(self.selected, weights, np.float32(0.0)).astype(np.float32))
+      weights = memo[2]
     return {
-      "kind": "static", "mode": 0, "agg": 0, "weights": np.asarray(self.cached_array, dtype=np.float32),
+      "kind": "static", "mode": 0, "agg": 0, "weights": weights, "selection_folded": self.selection is not None,
       "frame_offset": int(self.frame_offset or 0), "max_atoms": 0, "sigma": float(self.sigma),
     }
 

@@ -327,14 +327,15 @@ class Featurizer:
     def fingerprint(fidx):
       f, sp = self.FEATURESPACE[fidx], specs[fidx]
       return (fidx, tuple(int(v) for v in f.dims), float(f.spacing), float(f.cutoff), float(sp["sigma"]), float(f.padding),
-              bool(f.byres), f.selection is not None, sp["kind"], sp["mode"], sp["agg"], sp["frame_offset"], sp["max_atoms"])
+              bool(f.byres), f.selection is not None, bool(sp.get("selection_folded")), sp["kind"], sp["mode"], sp["agg"],
+              sp["frame_offset"], sp["max_atoms"])
 
     key = (tuple(fingerprint(f) for f in native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64))
     cache = self.__dict__.setdefault("_template_cache", {})
     if key in cache:
       return cache[key]
     table_of = {f: i for i, f in enumerate(native_feats)}
-    sel_feats = [f for f in native_feats if self.FEATURESPACE[f].selection is not None]
+    sel_feats = [f for f in native_feats if self.FEATURESPACE[f].selection is not None and not specs[f].get("selection_folded")]
     sel_of = {f: i for i, f in enumerate(sel_feats)}
     crops, crop_ids, crop_slots, tasks, shapes = [], {}, [], [], []
     order_feats, any_byres = [], False

@@ -179,3 +179,36 @@ def test_ragged_atom_counts(tmp_path, n_atoms):
   ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 2, buff_dim=_lib.buff_dim)
   assert np.array_equal(got["n"], ref["n"]) and np.array_equal(got["r"], ref["r"])
   assert rel_bad(got["m"], ref["m"]) == 0
+
+
+def test_shared_sweeps_multi_reducer_multi_weight(tmp_path):
+  """Features that share a crop and a grid are lowered to multi-channel work items (several
+  reducers of one observable, several weight tables per Gaussian sweep): results must equal the
+  one-task-at-a-time oracle."""
+  traj = io.synthetic_trajectory(2500, 12, seed=33)
+  parms = {"dimensions": 16, "lengths": 8, "time_window": 6, "cutoff": 3.5, "sigma": 1.2}
+  def feats():
+    fs = [features.MarchingObservers(obs="direct_count", agg=a, outkey=f"count_{a}")
+          for a in ("mean", "standard_deviation", "median", "max", "min", "drift", "information_entropy")]
+    fs += [features.MarchingObservers(obs="mean_distance", agg=a, weight_type="mass", outkey=f"md_{a}") for a in ("median", "mean")]
+    fs += [features.DensityFlow(agg="mean", weight_type="mass", outkey="pdf_mass_mean"),
+           features.DensityFlow(agg="median", weight_type="mass", outkey="pdf_mass_median"),
+           features.DensityFlow(agg="standard_deviation", weight_type="electronegativity", outkey="pdf_en_std"),
+           features.DensityFlow(agg="max", weight_type="hydrophobicity", outkey="pdf_hyd_max"),
+           features.DensityFlow(agg="mean", weight_type="atomic_number", outkey="pdf_z_mean"),
+           features.DensityFlow(agg="min", weight_type="heavy_atom", outkey="pdf_heavy_min")]
+    fs += [features.Mass(outkey="s_mass"), features.AtomType(focus_element=6, outkey="s_c"), features.AtomType(focus_element=8, outkey="s_o"),
+           features.HeavyAtom(outkey="s_heavy"), features.Electronegativity(outkey="s_en"), features.AtomicNumber(outkey="s_z")]
+    return fs
+  got, fz = build(traj, tmp_path, feats, parms)
+  ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 6, buff_dim=_lib.buff_dim)
+  for key in ref:
+    if key in ("count_median", "count_max", "count_min"):
+      assert np.array_equal(got[key], ref[key]), key
+    elif key == "count_information_entropy":
+      assert np.count_nonzero(~np.isclose(got[key], ref[key], atol=1e-3)) < 4, key
+    elif key.startswith("count_") or key in ("pdf_en_std",):
+      scale = max(float(np.abs(ref[key]).max()), 1e-30)
+      assert rel_bad(got[key], ref[key], atol=2e-5 * scale) == 0, key
+    else:
+      assert rel_bad(got[key], ref[key]) == 0, (key, np.abs(got[key] - ref[key]).max())
