@@ -72,6 +72,11 @@ struct Ctx {
   bool attr_set[32] = {false};
   cudaStream_t user_stream = nullptr;   // nrl_set_stream: run on the caller's stream instead of our own
   bool use_user_stream = false;
+  // side streams: the per-mode tile launches of one batch are independent of each other (and the observers do
+  // not wait for the voxeliser's normalisation), so they are forked off the work stream and joined at the end
+  static constexpr int kAux = 3;
+  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr};
   // optional per-kernel timing (nrl_profile): CUDA events around every launch, resolved at the next sync
   bool prof_on = false;
   struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -219,10 +224,25 @@ void fill_task_geometry(NrlTask &t, const int *dims, float spacing, float cutoff
   t.sphere_volume = (4.0 / 3.0) * M_PI * (double)cutoff * (double)cutoff * (double)cutoff;
 }
 
+int ensure_aux(Ctx &c) {
+  if (c.ev_fork) return NRL_OK;
+  for (int i = 0; i < Ctx::kAux; ++i) {
+    NRL_CUDA(cudaStreamCreateWithFlags(&c.aux[i], cudaStreamNonBlocking));
+    NRL_CUDA(cudaEventCreateWithFlags(&c.ev_join[i], cudaEventDisableTiming));
+  }
+  NRL_CUDA(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+  return NRL_OK;
+}
+
 // Runs `tasks` (device pointers already filled in) grouped by mode: one launch per mode present.
+// The launches are independent: the first range stays on `st`, the others are forked onto side
+// streams and joined back, so that their CTAs fill the SMs together (a 32^3 task is only 64 tiles).
+// `before_voxelize` (optional) enqueues, on `st`, whatever the voxeliser ranges depend on (the
+// per-atom normalisation); those ranges then stay on `st`, the observers do not wait for it.
 // max_atoms_per_frame bounds the per-CTA overflow candidate list.
+template <typename PreVox>
 int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, float *d_out, int max_atoms_per_frame,
-              cudaStream_t st) {
+              cudaStream_t st, PreVox before_voxelize) {
   if (tasks.empty()) return NRL_OK;
   std::vector<int> order(tasks.size());
   std::iota(order.begin(), order.end(), 0);
@@ -232,7 +252,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
   for (int i : order) sorted.push_back(tasks[i]);
 
   // per-mode ranges with their own tile prefix
-  struct Range { int mode, begin, end, n_work, max_frames; };
+  struct Range { int mode, begin, end, n_work, max_frames, grid, cand_cap, ser_cap; size_t smem, cand_rec, cand_per_cta, ser_per_cta, cand_off, ser_off; };
   std::vector<Range> ranges;
   for (size_t i = 0; i < sorted.size();) {
     size_t j = i;
@@ -243,46 +263,79 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
       maxf = std::max(maxf, sorted[j].n_frames * sorted[j].n_w);     // series rows a tile keeps
       ++j;
     }
-    ranges.push_back({mode_key_of(sorted[i]), (int)i, (int)j, work, maxf});
+    Range r{};
+    r.mode = mode_key_of(sorted[i]); r.begin = (int)i; r.end = (int)j; r.n_work = work; r.max_frames = maxf;
+    ranges.push_back(r);
     i = j;
   }
   NRL_TRY(c.tasks.reserve(sorted.size() * sizeof(NrlTask)));
   NRL_CUDA(cudaMemcpyAsync(c.tasks.p, sorted.data(), sorted.size() * sizeof(NrlTask), cudaMemcpyHostToDevice, st));
 
-  for (const Range &r : ranges) {
+  // launch geometry and overflow scratch of every range (disjoint slices: the ranges run concurrently)
+  size_t cand_total = 0, ser_total = 0;
+  for (Range &r : ranges) {
     // shared memory: the candidate list plus the time series when it fits (else per-CTA global scratch)
     const size_t ser_need = (size_t)r.max_frames * NRL_TILE_VOX;
-    const int ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
+    r.ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
     // candidate records held in shared memory: 512 atoms, 384 of the voxeliser's 48-byte records
-    const size_t cand_rec = (r.mode == kVoxelizeMulti ? 4 : r.mode == NRL_MODE_VOXELIZE ? 3 : 1) * sizeof(float4);
-    const int cand_cap = (r.mode == NRL_MODE_VOXELIZE || r.mode == kVoxelizeMulti) ? 384 : kCandCap;
-    const size_t smem = cand_cap * cand_rec + (size_t)ser_cap * sizeof(float) + (size_t)NRL_NW * cand_cap * sizeof(unsigned short);
-    const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (smem + 1024)));
-    int grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 12));
+    r.cand_rec = (r.mode == kVoxelizeMulti ? 4 : r.mode == NRL_MODE_VOXELIZE ? 3 : 1) * sizeof(float4);
+    r.cand_cap = (r.mode == NRL_MODE_VOXELIZE || r.mode == kVoxelizeMulti) ? 384 : kCandCap;
+    r.smem = r.cand_cap * r.cand_rec + (size_t)r.ser_cap * sizeof(float) + (size_t)NRL_NW * r.cand_cap * sizeof(unsigned short);
+    const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (r.smem + 1024)));
+    r.grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 12));
     // overflow scratch (candidate lists longer than kCandCap, series longer than kSerCapFloats)
-    const size_t cand_per_cta = max_atoms_per_frame + 4 > cand_cap ? (size_t)max_atoms_per_frame : 0;
-    const size_t ser_per_cta = ser_cap == 0 ? ser_need : 0;
-    const size_t per_cta = cand_per_cta * cand_rec + ser_per_cta * sizeof(float);
+    r.cand_per_cta = max_atoms_per_frame + 4 > r.cand_cap ? (size_t)max_atoms_per_frame : 0;
+    r.ser_per_cta = r.ser_cap == 0 ? ser_need : 0;
+    const size_t per_cta = r.cand_per_cta * r.cand_rec + r.ser_per_cta * sizeof(float);
     if (per_cta > 0) {
-      const int max_grid = (int)std::max<size_t>((size_t)c.sms, kScratchBudget / per_cta);
-      grid = std::max(1, std::min(grid, max_grid));
+      const int max_grid = (int)std::max<size_t>((size_t)c.sms, kScratchBudget / ranges.size() / per_cta);
+      r.grid = std::max(1, std::min(r.grid, max_grid));
     }
-    NRL_TRY(c.cand_scr.reserve(cand_per_cta * cand_rec * grid));
-    NRL_TRY(c.ser_scr.reserve(ser_per_cta * sizeof(float) * grid));
+    r.cand_off = cand_total;
+    r.ser_off = ser_total;
+    cand_total += (r.cand_per_cta * r.cand_rec * r.grid + 255) & ~(size_t)255;
+    ser_total += (r.ser_per_cta * sizeof(float) * r.grid + 255) & ~(size_t)255;
+  }
+  NRL_TRY(c.cand_scr.reserve(cand_total));
+  NRL_TRY(c.ser_scr.reserve(ser_total));
+
+  const bool fork = ranges.size() > 1;
+  if (fork) {
+    NRL_TRY(ensure_aux(c));
+    NRL_CUDA(cudaEventRecord(c.ev_fork, st));
+  }
+  bool aux_used[Ctx::kAux] = {false, false, false};
+  int next_aux = 0;
+  bool vox_ready = false;
+  for (const Range &r : ranges) {
+    const bool is_vox = r.mode == NRL_MODE_VOXELIZE || r.mode == kVoxelizeMulti;
+    cudaStream_t rs = st;
+    if (is_vox) {
+      if (!vox_ready) { NRL_TRY(before_voxelize()); vox_ready = true; }
+    } else if (fork) {
+      const int k = next_aux++ % Ctx::kAux;
+      rs = c.aux[k];
+      if (!aux_used[k]) { NRL_CUDA(cudaStreamWaitEvent(rs, c.ev_fork, 0)); aux_used[k] = true; }
+    }
     NrlTileParams p;
     p.tasks = c.tasks.as<NrlTask>() + r.begin;
     p.n_tasks = r.end - r.begin;
     p.n_work = r.n_work;
     p.frames = frames;
     p.out = d_out;
-    p.cand_scratch = c.cand_scr.as<float4>();
-    p.cand_scratch_stride = (long long)(cand_per_cta * cand_rec / sizeof(float4));
-    p.ser_scratch = c.ser_scr.as<float>();
-    p.ser_scratch_stride = (long long)ser_per_cta;
-    p.cand_cap = cand_cap;
-    p.ser_cap = ser_cap;
-    NRL_TRY(launch_tiles(c, r.mode, p, grid, smem, st));
+    p.cand_scratch = reinterpret_cast<float4 *>(c.cand_scr.as<char>() + r.cand_off);
+    p.cand_scratch_stride = (long long)(r.cand_per_cta * r.cand_rec / sizeof(float4));
+    p.ser_scratch = reinterpret_cast<float *>(c.ser_scr.as<char>() + r.ser_off);
+    p.ser_scratch_stride = (long long)r.ser_per_cta;
+    p.cand_cap = r.cand_cap;
+    p.ser_cap = r.ser_cap;
+    NRL_TRY(launch_tiles(c, r.mode, p, r.grid, r.smem, rs));
   }
+  for (int k = 0; k < Ctx::kAux; ++k)
+    if (aux_used[k]) {
+      NRL_CUDA(cudaEventRecord(c.ev_join[k], c.aux[k]));
+      NRL_CUDA(cudaStreamWaitEvent(st, c.ev_join[k], 0));
+    }
   return NRL_OK;
 }
 
@@ -421,11 +474,12 @@ int legacy_run(const LegacyArgs &a) {
       std::vector<int> fl(nF);
       std::iota(fl.begin(), fl.end(), 0);
       NRL_CUDA(cudaMemcpyAsync(c.flist.p, fl.data(), (size_t)nF * sizeof(int), cudaMemcpyHostToDevice, st));
-      NRL_TRY(launch_norm(c, frames, c.flist.as<int>(), nF, a.N, t, c.inv.as<float>(), st));
       t.inv_norm = c.inv.as<float>();
     }
     std::vector<NrlTask> tasks{t};
-    NRL_TRY(run_tasks(c, tasks, frames, d_out, a.N, st));
+    NRL_TRY(run_tasks(c, tasks, frames, d_out, a.N, st, [&]() -> int {
+      return launch_norm(c, frames, c.flist.as<int>(), nF, a.N, t, c.inv.as<float>(), st);
+    }));
   }
   if (!a.on_device) {
     NRL_CUDA(cudaMemcpyAsync(a.out, d_out, (size_t)G * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -142,18 +142,39 @@ _Pragma("unroll")
     float acc[NRL_VPT];
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) acc[k] = 0.0f;
-    NRL_CAND_LOOP(
-      const float4 a = cand[ci];
-      const float part = nrl_obs_partial(px, py, a.x, a.y);
-_Pragma("unroll")
-      for (int k = 0; k < NRL_VPT; ++k) {
-        const float dz = pz[k] - a.z;
-        const float d2 = fmaf(dz, dz, part);
-        if (!(d2 > c2)) {                                               // marching_observers.cu:40,77
-          if constexpr (MODE == NRL_OBS_EXISTENCE) acc[k] = 1.0f; else acc[k] = acc[k] + 1.0f;
+    if constexpr (MODE == NRL_OBS_EXISTENCE && INDEXED) {
+      // existence saturates: once every voxel of the warp has seen an atom the rest of the list cannot
+      // change the result (inside a protein that happens within the first few candidates)
+      for (int c4 = 0; c4 < ncand; c4 += 4) {
+        const ushort4 q4 = *reinterpret_cast<const ushort4 *>(idx + c4);
+        const int ii[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 a = cand[ii[u]];
+          const float part = nrl_obs_partial(px, py, a.x, a.y);
+#pragma unroll
+          for (int k = 0; k < NRL_VPT; ++k) {
+            const float dz = pz[k] - a.z;
+            const float d2 = fmaf(dz, dz, part);
+            if (!(d2 > c2)) acc[k] = 1.0f;                              // marching_observers.cu:40
+          }
         }
+        if (__all_sync(0xffffffffu, (acc[0] + acc[1]) + (acc[2] + acc[3]) == 4.0f)) break;
       }
-    )
+    } else {
+      NRL_CAND_LOOP(
+        const float4 a = cand[ci];
+        const float part = nrl_obs_partial(px, py, a.x, a.y);
+_Pragma("unroll")
+        for (int k = 0; k < NRL_VPT; ++k) {
+          const float dz = pz[k] - a.z;
+          const float d2 = fmaf(dz, dz, part);
+          if (!(d2 > c2)) {                                             // marching_observers.cu:40,77
+            if constexpr (MODE == NRL_OBS_EXISTENCE) acc[k] = 1.0f; else acc[k] = acc[k] + 1.0f;
+          }
+        }
+      )
+    }
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) val[k] = acc[k];
   } else if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) {

@@ -63,3 +63,48 @@ def describe(fz):
       d.update(kind="static")
     descs.append(d)
   return descs
+
+
+def misato_mixed(n_traj=1, n_atoms=6000, n_frames=100, seed_offset=0, outfile=None, pin=True):
+  """configs[3]: MISATO-style batch -- 3 static + 2 marching-observer + 2 density-flow channels at
+  32^3 over 20 A (spacing 0.625), window 10, cutoff 2.5 (static) / 5.0 (dynamic), sigma 1.5,
+  focus ':LIG'-free protein systems -> ':ARG', 6 000 atoms x 100 frames per trajectory
+  (/root/reference/scripts/slurm/featurize_misato.slurm:54-74)."""
+  trajs = [io.synthetic_trajectory(n_atoms, n_frames, seed=BASE_SEED + 4 + 1000 * (i + seed_offset), pin=pin) for i in range(n_traj)]
+  fz = featurizer.Featurizer({"dimensions": 32, "lengths": 20, "time_window": 10, "sigma": 1.5})
+  fz.register_features([
+    features.Mass(outkey="mass", cutoff=2.5, outfile=outfile),
+    features.HeavyAtom(outkey="heavy", cutoff=2.5, outfile=outfile),
+    features.Electronegativity(outkey="elecneg", cutoff=2.5, outfile=outfile),
+    features.MarchingObservers(obs="existence", agg="mean", weight_type="mass", cutoff=5.0, outkey="obs_existence", outfile=outfile),
+    features.MarchingObservers(obs="mean_distance", agg="standard_deviation", weight_type="mass", cutoff=5.0, outkey="obs_mean_distance", outfile=outfile),
+    features.DensityFlow(agg="mean", weight_type="mass", cutoff=5.0, outkey="pdf_mass", outfile=outfile),
+    features.DensityFlow(agg="standard_deviation", weight_type="electronegativity", cutoff=5.0, outkey="pdf_elecneg", outfile=outfile),
+  ])
+  fz.register_focus([":ARG"], "mask")
+  fz.register_trajloader(trajs)
+  return fz, trajs
+
+
+def stress_large(n_traj=1, n_atoms=200000, n_frames=200, window=100, dim=128, seed_offset=0, outfile=None, pin=True,
+                 native_atoms=False):
+  """configs[4]: 128^3 grid at 0.5 A over a 200 000-atom system, window 100, cutoff 5.0; observers
+  existence / distinct_count(atomic_number) / mean_distance(mass) and a mass density flow, mean and
+  standard deviation over the window.  `native_atoms` lifts the reference's 9 999-atom cap on
+  dynamic crops (/root/reference/nearl/features.py:1279,1353-1359); the default keeps it."""
+  trajs = [io.synthetic_trajectory(n_atoms, n_frames, seed=BASE_SEED + 5 + 1000 * (i + seed_offset), pin=pin) for i in range(n_traj)]
+  fz = featurizer.Featurizer({"dimensions": dim, "lengths": dim * 0.5, "time_window": window, "cutoff": 5.0, "sigma": 1.5})
+  feats = [
+    features.MarchingObservers(obs="existence", agg="mean", weight_type="mass", outkey="obs_existence", outfile=outfile),
+    features.MarchingObservers(obs="distinct_count", agg="mean", weight_type="atomic_number", outkey="obs_distinct", outfile=outfile),
+    features.MarchingObservers(obs="mean_distance", agg="standard_deviation", weight_type="mass", outkey="obs_mean_distance", outfile=outfile),
+    features.DensityFlow(agg="mean", weight_type="mass", outkey="pdf_mass", outfile=outfile),
+    features.DensityFlow(agg="standard_deviation", weight_type="mass", outkey="pdf_mass_std", outfile=outfile),
+  ]
+  if native_atoms:
+    for f in feats:
+      f.MAX_ALLOWED_ATOMS = 0
+  fz.register_features(feats)
+  fz.register_focus([":ARG"], "mask")
+  fz.register_trajloader(trajs)
+  return fz, trajs
