@@ -19,7 +19,7 @@ EXPORTED = [
   "nrl_frame_voxelize", "nrl_frame_observation", "nrl_marching_observer", "nrl_density_flow", "nrl_aggregate",
   "nrl_summation", "nrl_frame_voxelize_dev", "nrl_frame_observation_dev", "nrl_marching_observer_dev",
   "nrl_density_flow_dev", "nrl_aggregate_dev", "nrl_featurize_batch", "nrl_buff_dim", "nrl_device_count",
-  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_set_stream", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
+  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_set_stream", "nrl_set_option", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
   "nrl_last_error", "nrl_version",
 ]
 
@@ -97,6 +97,7 @@ def lib():
   L.nrl_set_stream.argtypes = [p, c_int]
   L.nrl_lane_synchronize.argtypes = [c_int]
   L.nrl_profile.argtypes = [c_int]
+  L.nrl_set_option.argtypes = [ctypes.c_char_p, c_int]
   L.nrl_profile_read.argtypes = [p, p, c_int]
   L.nrl_profile_name.argtypes = [c_int]
   L.nrl_profile_name.restype = ctypes.c_char_p
@@ -137,11 +138,15 @@ def kernel_launches():
   return int(lib().nrl_kernel_launches())
 
 
-PROFILE_CATEGORIES = 16
+PROFILE_CATEGORIES = 17
 
 
 def set_stream(stream_ptr, enable=True):
   check(lib().nrl_set_stream(c_void_p(stream_ptr), 1 if enable else 0))
+
+
+def set_option(name, value):
+  check(lib().nrl_set_option(name.encode(), int(value)))
 
 
 def profile(enable=True):

@@ -18,6 +18,7 @@
 
 #include "../../include/nearl_b200.h"
 #include "agg_kernels.cuh"
+#include "cell_kernels.cuh"
 #include "common.cuh"
 #include "pack_kernels.cuh"
 #include "tile_kernels.cuh"
@@ -26,6 +27,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_force_scan{0};    // nrl_set_option("force_scan", 1): never use the cell-list kernels
 
 int fail(int code, const std::string &msg) {
   g_err = msg;
@@ -69,7 +71,8 @@ struct Ctx {
   std::mutex mu;
   DevBuf coords, weights, perm, atoms, inv, off, cnt, out, tasks, flist, cand_scr, ser_scr, misc, series;
   DevBuf xyz, wtabs, sels, resid, orders, crops, fcrop, fsrc, keep, resflags;
-  bool attr_set[32] = {false};
+  DevBuf batoms, bcnt, cstart, grids, blist;     // cell lists: binned frames, cell prefixes, per-frame cell grids
+  bool attr_set[64] = {false};
   cudaStream_t user_stream = nullptr;   // nrl_set_stream: run on the caller's stream instead of our own
   bool use_user_stream = false;
   // side streams: the per-mode tile launches of one batch are independent of each other (and the observers do
@@ -87,11 +90,11 @@ struct Ctx {
   cudaStream_t work_stream() const { return use_user_stream ? user_stream : stream; }
 };
 
-enum { CAT_PACK_LEGACY = 0, CAT_CROP_PACK = 1, CAT_ATOM_NORM = 2, CAT_TILE0 = 3, CAT_AGGREGATE = 13, CAT_SUMMATION = 14, CAT_MISC = 15 };
+enum { CAT_PACK_LEGACY = 0, CAT_CROP_PACK = 1, CAT_ATOM_NORM = 2, CAT_TILE0 = 3, CAT_AGGREGATE = 13, CAT_SUMMATION = 14, CAT_MISC = 15, CAT_CELL_BIN = 16 };
 const char *kCatNames[NRL_PROFILE_CATEGORIES] = {
     "pack_legacy", "crop_pack", "atom_norm", "tile_voxelize", "tile_existence", "tile_direct_count", "tile_distinct_count",
     "tile_mean_distance", "tile_cumulative_weight", "tile_density", "tile_dispersion", "tile_eccentricity",
-    "tile_radius_of_gyration", "aggregate", "summation", "misc"};
+    "tile_radius_of_gyration", "aggregate", "summation", "misc", "cell_bin"};
 
 struct ScopedProf {
   Ctx &c; cudaStream_t st; int cat; cudaEvent_t a = nullptr, b = nullptr;
@@ -210,6 +213,139 @@ int launch_tiles(Ctx &c, int mode_key, const NrlTileParams &p, int grid, size_t 
   }
 }
 
+// ---- cell-list launches (cell_kernels.cuh) ----------------------------------------------------
+struct CellSetup {
+  bool on = false;
+  NrlFrames frames{};                 // binned frames
+  const NrlCellGrid *grids = nullptr; // per frame descriptor
+  const int *cell_start = nullptr;
+};
+
+bool cell_mode(int mode) {
+  return mode == NRL_MODE_VOXELIZE || mode == NRL_OBS_EXISTENCE || mode == NRL_OBS_DIRECT_COUNT ||
+         mode == NRL_OBS_MEAN_DISTANCE || mode == NRL_OBS_CUMULATIVE_WEIGHT || mode == NRL_OBS_DENSITY ||
+         mode == NRL_OBS_ECCENTRICITY;      // + distinct_count when its values have <= 32 ranks (decided by the caller)
+}
+
+template <int MODE, int NWT>
+int launch_cell_tiles_mode(Ctx &c, const NrlCellTileParams &p, int grid, size_t smem, cudaStream_t st, int slot) {
+  const int attr = 32 + (NWT > 1 ? 22 : slot);
+  if (!c.attr_set[attr]) {
+    NRL_CUDA(cudaFuncSetAttribute(nrl_cell_tile_kernel<MODE, NWT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(c.smem_optin - 2048)));
+    c.attr_set[attr] = true;
+  }
+  {
+    ScopedProf sp(c, st, CAT_TILE0 + slot);
+    nrl_cell_tile_kernel<MODE, NWT><<<grid, NRL_NT, smem, st>>>(p);
+  }
+  g_launches.fetch_add(1);
+  NRL_CUDA(cudaGetLastError());
+  return NRL_OK;
+}
+
+int launch_cell_tiles(Ctx &c, int mode_key, const NrlCellTileParams &p, int grid, size_t smem, cudaStream_t st) {
+  switch (mode_key) {
+    case -1: return launch_cell_tiles_mode<NRL_MODE_VOXELIZE, NRL_MAX_CH>(c, p, grid, smem, st, 0);
+    case NRL_MODE_VOXELIZE: return launch_cell_tiles_mode<NRL_MODE_VOXELIZE, 1>(c, p, grid, smem, st, 0);
+    case NRL_OBS_EXISTENCE: return launch_cell_tiles_mode<NRL_OBS_EXISTENCE, 1>(c, p, grid, smem, st, 1);
+    case NRL_OBS_DIRECT_COUNT: return launch_cell_tiles_mode<NRL_OBS_DIRECT_COUNT, 1>(c, p, grid, smem, st, 2);
+    case NRL_OBS_DISTINCT_COUNT: return launch_cell_tiles_mode<NRL_OBS_DISTINCT_COUNT, 1>(c, p, grid, smem, st, 3);
+    case NRL_OBS_MEAN_DISTANCE: return launch_cell_tiles_mode<NRL_OBS_MEAN_DISTANCE, 1>(c, p, grid, smem, st, 4);
+    case NRL_OBS_CUMULATIVE_WEIGHT: return launch_cell_tiles_mode<NRL_OBS_CUMULATIVE_WEIGHT, 1>(c, p, grid, smem, st, 5);
+    case NRL_OBS_DENSITY: return launch_cell_tiles_mode<NRL_OBS_DENSITY, 1>(c, p, grid, smem, st, 6);
+    case NRL_OBS_ECCENTRICITY: return launch_cell_tiles_mode<NRL_OBS_ECCENTRICITY, 1>(c, p, grid, smem, st, 8);
+    default: return fail(NRL_ERR_OBSERVABLE, "The observable type has no cell-list kernel");
+  }
+}
+
+// Cell grid of one crop: what its cell-list tasks need.  Cells are sized so that the search box of
+// a tile (7 voxel steps + twice the reach) spans at most 5 cells per axis: <= 25 runs + the NaN bucket.
+struct CropCells {
+  bool any = false;
+  float reach = 0.f, span = 0.f, ext[3] = {0.f, 0.f, 0.f};
+  void add(const int *dims, float spacing, float cutoff) {
+    const float r = cutoff * 1.001f + 1e-3f;
+    any = true;
+    reach = std::max(reach, r);
+    span = std::max(span, 7.0f * spacing + 2.0f * r);
+    ext[0] = std::max(ext[0], (float)(dims[2] - 1) * spacing);
+    ext[1] = std::max(ext[1], (float)(dims[1] - 1) * spacing);
+    ext[2] = std::max(ext[2], (float)(dims[0] - 1) * spacing);
+  }
+  // false: the grid would need more cells than the binning kernel can count in shared memory
+  bool grid(NrlCellGrid &g, size_t max_cells) const {
+    const float h = std::max(span / 3.9f, 1e-6f);
+    const float pad = reach + 2e-3f;
+    for (int zdiv = 3; zdiv >= 1; --zdiv) {
+      const float hz = h / (float)zdiv;
+      const double ncx = std::floor((ext[0] + 2.0 * pad) / h) + 1, ncy = std::floor((ext[1] + 2.0 * pad) / h) + 1,
+                   ncz = std::floor((ext[2] + 2.0 * pad) / hz) + 1;
+      if (ncx * ncy * ncz + 2 > (double)max_cells) continue;
+      g.ox = g.oy = g.oz = -pad;
+      g.inv_h = 1.0f / h;
+      g.inv_hz = 1.0f / hz;
+      g.ncx = (int)ncx; g.ncy = (int)ncy; g.ncz = (int)ncz;
+      g.cs_off = 0;
+      return true;
+    }
+    return false;
+  }
+};
+
+constexpr size_t kMaxCells = 48 * 1024;     // counters of the binning kernel: 192 KB of shared memory
+
+// bins `frame_list` (host) of `packed` into c.batoms / c.bcnt / c.cstart with the grids in `hgrids` (per frame
+// descriptor, cs_off filled here); returns the device-side setup
+int bin_frames(Ctx &c, const NrlFrames &packed, std::vector<NrlCellGrid> &hgrids, const std::vector<int> &frame_list,
+               size_t atoms_capacity, int capacity, cudaStream_t st, CellSetup &out) {
+  long long cs_total = 0;
+  int max_ncell = 0;
+  for (int fd : frame_list) {
+    NrlCellGrid &g = hgrids[fd];
+    const int ncell = g.ncx * g.ncy * g.ncz;
+    g.cs_off = cs_total;
+    cs_total += ncell + 2;
+    max_ncell = std::max(max_ncell, ncell);
+  }
+  NRL_TRY(c.batoms.reserve(std::max<size_t>(atoms_capacity, 1) * sizeof(float4)));
+  NRL_TRY(c.bcnt.reserve(hgrids.size() * sizeof(int)));
+  NRL_TRY(c.cstart.reserve((size_t)cs_total * sizeof(int)));
+  NRL_TRY(c.grids.reserve(hgrids.size() * sizeof(NrlCellGrid)));
+  NRL_TRY(c.blist.reserve(frame_list.size() * sizeof(int)));
+  NRL_CUDA(cudaMemcpyAsync(c.grids.p, hgrids.data(), hgrids.size() * sizeof(NrlCellGrid), cudaMemcpyHostToDevice, st));
+  NRL_CUDA(cudaMemcpyAsync(c.blist.p, frame_list.data(), frame_list.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  const size_t smem = (size_t)(max_ncell + 2) * sizeof(int);
+  if (!c.attr_set[63]) {
+    NRL_CUDA(cudaFuncSetAttribute(nrl_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c.smem_optin - 2048)));
+    c.attr_set[63] = true;
+  }
+  NrlBinParams bp;
+  bp.in = packed;
+  bp.grids = c.grids.as<NrlCellGrid>();
+  bp.frame_list = c.blist.as<int>();
+  bp.atoms_out = c.batoms.as<float4>();
+  bp.cnt_out = c.bcnt.as<int>();
+  bp.cell_start = c.cstart.as<int>();
+  bp.capacity = capacity;
+  for (size_t f0 = 0; f0 < frame_list.size(); f0 += 65535u * 16u) {
+    const unsigned n = (unsigned)std::min<size_t>(65535u * 16u, frame_list.size() - f0);
+    NrlBinParams q = bp;
+    q.frame_list = bp.frame_list + f0;
+    {
+      ScopedProf sp(c, st, CAT_CELL_BIN);
+      nrl_bin_kernel<<<n, NRL_BIN_NT, smem, st>>>(q);
+    }
+    g_launches.fetch_add(1);
+    NRL_CUDA(cudaGetLastError());
+  }
+  out.on = true;
+  out.frames = NrlFrames{c.batoms.as<float4>(), packed.off, c.bcnt.as<int>()};
+  out.grids = c.grids.as<NrlCellGrid>();
+  out.cell_start = c.cstart.as<int>();
+  return NRL_OK;
+}
+
 int mode_key_of(const NrlTask &t) { return (t.mode == NRL_MODE_VOXELIZE && t.n_w > 1) ? kVoxelizeMulti : t.mode; }
 
 void fill_task_geometry(NrlTask &t, const int *dims, float spacing, float cutoff, float sigma) {
@@ -234,37 +370,41 @@ int ensure_aux(Ctx &c) {
   return NRL_OK;
 }
 
-// Runs `tasks` (device pointers already filled in) grouped by mode: one launch per mode present.
-// The launches are independent: the first range stays on `st`, the others are forked onto side
-// streams and joined back, so that their CTAs fill the SMs together (a 32^3 task is only 64 tiles).
-// `before_voxelize` (optional) enqueues, on `st`, whatever the voxeliser ranges depend on (the
-// per-atom normalisation); those ranges then stay on `st`, the observers do not wait for it.
-// max_atoms_per_frame bounds the per-CTA overflow candidate list.
+// Runs `tasks` (device pointers already filled in) grouped by (kernel family, mode): one launch per
+// group.  `use_cell[i]` sends task i to the cell-list kernel (over cells.frames), otherwise it runs
+// on the scan kernel (over `frames`).  The launches are independent: the first group stays on `st`,
+// the others are forked onto side streams and joined back, so that their CTAs fill the SMs
+// together (a 32^3 task is only 64 tiles).  `before_voxelize` enqueues, on `st`, whatever the
+// voxeliser groups depend on (the per-atom normalisation); those groups then stay on `st`, the
+// observers do not wait for it.  max_atoms_per_frame bounds the per-CTA overflow candidate list.
 template <typename PreVox>
-int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, float *d_out, int max_atoms_per_frame,
-              cudaStream_t st, PreVox before_voxelize) {
+int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_cell, const NrlFrames &frames,
+              const CellSetup &cells, float *d_out, int max_atoms_per_frame, cudaStream_t st, PreVox before_voxelize) {
   if (tasks.empty()) return NRL_OK;
+  auto key_of = [&](int i) { return mode_key_of(tasks[i]) + (use_cell[i] ? 1000 : 0); };
   std::vector<int> order(tasks.size());
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return mode_key_of(tasks[a]) < mode_key_of(tasks[b]); });
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key_of(a) < key_of(b); });
   std::vector<NrlTask> sorted;
+  std::vector<int> keys;
   sorted.reserve(tasks.size());
-  for (int i : order) sorted.push_back(tasks[i]);
+  for (int i : order) { sorted.push_back(tasks[i]); keys.push_back(key_of(i)); }
 
-  // per-mode ranges with their own tile prefix
-  struct Range { int mode, begin, end, n_work, max_frames, grid, cand_cap, ser_cap; size_t smem, cand_rec, cand_per_cta, ser_per_cta, cand_off, ser_off; };
+  // per-group ranges with their own tile prefix
+  struct Range { int mode, begin, end, n_work, max_frames, grid, cand_cap, ser_cap, wcap; bool cell;
+                 size_t smem, cand_rec, cand_per_cta, ser_per_cta, cand_off, ser_off; };
   std::vector<Range> ranges;
   for (size_t i = 0; i < sorted.size();) {
     size_t j = i;
     int work = 0, maxf = 1;
-    while (j < sorted.size() && mode_key_of(sorted[j]) == mode_key_of(sorted[i])) {
+    while (j < sorted.size() && keys[j] == keys[i]) {
       sorted[j].tile_begin = work;
       work += sorted[j].ntx * sorted[j].nty * sorted[j].ntz;
       maxf = std::max(maxf, sorted[j].n_frames * sorted[j].n_w);     // series rows a tile keeps
       ++j;
     }
     Range r{};
-    r.mode = mode_key_of(sorted[i]); r.begin = (int)i; r.end = (int)j; r.n_work = work; r.max_frames = maxf;
+    r.mode = mode_key_of(sorted[i]); r.cell = keys[i] >= 500; r.begin = (int)i; r.end = (int)j; r.n_work = work; r.max_frames = maxf;
     ranges.push_back(r);
     i = j;
   }
@@ -274,17 +414,26 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
   // launch geometry and overflow scratch of every range (disjoint slices: the ranges run concurrently)
   size_t cand_total = 0, ser_total = 0;
   for (Range &r : ranges) {
-    // shared memory: the candidate list plus the time series when it fits (else per-CTA global scratch)
+    const bool is_vox = r.mode == NRL_MODE_VOXELIZE || r.mode == kVoxelizeMulti;
+    // shared memory: the candidate records plus the time series when it fits (else per-CTA global scratch)
     const size_t ser_need = (size_t)r.max_frames * NRL_TILE_VOX;
     r.ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
-    // candidate records held in shared memory: 512 atoms, 384 of the voxeliser's 48-byte records
-    r.cand_rec = (r.mode == kVoxelizeMulti ? 4 : r.mode == NRL_MODE_VOXELIZE ? 3 : 1) * sizeof(float4);
-    r.cand_cap = (r.mode == NRL_MODE_VOXELIZE || r.mode == kVoxelizeMulti) ? 384 : kCandCap;
-    r.smem = r.cand_cap * r.cand_rec + (size_t)r.ser_cap * sizeof(float) + (size_t)NRL_NW * r.cand_cap * sizeof(unsigned short);
+    if (r.cell) {
+      // staged cells + per-warp records (16 B; voxeliser 32 B / 48 B) + series
+      const int rec4 = r.mode == kVoxelizeMulti ? 3 : is_vox ? 2 : 1;
+      r.wcap = r.mode == kVoxelizeMulti ? 128 : is_vox ? 160 : 224;
+      r.smem = (size_t)NRL_STAGE_CAP * sizeof(float4) + (size_t)NRL_NW * r.wcap * rec4 * sizeof(float4) + (size_t)r.ser_cap * sizeof(float);
+      r.cand_per_cta = 0;
+    } else {
+      // candidate records held in shared memory: 512 atoms, 384 of the voxeliser's 48-byte records
+      r.cand_rec = (r.mode == kVoxelizeMulti ? 4 : is_vox ? 3 : 1) * sizeof(float4);
+      r.cand_cap = is_vox ? 384 : kCandCap;
+      r.smem = r.cand_cap * r.cand_rec + (size_t)r.ser_cap * sizeof(float) + (size_t)NRL_NW * r.cand_cap * sizeof(unsigned short);
+      // overflow scratch (candidate lists longer than kCandCap, series longer than kSerCapFloats)
+      r.cand_per_cta = max_atoms_per_frame + 4 > r.cand_cap ? (size_t)max_atoms_per_frame : 0;
+    }
     const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (r.smem + 1024)));
     r.grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 12));
-    // overflow scratch (candidate lists longer than kCandCap, series longer than kSerCapFloats)
-    r.cand_per_cta = max_atoms_per_frame + 4 > r.cand_cap ? (size_t)max_atoms_per_frame : 0;
     r.ser_per_cta = r.ser_cap == 0 ? ser_need : 0;
     const size_t per_cta = r.cand_per_cta * r.cand_rec + r.ser_per_cta * sizeof(float);
     if (per_cta > 0) {
@@ -317,19 +466,35 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const NrlFrames &frames, floa
       rs = c.aux[k];
       if (!aux_used[k]) { NRL_CUDA(cudaStreamWaitEvent(rs, c.ev_fork, 0)); aux_used[k] = true; }
     }
-    NrlTileParams p;
-    p.tasks = c.tasks.as<NrlTask>() + r.begin;
-    p.n_tasks = r.end - r.begin;
-    p.n_work = r.n_work;
-    p.frames = frames;
-    p.out = d_out;
-    p.cand_scratch = reinterpret_cast<float4 *>(c.cand_scr.as<char>() + r.cand_off);
-    p.cand_scratch_stride = (long long)(r.cand_per_cta * r.cand_rec / sizeof(float4));
-    p.ser_scratch = reinterpret_cast<float *>(c.ser_scr.as<char>() + r.ser_off);
-    p.ser_scratch_stride = (long long)r.ser_per_cta;
-    p.cand_cap = r.cand_cap;
-    p.ser_cap = r.ser_cap;
-    NRL_TRY(launch_tiles(c, r.mode, p, r.grid, r.smem, rs));
+    if (r.cell) {
+      NrlCellTileParams p;
+      p.tasks = c.tasks.as<NrlTask>() + r.begin;
+      p.n_tasks = r.end - r.begin;
+      p.n_work = r.n_work;
+      p.frames = cells.frames;
+      p.grids = cells.grids;
+      p.cell_start = cells.cell_start;
+      p.out = d_out;
+      p.ser_scratch = reinterpret_cast<float *>(c.ser_scr.as<char>() + r.ser_off);
+      p.ser_scratch_stride = (long long)r.ser_per_cta;
+      p.ser_cap = r.ser_cap;
+      p.wcap = r.wcap;
+      NRL_TRY(launch_cell_tiles(c, r.mode, p, r.grid, r.smem, rs));
+    } else {
+      NrlTileParams p;
+      p.tasks = c.tasks.as<NrlTask>() + r.begin;
+      p.n_tasks = r.end - r.begin;
+      p.n_work = r.n_work;
+      p.frames = frames;
+      p.out = d_out;
+      p.cand_scratch = reinterpret_cast<float4 *>(c.cand_scr.as<char>() + r.cand_off);
+      p.cand_scratch_stride = (long long)(r.cand_per_cta * r.cand_rec / sizeof(float4));
+      p.ser_scratch = reinterpret_cast<float *>(c.ser_scr.as<char>() + r.ser_off);
+      p.ser_scratch_stride = (long long)r.ser_per_cta;
+      p.cand_cap = r.cand_cap;
+      p.ser_cap = r.ser_cap;
+      NRL_TRY(launch_tiles(c, r.mode, p, r.grid, r.smem, rs));
+    }
   }
   for (int k = 0; k < Ctx::kAux; ++k)
     if (aux_used[k]) {
@@ -468,6 +633,20 @@ int legacy_run(const LegacyArgs &a) {
     t.frame0 = 0;
     t.wtab[0] = d_weights;
     t.inv_norm = nullptr;
+    // cell lists for every mode that has a cell-list kernel (g_force_scan: tests / A-B timing)
+    CellSetup cells;
+    if (cell_mode(a.mode) && !g_force_scan && n_atoms > 0) {
+      CropCells cc;
+      cc.add(a.dims, a.spacing, a.cutoff);
+      NrlCellGrid g;
+      if (cc.grid(g, kMaxCells)) {
+        std::vector<NrlCellGrid> hgrids((size_t)nF, g);
+        std::vector<int> fl(nF);
+        std::iota(fl.begin(), fl.end(), 0);
+        NRL_TRY(bin_frames(c, frames, hgrids, fl, n_atoms, a.N, st, cells));
+      }
+    }
+    const NrlFrames &vf = cells.on ? cells.frames : frames;
     if (a.mode == NRL_MODE_VOXELIZE) {
       NRL_TRY(c.inv.reserve(std::max<size_t>(n_atoms, 1) * sizeof(float)));
       NRL_TRY(c.flist.reserve((size_t)nF * sizeof(int)));
@@ -477,8 +656,9 @@ int legacy_run(const LegacyArgs &a) {
       t.inv_norm = c.inv.as<float>();
     }
     std::vector<NrlTask> tasks{t};
-    NRL_TRY(run_tasks(c, tasks, frames, d_out, a.N, st, [&]() -> int {
-      return launch_norm(c, frames, c.flist.as<int>(), nF, a.N, t, c.inv.as<float>(), st);
+    std::vector<char> use_cell{(char)(cells.on ? 1 : 0)};
+    NRL_TRY(run_tasks(c, tasks, use_cell, frames, cells, d_out, a.N, st, [&]() -> int {
+      return launch_norm(c, vf, c.flist.as<int>(), nF, a.N, t, c.inv.as<float>(), st);
     }));
   }
   if (!a.on_device) {
@@ -579,6 +759,11 @@ int nrl_set_stream(void *stream, int enable) {
   c->user_stream = (cudaStream_t)stream;
   c->use_user_stream = enable != 0;
   return NRL_OK;
+}
+int nrl_set_option(const char *name, int value) {
+  if (!name) return fail(NRL_ERR_ARGUMENT, "option name is NULL");
+  if (strcmp(name, "force_scan") == 0) { g_force_scan.store(value != 0); return NRL_OK; }
+  return fail(NRL_ERR_ARGUMENT, std::string("unknown option ") + name);
 }
 int nrl_profile(int enable) {
   Ctx *c = nullptr;

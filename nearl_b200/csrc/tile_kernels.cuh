@@ -39,14 +39,20 @@ __device__ __forceinline__ float nrl_obs_d2(float ox, float oy, float oz, float 
 // Candidate test of the scan: squared distance from the atom to the box spanned by the tile's
 // voxel centres against a slightly inflated cutoff.  Conservative for the exact float predicates
 // of the sweep (the margin dwarfs their rounding), ~30 % tighter than box-plus-cutoff on every
-// axis.  fmaxf drops NaNs, so a NaN coordinate survives the scan: the observers count it as in
-// range (d2 > c2 is false, marching_observers.cu:40), the voxeliser's d2 < c2 rejects it later.
+// axis.  An atom with a NaN coordinate must survive the scan: the observers count it as in range for
+// every voxel (d2 > c2 is false, marching_observers.cu:40), the voxeliser's d2 < c2 rejects it later.
 struct NrlTileBox { float x0, x1, y0, y1, z0, z1, r2; };
 __device__ __forceinline__ bool nrl_near_box(const float4 a, const NrlTileBox &b) {
   const float dx = fmaxf(fmaxf(b.x0 - a.x, a.x - b.x1), 0.0f);
   const float dy = fmaxf(fmaxf(b.y0 - a.y, a.y - b.y1), 0.0f);
   const float dz = fmaxf(fmaxf(b.z0 - a.z, a.z - b.z1), 0.0f);
   return !(fmaf(dz, dz, fmaf(dy, dy, dx * dx)) > b.r2);
+}
+// the same, but an atom with ANY NaN coordinate is a candidate wherever its other coordinates are
+// (fmaxf drops the NaN axis only); inf - inf false positives are settled by the exact predicate later
+__device__ __forceinline__ bool nrl_near_box_nan(const float4 a, const NrlTileBox &b) {
+  const float sum = (a.x + a.y) + a.z;
+  return nrl_near_box(a, b) || (sum != sum);
 }
 
 // shared-memory record per candidate: the atom (x, y, z, weight) and, for the voxeliser, the
@@ -396,7 +402,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
         }
 #pragma unroll
         for (int u = 0; u < NRL_SCAN_ILP; ++u)
-          mycnt += __popc(__ballot_sync(0xffffffffu, nrl_near_box(a[u], box)));
+          mycnt += __popc(__ballot_sync(0xffffffffu, nrl_near_box_nan(a[u], box)));
       }
       if (lane == 0) s_wcnt[warp] = mycnt;
       __syncthreads();
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
         for (int u = 0; u < NRL_SCAN_ILP; ++u) {
           const int i = i0 + u * 32 + lane;
           a[u] = i < a_end ? __ldg(atoms + i) : make_float4(NRL_FAR, NRL_FAR, NRL_FAR, 0.f);
-          keep[u] = nrl_near_box(a[u], box);
+          keep[u] = nrl_near_box_nan(a[u], box);
         }
         float w[NRL_SCAN_ILP][NWT];
 #pragma unroll
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
         int nsub = 0;
         for (int c0 = 0; c0 < total; c0 += 32) {
           const int ci = c0 + lane;
-          const bool k = ci < total && nrl_near_box(s_cand[ci * NrlCandStride<MODE, NWT>::value], wbox);
+          const bool k = ci < total && nrl_near_box_nan(s_cand[ci * NrlCandStride<MODE, NWT>::value], wbox);
           const unsigned m = __ballot_sync(0xffffffffu, k);
           if (k) my_idx[nsub + __popc(m & ((1u << lane) - 1u))] = (unsigned short)ci;
           nsub += __popc(m);
