@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(NRL_BIN_NT) nrl_bin_kernel(const NrlBinParams 
 
 // ---- the cell-list tile kernel -------------------------------------------------------------------
 #define NRL_MAX_RUNS 32
-#define NRL_STAGE_CAP 768          // atoms staged per frame (12 KB); fuller frames are read straight from global memory
+#define NRL_STAGE_CAP 640          // atoms staged per frame (10 KB); fuller frames are read straight from global memory
 
 struct NrlCellTileParams {
   const NrlTask *tasks;
@@ -156,6 +156,11 @@ struct NrlCellTileParams {
   int ser_cap;                   // series floats that fit in shared memory
   int wcap;                      // records per warp
 };
+
+// one channel reduced by mean / max / min: the reducer runs as a recurrence over the frames, no series is kept
+__host__ __device__ __forceinline__ bool nrl_streaming_task(const NrlTask &t) {
+  return t.n_ch == 1 && t.n_w == 1 && (t.ch_agg[0] == 1 || t.ch_agg[0] == 5 || t.ch_agg[0] == 6);
+}
 
 template <int MODE, int NWT> struct NrlRecStride {   // float4 per record
   static constexpr int value = (MODE == NRL_MODE_VOXELIZE) ? (NWT > 1 ? 3 : 2) : 1;
@@ -277,7 +282,7 @@ __device__ __forceinline__ void nrl_rec_finish(const NrlAcc<MODE, NWT> &A, const
 }
 
 template <int MODE, int NWT>
-__global__ void __launch_bounds__(NRL_NT) nrl_cell_tile_kernel(const NrlCellTileParams p) {
+__global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellTileParams p) {
   constexpr int S = NrlRecStride<MODE, NWT>::value;
   extern __shared__ __align__(16) unsigned char nrl_smem[];
   // layout: [stage: NRL_STAGE_CAP float4][records: NRL_NW * wcap * S float4][series: ser_cap floats]
@@ -335,6 +340,9 @@ __global__ void __launch_bounds__(NRL_NT) nrl_cell_tile_kernel(const NrlCellTile
     const float *wtabs[NWT];
 #pragma unroll
     for (int q = 0; q < NWT; ++q) wtabs[q] = t.wtab[q];
+    const int agg0 = t.ch_agg[0];
+    const bool streaming = nrl_streaming_task(t);
+    float racc[NRL_VPT] = {0.f, 0.f, 0.f, 0.f};
     const bool ser_in_smem = (long long)n_w * nF * NRL_TILE_VOX <= (long long)p.ser_cap;
     float4 *ser = ser_in_smem ? s_ser : g_ser;
 
@@ -411,8 +419,57 @@ __global__ void __launch_bounds__(NRL_NT) nrl_cell_tile_kernel(const NrlCellTile
       A.clear();
       int nrec = 0;
       bool saturated = false;
+      // Second half of the compaction + one sweep round.  The compaction below only moves (x, y, z,
+      // payload) records; here every lane resolves the weights of its share of the records with
+      // independent gathers (one exposed L2 round trip per round instead of one per 32 staged atoms),
+      // the voxeliser adds 1/S and its four per-plane Gaussian factors, then the list is padded to a
+      // multiple of four with far-away records and swept.
       auto flush = [&]() {
-        // pad to a multiple of four with far-away records, then sweep this round
+        __syncwarp();
+        if constexpr (NrlModeTraits<MODE>::kNeedsWeight) {
+          for (int r0 = 0; r0 < nrec; r0 += 128) {
+            float4 a[4];
+            float w[4][NWT];
+            float iv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + u * 32 + lane;
+              a[u] = r < nrec ? my_rec[(size_t)r * S] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + u * 32 + lane;
+              const int payload = __float_as_int(a[u].w);
+#pragma unroll
+              for (int q = 0; q < NWT; ++q) w[u][q] = (r < nrec && q < n_w) ? __ldg(wtabs[q] + payload) : 0.0f;
+              if constexpr (MODE == NRL_MODE_VOXELIZE)
+                iv[u] = r < nrec ? __ldg(inv + __float_as_int(my_rec[(size_t)r * S + 1].x)) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + u * 32 + lane;
+              if (r >= nrec) continue;
+              float4 *slot = my_rec + (size_t)r * S;
+              if constexpr (MODE == NRL_MODE_VOXELIZE) {
+#pragma unroll
+                for (int q = 0; q < NWT; ++q) w[u][q] = w[u][q] * iv[u];
+                float e[NRL_VPT];
+#pragma unroll
+                for (int k = 0; k < NRL_VPT; ++k) { const float dz = a[u].z - pz[k]; e[k] = nrl_ex2_approx(dz * dz * t.k2); }
+                slot[1] = make_float4(e[0], e[1], e[2], e[3]);
+                if constexpr (NWT > 1) slot[2] = make_float4(w[u][0], w[u][1 % NWT], w[u][2 % NWT], w[u][3 % NWT]);
+              }
+              if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) {
+                // the weight table of this mode holds the RANK of the atom's value among the distinct values
+                // (-1: the 99999.0 placeholder, never counted, marching_observers.cu:118-138)
+                const int rank = (int)w[u][0];
+                w[u][0] = __int_as_float(rank >= 0 ? (int)(1u << (rank & 31)) : 0);
+              }
+              a[u].w = w[u][0];
+              slot[0] = a[u];
+            }
+          }
+        }
         if (lane < ((4 - (nrec & 3)) & 3)) {
           float4 *slot = my_rec + (size_t)(nrec + lane) * S;
           slot[0] = make_float4(NRL_FAR, NRL_FAR, NRL_FAR, 0.f);
@@ -426,7 +483,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_cell_tile_kernel(const NrlCellTile
         nrec = 0;
       };
 
-      // ---- the warp's own candidate records
+      // ---- the warp's own candidate records: (x, y, z, payload) of the staged atoms that can reach its block
       for (int c0 = 0; c0 < total; c0 += 32) {
         const int i = c0 + lane;
         int gi = 0;
@@ -440,34 +497,12 @@ __global__ void __launch_bounds__(NRL_NT) nrl_cell_tile_kernel(const NrlCellTile
         if (m == 0u) continue;
         if (nrec + __popc(m) > wcap - 4) flush();
         if (keep) {
-          const int payload = __float_as_int(a.w);
-          float w[NWT];
-#pragma unroll
-          for (int q = 0; q < NWT; ++q) w[q] = 0.0f;
-          if constexpr (NrlModeTraits<MODE>::kNeedsWeight) {
-#pragma unroll
-            for (int q = 0; q < NWT; ++q) if (q < n_w) w[q] = __ldg(wtabs[q] + payload);
-          }
           float4 *slot = my_rec + (size_t)(nrec + __popc(m & ((1u << lane) - 1u))) * S;
+          slot[0] = a;
           if constexpr (MODE == NRL_MODE_VOXELIZE) {
             if (staged) gi = locate(i);
-            const float iv = __ldg(inv + gi);
-#pragma unroll
-            for (int q = 0; q < NWT; ++q) w[q] = w[q] * iv;
-            float e[NRL_VPT];
-#pragma unroll
-            for (int k = 0; k < NRL_VPT; ++k) { const float dz = a.z - pz[k]; e[k] = nrl_ex2_approx(dz * dz * t.k2); }
-            slot[1] = make_float4(e[0], e[1], e[2], e[3]);
-            if constexpr (NWT > 1) slot[2] = make_float4(w[0], w[1 % NWT], w[2 % NWT], w[3 % NWT]);
+            slot[1].x = __int_as_float(gi);             // position in the binned frame: 1/S is parallel to it
           }
-          if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) {
-            // the weight table of this mode holds the RANK of the atom's value among the distinct values
-            // (-1: the 99999.0 placeholder, never counted, marching_observers.cu:118-138)
-            const int rank = (int)w[0];
-            w[0] = __int_as_float(rank >= 0 ? (int)(1u << (rank & 31)) : 0);
-          }
-          a.w = w[0];
-          slot[0] = a;
         }
         nrec += __popc(m);
       }
@@ -493,6 +528,17 @@ __global__ void __launch_bounds__(NRL_NT) nrl_cell_tile_kernel(const NrlCellTile
               }
           }
         }
+      } else if (streaming) {
+        // mean / max / min of a single channel need no series: the reference's own sequential
+        // recurrences (sum_device, max_device, min_device, gpuutils.cuh:11-42) run as the frames pass
+#pragma unroll
+        for (int k = 0; k < NRL_VPT; ++k) {
+          const float x = val[0][k];
+          if (agg0 == 1) racc[k] = racc[k] + x;
+          else if (f == 0) racc[k] = x;
+          else if (agg0 == 5) { if (x > racc[k]) racc[k] = x; }
+          else { if (x < racc[k]) racc[k] = x; }
+        }
       } else {
 #pragma unroll
         for (int q = 0; q < NWT; ++q)
@@ -500,6 +546,14 @@ __global__ void __launch_bounds__(NRL_NT) nrl_cell_tile_kernel(const NrlCellTile
       }
     }
 
+    if (streaming) {
+      if (ix < nx && iy < ny) {
+        float *o = p.out + t.ch_out[0] + ((long long)ix * ny + iy) * nz;
+#pragma unroll
+        for (int k = 0; k < NRL_VPT; ++k)
+          if (iz + k < nz) o[iz + k] = agg0 == 1 ? nrl_div_approx(racc[k], (float)nF) : racc[k];   // mean_device :45-50
+      }
+    } else
     if (t.ch_agg[0] != 0) {
       // K3 fused: every thread reduces the series of its own four voxels (it wrote them), once per
       // channel.  The median sorts its series in place, so channels that need it go last.

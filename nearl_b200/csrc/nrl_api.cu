@@ -381,7 +381,8 @@ template <typename PreVox>
 int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_cell, const NrlFrames &frames,
               const CellSetup &cells, float *d_out, int max_atoms_per_frame, cudaStream_t st, PreVox before_voxelize) {
   if (tasks.empty()) return NRL_OK;
-  auto key_of = [&](int i) { return mode_key_of(tasks[i]) + (use_cell[i] ? 1000 : 0); };
+  // cell-list tasks whose reducer streams (no series) are launched apart: their CTAs need much less shared memory
+  auto key_of = [&](int i) { return mode_key_of(tasks[i]) + (use_cell[i] ? (nrl_streaming_task(tasks[i]) ? 2000 : 1000) : 0); };
   std::vector<int> order(tasks.size());
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key_of(a) < key_of(b); });
@@ -391,7 +392,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_
   for (int i : order) { sorted.push_back(tasks[i]); keys.push_back(key_of(i)); }
 
   // per-group ranges with their own tile prefix
-  struct Range { int mode, begin, end, n_work, max_frames, grid, cand_cap, ser_cap, wcap; bool cell;
+  struct Range { int mode, begin, end, n_work, max_frames, grid, cand_cap, ser_cap, wcap; bool cell, stream;
                  size_t smem, cand_rec, cand_per_cta, ser_per_cta, cand_off, ser_off; };
   std::vector<Range> ranges;
   for (size_t i = 0; i < sorted.size();) {
@@ -404,7 +405,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_
       ++j;
     }
     Range r{};
-    r.mode = mode_key_of(sorted[i]); r.cell = keys[i] >= 500; r.begin = (int)i; r.end = (int)j; r.n_work = work; r.max_frames = maxf;
+    r.mode = mode_key_of(sorted[i]); r.cell = keys[i] >= 500; r.stream = keys[i] >= 1500; r.begin = (int)i; r.end = (int)j; r.n_work = work; r.max_frames = maxf;
     ranges.push_back(r);
     i = j;
   }
@@ -416,12 +417,12 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_
   for (Range &r : ranges) {
     const bool is_vox = r.mode == NRL_MODE_VOXELIZE || r.mode == kVoxelizeMulti;
     // shared memory: the candidate records plus the time series when it fits (else per-CTA global scratch)
-    const size_t ser_need = (size_t)r.max_frames * NRL_TILE_VOX;
+    const size_t ser_need = r.stream ? 0 : (size_t)r.max_frames * NRL_TILE_VOX;
     r.ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
     if (r.cell) {
       // staged cells + per-warp records (16 B; voxeliser 32 B / 48 B) + series
       const int rec4 = r.mode == kVoxelizeMulti ? 3 : is_vox ? 2 : 1;
-      r.wcap = r.mode == kVoxelizeMulti ? 128 : is_vox ? 160 : 224;
+      r.wcap = r.mode == kVoxelizeMulti ? 128 : is_vox ? 160 : 192;
       r.smem = (size_t)NRL_STAGE_CAP * sizeof(float4) + (size_t)NRL_NW * r.wcap * rec4 * sizeof(float4) + (size_t)r.ser_cap * sizeof(float);
       r.cand_per_cta = 0;
     } else {
@@ -433,7 +434,10 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_
       r.cand_per_cta = max_atoms_per_frame + 4 > r.cand_cap ? (size_t)max_atoms_per_frame : 0;
     }
     const int ctas_per_sm = std::max(1, (int)(c.smem_optin / (r.smem + 1024)));
-    r.grid = std::min(r.n_work, c.sms * std::min(ctas_per_sm, 12));
+    // a tile is tens of microseconds of work: up to a few waves one CTA per tile lets the block scheduler
+    // balance the SMs; beyond that the CTAs stride over the tiles
+    const int slots = c.sms * std::min(ctas_per_sm, 12);
+    r.grid = r.n_work <= 8 * slots ? r.n_work : slots;
     r.ser_per_cta = r.ser_cap == 0 ? ser_need : 0;
     const size_t per_cta = r.cand_per_cta * r.cand_rec + r.ser_per_cta * sizeof(float);
     if (per_cta > 0) {
