@@ -122,6 +122,9 @@ typedef struct {
   int weight_table;      /* row of `weight_tables` */
   int dims[3];
   float spacing, cutoff, sigma;
+  int rank_table;        /* distinct_count only: row of `weight_tables` holding, as floats, the rank (0..31) of every
+                            atom's value among the distinct values of `weight_table` (-1 for the 99999.0 placeholder,
+                            which is never counted); -1 = no ranks: the crop must then be value ordered (sort_table) */
 } nrl_task_t;
 
 typedef struct {
@@ -153,6 +156,9 @@ typedef struct {
 #define NRL_MAX_LANES 4
 
 int nrl_featurize_batch(const nrl_batch_t *batch);
+
+/* *out = 1 when a grid of this geometry gets a cell list (rank-based distinct_count needs one), else 0 */
+int nrl_cell_list_fits(const int *dims, float spacing, float cutoff, int *out);
 
 /* ---- utilities -------------------------------------------------------------------------- */
 /* buff_dim exactly as the device evaluates (cutoff+spacing)/spacing (voxelize.cu:50, div.approx) */

@@ -19,7 +19,7 @@ EXPORTED = [
   "nrl_frame_voxelize", "nrl_frame_observation", "nrl_marching_observer", "nrl_density_flow", "nrl_aggregate",
   "nrl_summation", "nrl_frame_voxelize_dev", "nrl_frame_observation_dev", "nrl_marching_observer_dev",
   "nrl_density_flow_dev", "nrl_aggregate_dev", "nrl_featurize_batch", "nrl_buff_dim", "nrl_device_count",
-  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_set_stream", "nrl_set_option", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
+  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_set_stream", "nrl_set_option", "nrl_cell_list_fits", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
   "nrl_last_error", "nrl_version",
 ]
 
@@ -41,6 +41,7 @@ class TaskStruct(ctypes.Structure):
   _fields_ = [
     ("crop", c_int), ("mode", c_int), ("agg", c_int), ("weight_table", c_int),
     ("dims", c_int * 3), ("spacing", c_float), ("cutoff", c_float), ("sigma", c_float),
+    ("rank_table", c_int),
   ]
 
 
@@ -98,6 +99,7 @@ def lib():
   L.nrl_lane_synchronize.argtypes = [c_int]
   L.nrl_profile.argtypes = [c_int]
   L.nrl_set_option.argtypes = [ctypes.c_char_p, c_int]
+  L.nrl_cell_list_fits.argtypes = [p, c_float, c_float, p]
   L.nrl_profile_read.argtypes = [p, p, c_int]
   L.nrl_profile_name.argtypes = [c_int]
   L.nrl_profile_name.restype = ctypes.c_char_p
@@ -143,6 +145,13 @@ PROFILE_CATEGORIES = 17
 
 def set_stream(stream_ptr, enable=True):
   check(lib().nrl_set_stream(c_void_p(stream_ptr), 1 if enable else 0))
+
+
+def cell_list_fits(dims, spacing, cutoff):
+  d = (c_int * 3)(*[int(v) for v in dims])
+  out = c_int(0)
+  check(lib().nrl_cell_list_fits(d, float(spacing), float(cutoff), ctypes.byref(out)))
+  return bool(out.value)
 
 
 def set_option(name, value):

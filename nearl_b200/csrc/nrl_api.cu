@@ -764,6 +764,16 @@ int nrl_set_stream(void *stream, int enable) {
   c->use_user_stream = enable != 0;
   return NRL_OK;
 }
+int nrl_cell_list_fits(const int *dims, float spacing, float cutoff, int *out) {
+  long long G = 0;
+  NRL_TRY(check_dims(dims, &G));
+  if (!out) return fail(NRL_ERR_ARGUMENT, "out is NULL");
+  CropCells cc;
+  cc.add(dims, spacing, cutoff);
+  NrlCellGrid g;
+  *out = (!g_force_scan && cc.grid(g, kMaxCells)) ? 1 : 0;
+  return NRL_OK;
+}
 int nrl_set_option(const char *name, int value) {
   if (!name) return fail(NRL_ERR_ARGUMENT, "option name is NULL");
   if (strcmp(name, "force_scan") == 0) { g_force_scan.store(value != 0); return NRL_OK; }

@@ -18,7 +18,7 @@ import logging
 
 import numpy as np
 
-from . import commands, constants, utils
+from . import _lib, commands, constants, utils
 from . import printit, config
 from .io import Trajectory
 
@@ -48,6 +48,9 @@ SUPPORTED_OBSERVATION = {
 }
 
 _NUMBER_TYPES = (int, float, np.integer, np.floating)
+
+
+_CELL_FIT_MEMO = {}
 
 
 def _lut(table):
@@ -334,6 +337,29 @@ class Feature:
           hit[k] = v[:5] + (memo,)
     return memo[1]
 
+  def value_ranks(self):
+    """Rank of every atom's weight among the distinct weight values, as float32 (-1 for the 99999.0
+    placeholder, which distinct_count never counts: marching_observers.cu:118-138), or None when there are
+    more than 32 distinct values.  -0.0 == +0.0; every NaN is a value of its own.  Memoised per weight array."""
+    memos = self.__dict__.setdefault("_value_ranks_memos", {})
+    memo = memos.get(id(self.cached_array))
+    if memo is None or memo[0] is not self.cached_array:
+      if len(memos) >= 64:
+        memos.clear()
+      w = np.asarray(self.cached_array, dtype=np.float32) + np.float32(0.0)
+      order = self.value_order()
+      sv = w[order]
+      fresh = np.ones(len(sv), dtype=bool)
+      fresh[1:] = ~(sv[1:] == sv[:-1])
+      rank_sorted = np.cumsum(fresh) - 1
+      ranks = None
+      if len(sv) == 0 or rank_sorted[-1] < 32:
+        ranks = np.empty(len(sv), dtype=np.float32)
+        ranks[order] = rank_sorted
+        ranks[w == np.float32(99999.0)] = -1.0
+      memos[id(self.cached_array)] = memo = (self.cached_array, ranks)
+    return memo[1]
+
   def _is_builtin(self, *methods):
     """True when none of `methods` was overridden outside this module (a user subclass that
     customises query/run must go through the host protocol)."""
@@ -562,10 +588,18 @@ class DynamicFeature(Feature):
       return None
     if self.cached_array is None or self.center is None or self.padding is None or self.cutoff is None:
       return None
-    return {
+    spec = {
       "kind": "dynamic", "mode": int(mode), "agg": int(self.agg), "weights": np.asarray(self.cached_array, dtype=np.float32),
       "frame_offset": 0, "max_atoms": int(self.MAX_ALLOWED_ATOMS), "sigma": float(sigma),
     }
+    if int(mode) == 3:
+      # distinct_count over few distinct values (atomic numbers, atom types ...) runs on the cell-list kernel with
+      # per-atom value ranks; otherwise the crop is emitted in value order for the scan kernel
+      gkey = (tuple(int(v) for v in self.dims), float(self.spacing), float(self.cutoff))
+      if gkey not in _CELL_FIT_MEMO:
+        _CELL_FIT_MEMO[gkey] = _lib.cell_list_fits(*gkey)
+      spec["ranks"] = self.value_ranks() if _CELL_FIT_MEMO[gkey] else None
+    return spec
 
 
 class DensityFlow(DynamicFeature):

@@ -206,9 +206,11 @@ class Featurizer:
         assert len(item) == 3, "The focus should be a 3D coordinate"
         self.FOCALPOINTS[:, midx] = item
         continue
-      for fidx in range(self.SLICENUMBER):
-        frame = self.traj.xyz[fidx * self.time_window]
-        self.FOCALPOINTS[fidx, midx] = np.mean(frame[selection], axis=0)
+      if self.SLICENUMBER:
+        # first frame of every window, one gather: np.mean over axis 1 adds the selected rows in the same
+        # order as the reference's per-frame np.mean(frame[selection], axis=0) -- identical bits
+        firsts = self.traj.xyz[0:self.SLICENUMBER * self.time_window:self.time_window]
+        self.FOCALPOINTS[:, midx] = np.mean(firsts[:, selection], axis=1)
     return 1
 
   # ---- the loop -----------------------------------------------------------------------------
@@ -273,7 +275,7 @@ class Featurizer:
       xyz = self.traj.xyz
       if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
         xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
-      batch = self.lower_batch(native_feats, specs, xyz.shape[1], xyz.dtype == np.float64)
+      batch = self.lower_batch(native_feats, specs, xyz.shape[1], xyz.dtype == np.float64, lane=lane)
       buffers = self.__dict__.setdefault("_out_buffers", {})
       if lane not in buffers or buffers[lane].size < batch.out_floats:
         buffers[lane] = pinned_empty((batch.out_floats,), np.float32)     # page-locked, reused across trajectories
@@ -328,13 +330,16 @@ class Featurizer:
       f, sp = self.FEATURESPACE[fidx], specs[fidx]
       return (fidx, tuple(int(v) for v in f.dims), float(f.spacing), float(f.cutoff), float(sp["sigma"]), float(f.padding),
               bool(f.byres), f.selection is not None, bool(sp.get("selection_folded")), sp["kind"], sp["mode"], sp["agg"],
-              sp["frame_offset"], sp["max_atoms"])
+              sp["frame_offset"], sp["max_atoms"], sp.get("ranks") is not None)
 
     key = (tuple(fingerprint(f) for f in native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64))
     cache = self.__dict__.setdefault("_template_cache", {})
     if key in cache:
       return cache[key]
     table_of = {f: i for i, f in enumerate(native_feats)}
+    # distinct_count features whose values have <= 32 ranks: the ranks travel as extra weight-table rows
+    rank_feats = [f for f in native_feats if specs[f]["mode"] == 3 and specs[f].get("ranks") is not None]
+    rank_of = {f: len(native_feats) + i for i, f in enumerate(rank_feats)}
     sel_feats = [f for f in native_feats if self.FEATURESPACE[f].selection is not None and not specs[f].get("selection_folded")]
     sel_of = {f: i for i, f in enumerate(sel_feats)}
     crops, crop_ids, crop_slots, tasks, shapes = [], {}, [], [], []
@@ -345,7 +350,7 @@ class Featurizer:
           feat, spec = self.FEATURESPACE[fidx], specs[fidx]
           wid = table_of[fidx]
           sid = sel_of.get(fidx, -1)
-          sort_table = wid if spec["mode"] == 3 else -1
+          sort_table = wid if (spec["mode"] == 3 and fidx not in rank_of) else -1
           if sort_table >= 0 and fidx not in order_feats:
             order_feats.append(fidx)
           start = bid * self.time_window
@@ -377,19 +382,33 @@ class Featurizer:
             crop_slots.append((bid, pid))
           t = _lib.TaskStruct()
           t.crop, t.mode, t.agg, t.weight_table = crop_ids[ckey], spec["mode"], spec["agg"], wid
+          t.rank_table = rank_of.get(fidx, -1)
           t.dims[:] = [int(v) for v in feat.dims]
           t.spacing, t.cutoff, t.sigma = float(feat.spacing), float(feat.cutoff), float(spec["sigma"])
           tasks.append(t)
           shapes.append(tuple(int(v) for v in feat.dims))
     tpl = {"crops": crops, "crop_slots": crop_slots, "tasks": (_lib.TaskStruct * len(tasks))(*tasks), "shapes": shapes,
-           "sel_feats": sel_feats, "order_feats": order_feats, "any_byres": any_byres,
+           "sel_feats": sel_feats, "order_feats": order_feats, "rank_feats": rank_feats, "any_byres": any_byres,
            "out_floats": int(sum(sh[0] * sh[1] * sh[2] for sh in shapes))}
     cache[key] = tpl
     return tpl
 
-  def lower_batch(self, native_feats, specs, n_atoms, is_f64):
+  def _table_buffer(self, lane, name, shape, dtype):
+    """Re-used page-locked staging array (per pipeline lane): the table uploads inside the native call are DMA."""
+    if lane is None:
+      return np.empty(shape, dtype=dtype)
+    pool = self.__dict__.setdefault("_table_buffers", {})
+    need = int(np.prod(shape))
+    buf = pool.get((lane, name))
+    if buf is None or buf.size < need or buf.dtype != np.dtype(dtype):
+      buf = pool[(lane, name)] = pinned_empty((max(need, 1),), dtype)
+    return buf[:need].reshape(shape)
+
+  def lower_batch(self, native_feats, specs, n_atoms, is_f64, lane=None):
     """Crop and task tables of the C ABI for the active trajectory (tasks in the reference's
-    order window -> focal point -> feature, restricted to `native_feats`)."""
+    order window -> focal point -> feature, restricted to `native_feats`).  With a `lane` the
+    per-trajectory tables are written into that lane's page-locked buffers, which stay valid until
+    the lane's next submission."""
     tpl = self._template(native_feats, specs, n_atoms, is_f64)
     batch = LoweredBatch()
     batch.n_atoms, batch.is_f64 = n_atoms, bool(is_f64)
@@ -399,13 +418,18 @@ class Featurizer:
       focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else zero
       crops[ci].focal[0], crops[ci].focal[1], crops[ci].focal[2] = float(focal[0]), float(focal[1]), float(focal[2])
     batch.crops, batch.tasks, batch.shapes, batch.out_floats = crops, tpl["tasks"], tpl["shapes"], tpl["out_floats"]
-    batch.weight_tables = (np.stack([np.asarray(specs[f]["weights"], dtype=np.float32) for f in native_feats])
-                           if native_feats else np.zeros((0, n_atoms), dtype=np.float32))
-    batch.selections = (np.stack([np.asarray(self.FEATURESPACE[f].selected, dtype=np.uint8) for f in tpl["sel_feats"]])
-                        if tpl["sel_feats"] else None)
+    rows = [specs[f]["weights"] for f in native_feats] + [specs[f]["ranks"] for f in tpl["rank_feats"]]
+    batch.weight_tables = self._table_buffer(lane, "weights", (len(rows), n_atoms), np.float32)
+    for i, row in enumerate(rows):
+      batch.weight_tables[i] = row
+    batch.selections = None
+    if tpl["sel_feats"]:
+      batch.selections = self._table_buffer(lane, "selections", (len(tpl["sel_feats"]), n_atoms), np.uint8)
+      for i, f in enumerate(tpl["sel_feats"]):
+        batch.selections[i] = self.FEATURESPACE[f].selected
     batch.value_orders = None
     if tpl["order_feats"]:
-      batch.value_orders = np.zeros((len(native_feats), n_atoms), dtype=np.int32)
+      batch.value_orders = self._table_buffer(lane, "orders", (len(rows), n_atoms), np.int32)
       for f in tpl["order_feats"]:
         batch.value_orders[native_feats.index(f)] = self.FEATURESPACE[f].value_order()
     batch.residue_index, batch.n_residues = None, 0

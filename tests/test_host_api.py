@@ -116,6 +116,16 @@ def test_focus_parsing_and_frame_windows():
   assert fz.parse_focus() == 1 and fz.FOCALPOINTS.shape == (2, 2, 3) and fz.FOCALPOINTS.dtype == np.float32
   sel = traj.top.select(":LYS")
   assert np.array_equal(fz.FOCALPOINTS[1, 1], np.mean(traj.xyz[10][sel], axis=0).astype(np.float32))
+  # the one-gather form gives the bits of the reference's per-frame np.mean(frame[selection], axis=0), f32 and f64
+  for dtype in (np.float32, np.float64):
+    big = io.synthetic_trajectory(5000, 40, seed=2, dtype=dtype, pin=False)
+    fz.traj = big
+    assert fz.parse_focus() == 1
+    for midx, mask in enumerate((":ARG", ":LYS")):
+      sel = big.top.select(mask)
+      for w in range(fz.SLICENUMBER):
+        assert np.array_equal(fz.FOCALPOINTS[w, midx], np.mean(big.xyz[w * 10][sel], axis=0).astype(np.float32))
+  fz.traj = traj
   fz.register_focus([[0, 1, 2]], "index")
   assert fz.parse_focus() == 1 and np.allclose(fz.FOCALPOINTS[0, 0], traj.xyz[0][:3].mean(0))
   fz.register_focus([":NOPE"], "mask")
@@ -168,6 +178,26 @@ def test_weight_tables():
   assert np.array_equal(w(features.Hydrophobicity()), np.abs(en - constants.ELECNEG[6]))
   with pytest.raises(NotImplementedError):
     features.cache_properties(traj, 22)
+
+
+def test_value_ranks_for_distinct_count():
+  traj = io.synthetic_trajectory(800, 2, seed=3, pin=False)
+  fz = featurizer.Featurizer({"dimensions": 8, "lengths": 8, "time_window": 2, "cutoff": 3.0})
+  few = features.MarchingObservers(obs="distinct_count", weight_type="atomic_number", outkey="few")
+  many = features.MarchingObservers(obs="distinct_count", weight_type="residue_id", outkey="many")
+  fz.register_features([few, many])
+  few.cache(traj); many.cache(traj)
+  ranks = few.value_ranks()
+  w = np.asarray(few.cached_array, dtype=np.float32)
+  assert ranks.dtype == np.float32 and ranks.max() == len(np.unique(w)) - 1
+  for a, b in ((0, 1), (5, 700), (17, 333)):
+    assert (ranks[a] == ranks[b]) == (w[a] == w[b]) and (ranks[a] < ranks[b]) == (w[a] < w[b])
+  assert many.value_ranks() is None                      # 50 residues: more than 32 distinct values
+  few.cached_array = np.array([0.0, -0.0, 99999.0, np.nan, np.nan, 2.0], dtype=np.float32)
+  r = few.value_ranks()
+  assert r[0] == r[1] and r[2] == -1 and r[3] != r[4] and r[5] > r[0]
+  spec = few._dynamic_spec(3, 0.0)
+  assert spec["ranks"] is r
 
 
 def test_hdf5_layout_roundtrip(tmp_path):
