@@ -154,8 +154,13 @@ def cell_list_fits(dims, spacing, cutoff):
   return bool(out.value)
 
 
+OPTION_EPOCH = 0    # bumped by set_option: memoised answers of the library (cell_list_fits) depend on the options
+
+
 def set_option(name, value):
+  global OPTION_EPOCH
   check(lib().nrl_set_option(name.encode(), int(value)))
+  OPTION_EPOCH += 1
 
 
 def profile(enable=True):

@@ -215,7 +215,7 @@ struct NrlNormParams {
   float *inv_norm;           // parallel to frames.atoms
 };
 
-#define NRL_NORM_MAXZ 96     // lattice points along z inside one cutoff sphere handled by the fast path
+#define NRL_NORM_MAXZ 96     // lattice points along an axis inside one cutoff sphere handled by the fast path
 
 // in-cutoff predicate of the reference, bit for bit (voxelize.cu:92-95 as compiled)
 __device__ __forceinline__ bool nrl_norm_in(const float az, const int z, const float s, const float t2, const float c2) {
@@ -224,7 +224,9 @@ __device__ __forceinline__ bool nrl_norm_in(const float az, const int z, const f
 }
 
 __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams p, const int capacity) {
-  __shared__ double s_prefix[4][NRL_NORM_MAXZ + 1];
+  // per warp: prefix of the z-plane factors, and per-axis tables of the x / y offsets and factors
+  __shared__ float s_prefix[4][NRL_NORM_MAXZ + 1];
+  __shared__ float s_dx[4][NRL_NORM_MAXZ], s_ex[4][NRL_NORM_MAXZ], s_dy2[4][NRL_NORM_MAXZ], s_ey[4][NRL_NORM_MAXZ];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const int fd = p.frame_list[blockIdx.y];
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
   const long long off = p.frames.off[fd];
   const float s = p.spacing, c = p.cutoff, c2 = c * c, k2 = p.k2;
   const int b = nrl_buff_dim_device(c, s);
-  double *P = s_prefix[wid];
+  float *P = s_prefix[wid], *Dx = s_dx[wid], *Ex = s_ex[wid], *Dy2 = s_dy2[wid], *Ey = s_ey[wid];
   for (int i = blockIdx.x * warps_per_cta + wid; i < n; i += gridDim.x * warps_per_cta) {
     const float4 a = __ldg(p.frames.atoms + off + i);
     double sum = 0.0;
@@ -248,34 +250,41 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
       const int z_lo = (int)fmaxf(ceilf(a.z * is - cr - mz), (float)(-b));
       const int z_hi = (int)fminf(floorf(a.z * is + cr + mz), (float)(p.nz + b - 1));
       const int ex = x_hi - x_lo + 1, ey = y_hi - y_lo + 1, ez = z_hi - z_lo + 1;
-      if (ex > 0 && ey > 0 && ez > 0 && ez <= NRL_NORM_MAXZ) {
-        // Separable form.  exp(-(dx^2+dy^2+dz^2)/2s^2) = E_xy * E_z, and along z the lattice points
+      if (ex > 0 && ey > 0 && ez > 0 && ez <= NRL_NORM_MAXZ && ex <= NRL_NORM_MAXZ && ey <= NRL_NORM_MAXZ) {
+        // Separable form.  exp(-(dx^2+dy^2+dz^2)/2s^2) = E_x * E_y * E_z, and along z the lattice points
         // that pass the reference's float predicate form ONE interval (the predicate is monotone in
-        // |dz|), so a row contributes E_xy * (prefix[z_last+1] - prefix[z_first]).
+        // |dz|), so a row contributes E_x * E_y * (prefix[z_last+1] - prefix[z_first]).  The per-axis
+        // offsets are tabulated exactly as the predicate needs them (dx, and dy*dy rounded once).
         __syncwarp();
-        double carry = 0.0;
+        float carry = 0.0f;
         for (int j0 = 0; j0 < ez; j0 += 32) {
           const int j = j0 + lane;
-          double v = 0.0;
-          if (j < ez) { const float dz = a.z - (float)(z_lo + j) * s; v = (double)nrl_ex2_approx(dz * dz * k2); }
+          float v = 0.0f;
+          if (j < ez) { const float dz = a.z - (float)(z_lo + j) * s; v = nrl_ex2_approx(dz * dz * k2); }
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+          for (int o = 1; o < 32; o <<= 1) { const float u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
           if (j < ez) P[j + 1] = carry + v;
           carry += __shfl_sync(0xffffffffu, v, 31);
         }
-        if (lane == 0) P[0] = 0.0;
+        if (lane == 0) P[0] = 0.0f;
+        for (int j = lane; j < ex; j += 32) { const float dx = a.x - (float)(x_lo + j) * s; Dx[j] = dx; Ex[j] = nrl_ex2_approx(dx * dx * k2); }
+        for (int j = lane; j < ey; j += 32) { const float dy = a.y - (float)(y_lo + j) * s; const float d2 = dy * dy; Dy2[j] = d2; Ey[j] = nrl_ex2_approx(d2 * k2); }
         __syncwarp();
         const int rows = ex * ey;
-        const float rcp_ey = 1.0f / (float)ey;
         const float inv_s = 1.0f / s, zc = a.z * inv_s;
         // reach of float rounding, in lattice units, on the position of an interval end: coordinate
         // scaling (2 ulp of zc), the cancellation in c2 - t2 and the predicate's own last-bit fuzz
-        const float eps = 5e-4f + 4e-6f * fabsf(zc);
+        const float eps = 5e-4f + 4e-6f * fabsf(zc), one_m_eps = 1.0f - eps;
+        // rows q = lane, lane + 32, ... of the (x, y) rectangle, walked without a division per row
+        const int step_x = 32 / ey, step_y = 32 - step_x * ey;
+        int xi = lane / ey, yi = lane - xi * ey;
+        float part = 0.0f;
         for (int q = lane; q < rows; q += 32) {
-          const int xi = __float2int_rd(((float)q + 0.5f) * rcp_ey);
-          const int yi = q - xi * ey;
-          const float dx = a.x - (float)(x_lo + xi) * s, dy = a.y - (float)(y_lo + yi) * s;
-          const float t2 = fmaf(dx, dx, dy * dy);
+          const float dx = Dx[xi], dy2 = Dy2[yi];
+          const float exy = Ex[xi] * Ey[yi];
+          yi += step_y; xi += step_x;
+          if (yi >= ey) { yi -= ey; ++xi; }
+          const float t2 = fmaf(dx, dx, dy2);                     // voxelize.cu:92-94 as compiled, z term pending
           if (!(t2 < c2)) continue;
           const float gap = c2 - t2;
           const float r = nrl_sqrt_approx(gap) * inv_s;        // half-width of the interval in lattice units
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
           // within rounding reach of a lattice plane, or when the row is nearly tangent to the sphere
           // (gap of a few ulp).  Only then are the two ends settled on the exact predicate.
           const float el = fl - ul, eh = uh - fh;                // distances of the ends to the planes beside them
-          const bool fragile = (el < eps) || (el > 1.0f - eps) || (eh < eps) || (eh > 1.0f - eps) || (r < 0.05f);
+          const bool fragile = (el < eps) || (el > one_m_eps) || (eh < eps) || (eh > one_m_eps) || (r < 0.05f);
           if (fragile) {
             jl = max(jl, z_lo - 1); jh = min(jh, z_hi + 1);
             int guard = 0;
@@ -296,8 +305,9 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
             while (jh >= jl && !nrl_norm_in(a.z, jh, s, t2, c2) && guard < 32) { --jh; ++guard; }
           }
           jl = max(jl, z_lo); jh = min(jh, z_hi);
-          if (jl <= jh) sum += (double)nrl_ex2_approx(t2 * k2) * (P[jh - z_lo + 1] - P[jl - z_lo]);
+          if (jl <= jh) part = fmaf(exy, P[jh - z_lo + 1] - P[jl - z_lo], part);
         }
+        sum = (double)part;
       } else if (ex > 0 && ey > 0 && ez > 0) {
         // very fine lattices: plain sweep of the bounding cube
         const int plane = ey * ez;

@@ -595,9 +595,9 @@ class DynamicFeature(Feature):
     if int(mode) == 3:
       # distinct_count over few distinct values (atomic numbers, atom types ...) runs on the cell-list kernel with
       # per-atom value ranks; otherwise the crop is emitted in value order for the scan kernel
-      gkey = (tuple(int(v) for v in self.dims), float(self.spacing), float(self.cutoff))
+      gkey = (tuple(int(v) for v in self.dims), float(self.spacing), float(self.cutoff), _lib.OPTION_EPOCH)
       if gkey not in _CELL_FIT_MEMO:
-        _CELL_FIT_MEMO[gkey] = _lib.cell_list_fits(*gkey)
+        _CELL_FIT_MEMO[gkey] = _lib.cell_list_fits(*gkey[:3])
       spec["ranks"] = self.value_ranks() if _CELL_FIT_MEMO[gkey] else None
     return spec
 
