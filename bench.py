@@ -60,7 +60,8 @@ def make_workload(name, n_traj, seed_offset=0, pin=True):
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+  """SM clock and throttle reasons sampled DURING a timed region: NVML from a thread every 10 ms
+  (the timed regions are tens of milliseconds), `nvidia-smi -lms` as the fallback."""
   FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
             "clocks_event_reasons.sw_power_cap")
@@ -69,8 +70,41 @@ class ClockSampler:
     self.index = index
     self.proc = None
     self.lines = []
+    self.samples = []          # (sm_mhz, reasons bitmask)
+    self.max_mhz = None
+    self.thread = None
+    self.stop = threading.Event()
+    self.nvml = None
+
+  def _nvml_loop(self, handle):
+    nv = self.nvml
+    while not self.stop.is_set():
+      try:
+        self.samples.append((float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)),
+                             int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                             if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
+                             else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle))))
+      except Exception:
+        break
+      self.stop.wait(0.01)
 
   def __enter__(self):
+    try:
+      import pynvml as nv
+      nv.nvmlInit()
+      # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+      vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+      phys = self.index
+      if vis and all(tok.strip().isdigit() for tok in vis.split(",")):
+        phys = int(vis.split(",")[self.index])
+      handle = nv.nvmlDeviceGetHandleByIndex(phys)
+      self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+      self.nvml = nv
+      self.thread = threading.Thread(target=self._nvml_loop, args=(handle,), daemon=True)
+      self.thread.start()
+      return self
+    except Exception:
+      self.nvml = None
     try:
       self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                     "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
@@ -80,6 +114,9 @@ class ClockSampler:
     return self
 
   def __exit__(self, *exc):
+    self.stop.set()
+    if self.thread is not None:
+      self.thread.join(timeout=1)
     if self.proc is not None:
       time.sleep(0.25)
       self.proc.terminate()
@@ -89,8 +126,17 @@ class ClockSampler:
         pass
 
   def summary(self):
-    sm, mx, reasons = [], [], set()
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    if self.nvml is not None and self.samples:
+      nv = self.nvml
+      bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+              "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+              "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+              "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+      reasons = sorted({name for _, mask in self.samples for name, bit in bits.items() if mask & bit})
+      return {"sm_mhz": float(np.median([m for m, _ in self.samples])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+              "samples": len(self.samples), "source": "nvml, 10 ms period"}
+    sm, mx, reasons = [], [], set()
     for line in self.lines:
       parts = [p.strip() for p in line.split(",")]
       if len(parts) < 8:
@@ -104,7 +150,8 @@ class ClockSampler:
           reasons.add(name)
     if not sm:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+    return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+            "source": "nvidia-smi -lms 200"}
 
 
 def dist_env():
@@ -237,6 +284,13 @@ def run_native(args):
   n_in = int(np.mean([np.count_nonzero(_features.Feature.query(f0, trajs[0].top, trajs[0].xyz[i * fz.time_window], fz.FOCALPOINTS[i, 0])[0])
                       for i in range(min(3, fz.SLICENUMBER))]))
   G = int(np.prod(f0.dims))
+  # ncu --set full capture of the same kernels on the same workload (profiles/kernel_table.json, written by
+  # scripts/ncu_kernel_table.py from the committed capture): DRAM traffic and warp instructions per launch
+  table = {}
+  try:
+    table = json.load(open(os.path.join(ROOT, "profiles", "kernel_table.json"))).get("kernels", {}) if args.workload == "dynamic" else {}
+  except Exception:
+    pass
   if top is not None:
     t_launch = kernels[top]["ms_per_launch"] * 1e-3
     windows = n_frames // fz.time_window
@@ -245,15 +299,23 @@ def run_native(args):
     alg_bytes = windows * (fz.time_window * n_in * 16 + 4 * G)
     achieved = alg_bytes / t_launch / 1e9
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
+            "traffic": table.get(top, {}).get("dram_bytes"), "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
             "launch_ms": kernels[top]["ms_per_launch"],
-            "note": "the gather kernels are FP32-issue bound, not HBM bound: see roofline_compute"}
+            "note": "the gather kernels are FP32-issue bound, not HBM bound (see roofline_compute); the per-mode launches of a "
+                    "step run concurrently on side streams, so a launch's event span includes the time it shares the SMs"}
     # compute side: voxel x candidate pair tests per second against the FP32 issue rate
     sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     pair_tests = windows * fz.time_window * G * n_in     # upper bound actually swept: every voxel x in-box atom would be brute force
+    issue_peak = 148 * 4 * sm_mhz * 1e6               # warp instructions / s: 4 schedulers per SM, one issue per clock
+    step_inst = sum(table.get(k, {}).get("warp_instructions", 0.0) * v["launches"] for k, v in kernels.items()) / max(args.steps, 1)
     roof_c = {"bound": "fp32-issue", "kernel": top, "brute_force_pairs_per_launch": pair_tests,
               "brute_force_pairs_per_s": pair_tests / t_launch, "sm_mhz": sm_mhz,
-              "fp32_lane_ops_per_s_peak": 148 * 128 * sm_mhz * 1e6}
+              "fp32_lane_ops_per_s_peak": 148 * 128 * sm_mhz * 1e6,
+              "issue_peak_warp_inst_per_s": issue_peak,
+              # whole step: warp instructions of all its kernels (ncu) / device time of the step / issue peak
+              "step_warp_instructions": step_inst or None,
+              "step_issue_frac": (step_inst / (ms_dev / args.steps * 1e-3) / issue_peak) if step_inst else None,
+              "kernel_issue_active_pct_ncu": table.get(top, {}).get("issue_active_pct")}
   else:
     roof_c = None
 
@@ -380,9 +442,13 @@ def run_reference(args):
 
 
 def main():
+  # libraries (NCCL's version banner ...) print to stdout: everything but the result line goes to stderr
+  real_stdout = os.dup(1)
+  os.dup2(2, 1)
+  sys.stdout = os.fdopen(real_stdout, "w")
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--steps", type=int, default=100)
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
   ap.add_argument("--workload", default="dynamic", choices=sorted(WORKLOADS), help="default: the headline configs[1]")
@@ -390,9 +456,12 @@ def main():
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
   if args.impl == "reference":
+    if args.steps == 100 and "--steps" not in " ".join(sys.argv):
+      args.steps = 6                      # a reference step is ~0.5 s
     run_reference(args)
   else:
     run_native(args)
+  sys.stdout.flush()
 
 
 if __name__ == "__main__":
