@@ -111,6 +111,15 @@ typedef struct {
   int selection;         /* row of `selections`, -1 = every atom */
   int max_atoms;         /* 0 = no cap */
   int sort_table;        /* row of `value_orders` to emit atoms in (distinct_count), -1 = topology order */
+  /* Featurizer.loop_by_residue (/root/reference/nearl/featurizer.py:471-554) featurises a SLICE of the
+   * topology per task: only atoms atom_begin <= a < atom_end are looked at (atom_end <= 0: every atom).
+   * Per-atom tables (weights, selections, residue index) are read at a + table_shift: the reference re-caches
+   * a feature only when the slice length changes (features.py:452-457), so a slice can be read with the
+   * tables of an earlier slice of the same length. */
+  int atom_begin, atom_end;
+  int table_shift;
+  double focal_f64[3];   /* focal point for float64 coordinates (the float32 focal point widened, or the float64
+                            mean of a residue slice, featurizer.py:503) */
 } nrl_crop_t;
 
 /* A task is one (feature, crop): mode 0 = Gaussian voxelisation, otherwise an observable id;

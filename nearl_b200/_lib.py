@@ -34,6 +34,8 @@ class CropStruct(ctypes.Structure):
     ("half_spacing_f32", c_float), ("half_spacing_f64", c_double),
     ("lo", c_double * 3), ("hi", c_double * 3),
     ("byres", c_int), ("selection", c_int), ("max_atoms", c_int), ("sort_table", c_int),
+    ("atom_begin", c_int), ("atom_end", c_int), ("table_shift", c_int),
+    ("focal_f64", c_double * 3),
   ]
 
 

@@ -59,6 +59,19 @@ ELECNEG = _table(_ELECTRONEGATIVITY, float)
 
 RES = "ALA ARG ASN ASP CYS GLU GLN GLY HIS ILE LEU LYS MET PHE PRO SER THR TRP TYR VAL".split()
 
+# residue-classification labels of Featurizer.loop_by_residue (nearl/constants.py:218-237): single residues
+# are numbered in RES order, residue pairs row-major over RES x RES (nearl/constants.py:240-325);
+# protonation / disulfide variants are folded onto their parent residue
+LAB2RES = {i: name for i, name in enumerate(RES)}
+RES2LAB = {name: i for i, name in enumerate(RES)}
+RES_PATCH = {
+  "CYX": "CYS",
+  "HID": "HIS", "HIE": "HIS", "HIP": "HIS",
+  "HSD": "HIS", "HSE": "HIS", "HSP": "HIS",
+}
+RES2LAB_DUAL = {a + b: i * len(RES) + j for i, a in enumerate(RES) for j, b in enumerate(RES)}
+LAB2RES_DUAL = {lab: name for name, lab in RES2LAB_DUAL.items()}
+
 # parameters a Feature inherits from the Featurizer when it does not set them itself
 COMMON_FEATURE_PARMS = [
   "outfile",

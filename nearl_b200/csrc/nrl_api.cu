@@ -71,6 +71,7 @@ struct Ctx {
   std::mutex mu;
   DevBuf coords, weights, perm, atoms, inv, off, cnt, out, tasks, flist, cand_scr, ser_scr, misc, series;
   DevBuf xyz, wtabs, sels, resid, orders, crops, fcrop, fsrc, keep, resflags;
+  DevBuf foff;                                   // per crop frame: first packed atom
   DevBuf batoms, bcnt, cstart, grids, blist;     // cell lists: binned frames, cell prefixes, per-frame cell grids
   bool attr_set[64] = {false};
   cudaStream_t user_stream = nullptr;   // nrl_set_stream: run on the caller's stream instead of our own

@@ -45,6 +45,9 @@ struct NrlCropDev {
   int selection;            // row of the selection-mask table, -1: all atoms
   int max_atoms;            // DynamicFeature.MAX_ALLOWED_ATOMS (features.py:1279,1353-1359), 0: no cap
   int sort_table;           // row of the value-order permutation table, -1: topology order
+  int atom_begin, atom_end; // slice of the topology this crop looks at
+  int table_shift;          // per-atom tables are read at a + table_shift
+  double focal64[3];        // focal point for float64 coordinates
 };
 
 struct NrlCropParams {
@@ -57,7 +60,8 @@ struct NrlCropParams {
   const int *resid;             // [N_all] dense residue index
   int n_res_words;
   const int *perms;             // [n_tabs, N_all]
-  float4 *atoms;                // output, frame fd starts at fd * n_atoms
+  float4 *atoms;                // output, frame fd starts at frame_off[fd]
+  const long long *frame_off;   // per output frame: first packed atom (capacity = the crop's slice length)
   long long *off;
   int *cnt;
   unsigned char *keep;          // unused (kept for ABI stability of the struct)
@@ -67,46 +71,51 @@ struct NrlCropParams {
 template <typename T> struct NrlXform;
 template <> struct NrlXform<float> {
   // numpy: ((x - focal) + center) - float32(spacing/2), every step rounded to float32
-  static __device__ __forceinline__ float apply(float x, float f, float c, const NrlCropDev &cr) {
-    return ((x - f) + c) - cr.half_f32;
+  static __device__ __forceinline__ float apply(float x, int k, const NrlCropDev &cr) {
+    return ((x - cr.focal[k]) + cr.center[k]) - cr.half_f32;
   }
 };
 template <> struct NrlXform<double> {
   // numpy: float64 coordinates promote the float32 focal point and centre exactly
-  static __device__ __forceinline__ double apply(double x, float f, float c, const NrlCropDev &cr) {
-    return ((x - (double)f) + (double)c) - cr.half_f64;
+  static __device__ __forceinline__ double apply(double x, int k, const NrlCropDev &cr) {
+    return ((x - cr.focal64[k]) + (double)cr.center[k]) - cr.half_f64;
   }
 };
 
 #define NRL_CROP_NT 1024
 #define NRL_CROP_NW (NRL_CROP_NT / 32)
 
+// blockDim.x: any multiple of 32 up to NRL_CROP_NT (short slices of the topology get small CTAs)
 template <typename T>
 __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCropParams p) {
-  extern __shared__ unsigned int s_keep[];            // one bit per atom of the frame
+  extern __shared__ unsigned int s_keep[];            // one bit per atom of the slice
   __shared__ int s_wcnt[NRL_CROP_NW];
   const int fd = blockIdx.x;
   const NrlCropDev &cr = p.crops[p.frame_crop[fd]];
   const int N = p.n_atoms;
-  const T *__restrict__ xyz = reinterpret_cast<const T *>(p.xyz) + (long long)p.frame_src[fd] * N * 3;
+  const int a0 = cr.atom_begin, n = cr.atom_end - cr.atom_begin;   // the slice [a0, a0 + n) of the topology
+  const int shift = cr.table_shift;
+  const T *__restrict__ xyz = reinterpret_cast<const T *>(p.xyz) + ((long long)p.frame_src[fd] * N + a0) * 3;
   unsigned int *__restrict__ resflags = p.resflags + (long long)fd * p.n_res_words;
-  const unsigned char *__restrict__ sel = cr.selection >= 0 ? p.sel + (long long)cr.selection * N : nullptr;
+  const unsigned char *__restrict__ sel = cr.selection >= 0 ? p.sel + (long long)cr.selection * N + a0 + shift : nullptr;
+  const int *__restrict__ resid = p.resid + a0 + shift;
+  const int nt = blockDim.x, nw = nt >> 5;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n_pad = (N + 31) & ~31;
+  const int n_pad = (n + 31) & ~31;
 
   // phase A: transform + strict two-sided crop per axis, in the coordinate dtype; a warp handles 32
   // consecutive atoms (384 contiguous bytes of float32 coordinates) and ballots their flags into one word
 #pragma unroll 4
-  for (int a = tid; a < n_pad; a += NRL_CROP_NT) {
+  for (int a = tid; a < n_pad; a += nt) {
     bool in = false;
-    if (a < N) {
-      const T x = NrlXform<T>::apply(xyz[3 * a], cr.focal[0], cr.center[0], cr);
-      const T y = NrlXform<T>::apply(xyz[3 * a + 1], cr.focal[1], cr.center[1], cr);
-      const T z = NrlXform<T>::apply(xyz[3 * a + 2], cr.focal[2], cr.center[2], cr);
+    if (a < n) {
+      const T x = NrlXform<T>::apply(xyz[3 * a], 0, cr);
+      const T y = NrlXform<T>::apply(xyz[3 * a + 1], 1, cr);
+      const T z = NrlXform<T>::apply(xyz[3 * a + 2], 2, cr);
       in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
            ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
       if (cr.byres && in) {
-        const int r = p.resid[a];
+        const int r = resid[a];
         atomicOr(&resflags[r >> 5], 1u << (r & 31));
       }
       if (!cr.byres && sel) in = in && (sel[a] != 0);
@@ -117,10 +126,10 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
   __syncthreads();
   if (cr.byres) {
     // whole residues of any kept atom (features.py:471-475), then the selection mask
-    for (int a = tid; a < n_pad; a += NRL_CROP_NT) {
+    for (int a = tid; a < n_pad; a += nt) {
       bool k = false;
-      if (a < N) {
-        const int r = p.resid[a];
+      if (a < n) {
+        const int r = resid[a];
         k = (resflags[r >> 5] >> (r & 31)) & 1u;
         if (sel) k = k && (sel[a] != 0);
       }
@@ -129,6 +138,7 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
     }
     __syncthreads();
   }
+  // value-ordered emission: the permutation lists the atoms of the WHOLE topology (slices are not supported here)
   const int *__restrict__ perm = cr.sort_table >= 0 ? p.perms + (long long)cr.sort_table * N : nullptr;
   if (perm && cr.max_atoms > 0) {
     // the cap keeps the first max_atoms atoms in TOPOLOGY order; resolve it before the
@@ -152,8 +162,8 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
   }
 
   // phase B: order-preserving compaction in emission order, warp-contiguous segments
-  const int seg = ((N + NRL_CROP_NW - 1) / NRL_CROP_NW + 31) & ~31;
-  const int e_begin = min(warp * seg, N), e_end = min(e_begin + seg, N);
+  const int seg = ((n + nw - 1) / nw + 31) & ~31;
+  const int e_begin = min(warp * seg, n), e_end = min(e_begin + seg, n);
   int mycnt = 0;
   if (!perm) {
     if (e_begin < e_end)
@@ -171,10 +181,10 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
   if (lane == 0) s_wcnt[warp] = mycnt;
   __syncthreads();
   int base = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < NRL_CROP_NW; ++w) { const int c = s_wcnt[w]; if (w < warp) base += c; total += c; }
+  for (int w = 0; w < nw; ++w) { const int c = s_wcnt[w]; if (w < warp) base += c; total += c; }
   const int cap = (cr.max_atoms > 0 && !perm) ? cr.max_atoms : 0x7fffffff;
-  float4 *out = p.atoms + (long long)fd * N;
+  const long long foff = p.frame_off[fd];
+  float4 *out = p.atoms + foff;
   for (int e0 = e_begin; e0 < e_end; e0 += 32) {
     const int e = e0 + lane;
     bool k = false;
@@ -191,14 +201,14 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
     if (m == 0u) continue;
     const int pos = base + __popc(m & ((1u << lane) - 1u));
     if (k && pos < cap) {
-      const T x = NrlXform<T>::apply(xyz[3 * a], cr.focal[0], cr.center[0], cr);
-      const T y = NrlXform<T>::apply(xyz[3 * a + 1], cr.focal[1], cr.center[1], cr);
-      const T z = NrlXform<T>::apply(xyz[3 * a + 2], cr.focal[2], cr.center[2], cr);
-      out[pos] = make_float4((float)x, (float)y, (float)z, __int_as_float(a));   // commands.*: astype(float32)
+      const T x = NrlXform<T>::apply(xyz[3 * a], 0, cr);
+      const T y = NrlXform<T>::apply(xyz[3 * a + 1], 1, cr);
+      const T z = NrlXform<T>::apply(xyz[3 * a + 2], 2, cr);
+      out[pos] = make_float4((float)x, (float)y, (float)z, __int_as_float(a0 + a + shift));   // commands.*: astype(float32)
     }
     base += __popc(m);
   }
-  if (tid == 0) { p.off[fd] = (long long)fd * N; p.cnt[fd] = min(total, cap); }
+  if (tid == 0) { p.off[fd] = foff; p.cnt[fd] = min(total, cap); }
 }
 
 // ---- per-atom normalisation of the voxeliser -------------------------------------------

@@ -360,6 +360,16 @@ class Feature:
       memos[id(self.cached_array)] = memo = (self.cached_array, ranks)
     return memo[1]
 
+  def _slice_invariant(self):
+    """True when the cached per-atom values of an atom do not depend on which slice of the topology the
+    feature was cached on (Featurizer.loop_by_residue caches on residue slices): table lookups by element /
+    atom name are, positions inside the slice (atomic_id, residue_id) and number-based masks are not."""
+    if isinstance(self.selection, str) and any(ch.isdigit() for ch in self.selection):
+      return False
+    if self.selection is not None and not isinstance(self.selection, str):
+      return False
+    return True
+
   def _is_builtin(self, *methods):
     """True when none of `methods` was overridden outside this module (a user subclass that
     customises query/run must go through the host protocol)."""
@@ -529,6 +539,10 @@ class DynamicFeature(Feature):
 
   def __str__(self):
     return f"{self.classname} <agg:{self._agg_type}|weight:{self._weight_type}|cutoff:{self.cutoff}>"
+
+  def _slice_invariant(self):
+    # atomic_id / residue_id number atoms and residues inside the topology slice the feature was cached on
+    return super()._slice_invariant() and self.weight_type not in (1, 2)
 
   @property
   def agg(self):

@@ -417,6 +417,7 @@ class Featurizer:
     for ci, (bid, pid) in enumerate(tpl["crop_slots"]):
       focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else zero
       crops[ci].focal[0], crops[ci].focal[1], crops[ci].focal[2] = float(focal[0]), float(focal[1]), float(focal[2])
+      crops[ci].focal_f64[0], crops[ci].focal_f64[1], crops[ci].focal_f64[2] = float(focal[0]), float(focal[1]), float(focal[2])
     batch.crops, batch.tasks, batch.shapes, batch.out_floats = crops, tpl["tasks"], tpl["shapes"], tpl["out_floats"]
     rows = [specs[f]["weights"] for f in native_feats] + [specs[f]["ranks"] for f in tpl["rank_feats"]]
     batch.weight_tables = self._table_buffer(lane, "weights", (len(rows), n_atoms), np.float32)

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import constants
 
-__all__ = ["Atom", "Topology", "Trajectory", "synthetic_trajectory", "synthetic_complex", "pinned_empty"]
+__all__ = ["Atom", "Residue", "Topology", "Trajectory", "synthetic_trajectory", "synthetic_complex", "pinned_empty"]
 
 
 def pinned_empty(shape, dtype):
@@ -44,6 +44,20 @@ class Atom:
     self.atomic_number = int(atomic_number)
 
 
+class Residue:
+  """The attributes of a pytraj Residue the reference reads (utils.py:590-594,617-652)."""
+  __slots__ = ("index", "name", "first_atom_index", "last_atom_index")
+
+  def __init__(self, index, name, first_atom_index, last_atom_index):
+    self.index = int(index)
+    self.name = name
+    self.first_atom_index = int(first_atom_index)
+    self.last_atom_index = int(last_atom_index)
+
+  def __repr__(self):
+    return f"<Residue {self.name}{self.index} atoms {self.first_atom_index}:{self.last_atom_index}>"
+
+
 class Topology:
   """Column-store topology with an Amber-mask subset (``select``)."""
 
@@ -67,12 +81,22 @@ class Topology:
                      for i in range(self.n_atoms)]
     return self._atoms
 
+  def residue_blocks(self):
+    """(name, first_atom_index, last_atom_index) of every residue = maximal run of atoms with one residue id;
+    `last_atom_index` is one past the residue's last atom, as in pytraj / cpptraj."""
+    memo = self.__dict__.get("_residue_blocks")
+    if memo is None:
+      n = self.n_atoms
+      starts = np.flatnonzero(np.r_[True, self.resids[1:] != self.resids[:-1]]) if n else np.zeros(0, dtype=int)
+      ends = np.r_[starts[1:], n] if n else starts
+      memo = self._residue_blocks = [(str(self.resnames[b]), int(b), int(e)) for b, e in zip(starts, ends)]
+    return memo
+
   @property
   def residues(self):
-    seen = {}
-    for rid, rname in zip(self.resids.tolist(), self.resnames.tolist()):
-      seen.setdefault(rid, rname)
-    return list(seen.items())
+    """Iterator over the residues (pytraj's Topology.residues is one, and
+    /root/reference/nearl/utils.py:617-623 drives it with next())."""
+    return iter(Residue(i, name, b, e) for i, (name, b, e) in enumerate(self.residue_blocks()))
 
   def __getitem__(self, key):
     idx = np.arange(self.n_atoms)[key]

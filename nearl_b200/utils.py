@@ -9,6 +9,7 @@ active (the featuriser opens one per trajectory) appends are buffered per (file,
 written with one open/close per file, instead of the reference's open/close per result.
 """
 import contextlib
+import sys
 
 import numpy as np
 
@@ -17,9 +18,9 @@ try:
 except Exception:          # pragma: no cover - depends on the image
   _h5py = None
 
-from . import hdf5_lite
+from . import constants, hdf5_lite
 
-__all__ = ["append_hdf_data", "dump_dict", "batched_output", "open_hdf", "hdf_backend"]
+__all__ = ["append_hdf_data", "dump_dict", "batched_output", "open_hdf", "hdf_backend", "find_block_single", "find_block_dual"]
 
 _pending = None     # {(file, key): {"rows": [...], "dtype":, "maxshape":, "kwargs":}} while batching
 
@@ -89,3 +90,41 @@ def dump_dict(outfile, groupname, dic):
     grp = hdf.create_group(groupname)
     for key, val in dic.items():
       grp[key] = val
+
+
+# ---- residue blocks of Featurizer.loop_by_residue ---------------------------------------------------
+def _known_residue(name):
+  return name in constants.RES or name in constants.RES_PATCH
+
+
+def find_block_single(traj, key):
+  """Atom slices of every residue named `key`, in topology order (utils.py:573-596)."""
+  return [np.s_[res.first_atom_index:res.last_atom_index] for res in traj.top.residues if res.name == key]
+
+
+def find_block_dual(traj, key):
+  """Atom slices of every pair of consecutive residues whose names concatenate to `key` and whose
+  peptide bond (C of the first, N of the second, first frame of the trajectory) is at most
+  1.32 * 1.25 A long (utils.py:599-659)."""
+  threshold = 1.32 * 1.25
+  coord = np.asarray(traj.xyz[0])
+  results = []
+  previous = None
+  for this in traj.top.residues:
+    if previous is not None and f"{previous.name}{this.name}" == key:
+      top1 = traj.top[previous.first_atom_index:previous.last_atom_index]
+      top2 = traj.top[this.first_atom_index:this.last_atom_index]
+      atomc, atomn = top1.select("@C"), top2.select("@N")
+      if not (_known_residue(previous.name) and _known_residue(this.name)):
+        print(f"Residue pair {previous.name}-{this.name} is not supported yet", file=sys.stderr)
+      elif len(atomc) == 0 or len(atomn) == 0:
+        pass
+      elif len(atomc) > 1 or len(atomn) > 1:
+        print("Warning: More than one C or N atom found in the residue, meaning there are some problem with the input structure.")
+      else:
+        crd1 = coord[previous.first_atom_index:previous.last_atom_index]
+        crd2 = coord[this.first_atom_index:this.last_atom_index]
+        if np.linalg.norm(crd1[atomc[0]] - crd2[atomn[0]]) <= threshold:
+          results.append(np.s_[previous.first_atom_index:this.last_atom_index])
+    previous = this
+  return results
