@@ -318,6 +318,220 @@ class Featurizer:
     stats["frames"] += job["traj"].n_frames // self.time_window * self.time_window
     printit(f"{self.classname}: Finished the trajectory {tid + 1} / {self.TRAJECTORYNUMBER} with {len(task_keys)} tasks in {time.perf_counter() - job['start']:.6f} seconds")
 
+  # ---- residue-classification data sets ------------------------------------------------------------
+  def _residue_blocks(self, restype, tag_limit=0):
+    """[(atom slice, label)] of the active trajectory in the reference's order
+    (featurizer.py:487-532): residue names in constants.RES + RES_PATCH order, blocks in topology order."""
+    names = list(constants.RES) + list(constants.RES_PATCH.keys())
+    patched = lambda name: constants.RES_PATCH.get(name, name)
+    blocks = []
+    if restype == "single":
+      for name in names:
+        label = constants.RES2LAB[patched(name)]
+        for sidx, s_ in enumerate(utils.find_block_single(self.traj, name)):
+          if tag_limit > 0 and sidx >= tag_limit:
+            break
+          blocks.append((s_, label))
+    elif restype == "dual":
+      pairs = utils.dual_blocks_by_key(self.traj)         # one pass; same lists as find_block_dual(traj, key)
+      for res1 in names:
+        for res2 in names:
+          label = constants.RES2LAB_DUAL.get(patched(res1) + patched(res2), "Unknown")
+          for s_ in pairs.get(res1 + res2, ()):
+            blocks.append((s_, label))
+    else:
+      raise ValueError(f"Unexpected residue type {restype!r}; choose 'single' or 'dual'")
+    return blocks
+
+  def loop_by_residue(self, restype, tag_limit=0, process_nr=None, chunk_floats=1 << 26, **_ignored):
+    """Featurise every single residue (``restype="single"``) or every bonded residue pair (``"dual"``) of
+    every trajectory as its own sample: the atoms of the block only, the box centred on the block's centre
+    of geometry in the first frame of each window (/root/reference/nearl/featurizer.py:471-554).  Rows are
+    appended per feature in the order window -> residue name -> block; the class labels go to the
+    dataset ``label`` of the featuriser's ``outfile``.
+
+    All (window, block, feature) tasks of a window go to the device in a few batched calls (the crop
+    kernel reads the block's atoms only).  Two behaviours of the reference are reproduced on purpose:
+    a feature is re-cached only when the block length changes (features.py:452-457), so a block is read
+    with the per-atom tables of the last block of a different length that preceded one of its own length;
+    and ``label`` receives the first n_blocks entries of the per-TASK label list (featurizer.py:545-549).
+    `process_nr` (some scripts pass a worker count) is accepted and ignored."""
+    stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "blocks": 0, "seconds": 0.0}
+    t_run = time.perf_counter()
+    for tid in range(self.TRAJECTORYNUMBER):
+      self.traj = self.TRAJLOADER[tid]
+      printit(f"{self.classname}: Start processing the trajectory {tid + 1} with {self.SLICENUMBER} frames")
+      for feat in self.FEATURESPACE:
+        feat.cache(self.traj)
+      blocks = self._residue_blocks(restype, tag_limit)
+      specs = [feat._native_spec() if (self.use_native_batch and hasattr(feat, "_native_spec") and feat._slice_invariant())
+               else None for feat in self.FEATURESPACE]
+      for f, sp in enumerate(specs):
+        if sp is not None and sp["mode"] == 3 and sp.get("ranks") is None:
+          specs[f] = None          # value-ordered crops cannot be sliced: host protocol
+      native_feats = [f for f in range(self.FEATURENUMBER) if specs[f] is not None]
+      generic_feats = [f for f in range(self.FEATURENUMBER) if specs[f] is None]
+      xyz = self.traj.xyz
+      if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
+      n_all = xyz.shape[1]
+      labels = []
+      # the reference's cache state: length of the slice the features were last cached on, and where it starts
+      cached_len, src_first = n_all, 0
+      pending = None
+      with utils.batched_output():
+        for bid in range(self.SLICENUMBER):
+          first = bid * self.time_window
+          frames = xyz[self.FRAMESLICES[bid]]
+          starts = np.array([s_.start for s_, _ in blocks], dtype=np.int64)
+          stops = np.array([s_.stop for s_, _ in blocks], dtype=np.int64)
+          shifts = np.zeros(len(blocks), dtype=np.int64)
+          focal = np.zeros((len(blocks), 3), dtype=xyz.dtype)
+          for k, (s_, label) in enumerate(blocks):
+            if stops[k] - starts[k] != cached_len:
+              cached_len, src_first = int(stops[k] - starts[k]), int(starts[k])
+            shifts[k] = src_first - starts[k]
+            focal[k] = np.mean(frames[0, s_], axis=0)                   # featurizer.py:503
+            labels.extend([label] * self.FEATURENUMBER)
+          # host-protocol features first (they follow the reference call by call, cache state included)
+          generic = {}
+          for k, (s_, label) in enumerate(blocks):
+            for f in generic_feats:
+              feat = self.FEATURESPACE[f]
+              sub_top = self.traj.top[s_]
+              generic[(k, f)] = feat.run(*feat.query(sub_top, frames[:, s_, :].copy(), focal[k]))
+          # native features: chunks of blocks, pipelined over the two lanes
+          per_block = sum(int(np.prod(self.FEATURESPACE[f].dims)) for f in native_feats)
+          step = max(1, int(chunk_floats // max(per_block, 1))) if native_feats else max(len(blocks), 1)
+          for c0 in range(0, len(blocks), step):
+            c1 = min(c0 + step, len(blocks))
+            job = {"bid": bid, "c0": c0, "c1": c1, "generic": generic, "native": None}
+            if native_feats:
+              lane = (c0 // step + bid) % 2
+              batch = self._lower_residue_batch(native_feats, specs, xyz.dtype == np.float64, first, starts[c0:c1], stops[c0:c1],
+                                                shifts[c0:c1], focal[c0:c1], n_all, lane)
+              buffers = self.__dict__.setdefault("_out_buffers", {})
+              if lane not in buffers or buffers[lane].size < batch.out_floats:
+                buffers[lane] = pinned_empty((batch.out_floats,), np.float32)
+              out = buffers[lane][:batch.out_floats]
+              batch.execute(_lib.ptr(xyz), xyz.shape[0], _lib.ptr(out), no_sync=True, lane=lane)
+              job["native"] = (batch, out, lane)
+            if pending is not None:
+              self._finish_residue_chunk(pending, native_feats, generic_feats, stats)
+            pending = job
+        if pending is not None:
+          self._finish_residue_chunk(pending, native_feats, generic_feats, stats)
+          pending = None
+      stats["blocks"] += len(blocks) * self.SLICENUMBER
+      printit(f"{self.classname}: Tasks are finished, dumping the results to the feature space...")
+      outfile = self.FEATURE_PARMS.get("outfile", None)
+      if outfile is not None and self.FEATURENUMBER:
+        lab = np.array(labels, dtype=int)[:len(labels) // self.FEATURENUMBER]
+        opts = {"chunks": True}
+        if (self.FEATURE_PARMS.get("hdf_compress_level", 0) or 0) > 0:
+          opts.update(compression="gzip", compression_opts=int(self.FEATURE_PARMS["hdf_compress_level"]))
+        utils.append_hdf_data(outfile, "label", lab, dtype=int, maxshape=(None,), **opts)
+      if self.keep_results:
+        self.RESULTS.setdefault("label", []).extend(labels[:len(labels) // max(self.FEATURENUMBER, 1)])
+      stats["trajectories"] += 1
+    stats["seconds"] = time.perf_counter() - t_run
+    self.last_run_stats = stats
+    printit(f"{self.classname}: All trajectories and tasks are finished")
+    return stats
+
+  def _finish_residue_chunk(self, job, native_feats, generic_feats, stats):
+    """Dump the results of one chunk of blocks in the reference's order (block -> feature)."""
+    native = {}
+    if job["native"] is not None:
+      batch, out, lane = job["native"]
+      _lib.check(_lib.lib().nrl_lane_synchronize(lane))
+      grids = batch.split(out, copy=self.keep_results)
+      for i in range(job["c1"] - job["c0"]):
+        for j, f in enumerate(native_feats):
+          native[(job["c0"] + i, f)] = grids[i * len(native_feats) + j]
+    for k in range(job["c0"], job["c1"]):
+      for f in range(self.FEATURENUMBER):
+        result = native[(k, f)] if (k, f) in native else job["generic"][(k, f)]
+        feat = self.FEATURESPACE[f]
+        if self.result_sink is not None:
+          self.result_sink(feat.outkey, self.traj.identity, job["bid"], k, result)
+        if self.keep_results:
+          self.RESULTS.setdefault(feat.outkey, []).append(result)
+        if feat.outfile or (self.result_sink is None and not self.keep_results):
+          feat.dump(result)
+        stats["tasks"] += 1
+        stats["native_tasks"] += 1 if (k, f) in native else 0
+
+  def _lower_residue_batch(self, native_feats, specs, is_f64, first_frame, starts, stops, shifts, focal, n_atoms, lane):
+    """Crop / task tables for the blocks [starts, stops) of ONE window: per block one crop per crop class
+    (features that share frames, padding, by-residue, selection and cap) and one task per native feature."""
+    feats = [self.FEATURESPACE[f] for f in native_feats]
+    sel_feats = [f for f in native_feats if self.FEATURESPACE[f].selection is not None and not specs[f].get("selection_folded")]
+    sel_of = {f: i for i, f in enumerate(sel_feats)}
+    rank_feats = [f for f in native_feats if specs[f]["mode"] == 3]
+    rank_of = {f: len(native_feats) + i for i, f in enumerate(rank_feats)}
+    classes, class_of = [], {}
+    for f in native_feats:
+      feat, spec = self.FEATURESPACE[f], specs[f]
+      half = feat.spacing / 2
+      lo = 0 - feat.padding - half
+      lo_cmp = float(np.float32(lo)) if not is_f64 else lo
+      hi = tuple(float(feat.lengths[k] + feat.padding - half) for k in range(3))
+      static = spec["kind"] == "static"
+      key = (first_frame + (spec["frame_offset"] if static else 0), 1 if static else self.time_window, feat.center.tobytes(), half,
+             lo_cmp, hi, bool(feat.byres), sel_of.get(f, -1), spec["max_atoms"], bool(feat.force_recache))
+      if key not in classes:
+        classes.append(key)
+      class_of[f] = classes.index(key)
+    nb, nc, nf = len(starts), len(classes), len(native_feats)
+    crops = np.zeros((nb, nc), dtype=np.dtype(_lib.CropStruct, align=True))
+    for ci, (start, n_frames, center, half, lo_cmp, hi, byres, sid, max_atoms, recache) in enumerate(classes):
+      col = crops[:, ci]
+      col["frame_start"], col["n_frames"] = start, n_frames
+      col["focal"] = focal.astype(np.float32)
+      col["focal_f64"] = focal.astype(np.float64)
+      col["center"] = np.frombuffer(center, dtype=np.float32)
+      col["half_spacing_f32"], col["half_spacing_f64"] = np.float32(half), half
+      col["lo"], col["hi"] = lo_cmp, hi
+      col["byres"], col["selection"], col["max_atoms"], col["sort_table"] = int(byres), sid, max_atoms, -1
+      col["atom_begin"], col["atom_end"] = starts, stops
+      col["table_shift"] = 0 if recache else shifts
+    tasks = np.zeros((nb, nf), dtype=np.dtype(_lib.TaskStruct, align=True))
+    shapes = []
+    for j, f in enumerate(native_feats):
+      feat, spec = self.FEATURESPACE[f], specs[f]
+      col = tasks[:, j]
+      col["crop"] = np.arange(nb) * nc + class_of[f]
+      col["mode"], col["agg"], col["weight_table"] = spec["mode"], spec["agg"], j
+      col["dims"] = [int(v) for v in feat.dims]
+      col["spacing"], col["cutoff"], col["sigma"] = float(feat.spacing), float(feat.cutoff), float(spec["sigma"])
+      col["rank_table"] = rank_of.get(f, -1)
+      shapes.append(tuple(int(v) for v in feat.dims))
+    batch = LoweredBatch()
+    batch.n_atoms, batch.is_f64 = n_atoms, bool(is_f64)
+    batch._keep = (crops, tasks)       # the ctypes views below borrow these arrays
+    batch.crops = crops.ctypes.data_as(ctypes.POINTER(_lib.CropStruct))
+    batch.n_crops = nb * nc
+    batch.tasks = tasks.ctypes.data_as(ctypes.POINTER(_lib.TaskStruct))
+    batch.n_tasks = nb * nf
+    batch.shapes = shapes * nb
+    batch.out_floats = int(sum(sh[0] * sh[1] * sh[2] for sh in shapes)) * nb
+    rows = [specs[f]["weights"] for f in native_feats] + [specs[f]["ranks"] for f in rank_feats]
+    batch.weight_tables = self._table_buffer(lane, "weights", (len(rows), n_atoms), np.float32)
+    for i, row in enumerate(rows):
+      batch.weight_tables[i] = row
+    batch.selections = None
+    if sel_feats:
+      batch.selections = self._table_buffer(lane, "selections", (len(sel_feats), n_atoms), np.uint8)
+      for i, f in enumerate(sel_feats):
+        batch.selections[i] = self.FEATURESPACE[f].selected
+    batch.value_orders = None
+    batch.residue_index, batch.n_residues = None, 0
+    if any(c[6] for c in classes):
+      uniq, inverse = np.unique(feats[0].resids, return_inverse=True)
+      batch.residue_index, batch.n_residues = np.ascontiguousarray(inverse, dtype=np.int32), len(uniq)
+    return batch
+
   # ---- lowering to nrl_featurize_batch --------------------------------------------------------
   def _template(self, native_feats, specs, n_atoms, is_f64):
     """Crop / task tables for the current (features, windows, focal points) structure.  Only the
@@ -453,8 +667,8 @@ class LoweredBatch:
     b.residue_index = _lib.ptr(self.residue_index) if self.residue_index is not None else None
     b.n_residues = self.n_residues
     b.value_orders = _lib.ptr(self.value_orders) if self.value_orders is not None else None
-    b.crops, b.n_crops = self.crops, len(self.crops)
-    b.tasks, b.n_tasks = self.tasks, len(self.tasks)
+    b.crops, b.n_crops = self.crops, getattr(self, "n_crops", None) or len(self.crops)
+    b.tasks, b.n_tasks = self.tasks, getattr(self, "n_tasks", None) or len(self.tasks)
     b.out, b.out_on_device = out_ptr, int(out_on_device)
     b.atom_counts = None
     b.flags = 1 if no_sync else 0

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import constants
 
-__all__ = ["Atom", "Residue", "Topology", "Trajectory", "synthetic_trajectory", "synthetic_complex", "pinned_empty"]
+__all__ = ["Atom", "Residue", "Topology", "Trajectory", "synthetic_trajectory", "synthetic_complex", "synthetic_peptide", "pinned_empty"]
 
 
 def pinned_empty(shape, dtype):
@@ -268,3 +268,42 @@ def synthetic_complex(n_atoms, seed, ligand_atoms=30, dtype=np.float32, identity
   xyz = pinned_empty((1, n_atoms, 3), dtype) if pin else np.empty((1, n_atoms, 3), dtype=dtype)
   xyz[0] = frame.astype(dtype)
   return Trajectory(xyz, top, identity or f"complex_{n_atoms}_{seed}")
+
+
+def synthetic_peptide(n_residues, n_frames, seed, dtype=np.float32, identity=None, pin=False, break_every=0):
+  """A chain of residues of DIFFERENT lengths with real peptide geometry between neighbours (C of residue i
+  1.32 A from N of residue i+1), for Featurizer.loop_by_residue: residue names are drawn from the 20 amino
+  acids plus the HID / CYX variants, a residue of a given name always has the same number of atoms and some
+  names share a length.  `break_every` > 0 opens the chain after every that many residues."""
+  rng = np.random.default_rng(seed)
+  pool = list(constants.RES) + ["HID", "CYX"]
+  size_of = {name: 8 + (3 * i) % 11 for i, name in enumerate(pool)}
+  res_names = [pool[i] for i in rng.integers(0, len(pool), size=n_residues)]
+  centres = np.cumsum(rng.normal(0.0, 1.0, size=(n_residues + 1, 3)) * 2.2 + np.array([3.0, 0.0, 0.0]), axis=0)
+  names, resids, resnames, z, xyz0 = [], [], [], [], []
+  for r, rname in enumerate(res_names):
+    n = size_of[rname]
+    t_prev = centres[r] - centres[r - 1] if r > 0 else centres[1] - centres[0]
+    t_next = centres[r + 1] - centres[r]
+    t_prev, t_next = t_prev / np.linalg.norm(t_prev), t_next / np.linalg.norm(t_next)
+    pos = centres[r] + rng.normal(0.0, 1.3, size=(n, 3))
+    elem = rng.choice(_ELEMENTS, size=n, p=_ELEMENT_P)
+    nm = [f"X{j}" for j in range(n)]
+    # backbone: N next to the previous residue's C, CA at the centre, C towards the next residue, O beside it
+    gap = 3.0 if (break_every and r % break_every == 0) else 0.0
+    pos[0] = (centres[r - 1] + centres[r]) / 2 + (0.66 + gap) * t_prev if r > 0 else centres[r] - 1.4 * t_next
+    pos[1] = centres[r]
+    pos[2] = (centres[r] + centres[r + 1]) / 2 - 0.66 * t_next
+    pos[3] = pos[2] + np.array([0.0, 1.2, 0.0])
+    for slot, (an, zz) in enumerate((("N", 7), ("CA", 6), ("C", 6), ("O", 8))):
+      nm[slot], elem[slot] = an, zz
+    names += nm; resids += [r] * n; resnames += [rname] * n; z += list(elem); xyz0.append(pos)
+  top = Topology(names, resids, resnames, z)
+  frame = np.concatenate(xyz0, axis=0)
+  n_atoms = len(frame)
+  xyz = pinned_empty((n_frames, n_atoms, 3), dtype) if pin else np.empty((n_frames, n_atoms, 3), dtype=dtype)
+  for t in range(n_frames):
+    if t:
+      frame = frame + rng.normal(0.0, 0.15, size=(n_atoms, 3))
+    xyz[t] = frame.astype(dtype)
+  return Trajectory(xyz, top, identity or f"peptide_{n_residues}x{n_frames}_{seed}")

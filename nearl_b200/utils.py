@@ -20,7 +20,7 @@ except Exception:          # pragma: no cover - depends on the image
 
 from . import constants, hdf5_lite
 
-__all__ = ["append_hdf_data", "dump_dict", "batched_output", "open_hdf", "hdf_backend", "find_block_single", "find_block_dual"]
+__all__ = ["append_hdf_data", "dump_dict", "batched_output", "open_hdf", "hdf_backend", "find_block_single", "find_block_dual", "dual_blocks_by_key"]
 
 _pending = None     # {(file, key): {"rows": [...], "dtype":, "maxshape":, "kwargs":}} while batching
 
@@ -100,6 +100,31 @@ def _known_residue(name):
 def find_block_single(traj, key):
   """Atom slices of every residue named `key`, in topology order (utils.py:573-596)."""
   return [np.s_[res.first_atom_index:res.last_atom_index] for res in traj.top.residues if res.name == key]
+
+
+def dual_blocks_by_key(traj):
+  """{name1 + name2: [atom slices]} of every bonded pair of consecutive residues, in topology order: the lists
+  find_block_dual returns for each key, from one pass over the residues (memoised on the topology + first frame)."""
+  memo = traj.top.__dict__.get("_dual_blocks_memo")
+  if memo is not None and memo[0] is traj.xyz:
+    return memo[1]
+  threshold = 1.32 * 1.25
+  coord = np.asarray(traj.xyz[0])
+  out = {}
+  previous = None
+  names = np.asarray(traj.top.names, dtype=object) if hasattr(traj.top, "names") else None
+  for this in traj.top.residues:
+    if previous is not None and _known_residue(previous.name) and _known_residue(this.name):
+      b1, e1, b2, e2 = previous.first_atom_index, previous.last_atom_index, this.first_atom_index, this.last_atom_index
+      if names is not None:
+        atomc, atomn = np.flatnonzero(names[b1:e1] == "C"), np.flatnonzero(names[b2:e2] == "N")
+      else:
+        atomc, atomn = traj.top[b1:e1].select("@C"), traj.top[b2:e2].select("@N")
+      if len(atomc) == 1 and len(atomn) == 1 and np.linalg.norm(coord[b1 + atomc[0]] - coord[b2 + atomn[0]]) <= threshold:
+        out.setdefault(f"{previous.name}{this.name}", []).append(np.s_[b1:e2])
+    previous = this
+  traj.top.__dict__["_dual_blocks_memo"] = (traj.xyz, out)
+  return out
 
 
 def find_block_dual(traj, key):

@@ -11,6 +11,8 @@ trajectory and the native calls:
   static query/run  /root/reference/nearl/features.py:485-508,599-605
   dynamic query     /root/reference/nearl/features.py:1329-1368 (9999-atom padded layout)
   NaN -> 0 at dump  /root/reference/nearl/features.py:521-523
+  residue loop      /root/reference/nearl/featurizer.py:471-554 (loop_by_residue), with the feature
+                    re-cache rule of /root/reference/nearl/features.py:452-457
 
 Parity status: the reference's Python layers cannot be imported on this image (they need
 h5py and pytraj at module import), so this file is pinned only by reading the cited lines;
@@ -149,3 +151,32 @@ def featurize(xyz, resids, descs, focal, time_window, buff_dim=-1, scrub_nan=Tru
           res = np.nan_to_num(res).astype(res.dtype)
         out[d["outkey"]].append(res)
   return {k: np.array(v, dtype=np.float32) for k, v in out.items()}
+
+
+def featurize_by_residue(xyz, resids, descs, blocks, time_window, buff_dim=-1, scrub_nan=True, kernels=None):
+  """loop_by_residue for one trajectory: every block (atom slice, label) of every window is a sample made of
+  the block's atoms only, centred on the block's centre of geometry in the window's first frame
+  (featurizer.py:487-506).  `descs[i]["weights"]` / ["selection"] are whole-topology arrays of slice-invariant
+  per-atom values; a feature is re-cached on the block -- i.e. takes the block's part of them -- only when the
+  block length differs from the length it was last cached on (features.py:452-457), otherwise it keeps the
+  arrays of that earlier block.  Returns ({outkey: rows}, labels as written to the `label` dataset)."""
+  n_slices = xyz.shape[0] // time_window
+  out = {d["outkey"]: [] for d in descs}
+  state = [{"len": xyz.shape[1], "w": np.asarray(d["weights"]), "sel": d.get("selection"), "resids": resids} for d in descs]
+  task_labels = []
+  for bid in range(n_slices):
+    frames = xyz[bid * time_window:(bid + 1) * time_window]
+    for s_, label in blocks:
+      sub = frames[:, s_, :]
+      focal = np.mean(sub[0], axis=0)
+      for d, st in zip(descs, state):
+        if st["len"] != sub.shape[1]:
+          st.update(len=sub.shape[1], w=np.asarray(d["weights"])[s_], resids=resids[s_],
+                    sel=(np.asarray(d["selection"])[s_] if d.get("selection") is not None else None))
+        res = run_task(dict(d, weights=st["w"], selection=st["sel"]), st["resids"], sub.copy(), focal, buff_dim=buff_dim, kernels=kernels)
+        if scrub_nan and np.isnan(res).any():
+          res = np.nan_to_num(res).astype(res.dtype)
+        out[d["outkey"]].append(res)
+        task_labels.append(label)
+  labels = np.array(task_labels, dtype=int)[:len(task_labels) // max(len(descs), 1)]      # featurizer.py:545-549
+  return {k: np.array(v, dtype=np.float32) for k, v in out.items()}, labels
