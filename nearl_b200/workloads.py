@@ -108,3 +108,19 @@ def stress_large(n_traj=1, n_atoms=200000, n_frames=200, window=100, dim=128, se
   fz.register_focus([":ARG"], "mask")
   fz.register_trajloader(trajs)
   return fz, trajs
+
+
+def residue_classification(n_traj=1, n_residues=300, n_frames=100, seed_offset=0, outfile=None, pin=True):
+  """Residue-classification data set (Featurizer.loop_by_residue, /root/reference/scripts/residue_dynamic_generation.py):
+  every residue of a 300-residue chain is a sample per window of 10 frames, 2 static + 2 dynamic channels at 32^3 / 16 A."""
+  trajs = [io.synthetic_peptide(n_residues, n_frames, seed=BASE_SEED + 6 + 1000 * (i + seed_offset), pin=pin) for i in range(n_traj)]
+  fz = featurizer.Featurizer({"dimensions": 32, "lengths": 16, "time_window": 10, "cutoff": 4.0, "sigma": 1.5, "outfile": outfile} if outfile
+                             else {"dimensions": 32, "lengths": 16, "time_window": 10, "cutoff": 4.0, "sigma": 1.5})
+  fz.register_features([
+    features.Mass(outkey="mass", outfile=outfile),
+    features.HeavyAtom(outkey="heavy", outfile=outfile),
+    features.MarchingObservers(obs="existence", agg="mean", weight_type="mass", outkey="obs_existence", outfile=outfile),
+    features.DensityFlow(agg="standard_deviation", weight_type="mass", outkey="pdf_mass", outfile=outfile),
+  ])
+  fz.register_trajloader(trajs)
+  return fz, trajs

@@ -12,7 +12,11 @@ n_traj = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 make = {"misato": workloads.misato_mixed, "dynamic": workloads.dynamic_observers, "readme": workloads.readme_mass,
         "stress": workloads.stress_large, "stress_native": lambda **kw: workloads.stress_large(native_atoms=True, **kw)}
-if name == "pdbbind":
+loop = "run"
+if name in ("residue_single", "residue_dual"):
+  fz, trajs = workloads.residue_classification(n_traj=n_traj)
+  loop = name.split("_")[1]
+elif name == "pdbbind":
   fz, trajs = workloads.pdbbind_static(n_complex=n_traj)
 else:
   fz, trajs = make[name](n_traj=n_traj)
@@ -20,7 +24,8 @@ sums = {}
 def sink(outkey, tid, bid, pid, grid):
   sums[outkey] = sums.get(outkey, 0.0) + float(np.sum(grid, dtype=np.float64))
 fz.result_sink = sink
-fz.run()                       # warm-up: arenas, templates
+run = (lambda: fz.run()) if loop == "run" else (lambda: fz.loop_by_residue(loop))
+run()                          # warm-up: arenas, templates
 _lib.check(_lib.lib().nrl_synchronize())
 times = []
 for r in range(reps):
@@ -28,10 +33,10 @@ for r in range(reps):
   if r == reps - 1:
     _lib.profile(True)          # lane 0 only: every other trajectory
   t0 = time.perf_counter()
-  stats = fz.run()
+  stats = run()
   times.append(time.perf_counter() - t0)
 prof = _lib.profile_read(reset=True)
-frames = stats["frames"]
+frames = stats.get("frames", stats.get("blocks", 0))
 best = min(times)
 print(json.dumps({"workload": name, "n_traj": n_traj, "tasks": stats["tasks"], "frames": frames, "seconds_best": best,
                   "frames_per_s": frames / best, "tasks_per_s": stats["tasks"] / best,
