@@ -197,16 +197,17 @@ __device__ __forceinline__ bool nrl_rec_sweep(const float4 *rec, const int nrec,
         const float exy = nrl_ex2_approx(part * t.k2);
         const float ez[NRL_VPT] = {ezq.x, ezq.y, ezq.z, ezq.w};
         if constexpr (NWT > 1) {
+          // same association as the single-table form below, so a feature gets the same bits whether or not
+          // it shares its sweep with other weight tables
           const float4 ww = rec[(r0 + u) * S + 2];
-          const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+          const float wxy[4] = {exy * ww.x, exy * ww.y, exy * ww.z, exy * ww.w};
 #pragma unroll
           for (int k = 0; k < NRL_VPT; ++k) {
             const float dz = a.z - pz[k];
             const float d2 = fmaf(dz, dz, part);
             if (d2 < c2) {                                               // voxelize.cu:121-125
-              const float gk = exy * ez[k];
 #pragma unroll
-              for (int w = 0; w < NWT; ++w) A.f0[w][k] = fmaf(gk, wv[w], A.f0[w][k]);
+              for (int w = 0; w < NWT; ++w) A.f0[w][k] = fmaf(wxy[w], ez[k], A.f0[w][k]);
             }
           }
         } else {

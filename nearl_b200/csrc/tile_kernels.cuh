@@ -104,15 +104,14 @@ __device__ __forceinline__ void nrl_sweep(CandPtr cand, const unsigned short *id
       const float part = nrl_vox_partial(a.x, a.y, px, py);
       const float exy = nrl_ex2_approx(part * k2);
       const float ez[NRL_VPT] = {ezq.x, ezq.y, ezq.z, ezq.w};
-      const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+      const float wxy[4] = {exy * ww.x, exy * ww.y, exy * ww.z, exy * ww.w};     // same association as the single-table form
 _Pragma("unroll")
       for (int k = 0; k < NRL_VPT; ++k) {
         const float dz = a.z - pz[k];
         const float d2 = fmaf(dz, dz, part);
         if (d2 < c2) {
-          const float g = exy * ez[k];
 _Pragma("unroll")
-          for (int w = 0; w < NWT; ++w) acc[w][k] = fmaf(g, wv[w], acc[w][k]);
+          for (int w = 0; w < NWT; ++w) acc[w][k] = fmaf(wxy[w], ez[k], acc[w][k]);
         }
       }
     )

@@ -606,6 +606,9 @@ class DynamicFeature(Feature):
       "kind": "dynamic", "mode": int(mode), "agg": int(self.agg), "weights": np.asarray(self.cached_array, dtype=np.float32),
       "frame_offset": 0, "max_atoms": int(self.MAX_ALLOWED_ATOMS), "sigma": float(sigma),
     }
+    if self._is_builtin("cache") and self.selection is None:
+      # features with the same signature cache the same per-atom weights: they share one weight table (and one sweep)
+      spec["weight_sig"] = ("dynamic", self.weight_type, repr(sorted(self.feature_args.items())))
     if int(mode) == 3:
       # distinct_count over few distinct values (atomic numbers, atom types ...) runs on the cell-list kernel with
       # per-atom value ranks; otherwise the crop is emitted in value order for the scan kernel

@@ -544,16 +544,26 @@ class Featurizer:
       f, sp = self.FEATURESPACE[fidx], specs[fidx]
       return (fidx, tuple(int(v) for v in f.dims), float(f.spacing), float(f.cutoff), float(sp["sigma"]), float(f.padding),
               bool(f.byres), f.selection is not None, bool(sp.get("selection_folded")), sp["kind"], sp["mode"], sp["agg"],
-              sp["frame_offset"], sp["max_atoms"], sp.get("ranks") is not None)
+              sp["frame_offset"], sp["max_atoms"], sp.get("ranks") is not None, sp.get("weight_sig"))
 
     key = (tuple(fingerprint(f) for f in native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64))
     cache = self.__dict__.setdefault("_template_cache", {})
     if key in cache:
       return cache[key]
-    table_of = {f: i for i, f in enumerate(native_feats)}
+    # one weight-table row per distinct weight signature (features without one get their own row)
+    table_feats, table_of, sig_row = [], {}, {}
+    for f in native_feats:
+      sig = specs[f].get("weight_sig")
+      if sig is not None and sig in sig_row:
+        table_of[f] = sig_row[sig]
+        continue
+      table_of[f] = len(table_feats)
+      if sig is not None:
+        sig_row[sig] = len(table_feats)
+      table_feats.append(f)
     # distinct_count features whose values have <= 32 ranks: the ranks travel as extra weight-table rows
     rank_feats = [f for f in native_feats if specs[f]["mode"] == 3 and specs[f].get("ranks") is not None]
-    rank_of = {f: len(native_feats) + i for i, f in enumerate(rank_feats)}
+    rank_of = {f: len(table_feats) + i for i, f in enumerate(rank_feats)}
     sel_feats = [f for f in native_feats if self.FEATURESPACE[f].selection is not None and not specs[f].get("selection_folded")]
     sel_of = {f: i for i, f in enumerate(sel_feats)}
     crops, crop_ids, crop_slots, tasks, shapes = [], {}, [], [], []
@@ -602,7 +612,8 @@ class Featurizer:
           tasks.append(t)
           shapes.append(tuple(int(v) for v in feat.dims))
     tpl = {"crops": crops, "crop_slots": crop_slots, "tasks": (_lib.TaskStruct * len(tasks))(*tasks), "shapes": shapes,
-           "sel_feats": sel_feats, "order_feats": order_feats, "rank_feats": rank_feats, "any_byres": any_byres,
+           "sel_feats": sel_feats, "order_feats": order_feats, "rank_feats": rank_feats, "table_feats": table_feats,
+           "table_of": table_of, "any_byres": any_byres,
            "out_floats": int(sum(sh[0] * sh[1] * sh[2] for sh in shapes))}
     cache[key] = tpl
     return tpl
@@ -633,7 +644,7 @@ class Featurizer:
       crops[ci].focal[0], crops[ci].focal[1], crops[ci].focal[2] = float(focal[0]), float(focal[1]), float(focal[2])
       crops[ci].focal_f64[0], crops[ci].focal_f64[1], crops[ci].focal_f64[2] = float(focal[0]), float(focal[1]), float(focal[2])
     batch.crops, batch.tasks, batch.shapes, batch.out_floats = crops, tpl["tasks"], tpl["shapes"], tpl["out_floats"]
-    rows = [specs[f]["weights"] for f in native_feats] + [specs[f]["ranks"] for f in tpl["rank_feats"]]
+    rows = [specs[f]["weights"] for f in tpl["table_feats"]] + [specs[f]["ranks"] for f in tpl["rank_feats"]]
     batch.weight_tables = self._table_buffer(lane, "weights", (len(rows), n_atoms), np.float32)
     for i, row in enumerate(rows):
       batch.weight_tables[i] = row
@@ -646,7 +657,7 @@ class Featurizer:
     if tpl["order_feats"]:
       batch.value_orders = self._table_buffer(lane, "orders", (len(rows), n_atoms), np.int32)
       for f in tpl["order_feats"]:
-        batch.value_orders[native_feats.index(f)] = self.FEATURESPACE[f].value_order()
+        batch.value_orders[tpl["table_of"][f]] = self.FEATURESPACE[f].value_order()
     batch.residue_index, batch.n_residues = None, 0
     if tpl["any_byres"]:
       uniq, inverse = np.unique(self.FEATURESPACE[native_feats[0]].resids, return_inverse=True)
