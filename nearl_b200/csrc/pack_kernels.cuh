@@ -8,6 +8,7 @@
 //                           frame_interp_global, /root/reference/src/voxelize.cu:79-108)
 #pragma once
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <float.h>
 
 // ---- legacy layout ------------------------------------------------------------------
@@ -209,6 +210,116 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
     base += __popc(m);
   }
   if (tid == 0) { p.off[fd] = foff; p.cnt[fd] = min(total, cap); }
+}
+
+// Cluster form of the crop kernel for whole-topology crops in topology order: NRL_CROP_CLUSTER CTAs (one
+// thread-block cluster) share a frame, each owns a contiguous chunk of the atoms, and the kept counts are
+// exchanged through distributed shared memory so that the compaction stays order preserving.  One CTA per
+// frame leaves most SMs idle when a trajectory has ~100 frames of 20 000 atoms; four per frame do not.
+#define NRL_CROP_CLUSTER 4
+#define NRL_CROP_CNT 512
+
+template <typename T>
+__global__ void __cluster_dims__(NRL_CROP_CLUSTER, 1, 1) __launch_bounds__(NRL_CROP_CNT)
+nrl_crop_pack_cluster_kernel(const NrlCropParams p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ unsigned int s_keep[];            // one bit per atom of this CTA's chunk
+  __shared__ int s_wcnt[NRL_CROP_CNT / 32];
+  __shared__ int s_cta_total;
+  const int fd = blockIdx.x / NRL_CROP_CLUSTER;
+  const int rank = (int)cluster.block_rank();
+  const NrlCropDev &cr = p.crops[p.frame_crop[fd]];
+  const int N = p.n_atoms;
+  const int a0 = cr.atom_begin, n_all = cr.atom_end - cr.atom_begin;
+  const int shift = cr.table_shift;
+  // chunk of this CTA, on 32-atom boundaries
+  const int chunk = (((n_all + NRL_CROP_CLUSTER - 1) / NRL_CROP_CLUSTER) + 31) & ~31;
+  const int c0 = min(rank * chunk, n_all), n = min(c0 + chunk, n_all) - c0;
+  const T *__restrict__ xyz = reinterpret_cast<const T *>(p.xyz) + ((long long)p.frame_src[fd] * N + a0 + c0) * 3;
+  unsigned int *__restrict__ resflags = p.resflags + (long long)fd * p.n_res_words;
+  const unsigned char *__restrict__ sel = cr.selection >= 0 ? p.sel + (long long)cr.selection * N + a0 + c0 + shift : nullptr;
+  const int *__restrict__ resid = p.resid + a0 + c0 + shift;
+  constexpr int nt = NRL_CROP_CNT, nw = nt >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_pad = (n + 31) & ~31;
+
+#pragma unroll 4
+  for (int a = tid; a < n_pad; a += nt) {
+    bool in = false;
+    if (a < n) {
+      const T x = NrlXform<T>::apply(xyz[3 * a], 0, cr);
+      const T y = NrlXform<T>::apply(xyz[3 * a + 1], 1, cr);
+      const T z = NrlXform<T>::apply(xyz[3 * a + 2], 2, cr);
+      in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
+           ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
+      if (cr.byres && in) {
+        const int r = resid[a];
+        atomicOr(&resflags[r >> 5], 1u << (r & 31));
+      }
+      if (!cr.byres && sel) in = in && (sel[a] != 0);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) s_keep[a >> 5] = m;
+  }
+  if (cr.byres) {
+    // a residue can straddle two chunks: every CTA of the cluster must have flagged its residues first
+    __threadfence();
+    cluster.sync();
+    for (int a = tid; a < n_pad; a += nt) {
+      bool k = false;
+      if (a < n) {
+        const int r = resid[a];
+        k = (__ldcg(&resflags[r >> 5]) >> (r & 31)) & 1u;
+        if (sel) k = k && (sel[a] != 0);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, k);
+      if (lane == 0) s_keep[a >> 5] = m;
+    }
+  }
+  __syncthreads();
+
+  // order-preserving compaction: warp-contiguous segments inside the chunk, chunks in rank order
+  const int seg = ((n + nw - 1) / nw + 31) & ~31;
+  const int e_begin = min(warp * seg, n), e_end = min(e_begin + seg, n);
+  int mycnt = 0;
+  if (e_begin < e_end)
+    for (int w0 = (e_begin >> 5) + lane; w0 < ((e_end + 31) >> 5); w0 += 32) mycnt += __popc(s_keep[w0]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mycnt += __shfl_xor_sync(0xffffffffu, mycnt, o);
+  if (lane == 0) s_wcnt[warp] = mycnt;
+  __syncthreads();
+  int base = 0, cta_total = 0;
+#pragma unroll
+  for (int w = 0; w < nw; ++w) { const int c = s_wcnt[w]; if (w < warp) base += c; cta_total += c; }
+  if (tid == 0) s_cta_total = cta_total;
+  cluster.sync();
+  int total = 0;
+#pragma unroll
+  for (int q = 0; q < NRL_CROP_CLUSTER; ++q) {
+    const int c = *cluster.map_shared_rank(&s_cta_total, q);
+    if (q < rank) base += c;
+    total += c;
+  }
+  const int cap = cr.max_atoms > 0 ? cr.max_atoms : 0x7fffffff;
+  const long long foff = p.frame_off[fd];
+  float4 *out = p.atoms + foff;
+  for (int e0 = e_begin; e0 < e_end; e0 += 32) {
+    const unsigned m = s_keep[e0 >> 5];
+    if (m == 0u) continue;
+    const bool k = (m >> lane) & 1u;
+    const int a = e0 + lane;
+    const int pos = base + __popc(m & ((1u << lane) - 1u));
+    if (k && pos < cap) {
+      const T x = NrlXform<T>::apply(xyz[3 * a], 0, cr);
+      const T y = NrlXform<T>::apply(xyz[3 * a + 1], 1, cr);
+      const T z = NrlXform<T>::apply(xyz[3 * a + 2], 2, cr);
+      out[pos] = make_float4((float)x, (float)y, (float)z, __int_as_float(a0 + c0 + a + shift));
+    }
+    base += __popc(m);
+  }
+  if (rank == 0 && tid == 0) { p.off[fd] = foff; p.cnt[fd] = min(total, cap); }
+  cluster.sync();     // s_cta_total must outlive the remote reads
 }
 
 // ---- per-atom normalisation of the voxeliser -------------------------------------------
