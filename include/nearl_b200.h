@@ -169,6 +169,15 @@ int nrl_featurize_batch(const nrl_batch_t *batch);
 /* *out = 1 when a grid of this geometry gets a cell list (rank-based distinct_count needs one), else 0 */
 int nrl_cell_list_fits(const int *dims, float spacing, float cutoff, int *out);
 
+/* ---- trajectory preparation ---------------------------------------------------------------- */
+/* Least-squares superposition of every frame onto frame `ref_frame` over the atoms `fit_index`, IN PLACE
+ * (what MisatoTraj(..., superpose=True) asks pytraj for: pt.superpose(traj, mask="@CA"),
+ * /root/reference/nearl/io/traj.py:398-404).  xyz [n_frames, n_atoms, 3] float32 or float64, host or device
+ * (on_device: `stream`-ordered, no synchronisation); rmsd (optional, n_frames floats in the same memory space)
+ * receives the fitted RMSD of every frame.  The reference frame is left untouched. */
+int nrl_superpose(void *xyz, int xyz_is_f64, int n_frames, int n_atoms, const int *fit_index, int n_fit, int ref_frame,
+                  int on_device, float *rmsd, void *stream);
+
 /* ---- utilities -------------------------------------------------------------------------- */
 /* buff_dim exactly as the device evaluates (cutoff+spacing)/spacing (voxelize.cu:50, div.approx) */
 int nrl_buff_dim(float cutoff, float spacing, int *out);
@@ -186,7 +195,7 @@ int nrl_set_stream(void *stream, int enable);
 int nrl_set_option(const char *name, int value);
 /* per-kernel device timing: CUDA events around every launch of this library, accumulated per
  * category; nrl_profile_read synchronises and copies NRL_PROFILE_CATEGORIES totals (ms, launches) */
-#define NRL_PROFILE_CATEGORIES 17
+#define NRL_PROFILE_CATEGORIES 18
 int nrl_profile(int enable);
 int nrl_profile_read(double *ms, long long *counts, int reset);
 const char *nrl_profile_name(int category);

@@ -19,7 +19,7 @@ EXPORTED = [
   "nrl_frame_voxelize", "nrl_frame_observation", "nrl_marching_observer", "nrl_density_flow", "nrl_aggregate",
   "nrl_summation", "nrl_frame_voxelize_dev", "nrl_frame_observation_dev", "nrl_marching_observer_dev",
   "nrl_density_flow_dev", "nrl_aggregate_dev", "nrl_featurize_batch", "nrl_buff_dim", "nrl_device_count",
-  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_set_stream", "nrl_set_option", "nrl_cell_list_fits", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
+  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_set_stream", "nrl_set_option", "nrl_cell_list_fits", "nrl_superpose", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
   "nrl_last_error", "nrl_version",
 ]
 
@@ -102,6 +102,7 @@ def lib():
   L.nrl_profile.argtypes = [c_int]
   L.nrl_set_option.argtypes = [ctypes.c_char_p, c_int]
   L.nrl_cell_list_fits.argtypes = [p, c_float, c_float, p]
+  L.nrl_superpose.argtypes = [p, c_int, c_int, c_int, p, c_int, c_int, c_int, p, p]
   L.nrl_profile_read.argtypes = [p, p, c_int]
   L.nrl_profile_name.argtypes = [c_int]
   L.nrl_profile_name.restype = ctypes.c_char_p
@@ -142,7 +143,7 @@ def kernel_launches():
   return int(lib().nrl_kernel_launches())
 
 
-PROFILE_CATEGORIES = 17
+PROFILE_CATEGORIES = 18
 
 
 def set_stream(stream_ptr, enable=True):

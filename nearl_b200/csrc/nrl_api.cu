@@ -21,6 +21,7 @@
 #include "cell_kernels.cuh"
 #include "common.cuh"
 #include "pack_kernels.cuh"
+#include "superpose_kernels.cuh"
 #include "tile_kernels.cuh"
 
 namespace {
@@ -72,6 +73,7 @@ struct Ctx {
   DevBuf coords, weights, perm, atoms, inv, off, cnt, out, tasks, flist, cand_scr, ser_scr, misc, series;
   DevBuf xyz, wtabs, sels, resid, orders, crops, fcrop, fsrc, keep, resflags;
   DevBuf foff;                                   // per crop frame: first packed atom
+  DevBuf sup_idx, sup_ref, sup_rmsd;             // superposition: fitted atom indices, reference set, per-frame RMSD
   DevBuf batoms, bcnt, cstart, grids, blist;     // cell lists: binned frames, cell prefixes, per-frame cell grids
   bool attr_set[64] = {false};
   cudaStream_t user_stream = nullptr;   // nrl_set_stream: run on the caller's stream instead of our own
@@ -91,11 +93,11 @@ struct Ctx {
   cudaStream_t work_stream() const { return use_user_stream ? user_stream : stream; }
 };
 
-enum { CAT_PACK_LEGACY = 0, CAT_CROP_PACK = 1, CAT_ATOM_NORM = 2, CAT_TILE0 = 3, CAT_AGGREGATE = 13, CAT_SUMMATION = 14, CAT_MISC = 15, CAT_CELL_BIN = 16 };
+enum { CAT_PACK_LEGACY = 0, CAT_CROP_PACK = 1, CAT_ATOM_NORM = 2, CAT_TILE0 = 3, CAT_AGGREGATE = 13, CAT_SUMMATION = 14, CAT_MISC = 15, CAT_CELL_BIN = 16, CAT_SUPERPOSE = 17 };
 const char *kCatNames[NRL_PROFILE_CATEGORIES] = {
     "pack_legacy", "crop_pack", "atom_norm", "tile_voxelize", "tile_existence", "tile_direct_count", "tile_distinct_count",
     "tile_mean_distance", "tile_cumulative_weight", "tile_density", "tile_dispersion", "tile_eccentricity",
-    "tile_radius_of_gyration", "aggregate", "summation", "misc", "cell_bin"};
+    "tile_radius_of_gyration", "aggregate", "summation", "misc", "cell_bin", "superpose"};
 
 struct ScopedProf {
   Ctx &c; cudaStream_t st; int cat; cudaEvent_t a = nullptr, b = nullptr;
@@ -765,6 +767,54 @@ int nrl_set_stream(void *stream, int enable) {
   c->use_user_stream = enable != 0;
   return NRL_OK;
 }
+int nrl_superpose(void *xyz, int xyz_is_f64, int n_frames, int n_atoms, const int *fit_index, int n_fit, int ref_frame,
+                  int on_device, float *rmsd, void *stream) {
+  if (!xyz || !fit_index) return fail(NRL_ERR_ARGUMENT, "xyz / fit_index is NULL");
+  if (n_frames <= 0 || n_atoms <= 0 || n_fit <= 0) return fail(NRL_ERR_SHAPE, "empty trajectory or fit set");
+  if (ref_frame < 0 || ref_frame >= n_frames) return fail(NRL_ERR_ARGUMENT, "reference frame outside the trajectory");
+  for (int i = 0; i < n_fit; ++i)
+    if (fit_index[i] < 0 || fit_index[i] >= n_atoms) return fail(NRL_ERR_ARGUMENT, "fit index outside the topology");
+  Ctx *cp = nullptr;
+  NRL_TRY(get_ctx(&cp));
+  Ctx &c = *cp;
+  std::lock_guard<std::mutex> lk(c.mu);
+  cudaStream_t st = on_device ? (cudaStream_t)stream : c.work_stream();
+  const size_t esz = xyz_is_f64 ? sizeof(double) : sizeof(float);
+  const size_t bytes = (size_t)n_frames * n_atoms * 3 * esz;
+  void *d_xyz = xyz;
+  if (!on_device) {
+    NRL_TRY(c.xyz.reserve(bytes));
+    NRL_CUDA(cudaMemcpyAsync(c.xyz.p, xyz, bytes, cudaMemcpyHostToDevice, st));
+    d_xyz = c.xyz.p;
+  }
+  NRL_TRY(c.sup_idx.reserve((size_t)n_fit * sizeof(int)));
+  NRL_TRY(c.sup_ref.reserve((size_t)(3 + 3 * (size_t)n_fit) * sizeof(double)));
+  NRL_TRY(c.sup_rmsd.reserve((size_t)n_frames * sizeof(float)));
+  NRL_CUDA(cudaMemcpyAsync(c.sup_idx.p, fit_index, (size_t)n_fit * sizeof(int), cudaMemcpyHostToDevice, st));
+  {
+    ScopedProf sp(c, st, CAT_SUPERPOSE);
+    if (xyz_is_f64) {
+      nrl_superpose_ref_kernel<double><<<1, NRL_SUP_NT, 0, st>>>((const double *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, ref_frame, c.sup_ref.as<double>());
+      nrl_superpose_kernel<double><<<n_frames, NRL_SUP_NT, 0, st>>>((double *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, c.sup_ref.as<double>(), ref_frame, c.sup_rmsd.as<float>());
+    } else {
+      nrl_superpose_ref_kernel<float><<<1, NRL_SUP_NT, 0, st>>>((const float *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, ref_frame, c.sup_ref.as<double>());
+      nrl_superpose_kernel<float><<<n_frames, NRL_SUP_NT, 0, st>>>((float *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, c.sup_ref.as<double>(), ref_frame, c.sup_rmsd.as<float>());
+    }
+  }
+  g_launches.fetch_add(2);
+  NRL_CUDA(cudaGetLastError());
+  if (rmsd) {
+    if (on_device) NRL_CUDA(cudaMemcpyAsync(rmsd, c.sup_rmsd.p, (size_t)n_frames * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else NRL_CUDA(cudaMemcpyAsync(rmsd, c.sup_rmsd.p, (size_t)n_frames * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (!on_device) {
+    NRL_CUDA(cudaMemcpyAsync(xyz, d_xyz, bytes, cudaMemcpyDeviceToHost, st));
+    NRL_CUDA(cudaStreamSynchronize(st));
+    prof_collect(c);
+  }
+  return NRL_OK;
+}
+
 int nrl_cell_list_fits(const int *dims, float spacing, float cutoff, int *out) {
   long long G = 0;
   NRL_TRY(check_dims(dims, &G));

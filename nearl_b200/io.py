@@ -16,7 +16,8 @@ import numpy as np
 
 from . import constants
 
-__all__ = ["Atom", "Residue", "Topology", "Trajectory", "synthetic_trajectory", "synthetic_complex", "synthetic_peptide", "pinned_empty"]
+__all__ = ["Atom", "Residue", "Topology", "Trajectory", "TrajectoryLoader", "MisatoTraj", "load_amber_topology", "superpose",
+           "synthetic_trajectory", "synthetic_complex", "synthetic_peptide", "pinned_empty"]
 
 
 def pinned_empty(shape, dtype):
@@ -101,6 +102,17 @@ class Topology:
   def __getitem__(self, key):
     idx = np.arange(self.n_atoms)[key]
     return Topology(self.names[idx], self.resids[idx], self.resnames[idx], self.atomic_numbers[idx])
+
+  def strip(self, mask):
+    """Remove the atoms selected by `mask`, in place (pytraj's Topology.strip; MisatoTraj drops water and
+    ions this way, /root/reference/nearl/io/traj.py:362-369)."""
+    keep = np.ones(self.n_atoms, dtype=bool)
+    keep[self.select(mask)] = False
+    self.names, self.resids = self.names[keep], self.resids[keep]
+    self.resnames, self.atomic_numbers = self.resnames[keep], self.atomic_numbers[keep]
+    self._atoms = None
+    for key in ("_select_cache", "_residue_blocks", "_dual_blocks_memo"):
+      self.__dict__.pop(key, None)
 
   # ---- Amber mask subset: ':RES', ':1-10', ':A,B', ':*', '@NAME', '@1-5', ':RES@NAME', '@/El', '!', '&', '|', '()'
   def select(self, mask):
@@ -307,3 +319,149 @@ def synthetic_peptide(n_residues, n_frames, seed, dtype=np.float32, identity=Non
       frame = frame + rng.normal(0.0, 0.15, size=(n_atoms, 3))
     xyz[t] = frame.astype(dtype)
   return Trajectory(xyz, top, identity or f"peptide_{n_residues}x{n_frames}_{seed}")
+
+
+# ---- trajectory ingestion without pytraj ------------------------------------------------------------
+def _parm7_sections(text):
+  """{flag: (format, [data lines])} of an Amber parm7 / prmtop file."""
+  sections, flag = {}, None
+  for line in text.splitlines():
+    if line.startswith("%FLAG"):
+      flag = line.split()[1]
+      sections[flag] = [None, []]
+    elif line.startswith("%FORMAT") and flag is not None:
+      sections[flag][0] = line[line.index("(") + 1:line.rindex(")")]
+    elif line.startswith("%") or flag is None:
+      continue
+    else:
+      sections[flag][1].append(line)
+  return sections
+
+
+def _parm7_values(section):
+  """Fixed-width fields of one section: Fortran formats like 20a4, 10I8, 5E16.8."""
+  fmt, lines = section
+  m = re.fullmatch(r"(\d+)([aAiIeEfF])(\d+)(?:\.\d+)?", fmt.strip())
+  if not m:
+    raise ValueError(f"unsupported parm7 format {fmt!r}")
+  width, kind = int(m.group(3)), m.group(2).lower()
+  out = []
+  for line in lines:
+    line = line.rstrip("\n")
+    for i in range(0, len(line), width):
+      field = line[i:i + width]
+      if not field.strip() and kind != "a":
+        continue
+      out.append(field.strip() if kind == "a" else (int(field) if kind == "i" else float(field)))
+  return out
+
+
+def load_amber_topology(path):
+  """Topology from an Amber parm7 / prmtop file, optionally gzip-compressed (what pt.load_topology gives
+  MisatoTraj for production.top.gz, /root/reference/nearl/io/traj.py:361): atom names, residue labels and
+  pointers, atomic numbers (from the masses when the file predates the ATOMIC_NUMBER section)."""
+  import gzip
+  opener = gzip.open if str(path).endswith(".gz") else open
+  with opener(path, "rt") as fh:
+    sec = _parm7_sections(fh.read())
+  for need in ("POINTERS", "ATOM_NAME", "RESIDUE_LABEL", "RESIDUE_POINTER"):
+    if need not in sec:
+      raise ValueError(f"{path}: parm7 section {need} is missing")
+  pointers = _parm7_values(sec["POINTERS"])
+  n_atoms, n_res = pointers[0], pointers[11]
+  names = _parm7_values(sec["ATOM_NAME"])[:n_atoms]
+  labels = _parm7_values(sec["RESIDUE_LABEL"])[:n_res]
+  first = np.array(_parm7_values(sec["RESIDUE_POINTER"])[:n_res], dtype=np.int64) - 1
+  resids = np.repeat(np.arange(n_res), np.diff(np.r_[first, n_atoms]))
+  resnames = np.array(labels, dtype=object)[resids]
+  if "ATOMIC_NUMBER" in sec:
+    z = np.array(_parm7_values(sec["ATOMIC_NUMBER"])[:n_atoms], dtype=np.int64)
+  else:
+    masses = np.array(_parm7_values(sec["MASS"])[:n_atoms], dtype=float)
+    table = np.array([constants.ATOMICMASS.get(i, 1e9) for i in range(1, 119)])
+    z = np.abs(masses[:, None] - table[None, :]).argmin(axis=1) + 1
+  return Topology(names, resids, resnames, z)
+
+
+def superpose(traj, mask="@CA", ref=0):
+  """Fit every frame of `traj` onto frame `ref` over the atoms of `mask`, in place, on the device
+  (pt.superpose(traj, mask="@CA"), /root/reference/nearl/io/traj.py:398-404).  Returns the per-frame RMSD."""
+  from . import _lib
+  idx = np.ascontiguousarray(traj.top.select(mask), dtype=np.int32)
+  if len(idx) == 0:
+    raise ValueError(f"superpose: no atom matches {mask!r}")
+  xyz = traj.xyz
+  if not (isinstance(xyz, np.ndarray) and xyz.flags.c_contiguous and xyz.flags.writeable and xyz.dtype in (np.float32, np.float64)):
+    raise ValueError("superpose needs a writable C-contiguous float32 / float64 coordinate array")
+  rmsd = np.zeros(xyz.shape[0], dtype=np.float32)
+  _lib.check(_lib.lib().nrl_superpose(_lib.ptr(xyz), int(xyz.dtype == np.float64), xyz.shape[0], xyz.shape[1], _lib.ptr(idx), len(idx),
+                                      int(ref), 0, _lib.ptr(rmsd), None))
+  return rmsd
+
+
+class MisatoTraj(Trajectory):
+  """A trajectory of the MISATO data set (/root/reference/nearl/io/traj.py:287-423) without pytraj:
+  topology from ``{misatodir}/parameter_restart_files_MD/{pdbcode}/production.top.gz`` with water and ions
+  stripped, coordinates from ``{misatodir}/MD.hdf5:/{PDBCODE}/trajectory_coordinates``.  Keyword arguments as
+  in the reference: ``stride`` or ``frame_indices``, ``mask``, ``superpose`` (fit onto the first frame over
+  ``@CA``, done on the device)."""
+
+  def __init__(self, pdbcode, misatodir, **kwarg):
+    import os
+    from . import utils
+    self.topfile = f"{misatodir}/parameter_restart_files_MD/{pdbcode.lower()}/production.top.gz"
+    if not os.path.exists(self.topfile):
+      raise FileNotFoundError(f"The topology file of PDB {pdbcode} is not found ({self.topfile})")
+    self.trajfile = os.path.join(misatodir, "MD.hdf5")
+    if not os.path.exists(self.trajfile):
+      raise FileNotFoundError(f"The trajectory file is not found ({self.trajfile})")
+    self.pdbcode = pdbcode
+    top = load_amber_topology(self.topfile)
+    present = set(top.resnames.tolist())
+    for solvent in ("WAT", "Cl-", "Na+"):          # keep the coordinates aligned with the topology (traj.py:362-369)
+      if solvent in present:
+        top.strip(f":{solvent}")
+    with utils.open_hdf(self.trajfile, "r") as hdf:
+      if pdbcode.upper() not in hdf.keys():
+        raise ValueError(f"Not found the key for PDB code {pdbcode.upper()} in the HDF5 trajectory file.")
+      coord = hdf[f"{pdbcode.upper()}/trajectory_coordinates"][:]
+    if kwarg.get("stride", None) is not None:
+      coord = coord[::int(kwarg["stride"])]
+    elif kwarg.get("frame_indices", None) is not None:
+      coord = coord[kwarg["frame_indices"]]
+    if kwarg.get("mask", None) is not None:
+      sel = top.select(kwarg["mask"])
+      coord, top = coord[:, sel, :], top[sel]
+    xyz = pinned_empty(coord.shape, coord.dtype if coord.dtype in (np.float32, np.float64) else np.float32)
+    xyz[...] = coord
+    super().__init__(xyz, top, identity=str(pdbcode).lower())
+    assert self.xyz.ndim == 3, f"Fatal: The shape of the trajectory {self.identity} is {self.xyz.shape}!!! It should be (n_frames, n_atoms, 3). "
+    if kwarg.get("superpose", False):
+      superpose(self, mask="@CA")
+
+
+class TrajectoryLoader:
+  """Lazy list of trajectories (/root/reference/nearl/io/trajloader.py:165-200): every entry is a tuple of
+  constructor arguments (or an object that already is a trajectory); `trajtype` builds it on access."""
+
+  def __init__(self, trajs=None, trajtype=None, **kwarg):
+    self.trajs = list(trajs or [])
+    self.trajtype = trajtype
+    self.kwargs = kwarg
+
+  def __len__(self):
+    return len(self.trajs)
+
+  def __getitem__(self, index):
+    item = self.trajs[index]
+    if hasattr(item, "xyz") and hasattr(item, "top"):
+      return item
+    args = item if isinstance(item, (tuple, list)) else (item,)
+    builder = self.trajtype or Trajectory
+    return builder(*args, **self.kwargs)
+
+  def __iter__(self):
+    return (self[i] for i in range(len(self)))
+
+  def push(self, item):
+    self.trajs.append(item)

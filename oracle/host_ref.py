@@ -180,3 +180,27 @@ def featurize_by_residue(xyz, resids, descs, blocks, time_window, buff_dim=-1, s
         task_labels.append(label)
   labels = np.array(task_labels, dtype=int)[:len(task_labels) // max(len(descs), 1)]      # featurizer.py:545-549
   return {k: np.array(v, dtype=np.float32) for k, v in out.items()}, labels
+
+
+def superpose(xyz, fit_index, ref=0):
+  """Least-squares fit of every frame onto frame `ref` over the atoms `fit_index` (Kabsch, SVD in float64):
+  the textbook statement of pt.superpose(traj, mask) that MisatoTraj asks for
+  (/root/reference/nearl/io/traj.py:398-404; cpptraj's own arithmetic is not in the reference tree, so this
+  function is pinned by the algorithm's definition only).  Returns (fitted coordinates, per-frame RMSD)."""
+  xyz = np.asarray(xyz, dtype=np.float64)
+  out = xyz.copy()
+  target = xyz[ref][fit_index]
+  ct = target.mean(axis=0)
+  rmsd = np.zeros(len(xyz))
+  for f in range(len(xyz)):
+    a = xyz[f][fit_index]
+    ca = a.mean(axis=0)
+    h = (a - ca).T @ (target - ct)
+    u, _, vt = np.linalg.svd(h)
+    d = np.sign(np.linalg.det(vt.T @ u.T))
+    rot = vt.T @ np.diag([1.0, 1.0, d]) @ u.T
+    fitted = (xyz[f] - ca) @ rot.T + ct
+    rmsd[f] = np.sqrt(np.mean(np.sum((fitted[fit_index] - target) ** 2, axis=1)))
+    if f != ref:
+      out[f] = fitted
+  return out, rmsd

@@ -1,0 +1,141 @@
+"""Trajectory ingestion without pytraj: Amber parm7 topologies, the MISATO
+MD.hdf5 layout (/root/reference/nearl/io/traj.py:287-423), the lazy loader, and the device superposition
+(pt.superpose(traj, mask="@CA"), traj.py:398-404) against a float64 Kabsch fit."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import nearl_b200
+from nearl_b200 import _lib, constants, features, featurizer, io, utils
+from oracle import host_ref
+
+nearl_b200.update_config(quiet=True)
+
+
+def write_parm7(path, top, with_atomic_number=True):
+  """Minimal Amber parm7 with the sections the loader reads, in the file's own fixed-width formats."""
+  blocks = top.residue_blocks()
+
+  def sec(flag, fmt, vals, per, width, kind):
+    out = [f"%FLAG {flag}", f"%FORMAT({fmt})"]
+    for i in range(0, len(vals), per):
+      row = vals[i:i + per]
+      out.append("".join(f"{v:<{width}}" if kind == "a" else (f"{v:{width}d}" if kind == "i" else f"{v:{width}.8E}") for v in row))
+    return out
+
+  pointers = [0] * 31
+  pointers[0], pointers[11] = top.n_atoms, len(blocks)
+  lines = ["%VERSION  VERSION_STAMP = V0001.000  DATE = 01/01/24  00:00:00", "%FLAG TITLE", "%FORMAT(20a4)", "synthetic"]
+  lines += sec("POINTERS", "10I8", pointers, 10, 8, "i")
+  lines += sec("ATOM_NAME", "20a4", [str(x)[:4] for x in top.names], 20, 4, "a")
+  lines += sec("MASS", "5E16.8", [float(constants.ATOMICMASS[int(z)]) for z in top.atomic_numbers], 5, 16, "e")
+  if with_atomic_number:
+    lines += sec("ATOMIC_NUMBER", "10I8", [int(z) for z in top.atomic_numbers], 10, 8, "i")
+  lines += sec("RESIDUE_LABEL", "20a4", [b[0] for b in blocks], 20, 4, "a")
+  lines += sec("RESIDUE_POINTER", "10I8", [b[1] + 1 for b in blocks], 10, 8, "i")
+  opener = gzip.open if str(path).endswith(".gz") else open
+  with opener(path, "wt") as fh:
+    fh.write("\n".join(lines) + "\n")
+
+
+def make_misato_dir(root, code, traj, solvent_atoms=9):
+  """{root}/parameter_restart_files_MD/{code}/production.top.gz (with WAT / Na+ / Cl- appended) + {root}/MD.hdf5."""
+  top = traj.top
+  names = np.concatenate([top.names, np.array(["O", "H1", "H2"] * (solvent_atoms // 3), dtype=object), np.array(["Na+", "Cl-"], dtype=object)])
+  n_w = solvent_atoms // 3
+  last = int(top.resids.max())
+  resids = np.concatenate([top.resids, np.repeat(np.arange(last + 1, last + 1 + n_w), 3), [last + n_w + 1, last + n_w + 2]])
+  resnames = np.concatenate([top.resnames, np.array(["WAT"] * (3 * n_w) + ["Na+", "Cl-"], dtype=object)])
+  z = np.concatenate([top.atomic_numbers, np.array([8, 1, 1] * n_w + [11, 17])])
+  full = io.Topology(names, resids, resnames, z)
+  os.makedirs(os.path.join(root, "parameter_restart_files_MD", code.lower()), exist_ok=True)
+  write_parm7(os.path.join(root, "parameter_restart_files_MD", code.lower(), "production.top.gz"), full)
+  with utils.open_hdf(os.path.join(root, "MD.hdf5"), "a") as hdf:
+    grp = hdf.create_group(code.upper())
+    grp.create_dataset("trajectory_coordinates", data=np.asarray(traj.xyz, dtype=np.float32))
+
+
+def test_parm7_topology(tmp_path):
+  traj = io.synthetic_peptide(14, 2, seed=5)
+  for name, with_z in (("a.parm7", True), ("b.top.gz", False)):
+    write_parm7(str(tmp_path / name), traj.top, with_atomic_number=with_z)
+    top = io.load_amber_topology(str(tmp_path / name))
+    assert top.n_atoms == traj.top.n_atoms
+    assert list(top.names) == [str(n)[:4] for n in traj.top.names]
+    assert np.array_equal(top.resids, traj.top.resids) and list(top.resnames) == list(traj.top.resnames)
+    assert np.array_equal(top.atomic_numbers, traj.top.atomic_numbers)      # from the masses when the section is absent
+  assert np.array_equal(top.select("@CA"), traj.top.select("@CA"))
+  n = top.n_atoms
+  top.strip(":LEU")
+  assert top.n_atoms == n - np.count_nonzero(traj.top.resnames == "LEU") and "LEU" not in set(top.resnames)
+
+
+def test_misato_layout_and_loader(tmp_path):
+  root = str(tmp_path / "misato")
+  trajs = {code: io.synthetic_peptide(10 + i, 8, seed=20 + i) for i, code in enumerate(("1abc", "2XYZ"))}
+  for code, traj in trajs.items():
+    make_misato_dir(root, code, traj)
+  loader = io.TrajectoryLoader([("1abc", root), ("2XYZ", root)], trajtype=io.MisatoTraj)
+  assert len(loader) == 2
+  for (code, _), got in zip(loader.trajs, loader):
+    want = trajs[code]
+    assert got.identity == code.lower() and got.n_atoms == want.n_atoms          # water and ions stripped
+    assert np.array_equal(got.xyz, want.xyz.astype(np.float32)) and got.xyz.dtype == np.float32
+    assert list(got.top.resnames) == list(want.top.resnames)
+  strided = io.MisatoTraj("1abc", root, stride=3)
+  assert strided.n_frames == 3 and np.array_equal(strided.xyz, trajs["1abc"].xyz[::3])
+  picked = io.MisatoTraj("1abc", root, frame_indices=[5, 1], mask="@CA,C,N")
+  assert picked.n_frames == 2 and picked.n_atoms == 30 and np.array_equal(picked.xyz[0], trajs["1abc"].xyz[5][trajs["1abc"].top.select("@CA,C,N")])
+  os.makedirs(os.path.join(root, "parameter_restart_files_MD", "4kkk"))
+  write_parm7(os.path.join(root, "parameter_restart_files_MD", "4kkk", "production.top.gz"), trajs["1abc"].top)
+  with pytest.raises(ValueError):                 # a topology without coordinates in MD.hdf5
+    io.MisatoTraj("4kkk", root)
+  with pytest.raises(FileNotFoundError):
+    io.MisatoTraj("9zzz", root)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_superpose_vs_kabsch(dtype):
+  rng = np.random.default_rng(31)
+  traj = io.synthetic_peptide(80, 1, seed=31, dtype=dtype)
+  base = traj.xyz[0].astype(np.float64)
+  frames = [base]
+  for f in range(1, 12):
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    w, x, y, z = q
+    rot = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                    [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                    [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    frames.append((base + rng.normal(0.0, 0.4, size=base.shape)) @ rot.T + rng.uniform(-30, 30, size=3))
+  moved = io.Trajectory(np.ascontiguousarray(np.array(frames), dtype=dtype), traj.top, "moved")
+  fit = moved.top.select("@CA")
+  want, want_rmsd = host_ref.superpose(moved.xyz, fit, ref=0)
+  before = moved.xyz.copy()
+  rmsd = io.superpose(moved, mask="@CA")
+  tol = 2e-4 if dtype == np.float32 else 1e-9            # float32 coordinates of magnitude ~100 A carry ~1e-5 A each
+  assert np.array_equal(moved.xyz[0], before[0])            # the reference frame is untouched
+  assert np.abs(moved.xyz - want).max() <= tol, np.abs(moved.xyz - want).max()
+  assert np.allclose(rmsd, want_rmsd, atol=1e-3 if dtype == np.float32 else 1e-6)
+  assert rmsd[0] <= 1e-3 and 0.3 < rmsd[1:].mean() < 1.0
+  # idempotent: a second fit moves nothing beyond rounding
+  again = moved.xyz.copy()
+  io.superpose(moved, mask="@CA")
+  assert np.abs(moved.xyz - again).max() <= 10 * tol
+
+
+@pytest.mark.gpu
+def test_misato_trajectory_through_the_featurizer(tmp_path):
+  root = str(tmp_path / "misato")
+  make_misato_dir(root, "3eov", io.synthetic_peptide(60, 20, seed=33))
+  loader = io.TrajectoryLoader([("3EOV", root)], trajtype=io.MisatoTraj, superpose=True)
+  fz = featurizer.Featurizer({"dimensions": 16, "lengths": 12, "time_window": 10, "cutoff": 3.0, "sigma": 1.0})
+  fz.register_features([features.Mass(outkey="mass"), features.MarchingObservers(obs="existence", agg="mean", outkey="exist")])
+  fz.register_focus([":ARG,LYS,GLU"], "mask")
+  fz.register_trajloader(loader)
+  fz.keep_results = True
+  stats = fz.run()
+  assert stats["native_tasks"] == 4 and np.array(fz.RESULTS["mass"]).shape == (2, 16, 16, 16)
+  assert np.array(fz.RESULTS["mass"]).sum() > 0
