@@ -106,23 +106,36 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
 
   // phase A: transform + strict two-sided crop per axis, in the coordinate dtype; a warp handles 32
   // consecutive atoms (384 contiguous bytes of float32 coordinates) and ballots their flags into one word
-#pragma unroll 4
-  for (int a = tid; a < n_pad; a += nt) {
-    bool in = false;
-    if (a < n) {
-      const T x = NrlXform<T>::apply(xyz[3 * a], 0, cr);
-      const T y = NrlXform<T>::apply(xyz[3 * a + 1], 1, cr);
-      const T z = NrlXform<T>::apply(xyz[3 * a + 2], 2, cr);
-      in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
-           ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
-      if (cr.byres && in) {
-        const int r = resid[a];
-        atomicOr(&resflags[r >> 5], 1u << (r & 31));
-      }
-      if (!cr.byres && sel) in = in && (sel[a] != 0);
+  // four atoms per thread and step: all twelve coordinate loads are issued before the first ballot (the
+  // ballots keep the compiler from overlapping the loads of consecutive iterations on its own)
+  for (int a0 = tid; a0 < n_pad; a0 += 4 * nt) {
+    T cx[4], cy[4], cz[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int a = a0 + u * nt;
+      const bool live = a < n;
+      cx[u] = live ? xyz[3 * a] : (T)0; cy[u] = live ? xyz[3 * a + 1] : (T)0; cz[u] = live ? xyz[3 * a + 2] : (T)0;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, in);
-    if (lane == 0) s_keep[a >> 5] = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int a = a0 + u * nt;
+      if (a >= n_pad) break;                  // warp-uniform: n_pad and the strides are multiples of 32
+      bool in = false;
+      if (a < n) {
+        const T x = NrlXform<T>::apply(cx[u], 0, cr);
+        const T y = NrlXform<T>::apply(cy[u], 1, cr);
+        const T z = NrlXform<T>::apply(cz[u], 2, cr);
+        in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
+             ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
+        if (cr.byres && in) {
+          const int r = resid[a];
+          atomicOr(&resflags[r >> 5], 1u << (r & 31));
+        }
+        if (!cr.byres && sel) in = in && (sel[a] != 0);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) s_keep[a >> 5] = m;
+    }
   }
   __syncthreads();
   if (cr.byres) {
@@ -244,23 +257,36 @@ nrl_crop_pack_cluster_kernel(const NrlCropParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_pad = (n + 31) & ~31;
 
-#pragma unroll 4
-  for (int a = tid; a < n_pad; a += nt) {
-    bool in = false;
-    if (a < n) {
-      const T x = NrlXform<T>::apply(xyz[3 * a], 0, cr);
-      const T y = NrlXform<T>::apply(xyz[3 * a + 1], 1, cr);
-      const T z = NrlXform<T>::apply(xyz[3 * a + 2], 2, cr);
-      in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
-           ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
-      if (cr.byres && in) {
-        const int r = resid[a];
-        atomicOr(&resflags[r >> 5], 1u << (r & 31));
-      }
-      if (!cr.byres && sel) in = in && (sel[a] != 0);
+  // four atoms per thread and step: all twelve coordinate loads are issued before the first ballot (the
+  // ballots keep the compiler from overlapping the loads of consecutive iterations on its own)
+  for (int a0 = tid; a0 < n_pad; a0 += 4 * nt) {
+    T cx[4], cy[4], cz[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int a = a0 + u * nt;
+      const bool live = a < n;
+      cx[u] = live ? xyz[3 * a] : (T)0; cy[u] = live ? xyz[3 * a + 1] : (T)0; cz[u] = live ? xyz[3 * a + 2] : (T)0;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, in);
-    if (lane == 0) s_keep[a >> 5] = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int a = a0 + u * nt;
+      if (a >= n_pad) break;                  // warp-uniform: n_pad and the strides are multiples of 32
+      bool in = false;
+      if (a < n) {
+        const T x = NrlXform<T>::apply(cx[u], 0, cr);
+        const T y = NrlXform<T>::apply(cy[u], 1, cr);
+        const T z = NrlXform<T>::apply(cz[u], 2, cr);
+        in = ((double)x < cr.hi[0]) && ((double)x > cr.lo[0]) && ((double)y < cr.hi[1]) &&
+             ((double)y > cr.lo[1]) && ((double)z < cr.hi[2]) && ((double)z > cr.lo[2]);
+        if (cr.byres && in) {
+          const int r = resid[a];
+          atomicOr(&resflags[r >> 5], 1u << (r & 31));
+        }
+        if (!cr.byres && sel) in = in && (sel[a] != 0);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) s_keep[a >> 5] = m;
+    }
   }
   if (cr.byres) {
     // a residue can straddle two chunks: every CTA of the cluster must have flagged its residues first
