@@ -80,6 +80,120 @@ __global__ void __launch_bounds__(NRL_AGG_NT) nrl_aggregate_kernel(const float *
   }
 }
 
+// Streaming form for the reducers that are recurrences over the frames (mean, max, min, drift): every thread
+// owns VEC consecutive voxels and walks the frames with independent 16-byte loads (eight in flight), nothing is
+// staged.  The arithmetic is the one of nrl_reduce4 (reference order: sum_device / max_device / min_device /
+// slope_device, /root/reference/src/gpuutils.cuh:11-50,190-205).
+#define NRL_AGG_STREAM_NT 256
+
+template <int VEC>
+__global__ void __launch_bounds__(NRL_AGG_STREAM_NT) nrl_aggregate_stream_kernel(const float *__restrict__ series, const int n,
+                                                                                  const long long G, const int agg,
+                                                                                  float *__restrict__ out) {
+  const long long g = ((long long)blockIdx.x * NRL_AGG_STREAM_NT + threadIdx.x) * VEC;
+  if (g >= G) return;
+  const float fn = (float)n;
+  float acc[VEC], sxy[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) { acc[q] = 0.0f; sxy[q] = 0.0f; }
+  float sx = 0.0f, sx2 = 0.0f;
+  const float *col = series + g;
+  for (int i0 = 0; i0 < n; i0 += 8) {
+    float x[8][VEC];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (i0 + u < n) {
+        if constexpr (VEC == 4) {
+          const float4 v = __ldcs(reinterpret_cast<const float4 *>(col + (long long)(i0 + u) * G));
+          x[u][0] = v.x; x[u][1] = v.y; x[u][2] = v.z; x[u][3] = v.w;
+        } else {
+          x[u][0] = __ldcs(col + (long long)(i0 + u) * G);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u;
+      if (i >= n) break;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        if (agg == 1) acc[q] = acc[q] + x[u][q];
+        else if (agg == 5) { if (i == 0 || x[u][q] > acc[q]) acc[q] = x[u][q]; }
+        else if (agg == 6) { if (i == 0 || x[u][q] < acc[q]) acc[q] = x[u][q]; }
+        else { acc[q] = acc[q] + x[u][q]; sxy[q] = fmaf(x[u][q], (float)i, sxy[q]); }
+      }
+      if (agg == 8) { sx = sx + (float)i; sx2 = sx2 + (float)(i * i); }
+    }
+  }
+  float r[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) {
+    if (agg == 1) r[q] = nrl_div_approx(acc[q], fn);
+    else if (agg == 8) {
+      const float denom = fmaf(fn, sx2, -(sx * sx));
+      r[q] = (n > 1 && denom != 0.0f) ? nrl_div_approx(fmaf(fn, sxy[q], -(acc[q] * sx)), denom) : 0.0f;
+    } else r[q] = acc[q];
+  }
+  if constexpr (VEC == 4) *reinterpret_cast<float4 *>(out + g) = make_float4(r[0], r[1], r[2], r[3]);
+  else out[g] = r[0];
+}
+
+// Register form for the two-pass reducers (standard deviation, variance, entropy) over short series (n <= NMAX):
+// a thread owns ONE voxel and holds its whole series in registers -- all n loads are in flight at once, the
+// second pass never leaves the register file.  Arithmetic as in nrl_reduce4 (gpuutils.cuh:35-74,140-173).
+template <int NMAX>
+__global__ void __launch_bounds__(256) nrl_aggregate_reg_kernel(const float *__restrict__ series, const int n, const long long G,
+                                                                const int agg, float *__restrict__ out) {
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (g >= G) return;
+  float x[NMAX];
+  const float *col = series + g;
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) x[i] = i < n ? __ldcs(col + (long long)i * G) : 0.0f;
+  const float fn = (float)n;
+  float r = 0.0f;
+  if (agg == 2 || agg == 4) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) if (i < n) s = s + x[i];
+    const float mean = nrl_div_approx(s, fn);
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) if (i < n) { const float d = x[i] - mean; acc = fmaf(d, d, acc); }
+    r = agg == 2 ? nrl_sqrt_approx(nrl_div_approx(acc, fn)) : nrl_div_approx(acc, fn);
+  } else if (n > 1) {    // information entropy: 16-bin histogram between the series' extremes
+    float mn = x[0], mx = x[0];
+#pragma unroll
+    for (int i = 1; i < NMAX; ++i) if (i < n) { if (x[i] < mn) mn = x[i]; if (x[i] > mx) mx = x[i]; }
+    const float range = mx - mn;
+    unsigned long long h0 = 0ull, h1 = 0ull, h2 = 0ull, h3 = 0ull;      // 16 counters of 16 bits
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i)
+      if (i < n) {
+        const float sc = nrl_div_approx(x[i] - mn, range) * 16.0f;
+        int bin;
+        asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
+        bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
+        const unsigned long long inc = 1ull << ((bin & 3) * 16);
+        const int word = bin >> 2;
+        h0 += (word == 0) ? inc : 0ull; h1 += (word == 1) ? inc : 0ull;
+        h2 += (word == 2) ? inc : 0ull; h3 += (word == 3) ? inc : 0ull;
+      }
+    if (range != 0.0f) {
+      const unsigned long long h[4] = {h0, h1, h2, h3};
+#pragma unroll
+      for (int b = 0; b < NRL_ENTROPY_BINS; ++b) {
+        const int cnt = (int)((h[b >> 2] >> ((b & 3) * 16)) & 0xffffull);
+        if (cnt > 0) {
+          const float pr = nrl_div_approx((float)cnt, fn);
+          r = fmaf(-pr, nrl_lg2_approx(pr), r);
+        }
+      }
+    }
+  }
+  out[g] = r;
+}
+
 // summation: the reference's 256-wide shared-memory tree per block, then a sequential sum of
 // the block partials (/root/reference/src/gpuutils.cu:9-31,107-134) -- kept on the device.
 __global__ void __launch_bounds__(256) nrl_block_sum_kernel(const float *__restrict__ in, float *__restrict__ partial,

@@ -696,10 +696,33 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
   }
   if (!valid_agg(agg)) {
     NRL_CUDA(cudaMemsetAsync(d_out, 0, (size_t)G * sizeof(float), st));   // gpuutils.cu:73-76
+  } else if (agg == 1 || agg == 5 || agg == 6 || agg == 8) {
+    // recurrences over the frames: streamed straight out of HBM, nothing staged
+    const bool vec = (G % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
+    const long long threads = vec ? G / 4 : G;
+    const long long grid = (threads + NRL_AGG_STREAM_NT - 1) / NRL_AGG_STREAM_NT;
+    {
+      ScopedProf sp(c, st, CAT_AGGREGATE);
+      if (vec) nrl_aggregate_stream_kernel<4><<<(unsigned)grid, NRL_AGG_STREAM_NT, 0, st>>>(d_in, n, G, agg, d_out);
+      else nrl_aggregate_stream_kernel<1><<<(unsigned)grid, NRL_AGG_STREAM_NT, 0, st>>>(d_in, n, G, agg, d_out);
+    }
+    g_launches.fetch_add(1);
+    NRL_CUDA(cudaGetLastError());
+  } else if ((agg == 2 || agg == 4 || agg == 7) && n <= 64) {
+    // two passes over a short series: the series lives in registers (measured: beyond 64 frames the register
+    // footprint leaves one CTA per SM and the shared-memory form below is faster)
+    const long long grid = (G + 255) / 256;
+    {
+      ScopedProf sp(c, st, CAT_AGGREGATE);
+      if (n <= 32) nrl_aggregate_reg_kernel<32><<<(unsigned)grid, 256, 0, st>>>(d_in, n, G, agg, d_out);
+      else nrl_aggregate_reg_kernel<64><<<(unsigned)grid, 256, 0, st>>>(d_in, n, G, agg, d_out);
+    }
+    g_launches.fetch_add(1);
+    NRL_CUDA(cudaGetLastError());
   } else {
     // widest tile that still lets two CTAs share an SM
     int W = 512;
-    while (W > 64 && (size_t)n * W * sizeof(float) > 100 * 1024) W >>= 1;
+    while (W > 64 && (size_t)n * W * sizeof(float) > 56 * 1024) W >>= 1;   // four CTAs per SM: copies of some overlap the reduction of others
     const size_t smem = (size_t)n * W * sizeof(float);
     if (smem > c.smem_optin - 1024) return fail(NRL_ERR_FRAMES, "series too long for shared memory");
     if (!c.attr_set[20]) {

@@ -18,6 +18,7 @@ __device__ __noinline__ float4 nrl_reduce4(float4 *col, const int stride, const 
   const float fn = (float)n;
   if (agg == 1 || agg == 2 || agg == 4) {
     float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
     for (int i = 0; i < n; ++i) {                      // sum_device, gpuutils.cuh:35-42
       float x[4]; nrl_unpack4(col[(size_t)i * stride], x);
       NRL4(s[q] = s[q] + x[q]);
@@ -28,6 +29,7 @@ __device__ __noinline__ float4 nrl_reduce4(float4 *col, const int stride, const 
       NRL4(out[q] = mean[q]);
     } else {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
       for (int i = 0; i < n; ++i) {                    // :53-74
         float x[4]; nrl_unpack4(col[(size_t)i * stride], x);
         NRL4({ const float d = x[q] - mean[q]; acc[q] = fmaf(d, d, acc[q]); });
@@ -57,6 +59,7 @@ __device__ __noinline__ float4 nrl_reduce4(float4 *col, const int stride, const 
     }
   } else if (agg == 5 || agg == 6) {
     float m[4]; nrl_unpack4(col[0], m);
+#pragma unroll 8
     for (int i = 1; i < n; ++i) {                      // max_device / min_device :11-32
       float x[4]; nrl_unpack4(col[(size_t)i * stride], x);
       if (agg == 5) { NRL4(if (x[q] > m[q]) m[q] = x[q]); }
