@@ -191,11 +191,12 @@ int nrl_lane_synchronize(int lane);
  * (a cudaStream_t, e.g. torch's current stream) instead of the library's own stream */
 int nrl_set_stream(void *stream, int enable);
 /* tuning / test switches.  "force_scan" != 0: never use the cell-list kernels (every task runs on the
- * full-frame scan kernels; results are identical up to float summation order) */
+ * full-frame scan kernels; results are identical up to float summation order).  "no_fuse" != 0: observers of
+ * one focus box do not share a sweep across observables (results are bit-identical either way) */
 int nrl_set_option(const char *name, int value);
 /* per-kernel device timing: CUDA events around every launch of this library, accumulated per
  * category; nrl_profile_read synchronises and copies NRL_PROFILE_CATEGORIES totals (ms, launches) */
-#define NRL_PROFILE_CATEGORIES 18
+#define NRL_PROFILE_CATEGORIES 19
 int nrl_profile(int enable);
 int nrl_profile_read(double *ms, long long *counts, int reset);
 const char *nrl_profile_name(int category);

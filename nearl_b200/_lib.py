@@ -143,7 +143,7 @@ def kernel_launches():
   return int(lib().nrl_kernel_launches())
 
 
-PROFILE_CATEGORIES = 18
+PROFILE_CATEGORIES = 19
 
 
 def set_stream(stream_ptr, enable=True):

@@ -157,27 +157,38 @@ struct NrlCellTileParams {
   int wcap;                      // records per warp
 };
 
-// one channel reduced by mean / max / min: the reducer runs as a recurrence over the frames, no series is kept
+// every channel reduced by mean / max / min: the reducers run as recurrences over the frames, no series is kept
 __host__ __device__ __forceinline__ bool nrl_streaming_task(const NrlTask &t) {
-  return t.n_ch == 1 && t.n_w == 1 && (t.ch_agg[0] == 1 || t.ch_agg[0] == 5 || t.ch_agg[0] == 6);
+  if (t.n_ch < 1 || t.ch_agg[0] == 0) return false;
+  if (t.mode != NRL_OBS_FUSED && t.n_ch != 1) return false;      // single-observable kernels keep one recurrence (registers)
+  for (int ch = 0; ch < t.n_ch; ++ch)
+    if (!(t.ch_agg[ch] == 1 || t.ch_agg[ch] == 5 || t.ch_agg[ch] == 6)) return false;
+  return true;
 }
+// rows of the per-tile time series: one per weight slot, or one per channel of a fused sweep
+__host__ __device__ __forceinline__ int nrl_series_rows(const NrlTask &t) { return t.mode == NRL_OBS_FUSED ? t.n_ch : t.n_w; }
 
 template <int MODE, int NWT> struct NrlRecStride {   // float4 per record
-  static constexpr int value = (MODE == NRL_MODE_VOXELIZE) ? (NWT > 1 ? 3 : 2) : 1;
+  static constexpr int value = (MODE == NRL_MODE_VOXELIZE) ? (NWT > 1 ? 3 : 2) : (MODE == NRL_OBS_FUSED && (NWT & NRL_FUSE_SEEN)) ? 2 : 1;
+};
+// per-frame values a sweep produces: one per weight table (voxeliser), one per channel (fused observers), else one
+template <int MODE, int NWT> struct NrlValCount {
+  static constexpr int value = (MODE == NRL_OBS_FUSED) ? NRL_MAX_CH : NWT;
 };
 
 // accumulators of one thread's four voxels; a frame may be swept in several rounds
 template <int MODE, int NWT> struct NrlAcc {
-  float f0[NWT][NRL_VPT];   // vox: deposits / exist, count: flag, count / mean_distance: sum r*w / weights: sum w / ecc: sum w*x
-  float f1[NRL_VPT], f2[NRL_VPT], f3[NRL_VPT];
+  static constexpr int NF0 = (MODE == NRL_OBS_FUSED) ? 1 : NWT;
+  float f0[NF0][NRL_VPT];   // vox: deposits / exist, count: flag, count / mean_distance: sum r*w / weights: sum w / ecc: sum w*x
+  float f1[NRL_VPT], f2[NRL_VPT], f3[NRL_VPT], f4[NRL_VPT];
   int n[NRL_VPT];
   unsigned seen[NRL_VPT];
   __device__ __forceinline__ void clear() {
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) {
 #pragma unroll
-      for (int w = 0; w < NWT; ++w) f0[w][k] = 0.0f;
-      f1[k] = f2[k] = f3[k] = 0.0f; n[k] = 0; seen[k] = 0u;
+      for (int w = 0; w < NF0; ++w) f0[w][k] = 0.0f;
+      f1[k] = f2[k] = f3[k] = f4[k] = 0.0f; n[k] = 0; seen[k] = 0u;
     }
   }
 };
@@ -219,6 +230,28 @@ __device__ __forceinline__ bool nrl_rec_sweep(const float4 *rec, const int nrec,
             if (d2 < c2) A.f0[0][k] = fmaf(wxy, ez[k], A.f0[0][k]);
           }
         }
+      } else if constexpr (MODE == NRL_OBS_FUSED) {
+        // several observables of the same atoms: one distance test, every accumulator the channels need
+        // (f0: sum r*w, f1: sum w, f2..f4: sum w*(x, y, z); each with the arithmetic of its single-mode form)
+        unsigned mask = 0u;
+        if constexpr ((NWT & NRL_FUSE_SEEN) != 0) mask = (unsigned)__float_as_int(rec[(r0 + u) * S + 1].x);
+        const float part = nrl_obs_partial(px, py, a.x, a.y);
+#pragma unroll
+        for (int k = 0; k < NRL_VPT; ++k) {
+          const float dz = pz[k] - a.z;
+          const float d2 = fmaf(dz, dz, part);
+          if (!(d2 > c2)) {
+            A.n[k] += 1;
+            if constexpr ((NWT & NRL_FUSE_SEEN) != 0) A.seen[k] |= mask;
+            if constexpr ((NWT & NRL_FUSE_R) != 0) A.f0[0][k] = fmaf(nrl_sqrt_approx(d2), a.w, A.f0[0][k]);
+            if constexpr ((NWT & NRL_FUSE_WS) != 0) A.f1[k] = A.f1[k] + a.w;
+            if constexpr ((NWT & NRL_FUSE_COM) != 0) {
+              A.f2[k] = fmaf(a.w, a.x, A.f2[k]);
+              A.f3[k] = fmaf(a.w, a.y, A.f3[k]);
+              A.f4[k] = fmaf(a.w, a.z, A.f4[k]);
+            }
+          }
+        }
       } else {
         const float part = nrl_obs_partial(px, py, a.x, a.y);
 #pragma unroll
@@ -256,12 +289,38 @@ __device__ __forceinline__ bool nrl_rec_sweep(const float4 *rec, const int nrec,
 
 template <int MODE, int NWT>
 __device__ __forceinline__ void nrl_rec_finish(const NrlAcc<MODE, NWT> &A, const NrlTask &t, const float px, const float py,
-                                               const float (&pz)[NRL_VPT], float (&val)[NWT][NRL_VPT]) {
+                                               const float (&pz)[NRL_VPT], float (&val)[NrlValCount<MODE, NWT>::value][NRL_VPT]) {
+  if constexpr (MODE == NRL_OBS_FUSED) {
+#pragma unroll
+    for (int ch = 0; ch < NRL_MAX_CH; ++ch) {
+      const int m = ch < t.n_ch ? t.ch_mode[ch] : 0;
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) {
+        float v = 0.0f;
+        if (m == NRL_OBS_EXISTENCE) v = A.n[k] > 0 ? 1.0f : 0.0f;
+        else if (m == NRL_OBS_DIRECT_COUNT) v = (float)A.n[k];
+        else if (m == NRL_OBS_DISTINCT_COUNT) v = fminf((float)__popc(A.seen[k]), NRL_DISTINCT_LIMIT);
+        else if (m == NRL_OBS_MEAN_DISTANCE) v = A.n[k] > 0 ? nrl_div_approx(A.f0[0][k], A.f1[k]) : 0.0f;
+        else if (m == NRL_OBS_CUMULATIVE_WEIGHT) v = A.f1[k];
+        else if (m == NRL_OBS_DENSITY) v = (float)((double)A.f1[k] / t.sphere_volume);
+        else if (m == NRL_OBS_ECCENTRICITY) {
+          if (A.n[k] > 0 && A.f1[k] != 0.0f) {
+            const float m0 = nrl_div_approx(A.f2[k], A.f1[k]), m1 = nrl_div_approx(A.f3[k], A.f1[k]), m2 = nrl_div_approx(A.f4[k], A.f1[k]);
+            v = nrl_sqrt_approx(nrl_obs_d2(px, py, pz[k], m0, m1, m2));
+          } else {
+            v = t.cutoff;
+          }
+        }
+        val[ch][k] = v;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < NRL_VPT; ++k) {
     if constexpr (MODE == NRL_MODE_VOXELIZE) {
 #pragma unroll
-      for (int w = 0; w < NWT; ++w) val[w][k] = A.f0[w][k];
+      for (int w = 0; w < NrlAcc<MODE, NWT>::NF0; ++w) val[w][k] = A.f0[w][k];
     } else if constexpr (MODE == NRL_OBS_DISTINCT_COUNT) {
       val[0][k] = fminf((float)__popc(A.seen[k]), NRL_DISTINCT_LIMIT);
     } else if constexpr (MODE == NRL_OBS_MEAN_DISTANCE) {
@@ -337,14 +396,22 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) pz[k] = (float)(iz + k) * s;
 
+    constexpr bool FUSED = MODE == NRL_OBS_FUSED;
+    constexpr int NTAB = FUSED ? 2 : NWT;                 // weight tables a record reads
+    constexpr int NV = NrlValCount<MODE, NWT>::value;     // per-frame values of a sweep
     const int n_w = t.n_w;
-    const float *wtabs[NWT];
+    const int n_ch = t.n_ch;
+    const float *wtabs[NTAB];
 #pragma unroll
-    for (int q = 0; q < NWT; ++q) wtabs[q] = t.wtab[q];
-    const int agg0 = t.ch_agg[0];
+    for (int q = 0; q < NTAB; ++q) wtabs[q] = t.wtab[q];
     const bool streaming = nrl_streaming_task(t);
-    float racc[NRL_VPT] = {0.f, 0.f, 0.f, 0.f};
-    const bool ser_in_smem = (long long)n_w * nF * NRL_TILE_VOX <= (long long)p.ser_cap;
+    constexpr int NRACC = FUSED ? NRL_MAX_CH : 1;         // recurrences a thread may carry (see nrl_streaming_task)
+    float racc[NRACC][NRL_VPT];
+#pragma unroll
+    for (int ch = 0; ch < NRACC; ++ch)
+#pragma unroll
+      for (int k = 0; k < NRL_VPT; ++k) racc[ch][k] = 0.0f;
+    const bool ser_in_smem = (long long)nrl_series_rows(t) * nF * NRL_TILE_VOX <= (long long)p.ser_cap;
     float4 *ser = ser_in_smem ? s_ser : g_ser;
 
     // ---- runs of this tile: one per (cx, cy) cell column its search box touches, plus the NaN bucket
@@ -427,7 +494,38 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
       // multiple of four with far-away records and swept.
       auto flush = [&]() {
         __syncwarp();
-        if constexpr (NrlModeTraits<MODE>::kNeedsWeight) {
+        if constexpr (FUSED) {
+          if constexpr (NWT != 0) {
+            for (int r0 = 0; r0 < nrec; r0 += 128) {
+              float4 a[4];
+              float w[4], rk[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * 32 + lane;
+                a[u] = r < nrec ? my_rec[(size_t)r * S] : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * 32 + lane;
+                const int payload = __float_as_int(a[u].w);
+                w[u] = (r < nrec && (NWT & (NRL_FUSE_WS | NRL_FUSE_R | NRL_FUSE_COM)) != 0) ? __ldg(wtabs[0] + payload) : 0.0f;
+                rk[u] = (r < nrec && (NWT & NRL_FUSE_SEEN) != 0) ? __ldg(wtabs[1] + payload) : -1.0f;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * 32 + lane;
+                if (r >= nrec) continue;
+                float4 *slot = my_rec + (size_t)r * S;
+                a[u].w = w[u];
+                slot[0] = a[u];
+                if constexpr ((NWT & NRL_FUSE_SEEN) != 0) {
+                  const int rank = (int)rk[u];
+                  slot[1] = make_float4(__int_as_float(rank >= 0 ? (int)(1u << (rank & 31)) : 0), 0.f, 0.f, 0.f);
+                }
+              }
+            }
+          }
+        } else if constexpr (NrlModeTraits<MODE>::kNeedsWeight) {
           for (int r0 = 0; r0 < nrec; r0 += 128) {
             float4 a[4];
             float w[4][NWT];
@@ -511,18 +609,20 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
       if (warp == 0 && f + 1 < nF) issue(f + 1);
       flush();
 
-      float val[NWT][NRL_VPT];
+      float val[NV][NRL_VPT];
       nrl_rec_finish<MODE, NWT>(A, t, px, py, pz, val);
+      // value row of channel ch: its own (fused observers), its weight slot (voxeliser), else the only one
+      auto row_of = [&](const int ch) { return FUSED ? ch : (NWT > 1 ? t.ch_w[ch] : 0); };
 
       if (t.ch_agg[0] == 0) {
         // static channels: the single frame is the result
         if (ix < nx && iy < ny) {
-          for (int ch = 0; ch < t.n_ch; ++ch) {
+          for (int ch = 0; ch < n_ch; ++ch) {
             float *o = p.out + t.ch_out[ch] + ((long long)ix * ny + iy) * nz;
-            const int slot = NWT > 1 ? t.ch_w[ch] : 0;
+            const int row = row_of(ch);
 #pragma unroll
-            for (int q = 0; q < NWT; ++q)
-              if (q == slot) {
+            for (int q = 0; q < NV; ++q)
+              if (q == row) {
 #pragma unroll
                 for (int k = 0; k < NRL_VPT; ++k)
                   if (iz + k < nz) o[iz + k] = val[q][k];
@@ -530,39 +630,51 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
           }
         }
       } else if (streaming) {
-        // mean / max / min of a single channel need no series: the reference's own sequential
-        // recurrences (sum_device, max_device, min_device, gpuutils.cuh:11-42) run as the frames pass
+        // mean / max / min need no series: the reference's own sequential recurrences (sum_device,
+        // max_device, min_device, gpuutils.cuh:11-42) run as the frames pass, one per channel
 #pragma unroll
-        for (int k = 0; k < NRL_VPT; ++k) {
-          const float x = val[0][k];
-          if (agg0 == 1) racc[k] = racc[k] + x;
-          else if (f == 0) racc[k] = x;
-          else if (agg0 == 5) { if (x > racc[k]) racc[k] = x; }
-          else { if (x < racc[k]) racc[k] = x; }
+        for (int ch = 0; ch < NRACC; ++ch) {
+          if (ch >= n_ch) break;
+          const int agg = t.ch_agg[ch], row = row_of(ch);
+#pragma unroll
+          for (int k = 0; k < NRL_VPT; ++k) {
+            float x = 0.0f;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) if (q == row) x = val[q][k];
+            if (agg == 1) racc[ch][k] = racc[ch][k] + x;
+            else if (f == 0) racc[ch][k] = x;
+            else if (agg == 5) { if (x > racc[ch][k]) racc[ch][k] = x; }
+            else { if (x < racc[ch][k]) racc[ch][k] = x; }
+          }
         }
       } else {
+        const int rows = nrl_series_rows(t);
 #pragma unroll
-        for (int q = 0; q < NWT; ++q)
-          if (q < n_w) ser[((size_t)q * nF + f) * NRL_NT + tid] = make_float4(val[q][0], val[q][1], val[q][2], val[q][3]);
+        for (int q = 0; q < NV; ++q)
+          if (q < rows) ser[((size_t)q * nF + f) * NRL_NT + tid] = make_float4(val[q][0], val[q][1], val[q][2], val[q][3]);
       }
     }
 
     if (streaming) {
       if (ix < nx && iy < ny) {
-        float *o = p.out + t.ch_out[0] + ((long long)ix * ny + iy) * nz;
 #pragma unroll
-        for (int k = 0; k < NRL_VPT; ++k)
-          if (iz + k < nz) o[iz + k] = agg0 == 1 ? nrl_div_approx(racc[k], (float)nF) : racc[k];   // mean_device :45-50
+        for (int ch = 0; ch < NRACC; ++ch) {
+          if (ch >= n_ch) break;
+          float *o = p.out + t.ch_out[ch] + ((long long)ix * ny + iy) * nz;
+#pragma unroll
+          for (int k = 0; k < NRL_VPT; ++k)
+            if (iz + k < nz) o[iz + k] = t.ch_agg[ch] == 1 ? nrl_div_approx(racc[ch][k], (float)nF) : racc[ch][k];   // mean_device :45-50
+        }
       }
-    } else
-    if (t.ch_agg[0] != 0) {
+    } else if (t.ch_agg[0] != 0) {
       // K3 fused: every thread reduces the series of its own four voxels (it wrote them), once per
       // channel.  The median sorts its series in place, so channels that need it go last.
       for (int pass = 0; pass < 2; ++pass)
-        for (int ch = 0; ch < t.n_ch; ++ch) {
+        for (int ch = 0; ch < n_ch; ++ch) {
           const int agg = t.ch_agg[ch];
           if ((agg == 3) != (pass == 1)) continue;
-          const float4 r = nrl_reduce4(ser + (size_t)t.ch_w[ch] * nF * NRL_NT + tid, NRL_NT, nF, agg);
+          const int row = FUSED ? ch : t.ch_w[ch];
+          const float4 r = nrl_reduce4(ser + (size_t)row * nF * NRL_NT + tid, NRL_NT, nF, agg);
           if (ix < nx && iy < ny) {
             float *o = p.out + t.ch_out[ch] + ((long long)ix * ny + iy) * nz;
             if (iz + 0 < nz) o[iz + 0] = r.x;

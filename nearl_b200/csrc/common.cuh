@@ -38,7 +38,14 @@ enum NrlMode {
   NRL_OBS_DISPERSION = 14,
   NRL_OBS_ECCENTRICITY = 15,
   NRL_OBS_RADIUS_OF_GYRATION = 16,
+  NRL_OBS_FUSED = 100,           // several observables of one focus box from ONE sweep (cell-list kernel only)
 };
+
+// what a fused sweep has to accumulate besides the in-range count (NrlTask::fuse_flags, the kernel's second template argument)
+enum { NRL_FUSE_SEEN = 1,        // distinct_count: OR of the value-rank bits
+       NRL_FUSE_WS = 2,          // cumulative_weight, density, mean_distance, eccentricity: sum of weights
+       NRL_FUSE_R = 4,           // mean_distance: sum of distance * weight
+       NRL_FUSE_COM = 8 };       // eccentricity: weighted coordinate sums
 
 __device__ __forceinline__ float nrl_div_approx(float a, float b) {
   float r;
@@ -87,6 +94,8 @@ struct NrlTask {
   int n_w;                  // weight slots (1 unless voxeliser with several weight tables)
   int ch_agg[NRL_MAX_CH];   // per channel: 0 = single frame written as is, 1..8 reducer id
   int ch_w[NRL_MAX_CH];     // per channel: weight slot whose per-frame values it reduces
+  int ch_mode[NRL_MAX_CH];  // NRL_OBS_FUSED: the observable of every channel
+  int fuse_flags;           // NRL_OBS_FUSED: NRL_FUSE_* needed by the channels (wtab[0]: weights, wtab[1]: value ranks)
   long long ch_out[NRL_MAX_CH];   // per channel: first output float
   int mode;                 // NrlMode
   float spacing;

@@ -29,6 +29,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_force_scan{0};    // nrl_set_option("force_scan", 1): never use the cell-list kernels
+std::atomic<int> g_no_fuse{0};       // nrl_set_option("no_fuse", 1): one sweep per observable (tests / A-B timing)
 
 int fail(int code, const std::string &msg) {
   g_err = msg;
@@ -93,11 +94,11 @@ struct Ctx {
   cudaStream_t work_stream() const { return use_user_stream ? user_stream : stream; }
 };
 
-enum { CAT_PACK_LEGACY = 0, CAT_CROP_PACK = 1, CAT_ATOM_NORM = 2, CAT_TILE0 = 3, CAT_AGGREGATE = 13, CAT_SUMMATION = 14, CAT_MISC = 15, CAT_CELL_BIN = 16, CAT_SUPERPOSE = 17 };
+enum { CAT_PACK_LEGACY = 0, CAT_CROP_PACK = 1, CAT_ATOM_NORM = 2, CAT_TILE0 = 3, CAT_AGGREGATE = 13, CAT_SUMMATION = 14, CAT_MISC = 15, CAT_CELL_BIN = 16, CAT_SUPERPOSE = 17, CAT_TILE_FUSED = 18 };
 const char *kCatNames[NRL_PROFILE_CATEGORIES] = {
     "pack_legacy", "crop_pack", "atom_norm", "tile_voxelize", "tile_existence", "tile_direct_count", "tile_distinct_count",
     "tile_mean_distance", "tile_cumulative_weight", "tile_density", "tile_dispersion", "tile_eccentricity",
-    "tile_radius_of_gyration", "aggregate", "summation", "misc", "cell_bin", "superpose"};
+    "tile_radius_of_gyration", "aggregate", "summation", "misc", "cell_bin", "superpose", "tile_fused"};
 
 struct ScopedProf {
   Ctx &c; cudaStream_t st; int cat; cudaEvent_t a = nullptr, b = nullptr;
@@ -247,8 +248,37 @@ int launch_cell_tiles_mode(Ctx &c, const NrlCellTileParams &p, int grid, size_t 
   return NRL_OK;
 }
 
+template <int FLAGS>
+int launch_cell_fused(Ctx &c, const NrlCellTileParams &p, int grid, size_t smem, cudaStream_t st) {
+  static bool attr_done[64] = {false};
+  if (!attr_done[c.dev]) {
+    NRL_CUDA(cudaFuncSetAttribute(nrl_cell_tile_kernel<NRL_OBS_FUSED, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(c.smem_optin - 2048)));
+    attr_done[c.dev] = true;
+  }
+  {
+    ScopedProf sp(c, st, CAT_TILE_FUSED);
+    nrl_cell_tile_kernel<NRL_OBS_FUSED, FLAGS><<<grid, NRL_NT, smem, st>>>(p);
+  }
+  g_launches.fetch_add(1);
+  NRL_CUDA(cudaGetLastError());
+  return NRL_OK;
+}
+
+constexpr int kFusedKey = 100;     // mode key of a fused observer group: kFusedKey + NRL_FUSE_* flags
+
 int launch_cell_tiles(Ctx &c, int mode_key, const NrlCellTileParams &p, int grid, size_t smem, cudaStream_t st) {
   switch (mode_key) {
+    case kFusedKey + 0: return launch_cell_fused<0>(c, p, grid, smem, st);
+    case kFusedKey + 1: return launch_cell_fused<1>(c, p, grid, smem, st);
+    case kFusedKey + 2: return launch_cell_fused<2>(c, p, grid, smem, st);
+    case kFusedKey + 3: return launch_cell_fused<3>(c, p, grid, smem, st);
+    case kFusedKey + 6: return launch_cell_fused<6>(c, p, grid, smem, st);
+    case kFusedKey + 7: return launch_cell_fused<7>(c, p, grid, smem, st);
+    case kFusedKey + 10: return launch_cell_fused<10>(c, p, grid, smem, st);
+    case kFusedKey + 11: return launch_cell_fused<11>(c, p, grid, smem, st);
+    case kFusedKey + 14: return launch_cell_fused<14>(c, p, grid, smem, st);
+    case kFusedKey + 15: return launch_cell_fused<15>(c, p, grid, smem, st);
     case -1: return launch_cell_tiles_mode<NRL_MODE_VOXELIZE, NRL_MAX_CH>(c, p, grid, smem, st, 0);
     case NRL_MODE_VOXELIZE: return launch_cell_tiles_mode<NRL_MODE_VOXELIZE, 1>(c, p, grid, smem, st, 0);
     case NRL_OBS_EXISTENCE: return launch_cell_tiles_mode<NRL_OBS_EXISTENCE, 1>(c, p, grid, smem, st, 1);
@@ -349,7 +379,21 @@ int bin_frames(Ctx &c, const NrlFrames &packed, std::vector<NrlCellGrid> &hgrids
   return NRL_OK;
 }
 
-int mode_key_of(const NrlTask &t) { return (t.mode == NRL_MODE_VOXELIZE && t.n_w > 1) ? kVoxelizeMulti : t.mode; }
+int mode_key_of(const NrlTask &t) {
+  if (t.mode == NRL_OBS_FUSED) return kFusedKey + t.fuse_flags;
+  return (t.mode == NRL_MODE_VOXELIZE && t.n_w > 1) ? kVoxelizeMulti : t.mode;
+}
+// flags of a set of observables (R and COM imply WS: their results divide by the sum of weights)
+int fuse_flags_of(const int *modes, int n) {
+  int f = 0;
+  for (int i = 0; i < n; ++i) {
+    if (modes[i] == NRL_OBS_DISTINCT_COUNT) f |= NRL_FUSE_SEEN;
+    if (modes[i] == NRL_OBS_CUMULATIVE_WEIGHT || modes[i] == NRL_OBS_DENSITY) f |= NRL_FUSE_WS;
+    if (modes[i] == NRL_OBS_MEAN_DISTANCE) f |= NRL_FUSE_WS | NRL_FUSE_R;
+    if (modes[i] == NRL_OBS_ECCENTRICITY) f |= NRL_FUSE_WS | NRL_FUSE_COM;
+  }
+  return f;
+}
 
 void fill_task_geometry(NrlTask &t, const int *dims, float spacing, float cutoff, float sigma) {
   t.nx = dims[2]; t.ny = dims[1]; t.nz = dims[0];
@@ -404,7 +448,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_
     while (j < sorted.size() && keys[j] == keys[i]) {
       sorted[j].tile_begin = work;
       work += sorted[j].ntx * sorted[j].nty * sorted[j].ntz;
-      maxf = std::max(maxf, sorted[j].n_frames * sorted[j].n_w);     // series rows a tile keeps
+      maxf = std::max(maxf, sorted[j].n_frames * nrl_series_rows(sorted[j]));     // series rows a tile keeps
       ++j;
     }
     Range r{};
@@ -424,8 +468,9 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_
     r.ser_cap = ser_need <= (size_t)kSerCapFloats ? (int)ser_need : 0;
     if (r.cell) {
       // staged cells + per-warp records (16 B; voxeliser 32 B / 48 B) + series
-      const int rec4 = r.mode == kVoxelizeMulti ? 3 : is_vox ? 2 : 1;
-      r.wcap = r.mode == kVoxelizeMulti ? 128 : is_vox ? 160 : 192;
+      const bool fused_seen = r.mode >= kFusedKey && ((r.mode - kFusedKey) & NRL_FUSE_SEEN);
+      const int rec4 = r.mode == kVoxelizeMulti ? 3 : (is_vox || fused_seen) ? 2 : 1;
+      r.wcap = r.mode == kVoxelizeMulti ? 128 : (is_vox || fused_seen) ? 160 : 192;
       r.smem = (size_t)NRL_STAGE_CAP * sizeof(float4) + (size_t)NRL_NW * r.wcap * rec4 * sizeof(float4) + (size_t)r.ser_cap * sizeof(float);
       r.cand_per_cta = 0;
     } else {
@@ -851,6 +896,7 @@ int nrl_cell_list_fits(const int *dims, float spacing, float cutoff, int *out) {
 int nrl_set_option(const char *name, int value) {
   if (!name) return fail(NRL_ERR_ARGUMENT, "option name is NULL");
   if (strcmp(name, "force_scan") == 0) { g_force_scan.store(value != 0); return NRL_OK; }
+  if (strcmp(name, "no_fuse") == 0) { g_no_fuse.store(value != 0); return NRL_OK; }
   return fail(NRL_ERR_ARGUMENT, std::string("unknown option ") + name);
 }
 int nrl_profile(int enable) {

@@ -212,3 +212,52 @@ def test_shared_sweeps_multi_reducer_multi_weight(tmp_path):
       assert rel_bad(got[key], ref[key], atol=2e-5 * scale) == 0, key
     else:
       assert rel_bad(got[key], ref[key]) == 0, (key, np.abs(got[key] - ref[key]).max())
+
+
+def test_fused_observers_give_the_bits_of_separate_sweeps(tmp_path):
+  """Observers of one focus box share a sweep whatever their observable (csrc/cell_kernels.cuh, NRL_OBS_FUSED);
+  every accumulator is updated with the arithmetic of its single-observable kernel, so the results are bit-identical
+  to one sweep per observable -- for streaming reducers and for reducers that keep a series."""
+  traj = io.synthetic_trajectory(3000, 12, seed=77, pin=False)
+  parms = {"dimensions": 24, "lengths": 14, "time_window": 6, "cutoff": 4.0, "sigma": 1.2}
+
+  def feats(aggs):
+    a = iter(aggs)
+    return [features.MarchingObservers(obs="existence", agg=next(a), weight_type="mass", outkey="exist"),
+            features.MarchingObservers(obs="direct_count", agg=next(a), weight_type="mass", outkey="count"),
+            features.MarchingObservers(obs="distinct_count", agg=next(a), weight_type="atomic_number", outkey="distinct"),
+            features.MarchingObservers(obs="mean_distance", agg=next(a), weight_type="mass", outkey="mean_distance"),
+            features.MarchingObservers(obs="cumulative_weight", agg=next(a), weight_type="mass", outkey="cumw"),
+            features.MarchingObservers(obs="density", agg=next(a), weight_type="mass", outkey="density"),
+            features.MarchingObservers(obs="eccentricity", agg=next(a), weight_type="mass", outkey="ecc"),
+            # a different weight table: cannot join the mass group's float channels
+            features.MarchingObservers(obs="cumulative_weight", agg=next(a), weight_type="electronegativity", outkey="cumw_en")]
+
+  for aggs in (["mean", "max", "mean", "mean", "min", "mean", "max", "mean"],                       # all streaming
+               ["standard_deviation", "median", "mean", "drift", "variance", "information_entropy", "mean", "max"]):
+    got = {}
+    for fuse in (True, False):
+      _lib.set_option("no_fuse", 0 if fuse else 1)
+      try:
+        fz = featurizer.Featurizer(parms)
+        fz.register_features(feats(aggs))
+        fz.register_focus([":ARG"], "mask")
+        fz.register_trajloader([traj])
+        fz.keep_results = True
+        launches = _lib.kernel_launches()
+        fz.run()
+        got[fuse] = ({k: np.array(v) for k, v in fz.RESULTS.items()}, _lib.kernel_launches() - launches)
+      finally:
+        _lib.set_option("no_fuse", 0)
+    assert got[True][1] < got[False][1]                        # fewer launches: the sweeps really were shared
+    for key, want in got[False][0].items():
+      assert np.array_equal(got[True][0][key], want, equal_nan=True), (aggs, key)
+    # and against the oracle
+    fz.traj = traj
+    fz.parse_focus()
+    for f in fz.FEATURESPACE:
+      f.cache(traj)
+    ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 6, buff_dim=_lib.buff_dim, scrub_nan=False)
+    for key in ("exist", "count", "distinct"):
+      r = ref[key]
+      assert np.allclose(got[True][0][key], r, rtol=1e-5, atol=1e-5), key
