@@ -88,6 +88,8 @@ class Featurizer:
     # re-used page-locked buffer and must be consumed inside the call
     self.result_sink = None
     self.last_run_stats = {}
+    # nearl_b200: trajectories in flight in run() (upload of i+1 and i+2 under the kernels of i); 1 = no overlap
+    self.pipeline_depth = 3
     if config.verbose():
       printit(f"{self.classname}: Featurizer is initialized successfully with dimensions: {self.dims} and lengths: {self.lengths}")
     if "outfile" in parms:
@@ -219,26 +221,28 @@ class Featurizer:
     (the worker counts some scripts pass) are accepted and ignored.  `trajectory_indices`
     restricts the loop to a shard (multi-GPU: one process per GPU, see nearl_b200.sharding).
 
-    Trajectories are software-pipelined over two lanes of the native library: while the
-    kernels of trajectory i run, the host lowers trajectory i+1 and its frames upload; results
-    are dumped in trajectory order."""
+    Trajectories are software-pipelined over `pipeline_depth` lanes of the native library: while
+    the kernels of trajectory i run, the host lowers the next ones and their frames upload;
+    results are dumped in trajectory order."""
     indices = range(self.TRAJECTORYNUMBER) if trajectory_indices is None else trajectory_indices
     stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "frames": 0, "seconds": 0.0}
     t_run = time.perf_counter()
-    pending = None
+    depth = max(1, min(int(self.pipeline_depth), 4))        # lanes of the native library (NRL_MAX_LANES)
+    pending = []                                             # submitted, not yet finished, oldest first
     for count, tid in enumerate(indices):
-      job = self._submit(tid, lane=count % 2)
-      if pending is not None:
-        self._finish(pending, stats)
-        pending = None
+      if len(pending) >= depth:
+        self._finish(pending.pop(0), stats)                  # frees the lane (and its buffers) about to be reused
+      job = self._submit(tid, lane=count % depth)
       if job is None:
         continue
       if job["generic_ids"]:
+        while pending:
+          self._finish(pending.pop(0), stats)
         self._finish(job, stats)        # host-protocol features read self.traj: no overlap with the next trajectory
       else:
-        pending = job
-    if pending is not None:
-      self._finish(pending, stats)
+        pending.append(job)
+    while pending:
+      self._finish(pending.pop(0), stats)
     stats["seconds"] = time.perf_counter() - t_run
     self.last_run_stats = stats
     printit(f"{self.classname}: All trajectories and tasks are finished. \n")
