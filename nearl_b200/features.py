@@ -51,6 +51,7 @@ _NUMBER_TYPES = (int, float, np.integer, np.floating)
 
 
 _CELL_FIT_MEMO = {}
+_BUILTIN_MEMO = {}
 
 
 def _lut(table):
@@ -373,7 +374,11 @@ class Feature:
   def _is_builtin(self, *methods):
     """True when none of `methods` was overridden outside this module (a user subclass that
     customises query/run must go through the host protocol)."""
-    return all(getattr(type(self), m).__module__ == __name__ for m in methods)
+    key = (type(self), methods)
+    hit = _BUILTIN_MEMO.get(key)
+    if hit is None:
+      hit = _BUILTIN_MEMO[key] = all(getattr(type(self), m).__module__ == __name__ for m in methods)
+    return hit
 
   def _native_spec(self):
     """Description of this feature for nrl_featurize_batch, or None for the host protocol."""

@@ -228,6 +228,7 @@ class Featurizer:
     stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "frames": 0, "seconds": 0.0}
     t_run = time.perf_counter()
     depth = max(1, min(int(self.pipeline_depth), 4))        # lanes of the native library (NRL_MAX_LANES)
+    self.__dict__.pop("_fingerprint_memo", None)
     pending = []                                             # submitted, not yet finished, oldest first
     for count, tid in enumerate(indices):
       if len(pending) >= depth:
@@ -544,11 +545,16 @@ class Featurizer:
     through the same box (same padding / by-residue / selection / cap / emission order)."""
     n_focal = self.FOCALNUMBER if self.FOCALNUMBER > 0 else 1
 
+    memo = self.__dict__.setdefault("_fingerprint_memo", {})      # cleared by run(): feature parameters are fixed inside a run
+
     def fingerprint(fidx):
       f, sp = self.FEATURESPACE[fidx], specs[fidx]
-      return (fidx, tuple(int(v) for v in f.dims), float(f.spacing), float(f.cutoff), float(sp["sigma"]), float(f.padding),
-              bool(f.byres), f.selection is not None, bool(sp.get("selection_folded")), sp["kind"], sp["mode"], sp["agg"],
-              sp["frame_offset"], sp["max_atoms"], sp.get("ranks") is not None, sp.get("weight_sig"))
+      fixed = memo.get(fidx)
+      if fixed is None:
+        fixed = memo[fidx] = (fidx, tuple(int(v) for v in f.dims), float(f.spacing), float(f.cutoff), float(f.padding), bool(f.byres),
+                              f.selection is not None)
+      return fixed + (float(sp["sigma"]), bool(sp.get("selection_folded")), sp["kind"], sp["mode"], sp["agg"],
+                      sp["frame_offset"], sp["max_atoms"], sp.get("ranks") is not None, sp.get("weight_sig"))
 
     key = (tuple(fingerprint(f) for f in native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64))
     cache = self.__dict__.setdefault("_template_cache", {})
