@@ -6,7 +6,7 @@ import csv, json, re, sys
 
 CATEGORY = {0: "tile_voxelize", 1: "tile_existence", 2: "tile_direct_count", 3: "tile_distinct_count", 11: "tile_mean_distance",
             12: "tile_cumulative_weight", 13: "tile_density", 14: "tile_dispersion", 15: "tile_eccentricity",
-            16: "tile_radius_of_gyration"}
+            16: "tile_radius_of_gyration", 100: "tile_fused"}
 
 def category(name):
   m = re.search(r"nrl_(cell_)?tile_kernel<\(?(?:int\))?(\d+)", name)
