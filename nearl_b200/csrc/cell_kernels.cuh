@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
       const int nan_begin = s_run_dst[s_n_runs - 1];       // the last run is the NaN bucket
       const bool staged = total <= NRL_STAGE_CAP;
       const float4 *gat = p.frames.atoms + aoff;
-      const float *inv = (MODE == NRL_MODE_VOXELIZE) ? t.inv_norm + aoff : nullptr;
+      const float *inv = (MODE == NRL_MODE_VOXELIZE) ? t.inv_norm + aoff - p.frames.pbase[fd] : nullptr;    // addressed by payload
 
       // position of staged / flat slot i in the binned frame
       auto locate = [&](const int i) {
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
 #pragma unroll
               for (int q = 0; q < NWT; ++q) w[u][q] = (r < nrec && q < n_w) ? __ldg(wtabs[q] + payload) : 0.0f;
               if constexpr (MODE == NRL_MODE_VOXELIZE)
-                iv[u] = r < nrec ? __ldg(inv + __float_as_int(my_rec[(size_t)r * S + 1].x)) : 0.0f;
+                iv[u] = r < nrec ? __ldg(inv + payload) : 0.0f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -598,10 +598,6 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
         if (keep) {
           float4 *slot = my_rec + (size_t)(nrec + __popc(m & ((1u << lane) - 1u))) * S;
           slot[0] = a;
-          if constexpr (MODE == NRL_MODE_VOXELIZE) {
-            if (staged) gi = locate(i);
-            slot[1].x = __int_as_float(gi);             // position in the binned frame: 1/S is parallel to it
-          }
         }
         nrec += __popc(m);
       }

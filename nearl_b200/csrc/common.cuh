@@ -112,6 +112,8 @@ struct NrlFrames {
   const float4 *atoms;      // packed (x, y, z, index-payload) per atom
   const long long *off;     // per frame: first packed atom
   const int *cnt;           // per frame: number of packed atoms (device-produced)
+  const int *pbase;         // per frame: payload of the frame's first POSSIBLE atom; per-atom side arrays of a frame
+                            // (1/S of the voxeliser) are addressed by payload - pbase, whatever order the atoms are stored in
 };
 
 struct NrlTileParams {

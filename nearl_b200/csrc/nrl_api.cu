@@ -73,7 +73,7 @@ struct Ctx {
   std::mutex mu;
   DevBuf coords, weights, perm, atoms, inv, off, cnt, out, tasks, flist, cand_scr, ser_scr, misc, series;
   DevBuf xyz, wtabs, sels, resid, orders, crops, fcrop, fsrc, keep, resflags;
-  DevBuf foff;                                   // per crop frame: first packed atom
+  DevBuf foff, pbase;                            // per crop frame: first packed atom, payload base
   DevBuf sup_idx, sup_ref, sup_rmsd;             // superposition: fitted atom indices, reference set, per-frame RMSD
   DevBuf batoms, bcnt, cstart, grids, blist;     // cell lists: binned frames, cell prefixes, per-frame cell grids
   bool attr_set[64] = {false};
@@ -373,7 +373,7 @@ int bin_frames(Ctx &c, const NrlFrames &packed, std::vector<NrlCellGrid> &hgrids
     NRL_CUDA(cudaGetLastError());
   }
   out.on = true;
-  out.frames = NrlFrames{c.batoms.as<float4>(), packed.off, c.bcnt.as<int>()};
+  out.frames = NrlFrames{c.batoms.as<float4>(), packed.off, c.bcnt.as<int>(), packed.pbase};
   out.grids = c.grids.as<NrlCellGrid>();
   out.cell_start = c.cstart.as<int>();
   return NRL_OK;
@@ -659,6 +659,7 @@ int legacy_run(const LegacyArgs &a) {
     NRL_TRY(c.atoms.reserve(std::max<size_t>(n_atoms, 1) * sizeof(float4)));
     NRL_TRY(c.off.reserve((size_t)nF * sizeof(long long)));
     NRL_TRY(c.cnt.reserve((size_t)nF * sizeof(int)));
+    NRL_TRY(c.pbase.reserve((size_t)nF * sizeof(int)));
     {
       const long long total = (long long)n_atoms;
       const int grid = (int)std::min<long long>(std::max<long long>((std::max<long long>(total, nF) + 255) / 256, 1), 4096);
@@ -666,12 +667,12 @@ int legacy_run(const LegacyArgs &a) {
         ScopedProf sp(c, st, CAT_PACK_LEGACY);
         nrl_pack_legacy_kernel<<<grid, 256, 0, st>>>(d_coords, d_weights, d_perm, nF, a.N,
                                                       a.mode == NRL_OBS_DISTINCT_COUNT ? 1 : 0, c.atoms.as<float4>(),
-                                                      c.off.as<long long>(), c.cnt.as<int>());
+                                                      c.off.as<long long>(), c.cnt.as<int>(), c.pbase.as<int>());
       }
       g_launches.fetch_add(1);
       NRL_CUDA(cudaGetLastError());
     }
-    NrlFrames frames{c.atoms.as<float4>(), c.off.as<long long>(), c.cnt.as<int>()};
+    NrlFrames frames{c.atoms.as<float4>(), c.off.as<long long>(), c.cnt.as<int>(), c.pbase.as<int>()};
     NrlTask t;
     memset(&t, 0, sizeof t);
     fill_task_geometry(t, a.dims, a.spacing, a.cutoff, a.sigma);

@@ -19,7 +19,7 @@
 __global__ void nrl_pack_legacy_kernel(const float *__restrict__ coords, const float *__restrict__ weights,
                                        const int *__restrict__ perm, const int F, const int N,
                                        const int hide_placeholder_weights, float4 *__restrict__ atoms,
-                                       long long *__restrict__ off, int *__restrict__ cnt) {
+                                       long long *__restrict__ off, int *__restrict__ cnt, int *__restrict__ pbase) {
   const long long total = (long long)F * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -29,10 +29,10 @@ __global__ void nrl_pack_legacy_kernel(const float *__restrict__ coords, const f
     float x = coords[src * 3], y = coords[src * 3 + 1], z = coords[src * 3 + 2];
     if (hide_placeholder_weights && weights[src] == NRL_PLACEHOLDER) x = FLT_MAX;
     atoms[i] = make_float4(x, y, z, __int_as_float((int)src));
-    if (j == 0) { off[f] = (long long)f * N; cnt[f] = N; }
+    if (j == 0) { off[f] = (long long)f * N; cnt[f] = N; pbase[f] = f * N; }
   }
   if (N == 0)
-    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) { off[f] = 0; cnt[f] = 0; }
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < F; f += gridDim.x * blockDim.x) { off[f] = 0; cnt[f] = 0; pbase[f] = 0; }
 }
 
 // ---- device-side focus box -----------------------------------------------------------
@@ -65,6 +65,7 @@ struct NrlCropParams {
   const long long *frame_off;   // per output frame: first packed atom (capacity = the crop's slice length)
   long long *off;
   int *cnt;
+  int *pbase;                   // per output frame: payload base (atom_begin + table_shift)
   unsigned char *keep;          // unused (kept for ABI stability of the struct)
   unsigned int *resflags;       // scratch [n_frames_out, n_res_words], zero-initialised
 };
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(NRL_CROP_NT) nrl_crop_pack_kernel(const NrlCro
     }
     base += __popc(m);
   }
-  if (tid == 0) { p.off[fd] = foff; p.cnt[fd] = min(total, cap); }
+  if (tid == 0) { p.off[fd] = foff; p.cnt[fd] = min(total, cap); p.pbase[fd] = a0 + shift; }
 }
 
 // Cluster form of the crop kernel for whole-topology crops in topology order: NRL_CROP_CLUSTER CTAs (one
@@ -344,7 +345,7 @@ nrl_crop_pack_cluster_kernel(const NrlCropParams p) {
     }
     base += __popc(m);
   }
-  if (rank == 0 && tid == 0) { p.off[fd] = foff; p.cnt[fd] = min(total, cap); }
+  if (rank == 0 && tid == 0) { p.off[fd] = foff; p.cnt[fd] = min(total, cap); p.pbase[fd] = a0 + shift; }
   cluster.sync();     // s_cta_total must outlive the remote reads
 }
 
@@ -359,7 +360,7 @@ struct NrlNormParams {
   const int *frame_list;     // frames to process
   int nx, ny, nz;
   float spacing, cutoff, k2;
-  float *inv_norm;           // parallel to frames.atoms
+  float *inv_norm;           // per frame at frames.off, addressed by payload - frames.pbase
 };
 
 #define NRL_NORM_MAXZ 96     // lattice points along an axis inside one cutoff sphere handled by the fast path
@@ -379,6 +380,7 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
   const int fd = p.frame_list[blockIdx.y];
   const int n = min(p.frames.cnt[fd], capacity);
   const long long off = p.frames.off[fd];
+  const int pb = p.frames.pbase[fd];
   const float s = p.spacing, c = p.cutoff, c2 = c * c, k2 = p.k2;
   const int b = nrl_buff_dim_device(c, s);
   float *P = s_prefix[wid], *Dx = s_dx[wid], *Ex = s_ex[wid], *Dy2 = s_dy2[wid], *Ey = s_ey[wid];
@@ -474,6 +476,6 @@ __global__ void __launch_bounds__(128) nrl_atom_norm_kernel(const NrlNormParams 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) p.inv_norm[off + i] = sum > 0.0 ? (float)(1.0 / sum) : 0.0f;
+    if (lane == 0) p.inv_norm[off + (__float_as_int(a.w) - pb)] = sum > 0.0 ? (float)(1.0 / sum) : 0.0f;
   }
 }

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
       const long long aoff = p.frames.off[t.frame0 + f];
       const int n = p.frames.cnt[t.frame0 + f];
       const float4 *atoms = p.frames.atoms + aoff;
-      const float *inv = (MODE == NRL_MODE_VOXELIZE) ? t.inv_norm + aoff : nullptr;
+      const float *inv = (MODE == NRL_MODE_VOXELIZE) ? t.inv_norm + aoff - p.frames.pbase[t.frame0 + f] : nullptr;   // addressed by payload
 
       // ---- pass 1: each warp counts the survivors of its contiguous atom segment.  Four
       // independent coalesced float4 loads are in flight per lane (the scan is latency bound).
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(NRL_NT) nrl_tile_kernel(const NrlTileParams p)
               for (int q = 0; q < NWT; ++q) if (q < n_w) w[u][q] = __ldg(wtabs[q] + payload);
             }
             if constexpr (MODE == NRL_MODE_VOXELIZE) {
-              const float iv = __ldg(inv + i0 + u * 32 + lane);
+              const float iv = __ldg(inv + payload);
 #pragma unroll
               for (int q = 0; q < NWT; ++q) w[u][q] = w[u][q] * iv;
             }
