@@ -570,8 +570,10 @@ int launch_norm(Ctx &c, const NrlFrames &frames, const int *d_frame_list, int n_
     const int ny = std::min(65535, n_list - f0);
     NrlNormParams q = np;
     q.frame_list = d_frame_list + f0;
-    // warps stride over the atoms of their frame: 48 CTAs x 4 warps per frame keep short frames cheap
-    dim3 grid((unsigned)std::max(1, std::min((capacity + warps_per_cta - 1) / warps_per_cta, 48)), (unsigned)ny);
+    // warps stride over the atoms of their frame: at least 48 CTAs x 4 warps per frame, and for a launch of few
+    // frames enough CTAs to put ~32 warps on every SM (a single-frame call is latency bound otherwise)
+    const int want = std::max(48, (c.sms * 32 / warps_per_cta + ny - 1) / ny);
+    dim3 grid((unsigned)std::max(1, std::min((capacity + warps_per_cta - 1) / warps_per_cta, want)), (unsigned)ny);
     {
       ScopedProf sp(c, st, CAT_ATOM_NORM);
       nrl_atom_norm_kernel<<<grid, warps_per_cta * 32, 0, st>>>(q, capacity);
@@ -641,8 +643,64 @@ int legacy_run(const LegacyArgs &a) {
       d_coords = c.coords.as<float>();
       d_weights = c.weights.as<float>();
     }
+    NrlCellGrid cell_grid;
+    bool grid_ok = false;
+    {
+      CropCells cc;
+      cc.add(a.dims, a.spacing, a.cutoff);
+      grid_ok = cc.grid(cell_grid, kMaxCells);
+    }
     const int *d_perm = nullptr;
+    const float *d_ranks = nullptr;       // distinct_count over <= 32 distinct values: value ranks for the cell-list kernel
     if (a.mode == NRL_OBS_DISTINCT_COUNT && n_atoms > 0) {
+      std::vector<float> hw;
+      const float *w_host = a.weights;
+      if (a.on_device) {
+        hw.resize(n_atoms);
+        NRL_CUDA(cudaMemcpyAsync(hw.data(), a.weights, n_atoms * sizeof(float), cudaMemcpyDeviceToHost, st));
+        NRL_CUDA(cudaStreamSynchronize(st));
+        w_host = hw.data();
+      }
+      // few distinct values (atomic numbers, flags ...): one pass collects them, their sorted position is the rank
+      if (!g_force_scan && grid_ok) {
+        // 64-slot open-addressing set keyed on the value's bits (-0.0 folded onto +0.0, as float == does)
+        uint32_t keys[64];
+        int slot_val[64], nv = 0;
+        float vals[32];
+        bool used[64] = {false}, few = true;
+        auto find = [&](float v, bool insert) -> int {
+          if (v == 0.0f) v = 0.0f;
+          uint32_t bits;
+          memcpy(&bits, &v, 4);
+          uint32_t h = (bits * 2654435761u) >> 26;
+          while (used[h] && keys[h] != bits) h = (h + 1) & 63;
+          if (!used[h]) {
+            if (!insert || nv == 32) return -1;
+            used[h] = true; keys[h] = bits; slot_val[h] = nv; vals[nv++] = v;
+          }
+          return slot_val[h];
+        };
+        for (size_t i = 0; i < n_atoms && few; ++i) {
+          const float v = w_host[i];
+          if (v != v || find(v, true) < 0) few = false;       // every NaN is a value of its own: leave it to the scan kernel
+        }
+        if (few) {
+          int order[32], rank_of[32];
+          std::iota(order, order + nv, 0);
+          std::sort(order, order + nv, [&](int x, int y) { return vals[x] < vals[y]; });
+          for (int r = 0; r < nv; ++r) rank_of[order[r]] = r;
+          std::vector<float> ranks(n_atoms);
+          for (size_t i = 0; i < n_atoms; ++i) {
+            const float v = w_host[i];
+            ranks[i] = (v == NRL_PLACEHOLDER) ? -1.0f : (float)rank_of[find(v, false)];            // marching_observers.cu:118-138
+          }
+          NRL_TRY(c.perm.reserve(n_atoms * sizeof(float)));
+          NRL_CUDA(cudaMemcpyAsync(c.perm.p, ranks.data(), n_atoms * sizeof(float), cudaMemcpyHostToDevice, st));
+          d_ranks = c.perm.as<float>();
+        }
+      }
+    }
+    if (a.mode == NRL_OBS_DISTINCT_COUNT && n_atoms > 0 && !d_ranks) {
       std::vector<float> hw;
       const float *w_host = a.weights;
       if (a.on_device) {
@@ -666,7 +724,7 @@ int legacy_run(const LegacyArgs &a) {
       {
         ScopedProf sp(c, st, CAT_PACK_LEGACY);
         nrl_pack_legacy_kernel<<<grid, 256, 0, st>>>(d_coords, d_weights, d_perm, nF, a.N,
-                                                      a.mode == NRL_OBS_DISTINCT_COUNT ? 1 : 0, c.atoms.as<float4>(),
+                                                      (a.mode == NRL_OBS_DISTINCT_COUNT && !d_ranks) ? 1 : 0, c.atoms.as<float4>(),
                                                       c.off.as<long long>(), c.cnt.as<int>(), c.pbase.as<int>());
       }
       g_launches.fetch_add(1);
@@ -684,16 +742,15 @@ int legacy_run(const LegacyArgs &a) {
     t.ch_out[0] = 0;
     t.mode = a.mode;
     t.frame0 = 0;
-    t.wtab[0] = d_weights;
+    t.wtab[0] = d_ranks ? d_ranks : d_weights;
     t.inv_norm = nullptr;
     // cell lists for every mode that has a cell-list kernel (g_force_scan: tests / A-B timing)
     CellSetup cells;
-    if (cell_mode(a.mode) && !g_force_scan && n_atoms > 0) {
-      CropCells cc;
-      cc.add(a.dims, a.spacing, a.cutoff);
-      NrlCellGrid g;
-      if (cc.grid(g, kMaxCells)) {
-        std::vector<NrlCellGrid> hgrids((size_t)nF, g);
+    // (a single short frame is cheaper on the scan kernel: nothing to amortise the binning launch over;
+    //  rank-based distinct_count exists on the cell-list kernel only)
+    if ((cell_mode(a.mode) || d_ranks) && !g_force_scan && n_atoms > 0 && (d_ranks || !(nF == 1 && a.N <= 4096))) {
+      if (grid_ok) {
+        std::vector<NrlCellGrid> hgrids((size_t)nF, cell_grid);
         std::vector<int> fl(nF);
         std::iota(fl.begin(), fl.end(), 0);
         NRL_TRY(bin_frames(c, frames, hgrids, fl, n_atoms, a.N, st, cells));
