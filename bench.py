@@ -44,6 +44,10 @@ WORKLOADS = {
              "synthetic 5k-atom x 100-frame trajectory"),
   "pdbbind": ("configs[2]: PDBBind-style static featurisation, 8 atom-property channels at 24^3 over 20 A, cutoff 2.5, sigma 1.5, "
               "focus ':LIG', synthetic 3k-atom complexes (one frame each; a step = one complex)"),
+  "misato": ("configs[3]: MISATO-style batch, 3 static + 2 marching-observer + 2 density-flow channels at 32^3 over 20 A, window 10, "
+             "cutoff 2.5 static / 5.0 dynamic, sigma 1.5, focus ':ARG', synthetic 6k-atom x 100-frame trajectories"),
+  "stress": ("configs[4]: 128^3 grid at 0.5 A, synthetic 200k-atom x 200-frame trajectory, time_window=100, cutoff 5.0, observers existence / "
+             "distinct_count / mean_distance + 2 density flows, mean and standard deviation (reference's 9999-atom cap kept)"),
 }
 WORKLOAD = WORKLOADS["dynamic"]
 
@@ -56,6 +60,10 @@ def make_workload(name, n_traj, seed_offset=0, pin=True):
     return workloads.readme_mass(n_traj=n_traj, seed_offset=seed_offset, pin=pin)
   if name == "pdbbind":
     return workloads.pdbbind_static(n_complex=n_traj * 8, seed_offset=seed_offset, pin=pin)
+  if name == "misato":
+    return workloads.misato_mixed(n_traj=n_traj, seed_offset=seed_offset, pin=pin)
+  if name == "stress":
+    return workloads.stress_large(n_traj=min(n_traj, 2), seed_offset=seed_offset, pin=pin)
   raise SystemExit(f"unknown workload {name}")
 
 
@@ -320,7 +328,11 @@ def run_native(args):
     roof_c = None
 
   # ---- CPU baseline: oracle port on the host cores, bounded sample of the same workload -----------
-  cpu = cpu_baseline_sample(fz, trajs[0])
+  if args.workload == "stress":
+    cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+           "sample": "skipped: one window of this workload is ~2e12 brute-force pair tests per feature on the CPU oracle (hours)"}
+  else:
+    cpu = cpu_baseline_sample(fz, trajs[0])
 
   line = {
     "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -455,6 +467,8 @@ def main():
   ap.add_argument("--cold-context", action="store_true", help="reference arm: do not pre-create a torch CUDA context")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+  if args.workload == "stress" and "--steps" not in " ".join(sys.argv):
+    args.steps = 10 if args.impl == "native" else 1          # a step is 50 ms here, ~10 s for the reference arm
   if args.impl == "reference":
     if args.steps == 100 and "--steps" not in " ".join(sys.argv):
       args.steps = 6                      # a reference step is ~0.5 s
