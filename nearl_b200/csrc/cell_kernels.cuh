@@ -441,13 +441,23 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
       __syncwarp();
     }
 
-    // stage the runs of frame `f` (warp 0): sizes from the frame's cell prefix, one bulk copy per run
+    // Per-frame descriptors are affine in the frame index inside a crop (the host lays the frames of a crop out
+    // back to back): two loads per tile instead of a dependent load per frame.
+    const long long off0 = p.frames.off[fd0], cs0 = p.grids[fd0].cs_off;
+    const long long off_step = nF > 1 ? p.frames.off[fd0 + 1] - off0 : 0, cs_step = nF > 1 ? p.grids[fd0 + 1].cs_off - cs0 : 0;
+    const int pb0 = p.frames.pbase[fd0], pb_step = nF > 1 ? p.frames.pbase[fd0 + 1] - pb0 : 0;
+
+    // Staging of frame f (warp 0), software-pipelined so that no load sits on the critical path of the frame loop:
+    // fetch_runs(f) only ISSUES the loads of the frame's cell-prefix entries (two per run), issue(f) consumes them
+    // one frame later: sizes -> slots by a warp scan, one bulk copy per run.
+    int nx_beg = 0, nx_end = 0;
+    auto fetch_runs = [&](const int f) {
+      const int *row = p.cell_start + (cs0 + (long long)f * cs_step);
+      nx_beg = 0; nx_end = 0;
+      if (lane < s_n_runs) { nx_beg = __ldg(row + s_run_first[lane]); nx_end = __ldg(row + s_run_last[lane] + 1); }
+    };
     auto issue = [&](const int f) {
-      const long long fd = fd0 + f;
-      const int *row = p.cell_start + p.grids[fd].cs_off;
-      const int n_runs = s_n_runs;
-      int beg = 0, len = 0;
-      if (lane < n_runs) { beg = __ldg(row + s_run_first[lane]); len = __ldg(row + s_run_last[lane] + 1) - beg; }
+      const int beg = nx_beg, len = nx_end - nx_beg;
       int incl = len;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
@@ -461,20 +471,23 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
       if (lane == 0) nrl_mbar_expect_tx(&s_bar, staged ? (uint32_t)total * 16u : 0u);
       __syncwarp();
       if (staged && len > 0)
-        nrl_bulk_g2s(s_stage + dst, p.frames.atoms + p.frames.off[fd] + beg, (uint32_t)len * 16u, &s_bar);
+        nrl_bulk_g2s(s_stage + dst, p.frames.atoms + (off0 + (long long)f * off_step) + beg, (uint32_t)len * 16u, &s_bar);
     };
-    if (warp == 0) issue(0);
+    if (warp == 0) {
+      fetch_runs(0);
+      issue(0);
+      if (nF > 1) fetch_runs(1);
+    }
 
     for (int f = 0; f < nF; ++f) {
-      const long long fd = fd0 + f;
-      const long long aoff = p.frames.off[fd];
+      const long long aoff = off0 + (long long)f * off_step;
       nrl_mbar_wait(&s_bar, phase & 1u);
       ++phase;
       const int total = s_total;
       const int nan_begin = s_run_dst[s_n_runs - 1];       // the last run is the NaN bucket
       const bool staged = total <= NRL_STAGE_CAP;
       const float4 *gat = p.frames.atoms + aoff;
-      const float *inv = (MODE == NRL_MODE_VOXELIZE) ? t.inv_norm + aoff - p.frames.pbase[fd] : nullptr;    // addressed by payload
+      const float *inv = (MODE == NRL_MODE_VOXELIZE) ? t.inv_norm + aoff - (pb0 + f * pb_step) : nullptr;    // addressed by payload
 
       // position of staged / flat slot i in the binned frame
       auto locate = [&](const int i) {
@@ -602,7 +615,10 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
         nrec += __popc(m);
       }
       __syncthreads();                       // every warp is done with the staged cells
-      if (warp == 0 && f + 1 < nF) issue(f + 1);
+      if (warp == 0 && f + 1 < nF) {
+        issue(f + 1);
+        if (f + 2 < nF) fetch_runs(f + 2);
+      }
       flush();
 
       float val[NV][NRL_VPT];

@@ -613,7 +613,8 @@ class DynamicFeature(Feature):
     }
     if self._is_builtin("cache") and self.selection is None:
       # features with the same signature cache the same per-atom weights: they share one weight table (and one sweep)
-      spec["weight_sig"] = ("dynamic", self.weight_type, repr(sorted(self.feature_args.items())))
+      spec["weight_sig"] = ("dynamic", self.weight_type, repr(self.feature_args.get("manual_weight", 1)),
+                            repr(self.feature_args.get("element_type", None)))       # what cache_properties reads
     if int(mode) == 3:
       # distinct_count over few distinct values (atomic numbers, atom types ...) runs on the cell-list kernel with
       # per-atom value ranks; otherwise the crop is emitted in value order for the scan kernel

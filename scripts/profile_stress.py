@@ -1,0 +1,23 @@
+"""Device-resident step of the stress workload (configs[4]) for ncu: python scripts/profile_stress.py [steps]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import nearl_b200
+from nearl_b200 import workloads
+nearl_b200.update_config(quiet=True)
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+fz, trajs = workloads.stress_large(n_traj=1, pin=False)
+traj = trajs[0]
+fz.traj = traj
+fz.parse_focus()
+for f in fz.FEATURESPACE:
+  f.cache(traj)
+specs = [f._native_spec() for f in fz.FEATURESPACE]
+batch = fz.lower_batch(list(range(fz.FEATURENUMBER)), specs, traj.n_atoms, False)
+xyz = torch.from_numpy(traj.xyz).cuda()
+out = torch.empty(batch.out_floats, dtype=torch.float32, device="cuda")
+for _ in range(steps):
+  batch.execute(xyz.data_ptr(), traj.n_frames, out.data_ptr(), xyz_on_device=True, out_on_device=True)
+torch.cuda.synchronize()
+print("ok", float(out.sum()))
