@@ -36,6 +36,8 @@ struct NrlCellGrid {          // one per frame descriptor; the frames of a crop 
   int ncx, ncy, ncz;          // cells per axis, cell = (cx*ncy + cy)*ncz + cz
   float inv_hz;               // 1 / cell edge along z: a tile reads whole z-runs of cells, finer cells trim the run ends
   long long cs_off;           // this frame's row of cell_start: ncell + 2 ints (prefix, NaN bucket last)
+  float bx, by, bz;           // far corner of the box spanned by the voxel centres (near corner: the origin)
+  float reach2;               // squared reach: an atom farther than this from that box touches no voxel and is dropped
 };
 
 // Cell of an atom.  Monotone in every coordinate (float rounding is monotone), and the tile kernel
@@ -45,6 +47,9 @@ __device__ __forceinline__ int nrl_cell_of(const float4 a, const NrlCellGrid &g,
   if (a.x != a.x || a.y != a.y || a.z != a.z) return ncell;                 // NaN bucket
   const float fx = nrl_cell_coord(a.x, g.ox, g.inv_h), fy = nrl_cell_coord(a.y, g.oy, g.inv_h), fz = nrl_cell_coord(a.z, g.oz, g.inv_hz);
   if (!(fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < (float)g.ncx && fy < (float)g.ncy && fz < (float)g.ncz)) return -1;
+  // corners of the padded box: inside the cell grid, yet out of every voxel's reach (reach2 carries the margin)
+  const float qx = fmaxf(fmaxf(-a.x, a.x - g.bx), 0.0f), qy = fmaxf(fmaxf(-a.y, a.y - g.by), 0.0f), qz = fmaxf(fmaxf(-a.z, a.z - g.bz), 0.0f);
+  if (fmaf(qz, qz, fmaf(qy, qy, qx * qx)) > g.reach2) return -1;
   return ((int)fx * g.ncy + (int)fy) * g.ncz + (int)fz;
 }
 

@@ -320,6 +320,8 @@ struct CropCells {
       g.inv_hz = 1.0f / hz;
       g.ncx = (int)ncx; g.ncy = (int)ncy; g.ncz = (int)ncz;
       g.cs_off = 0;
+      g.bx = ext[0]; g.by = ext[1]; g.bz = ext[2];
+      g.reach2 = pad * pad;
       return true;
     }
     return false;
