@@ -261,3 +261,33 @@ def test_fused_observers_give_the_bits_of_separate_sweeps(tmp_path):
     for key in ("exist", "count", "distinct"):
       r = ref[key]
       assert np.allclose(got[True][0][key], r, rtol=1e-5, atol=1e-5), key
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cluster_crop_byres_selection_and_cap(tmp_path, dtype):
+  """Long frames in topology order go through the cluster form of the crop kernel (four CTAs per frame, counts
+  over distributed shared memory): by-residue expansion across chunk borders, selection masks and the atom cap
+  must come out exactly as the host pipeline's."""
+  traj = io.synthetic_trajectory(9000, 6, seed=91, dtype=dtype)
+  parms = {"dimensions": 20, "lengths": 14, "time_window": 3, "cutoff": 3.5, "sigma": 1.2}
+
+  def feats():
+    capped = features.MarchingObservers(obs="direct_count", agg="max", weight_type="mass", outkey="count_capped", byres=True)
+    capped.MAX_ALLOWED_ATOMS = 300                         # the first 300 in-box atoms in topology order
+    return [features.Mass(outkey="mass", byres=True, padding=2.0),
+            features.Selection(selection=":ARG,LYS,GLU", outkey="sel"),
+            features.MarchingObservers(obs="mean_distance", agg="mean", weight_type="mass", outkey="mean_distance", byres=True),
+            features.MarchingObservers(obs="direct_count", agg="mean", weight_type="mass", outkey="count", selection=":ALA,GLY,SER,THR"),
+            capped]
+
+  got, fz = build(traj, tmp_path, feats, parms)
+  descs = descs_from(fz)
+  for d, f in zip(descs, fz.FEATURESPACE):
+    d["max_atoms"] = getattr(f, "MAX_ALLOWED_ATOMS", None)
+  host, _ = build(traj, tmp_path, feats, parms, native=False)
+  for key in got:
+    if key in ("count", "count_capped"):
+      assert np.array_equal(got[key], host[key]), key
+    else:
+      assert rel_bad(got[key], host[key]) == 0, (key, np.abs(got[key] - host[key]).max())
+  assert got["count_capped"].max() <= 300 and got["count"].max() > 0 and got["sel"].sum() > 0
