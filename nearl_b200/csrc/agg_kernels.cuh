@@ -66,6 +66,23 @@ __global__ void __launch_bounds__(NRL_AGG_NT) nrl_aggregate_kernel(const float *
       for (int v = tid; v < W; v += NRL_AGG_NT) fb[(size_t)i * W + v] = v < w ? series[(long long)i * G + g0 + v] : 0.0f;
     __syncthreads();
   }
+  if (agg == 2 || agg == 4) {
+    // standard deviation / variance: one voxel per thread keeps all 128 threads busy (a float4 column per thread
+    // leaves three warps of a narrow tile idle); same arithmetic as nrl_reduce4 (gpuutils.cuh:35-74)
+    const float *fb = reinterpret_cast<const float *>(buf);
+    const float fn = (float)n;
+    for (int v = tid; v < w; v += NRL_AGG_NT) {
+      float sum = 0.0f;
+#pragma unroll 8
+      for (int i = 0; i < n; ++i) sum = sum + fb[(size_t)i * W + v];
+      const float mean = nrl_div_approx(sum, fn);
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int i = 0; i < n; ++i) { const float d = fb[(size_t)i * W + v] - mean; acc = fmaf(d, d, acc); }
+      out[g0 + v] = agg == 2 ? nrl_sqrt_approx(nrl_div_approx(acc, fn)) : nrl_div_approx(acc, fn);
+    }
+    return;
+  }
   for (int t4 = tid; t4 * 4 < w; t4 += NRL_AGG_NT) {
     const float4 r = nrl_reduce4(buf + t4, W4, n, agg);
     float *o = out + g0 + 4 * t4;

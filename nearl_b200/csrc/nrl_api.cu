@@ -827,7 +827,7 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
   } else {
     // widest tile that still lets two CTAs share an SM
     int W = 512;
-    while (W > 64 && (size_t)n * W * sizeof(float) > 56 * 1024) W >>= 1;   // four CTAs per SM: copies of some overlap the reduction of others
+    while (W > 64 && (size_t)n * W * sizeof(float) > 56 * 1024) W >>= 1;   // four CTAs per SM: copies of some overlap the reduction of others   // four CTAs per SM: copies of some overlap the reduction of others
     const size_t smem = (size_t)n * W * sizeof(float);
     if (smem > c.smem_optin - 1024) return fail(NRL_ERR_FRAMES, "series too long for shared memory");
     if (!c.attr_set[20]) {
