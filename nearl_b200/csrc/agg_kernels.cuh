@@ -83,6 +83,63 @@ __global__ void __launch_bounds__(NRL_AGG_NT) nrl_aggregate_kernel(const float *
     }
     return;
   }
+  if (agg == 3 && W <= NRL_AGG_NT) {
+    // median, one voxel per thread (narrow tiles, i.e. long series; wider tiles keep the float4 columns below): the reference's in-place exchange sort (median_device, gpuutils.cuh:227-245)
+    float *fb = reinterpret_cast<float *>(buf);
+    for (int v = tid; v < w; v += NRL_AGG_NT) {
+      for (int i = 0; i < n; ++i) {
+        float a = fb[(size_t)i * W + v];
+        for (int j = i + 1; j < n; ++j) {
+          const float b = fb[(size_t)j * W + v];
+          if (a > b) { fb[(size_t)j * W + v] = a; a = b; }
+        }
+        fb[(size_t)i * W + v] = a;
+      }
+      out[g0 + v] = (n & 1) ? fb[(size_t)(n / 2) * W + v]
+                            : nrl_div_approx(fb[(size_t)(n / 2 - 1) * W + v] + fb[(size_t)(n / 2) * W + v], 2.0f);
+    }
+    return;
+  }
+  if (agg == 7) {
+    // information entropy, one voxel per thread (the histogram is ALU work: all four warps share it);
+    // arithmetic of information_entropy_histogram_device (gpuutils.cuh:140-173) as in nrl_reduce4
+    const float *fb = reinterpret_cast<const float *>(buf);
+    const float fn = (float)n;
+    for (int v = tid; v < w; v += NRL_AGG_NT) {
+      float r = 0.0f;
+      if (n > 1) {
+        float mn = fb[v], mx = fb[v];
+#pragma unroll 8
+        for (int i = 1; i < n; ++i) { const float x = fb[(size_t)i * W + v]; if (x < mn) mn = x; if (x > mx) mx = x; }
+        const float range = mx - mn;
+        unsigned long long h0 = 0ull, h1 = 0ull, h2 = 0ull, h3 = 0ull;      // 16 counters of 16 bits
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+          const float sc = nrl_div_approx(fb[(size_t)i * W + v] - mn, range) * 16.0f;
+          int bin;
+          asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
+          bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
+          const unsigned long long inc = 1ull << ((bin & 3) * 16);
+          const int word = bin >> 2;
+          h0 += (word == 0) ? inc : 0ull; h1 += (word == 1) ? inc : 0ull;
+          h2 += (word == 2) ? inc : 0ull; h3 += (word == 3) ? inc : 0ull;
+        }
+        if (range != 0.0f) {
+          const unsigned long long h[4] = {h0, h1, h2, h3};
+#pragma unroll
+          for (int b = 0; b < NRL_ENTROPY_BINS; ++b) {
+            const int cnt = (int)((h[b >> 2] >> ((b & 3) * 16)) & 0xffffull);
+            if (cnt > 0) {
+              const float pr = nrl_div_approx((float)cnt, fn);
+              r = fmaf(-pr, nrl_lg2_approx(pr), r);
+            }
+          }
+        }
+      }
+      out[g0 + v] = r;
+    }
+    return;
+  }
   for (int t4 = tid; t4 * 4 < w; t4 += NRL_AGG_NT) {
     const float4 r = nrl_reduce4(buf + t4, W4, n, agg);
     float *o = out + g0 + 4 * t4;
