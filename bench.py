@@ -210,7 +210,7 @@ def run_native(args):
                        no_sync=True)
 
   # e2e: the public call, Featurizer.run() over a list of host trajectories (it pipelines them over
-  # two lanes internally); every result grid is read on the host by the sink
+  # `pipeline_depth` lanes internally); every result grid is read on the host by the sink
   touched = [0.0]
 
   def sink(outkey, tid, bid, pid, grid):
