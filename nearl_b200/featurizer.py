@@ -90,6 +90,9 @@ class Featurizer:
     self.last_run_stats = {}
     # nearl_b200: trajectories in flight in run() (upload of i+1 and i+2 under the kernels of i); 1 = no overlap
     self.pipeline_depth = 3
+    # nearl_b200: single-frame systems featurised per native call when every feature is static (time_window 1);
+    # 1 = one system per call
+    self.static_group = 32
     if config.verbose():
       printit(f"{self.classname}: Featurizer is initialized successfully with dimensions: {self.dims} and lengths: {self.lengths}")
     if "outfile" in parms:
@@ -229,6 +232,12 @@ class Featurizer:
     t_run = time.perf_counter()
     depth = max(1, min(int(self.pipeline_depth), 4))        # lanes of the native library (NRL_MAX_LANES)
     self.__dict__.pop("_fingerprint_memo", None)
+    if self._static_groupable():
+      self._run_static_groups(list(indices), depth, stats)
+      stats["seconds"] = time.perf_counter() - t_run
+      self.last_run_stats = stats
+      printit(f"{self.classname}: All trajectories and tasks are finished. \n")
+      return stats
     pending = []                                             # submitted, not yet finished, oldest first
     for count, tid in enumerate(indices):
       if len(pending) >= depth:
@@ -248,6 +257,136 @@ class Featurizer:
     self.last_run_stats = stats
     printit(f"{self.classname}: All trajectories and tasks are finished. \n")
     return stats
+
+  # ---- single-frame systems (PDBBind-style): many systems per native call ------------------------------
+  def _static_groupable(self):
+    """Static featurisation of single-frame systems, every feature on the device path: `static_group` systems
+    are concatenated into one pseudo-system per native call, each a slice of its atoms with its own focus box."""
+    if not (self.use_native_batch and self.time_window == 1 and int(self.static_group) > 1 and self.FEATURENUMBER > 0):
+      return False
+    for feat in self.FEATURESPACE:
+      if getattr(feat, "_native_kind", None) != "static" or not feat._is_builtin("query", "run", "cache"):
+        return False
+      if feat.selection is not None and not isinstance(feat.selection, str):
+        return False
+      if int(feat.frame_offset or 0) != 0:
+        return False
+    return True
+
+  def _run_static_groups(self, indices, depth, stats):
+    group = max(2, int(self.static_group))
+    pending = []
+    singles = []          # systems that do not fit the scheme: ordinary path, in order, after their group
+    count = 0
+    for g0 in range(0, len(indices), group):
+      tids = indices[g0:g0 + group]
+      if len(pending) >= depth:
+        self._finish_static_group(pending.pop(0), stats)
+      job = self._submit_static_group(tids, lane=count % depth)
+      count += 1
+      if job is None:
+        # a multi-frame trajectory (or a feature without weights) in this group: one by one, reference order kept
+        while pending:
+          self._finish_static_group(pending.pop(0), stats)
+        for tid in tids:
+          single = self._submit(tid, lane=0)
+          if single is not None:
+            self._finish(single, stats)
+        continue
+      pending.append(job)
+    while pending:
+      self._finish_static_group(pending.pop(0), stats)
+
+  def _submit_static_group(self, tids, lane):
+    members = []
+    n_focal = None
+    for tid in tids:
+      self.traj = self.TRAJLOADER[tid]
+      traj = self.traj
+      if traj.n_frames != 1:
+        return None
+      if self.FOCALPOINTS_PROTOTYPE is not None:
+        if not self.parse_focus():
+          printit(f"{self.classname} Warning: Skipping the trajectory {traj.identity}(index {tid + 1}) because focal points parsing is failed. ")
+          continue
+        focal = np.array(self.FOCALPOINTS[0], dtype=np.float32)
+      else:
+        focal = np.zeros((1, 3), dtype=np.float32)
+      for feat in self.FEATURESPACE:
+        feat.cache(traj)
+      specs = [feat._native_spec() for feat in self.FEATURESPACE]
+      if any(sp is None for sp in specs):
+        return None
+      if n_focal is None:
+        n_focal = len(focal)
+      if len(focal) != n_focal:
+        return None
+      xyz = traj.xyz
+      if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64):
+        xyz = np.asarray(xyz, dtype=np.float32)
+      members.append({"tid": tid, "identity": traj.identity, "xyz": xyz, "focal": focal, "specs": specs,
+                      "resids": self.FEATURESPACE[0].resids})
+    if not members:
+      return {"members": [], "batch": None, "lane": lane}
+    dtype = members[0]["xyz"].dtype
+    if any(m["xyz"].dtype != dtype for m in members):
+      return None
+    sizes = np.array([m["xyz"].shape[1] for m in members], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(sizes)])
+    n_total = int(offsets[-1])
+    cat = self._table_buffer(lane, "group_xyz_" + dtype.name, (1, n_total, 3), dtype)
+    for m, o in zip(members, offsets):
+      cat[0, o:o + m["xyz"].shape[1]] = m["xyz"][0]
+    nf = self.FEATURENUMBER
+    specs_cat = []
+    for f in range(nf):
+      sp = dict(members[0]["specs"][f])
+      sp["weights"] = np.concatenate([np.asarray(m["specs"][f]["weights"], dtype=np.float32) for m in members])
+      specs_cat.append(sp)
+    residue_index = None
+    if any(feat.byres for feat in self.FEATURESPACE):
+      dense, most = [], 1
+      for m in members:
+        _, inv = np.unique(m["resids"], return_inverse=True)
+        dense.append(inv)
+        most = max(most, int(inv.max()) + 1 if len(inv) else 1)
+      residue_index = (np.concatenate(dense), most)
+    starts = np.repeat(offsets[:-1], n_focal)
+    stops = np.repeat(offsets[1:], n_focal)
+    focal = np.concatenate([m["focal"] for m in members], axis=0)
+    batch = self._lower_residue_batch(list(range(nf)), specs_cat, dtype == np.float64, 0, starts, stops, np.zeros(len(starts), dtype=np.int64),
+                                      focal, n_total, lane, residue_index=residue_index)
+    buffers = self.__dict__.setdefault("_out_buffers", {})
+    if lane not in buffers or buffers[lane].size < batch.out_floats:
+      buffers[lane] = pinned_empty((batch.out_floats,), np.float32)
+    out = buffers[lane][:batch.out_floats]
+    batch.execute(_lib.ptr(cat), 1, _lib.ptr(out), no_sync=True, lane=lane)
+    return {"members": members, "batch": batch, "out": out, "lane": lane, "n_focal": n_focal, "xyz": cat}
+
+  def _finish_static_group(self, job, stats):
+    if job["batch"] is None:
+      return
+    _lib.check(_lib.lib().nrl_lane_synchronize(job["lane"]))
+    grids = job["batch"].split(job["out"], copy=self.keep_results)
+    nf, n_focal = self.FEATURENUMBER, job["n_focal"]
+    k = 0
+    with utils.batched_output():
+      for m in job["members"]:
+        for pid in range(n_focal):
+          for fidx in range(nf):
+            result = grids[k]
+            k += 1
+            feat = self.FEATURESPACE[fidx]
+            if self.result_sink is not None:
+              self.result_sink(feat.outkey, m["tid"], 0, pid, result)
+            if self.keep_results:
+              self.RESULTS.setdefault(feat.outkey, []).append(result)
+            if feat.outfile or (self.result_sink is None and not self.keep_results):
+              feat.dump(result)
+        stats["trajectories"] += 1
+        stats["tasks"] += n_focal * nf
+        stats["native_tasks"] += n_focal * nf
+        stats["frames"] += 1
 
   def main_loop(self, *args, **kwargs):
     """Name used by the README / older scripts for the same loop."""
@@ -467,9 +606,12 @@ class Featurizer:
         stats["tasks"] += 1
         stats["native_tasks"] += 1 if (k, f) in native else 0
 
-  def _lower_residue_batch(self, native_feats, specs, is_f64, first_frame, starts, stops, shifts, focal, n_atoms, lane):
+  def _lower_residue_batch(self, native_feats, specs, is_f64, first_frame, starts, stops, shifts, focal, n_atoms, lane,
+                           selection_rows=None, residue_index=None):
     """Crop / task tables for the blocks [starts, stops) of ONE window: per block one crop per crop class
-    (features that share frames, padding, by-residue, selection and cap) and one task per native feature."""
+    (features that share frames, padding, by-residue, selection and cap) and one task per native feature.
+    `selection_rows` ({feature index: mask over all atoms}) and `residue_index` ((dense index per atom, count))
+    override the features' own cached arrays (used when several systems are concatenated into one call)."""
     feats = [self.FEATURESPACE[f] for f in native_feats]
     sel_feats = [f for f in native_feats if self.FEATURESPACE[f].selection is not None and not specs[f].get("selection_folded")]
     sel_of = {f: i for i, f in enumerate(sel_feats)}
@@ -529,12 +671,15 @@ class Featurizer:
     if sel_feats:
       batch.selections = self._table_buffer(lane, "selections", (len(sel_feats), n_atoms), np.uint8)
       for i, f in enumerate(sel_feats):
-        batch.selections[i] = self.FEATURESPACE[f].selected
+        batch.selections[i] = selection_rows[f] if selection_rows is not None else self.FEATURESPACE[f].selected
     batch.value_orders = None
     batch.residue_index, batch.n_residues = None, 0
     if any(c[6] for c in classes):
-      uniq, inverse = np.unique(feats[0].resids, return_inverse=True)
-      batch.residue_index, batch.n_residues = np.ascontiguousarray(inverse, dtype=np.int32), len(uniq)
+      if residue_index is not None:
+        batch.residue_index, batch.n_residues = np.ascontiguousarray(residue_index[0], dtype=np.int32), int(residue_index[1])
+      else:
+        uniq, inverse = np.unique(feats[0].resids, return_inverse=True)
+        batch.residue_index, batch.n_residues = np.ascontiguousarray(inverse, dtype=np.int32), len(uniq)
     return batch
 
   # ---- lowering to nrl_featurize_batch --------------------------------------------------------

@@ -297,3 +297,31 @@ def test_cluster_crop_byres_selection_and_cap(tmp_path, dtype):
     else:
       assert rel_bad(got[key], host[key]) == 0, (key, np.abs(got[key] - host[key]).max())
   assert got["count_capped"].max() <= 300 and got["count"].max() > 0 and got["sel"].sum() > 0
+
+
+def test_single_frame_systems_grouped_per_call(tmp_path):
+  """Static featurisation of single-frame systems sends `static_group` systems per native call (each a slice of a
+  concatenated pseudo-system with its own focus boxes); results and their order equal one call per system."""
+  systems = [io.synthetic_complex(1200 + 37 * i, seed=300 + i) for i in range(11)]
+  systems.insert(5, io.synthetic_trajectory(900, 2, seed=299, pin=False))       # a two-frame system: falls back, order kept
+
+  def run(group):
+    fz = featurizer.Featurizer({"dimensions": 20, "lengths": 16, "time_window": 1, "cutoff": 3.0, "sigma": 1.2})
+    fz.static_group = group
+    fz.register_features([features.Mass(outkey="mass"), features.HeavyAtom(outkey="heavy", byres=True, padding=1.5),
+                          features.AtomType(focus_element=8, outkey="oxygen"), features.Selection(selection=":ARG,LYS", outkey="sel")])
+    fz.register_focus([":ARG", ":LYS"], "mask")                 # two focal points per system
+    fz.register_trajloader(systems)
+    fz.keep_results = True
+    launches = _lib.kernel_launches()
+    stats = fz.run()
+    return {k: np.array(v) for k, v in fz.RESULTS.items()}, stats, _lib.kernel_launches() - launches
+
+  grouped, gstats, glaunch = run(4)              # three groups of four; the one holding the two-frame system falls back
+  single, sstats, slaunch = run(1)
+  assert gstats["tasks"] == sstats["tasks"] == (11 * 2 + 2 * 2) * 4 and gstats["native_tasks"] == gstats["tasks"]
+  assert glaunch < slaunch
+  for key, want in single.items():
+    assert grouped[key].shape == want.shape == (26, 20, 20, 20)
+    assert np.array_equal(grouped[key], want), key
+  assert grouped["mass"].sum() > 0 and grouped["sel"].sum() > 0
