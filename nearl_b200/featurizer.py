@@ -276,33 +276,39 @@ class Featurizer:
   def _run_static_groups(self, indices, depth, stats):
     group = max(2, int(self.static_group))
     pending = []
-    singles = []          # systems that do not fit the scheme: ordinary path, in order, after their group
+    grouping_off = False
     count = 0
     for g0 in range(0, len(indices), group):
       tids = indices[g0:g0 + group]
       if len(pending) >= depth:
         self._finish_static_group(pending.pop(0), stats)
-      job = self._submit_static_group(tids, lane=count % depth)
+      loaded = {}
+      job = None if grouping_off else self._submit_static_group(tids, lane=count % depth, loaded=loaded)
       count += 1
       if job is None:
-        # a multi-frame trajectory (or a feature without weights) in this group: one by one, reference order kept
+        # a multi-frame trajectory (or a feature without weights) in this group: one by one, reference order kept,
+        # re-using the trajectories the attempt already loaded; a multi-frame trajectory switches grouping off for
+        # the rest of the run (trajectory lists are homogeneous in practice)
         while pending:
           self._finish_static_group(pending.pop(0), stats)
         for tid in tids:
-          single = self._submit(tid, lane=0)
+          single = self._submit(tid, lane=0, traj=loaded.get(tid))
           if single is not None:
             self._finish(single, stats)
+          grouping_off |= self.traj.n_frames != 1
         continue
       pending.append(job)
     while pending:
       self._finish_static_group(pending.pop(0), stats)
 
-  def _submit_static_group(self, tids, lane):
+  def _submit_static_group(self, tids, lane, loaded=None):
     members = []
     n_focal = None
     for tid in tids:
       self.traj = self.TRAJLOADER[tid]
       traj = self.traj
+      if loaded is not None:
+        loaded[tid] = traj
       if traj.n_frames != 1:
         return None
       if self.FOCALPOINTS_PROTOTYPE is not None:
@@ -392,9 +398,9 @@ class Featurizer:
     """Name used by the README / older scripts for the same loop."""
     return self.run(*args, **kwargs)
 
-  def _submit(self, tid, lane=0):
+  def _submit(self, tid, lane=0, traj=None):
     """Everything up to and including the asynchronous native call for trajectory `tid`."""
-    self.traj = self.TRAJLOADER[tid]
+    self.traj = traj if traj is not None else self.TRAJLOADER[tid]
     printit(f"{self.classname}: Processing the trajectory {tid + 1} ({self.traj.identity}) with {self.SLICENUMBER} frame slices")
     st = time.perf_counter()
     if self.FOCALPOINTS_PROTOTYPE is not None:
