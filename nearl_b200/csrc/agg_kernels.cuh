@@ -9,6 +9,7 @@
 // Replaces gridwise_aggregation_global + aggregate_host (/root/reference/src/gpuutils.cu:48-105),
 // which copies every series into a 2 KB per-thread local-memory array first.
 #pragma once
+#include <cuda.h>   // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no link against libcuda)
 #include "common.cuh"
 #include "reducers.cuh"
 
@@ -36,6 +37,87 @@ __device__ __forceinline__ void nrl_mbar_wait(uint64_t *bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   }
+}
+
+
+// One voxel's series out of a staged [n, W] tile (column v), reduced by one thread: standard deviation / variance
+// (same arithmetic as nrl_reduce4, gpuutils.cuh:35-74), median (the reference's in-place exchange sort,
+// median_device, gpuutils.cuh:227-245 -- the tile column is overwritten) and information entropy
+// (information_entropy_histogram_device, gpuutils.cuh:140-173).
+#define NRL_AGG_BLOCK 16
+__device__ __forceinline__ float nrl_agg_voxel(float *fb, const int W, const int v, const int n, const int agg) {
+  const float fn = (float)n;
+  if (agg == 2 || agg == 4) {
+    // the additions are a dependent chain in the reference's order; the shared-memory reads are not: fetch a block
+    // of them first, so that a thread has NRL_AGG_BLOCK loads in flight instead of one per addition
+    const float *col = fb + v;
+    float sum = 0.0f;
+    int i = 0;
+    for (; i + NRL_AGG_BLOCK <= n; i += NRL_AGG_BLOCK) {
+      float x[NRL_AGG_BLOCK];
+#pragma unroll
+      for (int u = 0; u < NRL_AGG_BLOCK; ++u) x[u] = col[(i + u) * W];
+#pragma unroll
+      for (int u = 0; u < NRL_AGG_BLOCK; ++u) sum = sum + x[u];
+    }
+    for (; i < n; ++i) sum = sum + col[i * W];
+    const float mean = nrl_div_approx(sum, fn);
+    float acc = 0.0f;
+    i = 0;
+    for (; i + NRL_AGG_BLOCK <= n; i += NRL_AGG_BLOCK) {
+      float d[NRL_AGG_BLOCK];
+#pragma unroll
+      for (int u = 0; u < NRL_AGG_BLOCK; ++u) d[u] = col[(i + u) * W] - mean;
+#pragma unroll
+      for (int u = 0; u < NRL_AGG_BLOCK; ++u) acc = fmaf(d[u], d[u], acc);
+    }
+    for (; i < n; ++i) { const float d = col[i * W] - mean; acc = fmaf(d, d, acc); }
+    return agg == 2 ? nrl_sqrt_approx(nrl_div_approx(acc, fn)) : nrl_div_approx(acc, fn);
+  }
+  if (agg == 3) {
+    for (int i = 0; i < n; ++i) {
+      float a = fb[(size_t)i * W + v];
+      for (int j = i + 1; j < n; ++j) {
+        const float b = fb[(size_t)j * W + v];
+        if (a > b) { fb[(size_t)j * W + v] = a; a = b; }
+      }
+      fb[(size_t)i * W + v] = a;
+    }
+    return (n & 1) ? fb[(size_t)(n / 2) * W + v]
+                   : nrl_div_approx(fb[(size_t)(n / 2 - 1) * W + v] + fb[(size_t)(n / 2) * W + v], 2.0f);
+  }
+  // information entropy: the histogram is ALU work
+  float r = 0.0f;
+  if (n > 1) {
+    float mn = fb[v], mx = fb[v];
+#pragma unroll 8
+    for (int i = 1; i < n; ++i) { const float x = fb[(size_t)i * W + v]; if (x < mn) mn = x; if (x > mx) mx = x; }
+    const float range = mx - mn;
+    unsigned long long h0 = 0ull, h1 = 0ull, h2 = 0ull, h3 = 0ull;      // 16 counters of 16 bits
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      const float sc = nrl_div_approx(fb[(size_t)i * W + v] - mn, range) * 16.0f;
+      int bin;
+      asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
+      bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
+      const unsigned long long inc = 1ull << ((bin & 3) * 16);
+      const int word = bin >> 2;
+      h0 += (word == 0) ? inc : 0ull; h1 += (word == 1) ? inc : 0ull;
+      h2 += (word == 2) ? inc : 0ull; h3 += (word == 3) ? inc : 0ull;
+    }
+    if (range != 0.0f) {
+      const unsigned long long h[4] = {h0, h1, h2, h3};
+#pragma unroll
+      for (int b = 0; b < NRL_ENTROPY_BINS; ++b) {
+        const int cnt = (int)((h[b >> 2] >> ((b & 3) * 16)) & 0xffffull);
+        if (cnt > 0) {
+          const float pr = nrl_div_approx((float)cnt, fn);
+          r = fmaf(-pr, nrl_lg2_approx(pr), r);
+        }
+      }
+    }
+  }
+  return r;
 }
 
 #define NRL_AGG_NT 128
@@ -66,78 +148,11 @@ __global__ void __launch_bounds__(NRL_AGG_NT) nrl_aggregate_kernel(const float *
       for (int v = tid; v < W; v += NRL_AGG_NT) fb[(size_t)i * W + v] = v < w ? series[(long long)i * G + g0 + v] : 0.0f;
     __syncthreads();
   }
-  if (agg == 2 || agg == 4) {
-    // standard deviation / variance: one voxel per thread keeps all 128 threads busy (a float4 column per thread
-    // leaves three warps of a narrow tile idle); same arithmetic as nrl_reduce4 (gpuutils.cuh:35-74)
-    const float *fb = reinterpret_cast<const float *>(buf);
-    const float fn = (float)n;
-    for (int v = tid; v < w; v += NRL_AGG_NT) {
-      float sum = 0.0f;
-#pragma unroll 8
-      for (int i = 0; i < n; ++i) sum = sum + fb[(size_t)i * W + v];
-      const float mean = nrl_div_approx(sum, fn);
-      float acc = 0.0f;
-#pragma unroll 8
-      for (int i = 0; i < n; ++i) { const float d = fb[(size_t)i * W + v] - mean; acc = fmaf(d, d, acc); }
-      out[g0 + v] = agg == 2 ? nrl_sqrt_approx(nrl_div_approx(acc, fn)) : nrl_div_approx(acc, fn);
-    }
-    return;
-  }
-  if (agg == 3 && W <= NRL_AGG_NT) {
-    // median, one voxel per thread (narrow tiles, i.e. long series; wider tiles keep the float4 columns below): the reference's in-place exchange sort (median_device, gpuutils.cuh:227-245)
+  if (agg == 2 || agg == 4 || agg == 7 || (agg == 3 && W <= NRL_AGG_NT)) {
+    // one voxel per thread keeps all 128 threads busy (a float4 column per thread leaves three warps of a narrow
+    // tile idle); the median does so only for narrow tiles, i.e. long series
     float *fb = reinterpret_cast<float *>(buf);
-    for (int v = tid; v < w; v += NRL_AGG_NT) {
-      for (int i = 0; i < n; ++i) {
-        float a = fb[(size_t)i * W + v];
-        for (int j = i + 1; j < n; ++j) {
-          const float b = fb[(size_t)j * W + v];
-          if (a > b) { fb[(size_t)j * W + v] = a; a = b; }
-        }
-        fb[(size_t)i * W + v] = a;
-      }
-      out[g0 + v] = (n & 1) ? fb[(size_t)(n / 2) * W + v]
-                            : nrl_div_approx(fb[(size_t)(n / 2 - 1) * W + v] + fb[(size_t)(n / 2) * W + v], 2.0f);
-    }
-    return;
-  }
-  if (agg == 7) {
-    // information entropy, one voxel per thread (the histogram is ALU work: all four warps share it);
-    // arithmetic of information_entropy_histogram_device (gpuutils.cuh:140-173) as in nrl_reduce4
-    const float *fb = reinterpret_cast<const float *>(buf);
-    const float fn = (float)n;
-    for (int v = tid; v < w; v += NRL_AGG_NT) {
-      float r = 0.0f;
-      if (n > 1) {
-        float mn = fb[v], mx = fb[v];
-#pragma unroll 8
-        for (int i = 1; i < n; ++i) { const float x = fb[(size_t)i * W + v]; if (x < mn) mn = x; if (x > mx) mx = x; }
-        const float range = mx - mn;
-        unsigned long long h0 = 0ull, h1 = 0ull, h2 = 0ull, h3 = 0ull;      // 16 counters of 16 bits
-#pragma unroll 4
-        for (int i = 0; i < n; ++i) {
-          const float sc = nrl_div_approx(fb[(size_t)i * W + v] - mn, range) * 16.0f;
-          int bin;
-          asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
-          bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
-          const unsigned long long inc = 1ull << ((bin & 3) * 16);
-          const int word = bin >> 2;
-          h0 += (word == 0) ? inc : 0ull; h1 += (word == 1) ? inc : 0ull;
-          h2 += (word == 2) ? inc : 0ull; h3 += (word == 3) ? inc : 0ull;
-        }
-        if (range != 0.0f) {
-          const unsigned long long h[4] = {h0, h1, h2, h3};
-#pragma unroll
-          for (int b = 0; b < NRL_ENTROPY_BINS; ++b) {
-            const int cnt = (int)((h[b >> 2] >> ((b & 3) * 16)) & 0xffffull);
-            if (cnt > 0) {
-              const float pr = nrl_div_approx((float)cnt, fn);
-              r = fmaf(-pr, nrl_lg2_approx(pr), r);
-            }
-          }
-        }
-      }
-      out[g0 + v] = r;
-    }
+    for (int v = tid; v < w; v += NRL_AGG_NT) out[g0 + v] = nrl_agg_voxel(fb, W, v, n, agg);
     return;
   }
   for (int t4 = tid; t4 * 4 < w; t4 += NRL_AGG_NT) {
@@ -151,6 +166,67 @@ __global__ void __launch_bounds__(NRL_AGG_NT) nrl_aggregate_kernel(const float *
       if (4 * t4 + 2 < w) o[2] = r.z;
       if (4 * t4 + 3 < w) o[3] = r.w;
     }
+  }
+}
+
+// Pipelined form for the two-pass reducers over long series (standard deviation, variance, median, entropy):
+// a persistent CTA walks tiles of W voxels through a ring of `stages` shared-memory buffers; while the threads
+// reduce tile k (one voxel per thread) the copies of tiles k+1 .. k+stages-1 are in flight, so the HBM stream
+// never waits for a reduction.  A tile is ONE 2-D tiled TMA copy ([rows, W] box of the [n, G] series through a
+// tensor map; SASS UTMALDG) -- measured on B200: an SM retires one 1-D bulk copy per ~46 clocks whatever its
+// size, so F row copies of W*4 bytes cap a tile at W*4/46 B/clk per SM (512-byte rows: 66 % of the HBM peak).
+// Needs G % 4 == 0 and a 16-byte aligned series (the host checks).  Out-of-range voxels / rows of the last
+// box are zero-filled by the copy and never read.
+#define NRL_AGG_PIPE_NT 256
+#define NRL_AGG_PIPE_MAX_STAGES 8
+
+__device__ __forceinline__ void nrl_tma_2d_g2s(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   nrl_smem_u32(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(nrl_smem_u32(bar))
+               : "memory");
+}
+
+// rows_per_box * n_boxes >= n rows are staged per tile (n_boxes = 1 up to 256 frames)
+__global__ void __launch_bounds__(NRL_AGG_PIPE_NT, 1) nrl_aggregate_pipe_kernel(const __grid_constant__ CUtensorMap map, const int n,
+                                                                                const long long G, const int agg, const int W,
+                                                                                const int stages, const long long n_tiles,
+                                                                                const int rows_per_box, const int n_boxes,
+                                                                                float *__restrict__ out) {
+  extern __shared__ __align__(1024) unsigned char nrl_agg_ring[];
+  __shared__ __align__(8) uint64_t s_bar[NRL_AGG_PIPE_MAX_STAGES];
+  // the destination of a tiled copy must be 128-byte aligned: round the dynamic window up (the host adds the slack)
+  float *ring = reinterpret_cast<float *>(nrl_agg_ring + ((128u - (nrl_smem_u32(nrl_agg_ring) & 127u)) & 127u));
+  const int tid = threadIdx.x;
+  const size_t tile_floats = (size_t)rows_per_box * n_boxes * W;
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map) : "memory");
+    for (int s = 0; s < stages; ++s) nrl_mbar_init(&s_bar[s], 1);
+  }
+  __syncthreads();
+  // tile j of this CTA is global tile blockIdx.x + j * gridDim.x and lives in stage j % stages
+  auto issue = [&](const long long j) {
+    const long long tile = (long long)blockIdx.x + j * (long long)gridDim.x;
+    if (tile >= n_tiles || tid != 0) return;
+    const int s = (int)(j % stages);
+    float *dst = ring + (size_t)s * tile_floats;
+    nrl_mbar_expect_tx(&s_bar[s], (uint32_t)(tile_floats * sizeof(float)));
+    for (int b = 0; b < n_boxes; ++b)
+      nrl_tma_2d_g2s(dst + (size_t)b * rows_per_box * W, &map, (int)(tile * W), b * rows_per_box, &s_bar[s]);
+  };
+  for (int j = 0; j < stages - 1; ++j) issue(j);
+  for (long long j = 0;; ++j) {
+    const long long tile = (long long)blockIdx.x + j * (long long)gridDim.x;
+    if (tile >= n_tiles) break;
+    issue(j + stages - 1);          // its stage was drained in iteration j - 1 (barrier below)
+    const int s = (int)(j % stages);
+    nrl_mbar_wait(&s_bar[s], (uint32_t)((j / stages) & 1));
+    const long long g0 = tile * W;
+    const int w = (int)min((long long)W, G - g0);
+    float *fb = ring + (size_t)s * tile_floats;
+    for (int v = tid; v < w; v += NRL_AGG_PIPE_NT) out[g0 + v] = nrl_agg_voxel(fb, W, v, n, agg);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the median wrote the tile; the next copy overwrites it
+    __syncthreads();
   }
 }
 

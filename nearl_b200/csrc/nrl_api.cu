@@ -29,6 +29,8 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_force_scan{0};    // nrl_set_option("force_scan", 1): never use the cell-list kernels
+std::atomic<int> g_agg_pipe_w{0};    // nrl_set_option("agg_pipe_w" / "agg_pipe_stages"): tile width / ring depth of the pipelined K3
+std::atomic<int> g_agg_pipe_stages{0};  // (0 = chosen from the series length; -1 stages = staged one-shot kernel instead)
 std::atomic<int> g_no_fuse{0};       // nrl_set_option("no_fuse", 1): one sweep per observable (tests / A-B timing)
 
 int fail(int code, const std::string &msg) {
@@ -781,6 +783,23 @@ int legacy_run(const LegacyArgs &a) {
   return NRL_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime (the library does not link libcuda); nullptr when the driver lacks it
+typedef CUresult (*nrl_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+nrl_encode_tiled_fn tensor_map_encoder() {
+  static nrl_encode_tiled_fn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<nrl_encode_tiled_fn>(p);
+  }();
+  return fn;
+}
+
 int aggregate_impl(const float *series, int F, long long G, int agg, float *out, bool on_device, cudaStream_t user) {
   if (F <= 0 || G <= 0) return fail(NRL_ERR_SHAPE, "series must be [n_frames > 0, n_voxels > 0]");
   if (!series || !out) return fail(NRL_ERR_ARGUMENT, "series / out is NULL");
@@ -821,6 +840,51 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
       ScopedProf sp(c, st, CAT_AGGREGATE);
       if (n <= 32) nrl_aggregate_reg_kernel<32><<<(unsigned)grid, 256, 0, st>>>(d_in, n, G, agg, d_out);
       else nrl_aggregate_reg_kernel<64><<<(unsigned)grid, 256, 0, st>>>(d_in, n, G, agg, d_out);
+    }
+    g_launches.fetch_add(1);
+    NRL_CUDA(cudaGetLastError());
+  } else if (n > 64 && agg != 3 && (G % 4 == 0) && G < (1ll << 31) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) &&
+             g_agg_pipe_stages.load() >= 0 && tensor_map_encoder() != nullptr) {
+    // long series, two-pass reducers (the median is ALU-bound and keeps the one-shot kernel, 4 CTAs per SM): persistent
+    // CTAs, ring of staged tiles, one tiled TMA copy per tile (the copies of the next tiles run under the reduction)
+    const size_t budget = c.smem_optin - 2048 - 128;
+    const int n_boxes = (n + 255) / 256;
+    const int rows = (n + n_boxes - 1) / n_boxes;
+    const size_t tile_rows = (size_t)rows * n_boxes;
+    int W = g_agg_pipe_w.load();
+    if (W <= 0) {
+      // measured on B200 (scripts/k3_pipe_probe.py): the widest tile that fits twice while it is >= 128 voxels wide,
+      // else the widest that fits once (a reduction keeps W of the 256 threads busy: width beats ring depth)
+      W = 256;
+      while (W > 128 && tile_rows * W * sizeof(float) * 2 > budget) W >>= 1;
+      while (W > 32 && tile_rows * W * sizeof(float) > budget) W >>= 1;
+    }
+    W = std::max(32, std::min(256, W & ~31));
+    int stages = g_agg_pipe_stages.load();
+    const int fit = (int)std::min<size_t>(NRL_AGG_PIPE_MAX_STAGES, budget / (tile_rows * W * sizeof(float)));
+    if (fit < 1) return fail(NRL_ERR_FRAMES, "series too long for shared memory");
+    stages = stages <= 0 ? fit : std::min(stages, fit);
+    const size_t smem = (size_t)stages * tile_rows * W * sizeof(float) + 128;
+    CUtensorMap map;
+    {
+      const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)n};
+      const cuuint64_t strides[1] = {(cuuint64_t)G * sizeof(float)};
+      const cuuint32_t box[2] = {(cuuint32_t)W, (cuuint32_t)rows};
+      const cuuint32_t estr[2] = {1, 1};
+      const CUresult r = tensor_map_encoder()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(d_in), dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(NRL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    }
+    if (!c.attr_set[21]) {
+      NRL_CUDA(cudaFuncSetAttribute(nrl_aggregate_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 128)));
+      c.attr_set[21] = true;
+    }
+    const long long n_tiles = (G + W - 1) / W;
+    const long long grid = std::min<long long>(n_tiles, c.sms);
+    {
+      ScopedProf sp(c, st, CAT_AGGREGATE);
+      nrl_aggregate_pipe_kernel<<<(unsigned)grid, NRL_AGG_PIPE_NT, smem, st>>>(map, n, G, agg, W, stages, n_tiles, rows, n_boxes, d_out);
     }
     g_launches.fetch_add(1);
     NRL_CUDA(cudaGetLastError());
@@ -957,6 +1021,8 @@ int nrl_set_option(const char *name, int value) {
   if (!name) return fail(NRL_ERR_ARGUMENT, "option name is NULL");
   if (strcmp(name, "force_scan") == 0) { g_force_scan.store(value != 0); return NRL_OK; }
   if (strcmp(name, "no_fuse") == 0) { g_no_fuse.store(value != 0); return NRL_OK; }
+  if (strcmp(name, "agg_pipe_w") == 0) { g_agg_pipe_w.store((int)value); return NRL_OK; }
+  if (strcmp(name, "agg_pipe_stages") == 0) { g_agg_pipe_stages.store((int)value); return NRL_OK; }
   return fail(NRL_ERR_ARGUMENT, std::string("unknown option ") + name);
 }
 int nrl_profile(int enable) {

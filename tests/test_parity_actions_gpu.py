@@ -165,6 +165,35 @@ def test_aggregate_ragged_and_unknown():
     assert np.allclose(nb.aggregate(x1, agg), orc.aggregate(x1, agg), rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("F,G", [(65, 1000), (100, 4 * 6007), (257, 4 * 1001), (300, 2048), (512, 1028), (100, 1003)])
+def test_aggregate_long_series_every_dispatch_branch(F, G):
+  # > 64 frames: std / var / entropy go through the pipelined kernel (tiled TMA copies, partial last tile, two row
+  # boxes beyond 256 frames, an odd row count), the median through the one-shot staged kernel, the recurrences
+  # through the streaming kernel; G = 1003 is not a multiple of 4 and takes the non-bulk path
+  rng = np.random.default_rng(F * 7 + G)
+  x = (rng.random((F, G)) * 3.0).astype(np.float32)
+  x[:, ::5] = 1.25                        # constant series: zero variance, entropy of a zero range
+  x[F // 2, 3::11] = -7.5                 # one outlier frame
+  for agg in range(1, 9):
+    got = nb.aggregate(x, agg)
+    ref = orc.aggregate(x, agg)
+    if agg in (3, 5, 6):
+      assert np.array_equal(got, ref), agg
+    elif agg == 7:
+      assert np.count_nonzero(~np.isclose(got, ref, atol=1e-3)) <= max(1, G // 3000), agg     # reference criterion (test_features.py:119-125)
+    else:
+      assert np.allclose(got, ref, rtol=1e-5, atol=2e-6), (agg, np.abs(got - ref).max())
+  # the pipelined kernel gives the bits of the one-shot staged kernel
+  for agg in (2, 4, 7):
+    a = nb.aggregate(x, agg)
+    _lib.set_option("agg_pipe_stages", -1)
+    try:
+      b = nb.aggregate(x, agg)
+    finally:
+      _lib.set_option("agg_pipe_stages", 0)
+    assert np.array_equal(a.view(np.int32), b.view(np.int32)), agg
+
+
 def test_summation():
   rng = np.random.default_rng(7)
   a = rng.random(100003).astype(np.float32)
