@@ -1,11 +1,11 @@
 // nearl_b200 -- standalone K3 (`aggregate`) and `summation`.
 //
-// nrl_aggregate_kernel streams a frame-major [F, G] series out of HBM exactly once: a CTA
-// owns W consecutive voxels, one elected warp stages the F row segments (W*4 bytes each)
-// into shared memory with 1-D bulk asynchronous copies (TMA engine, cp.async.bulk ->
-// UBLKCP) completing on one mbarrier, and W/4 threads reduce float4 columns with the
-// reducers of reducers.cuh.  W is chosen by the host so that two CTAs fit per SM: the
-// copies of one overlap the reduction of the other.
+// Every form reads the frame-major [F, G] series out of HBM exactly once:
+//   nrl_aggregate_stream_kernel  mean / max / min / drift (recurrences over the frames): nothing staged
+//   nrl_aggregate_reg_kernel     std / var / entropy over <= 64 frames: the series lives in registers
+//   nrl_aggregate_pipe_kernel    std / var / entropy over longer series: persistent CTAs, ring of [F, W] tiles in
+//                                shared memory, one 2-D tiled TMA copy per tile (UTMALDG) on an mbarrier
+//   nrl_aggregate_kernel         one-shot staged tile (one cp.async.bulk per row, UBLKCP): the median, ragged G
 // Replaces gridwise_aggregation_global + aggregate_host (/root/reference/src/gpuutils.cu:48-105),
 // which copies every series into a 2 KB per-thread local-memory array first.
 #pragma once

@@ -78,7 +78,7 @@ struct Ctx {
   DevBuf foff, pbase;                            // per crop frame: first packed atom, payload base
   DevBuf sup_idx, sup_ref, sup_rmsd;             // superposition: fitted atom indices, reference set, per-frame RMSD
   DevBuf batoms, bcnt, cstart, grids, blist;     // cell lists: binned frames, cell prefixes, per-frame cell grids
-  bool attr_set[64] = {false};
+  bool attr_set[64] = {false};          // "dynamic shared memory opt-in done" per kernel family, indexed by kAttr*
   cudaStream_t user_stream = nullptr;   // nrl_set_stream: run on the caller's stream instead of our own
   bool use_user_stream = false;
   // side streams: the per-mode tile launches of one batch are independent of each other (and the observers do
@@ -96,6 +96,8 @@ struct Ctx {
   cudaStream_t work_stream() const { return use_user_stream ? user_stream : stream; }
 };
 
+// slots of Ctx::attr_set: 0-9 scan tile kernels by launch slot, kAttrCell + the same for the cell-list kernels
+enum { kAttrAggStaged = 20, kAttrCrop = 21, kAttrMultiTable = 22, kAttrAggPipe = 23, kAttrCell = 32, kAttrBin = 63 };
 enum { CAT_PACK_LEGACY = 0, CAT_CROP_PACK = 1, CAT_ATOM_NORM = 2, CAT_TILE0 = 3, CAT_AGGREGATE = 13, CAT_SUMMATION = 14, CAT_MISC = 15, CAT_CELL_BIN = 16, CAT_SUPERPOSE = 17, CAT_TILE_FUSED = 18 };
 const char *kCatNames[NRL_PROFILE_CATEGORIES] = {
     "pack_legacy", "crop_pack", "atom_norm", "tile_voxelize", "tile_existence", "tile_direct_count", "tile_distinct_count",
@@ -185,7 +187,7 @@ constexpr size_t kScratchBudget = (size_t)1 << 30;
 
 template <int MODE, int NWT>
 int launch_tiles_mode(Ctx &c, const NrlTileParams &p, int grid, size_t smem, cudaStream_t st, int slot) {
-  const int attr = NWT > 1 ? 22 : slot;
+  const int attr = NWT > 1 ? kAttrMultiTable : slot;
   if (!c.attr_set[attr]) {
     NRL_CUDA(cudaFuncSetAttribute(nrl_tile_kernel<MODE, NWT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(c.smem_optin - 2048)));
@@ -235,7 +237,7 @@ bool cell_mode(int mode) {
 
 template <int MODE, int NWT>
 int launch_cell_tiles_mode(Ctx &c, const NrlCellTileParams &p, int grid, size_t smem, cudaStream_t st, int slot) {
-  const int attr = 32 + (NWT > 1 ? 22 : slot);
+  const int attr = kAttrCell + (NWT > 1 ? kAttrMultiTable : slot);
   if (!c.attr_set[attr]) {
     NRL_CUDA(cudaFuncSetAttribute(nrl_cell_tile_kernel<MODE, NWT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(c.smem_optin - 2048)));
@@ -353,9 +355,9 @@ int bin_frames(Ctx &c, const NrlFrames &packed, std::vector<NrlCellGrid> &hgrids
   NRL_CUDA(cudaMemcpyAsync(c.grids.p, hgrids.data(), hgrids.size() * sizeof(NrlCellGrid), cudaMemcpyHostToDevice, st));
   NRL_CUDA(cudaMemcpyAsync(c.blist.p, frame_list.data(), frame_list.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   const size_t smem = (size_t)(max_ncell + 2) * sizeof(int);
-  if (!c.attr_set[63]) {
+  if (!c.attr_set[kAttrBin]) {
     NRL_CUDA(cudaFuncSetAttribute(nrl_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c.smem_optin - 2048)));
-    c.attr_set[63] = true;
+    c.attr_set[kAttrBin] = true;
   }
   NrlBinParams bp;
   bp.in = packed;
@@ -876,9 +878,9 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) return fail(NRL_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     }
-    if (!c.attr_set[21]) {
+    if (!c.attr_set[kAttrAggPipe]) {
       NRL_CUDA(cudaFuncSetAttribute(nrl_aggregate_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget + 128)));
-      c.attr_set[21] = true;
+      c.attr_set[kAttrAggPipe] = true;
     }
     const long long n_tiles = (G + W - 1) / W;
     const long long grid = std::min<long long>(n_tiles, c.sms);
@@ -894,10 +896,10 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
     while (W > 64 && (size_t)n * W * sizeof(float) > 56 * 1024) W >>= 1;   // four CTAs per SM: copies of some overlap the reduction of others   // four CTAs per SM: copies of some overlap the reduction of others
     const size_t smem = (size_t)n * W * sizeof(float);
     if (smem > c.smem_optin - 1024) return fail(NRL_ERR_FRAMES, "series too long for shared memory");
-    if (!c.attr_set[20]) {
+    if (!c.attr_set[kAttrAggStaged]) {
       NRL_CUDA(cudaFuncSetAttribute(nrl_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(c.smem_optin - 1024)));
-      c.attr_set[20] = true;
+      c.attr_set[kAttrAggStaged] = true;
     }
     const int bulk = (G % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
