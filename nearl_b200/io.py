@@ -114,7 +114,8 @@ class Topology:
     for key in ("_select_cache", "_residue_blocks", "_dual_blocks_memo"):
       self.__dict__.pop(key, None)
 
-  # ---- Amber mask subset: ':RES', ':1-10', ':A,B', ':*', '@NAME', '@1-5', ':RES@NAME', '@/El', '!', '&', '|', '()'
+  # ---- Amber mask subset: ':RES', ':1-10', ':A,B', ':*', '@NAME', '@1-5', ':RES@NAME', '@/El', '!', '&', '|', '()',
+  # ---- name wildcards '*' / '=' (any run of characters) and '?' (one character), e.g. '!@H='
   def select(self, mask):
     cache = self.__dict__.setdefault("_select_cache", {})
     if mask not in cache:
@@ -125,7 +126,7 @@ class Topology:
     mask = mask.strip()
     tokens = re.findall(r"[()!&|]|[:@][^()!&|:@\s]+", mask)
     if "".join(tokens) != re.sub(r"\s+", "", mask) or any(
-        t[0] in ":@" and not re.fullmatch(r"[:@][A-Za-z0-9*,\-+'/_]+", t) for t in tokens):
+        t[0] in ":@" and not re.fullmatch(r"[:@][A-Za-z0-9*=?,\-+'/_]+", t) for t in tokens):
       raise ValueError(f"unsupported Amber mask: {mask!r}")
     pos = [0]
 
@@ -186,7 +187,7 @@ class Topology:
           lo, _, hi = part.partition("-")
           out |= (resnum >= int(lo)) & (resnum <= int(hi or lo))
         else:
-          out |= self.resnames == part
+          out |= self._name_match(self.resnames, part)
     else:
       if body.startswith("/"):
         for sym in body[1:].split(","):
@@ -200,8 +201,16 @@ class Topology:
           idx = np.arange(1, self.n_atoms + 1)
           out |= (idx >= int(lo)) & (idx <= int(hi or lo))
         else:
-          out |= self.names == part
+          out |= self._name_match(self.names, part)
     return out
+
+  @staticmethod
+  def _name_match(names, pattern):
+    if not any(ch in pattern for ch in "*=?"):
+      return names == pattern
+    rx = re.compile("".join(".*" if ch in "*=" else "." if ch == "?" else re.escape(ch) for ch in pattern))
+    uniq, inverse = np.unique(names, return_inverse=True)
+    return np.array([rx.fullmatch(str(u)) is not None for u in uniq], dtype=bool)[inverse]
 
 
 class Trajectory:

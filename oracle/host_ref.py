@@ -14,9 +14,13 @@ trajectory and the native calls:
   residue loop      /root/reference/nearl/featurizer.py:471-554 (loop_by_residue), with the feature
                     re-cache rule of /root/reference/nearl/features.py:452-457
 
-Parity status: the reference's Python layers cannot be imported on this image (they need
-h5py and pytraj at module import), so this file is pinned only by reading the cited lines;
-the kernels it calls are pinned as described in nearl_oracle.c.
+Parity status: PINNED against the reference's own Python.  tests/golden/make_host_golden.py imports the
+unmodified /root/reference/nearl package in the build container (inert stand-ins for h5py / pytraj / rdkit /
+openbabel, which it only needs at import, and a recorder in place of the compiled `all_actions`), runs its
+Featurizer.run and loop_by_residue on seeded systems and keeps what reaches the FFI boundary; the committed
+record (tests/golden/host_vectors.npz) is replayed by tests/test_host_golden.py, which demands that this file
+hand the kernels bit-identical coordinate / weight arrays, dimensions, scalars, task order and labels.
+The kernels it calls are pinned as described in nearl_oracle.c.
 """
 import numpy as np
 
