@@ -74,6 +74,99 @@ def make_peptide():
   return bio.synthetic_peptide(PEPTIDE["n_residues"], PEPTIDE["n_frames"], seed=PEPTIDE["seed"], pin=False, break_every=PEPTIDE["break_every"])
 
 
+# ---- result sink (Feature.dump -> utils.append_hdf_data, features.py:510-534, utils.py:491-570) --------------------------
+SINK_PARMS = {"dimensions": [8, 9, 10], "lengths": [6.0, 6.75, 7.5], "time_window": 3, "sigma": 1.1, "cutoff": 2.5}
+SINK_SYSTEM = dict(n_atoms=300, n_frames=7, seed=555)
+
+
+def sink_feature_set(F, outfile):
+  return [
+    F.Mass(outkey="mass", outfile=outfile),
+    F.HeavyAtom(outkey="heavy", outfile=outfile, hdf_compress_level=4),
+    F.MarchingObservers(obs="existence", agg="mean", weight_type="mass", outkey="obs/exist", outfile=outfile),
+    F.DensityFlow(agg="mean", weight_type="mass", outkey="flow", outfile=outfile),
+  ]
+
+
+def file_manifest(path):
+  """{dataset path: (shape, dtype, chunks, maxshape, compression, digest)} of an HDF5 file read through hdf5_lite."""
+  from nearl_b200 import hdf5_lite
+  rows = {}
+  def walk(group, prefix):
+    for key in sorted(group.keys()):
+      node = group[key]
+      if hasattr(node, "keys"):
+        walk(node, prefix + key + "/")
+      else:
+        val = np.asarray(node[()] if node.shape == () else node[:])
+        rows[prefix + key] = (tuple(node.shape), str(val.dtype), node.chunks, tuple(node.maxshape), node.compression, digest(val) if val.dtype.kind in "fiub" else None, val if val.dtype.kind not in "fiub" else None)
+  with hdf5_lite.File(path, "r") as hdf:
+    walk(hdf, "")
+  return rows
+
+
+def pack_manifest(prefix, rows, out):
+  out[f"{prefix}/keys"] = np.array(sorted(rows))
+  for key, (shape, dtype, chunks, maxshape, compression, dig, val) in rows.items():
+    out[f"{prefix}/{key}/meta"] = np.array([repr(shape), dtype, repr(chunks), repr(maxshape), repr(compression)])
+    if dig is not None:
+      out[f"{prefix}/{key}/digest"] = dig
+    else:
+      out[f"{prefix}/{key}/text"] = np.array([str(v) for v in np.asarray(val).reshape(-1)])
+
+
+# ---- dataset consumer (nearl/io/dataset.py) ----------------------------------------------------------------
+DATASET_KEYS = ["mass", "obs"]
+DATASET_CASES = [       # (name, Dataset kwargs, mini_batches kwargs, numpy / torch seed)
+  ("ds_plain", dict(normalize=True), dict(batch_size=5, shuffle=False, process_nr=2), 11),
+  ("ds_minmax_shuffle", dict(normalize="minmax"), dict(batch_size=4, shuffle=True, process_nr=2), 12),
+  ("ds_zscore_nr", dict(normalize="zscore"), dict(batch_nr=3, shuffle=True, process_nr=2), 13),
+  ("ds_augment", dict(normalize=False), dict(batch_size=6, shuffle=True, process_nr=2, augment=True, augment_translation=2), 14),
+  ("ds_griddim", dict(normalize=False, grid_dim=6), dict(batch_size=7, shuffle=False, process_nr=2, augment=True, augment_translation=1), 15),
+]
+
+
+def write_dataset_files(folder):
+  """Two small HDF5 files in the featuriser's layout (written through nearl_b200.utils, i.e. hdf5_lite here)."""
+  from nearl_b200 import utils as butils
+  rng = np.random.default_rng(2718)
+  files = []
+  for fi, n in enumerate((9, 8)):
+    path = os.path.join(folder, f"nearl_golden_ds{fi}.h5")
+    if os.path.exists(path):
+      os.remove(path)
+    butils.dump_dict(path, "featurizer_parms", {"dimensions": np.array([6, 6, 6]), "time_window": 4})
+    for key in DATASET_KEYS:
+      data = rng.random((n, 6, 6, 6)).astype(np.float32) * (fi + 1.5)
+      data[1] = 0.75                                          # a constant sample: the normalisations return zeros
+      butils.append_hdf_data(path, key, data, dtype=np.float32, maxshape=(None, 6, 6, 6), chunks=(1, 6, 6, 6))
+    butils.append_hdf_data(path, "label", rng.integers(0, 20, size=n), dtype=int, maxshape=(None,), chunks=True)
+    files.append(path)
+  return files
+
+
+def run_dataset_case(D, torch, files, ds_kw, mb_kw, seed):
+  """Everything recorded for one case, from module `D` (the reference's nearl.io.dataset or nearl_b200.dataset)."""
+  rec = {}
+  ds = D.Dataset(files, feature_keys=list(DATASET_KEYS), **ds_kw)
+  rec["len"] = np.array([len(ds)])
+  rec["size"] = np.asarray(ds.size, dtype=np.int64)
+  items = [ds[i] for i in (0, 1, 8, 9, len(ds) - 1)]
+  rec["item_data"] = np.stack([digest(d.numpy()) for d, _ in items])
+  rec["item_label"] = np.array([int(l.reshape(-1)[0]) for _, l in items])
+  np.random.seed(seed)
+  torch.manual_seed(seed)
+  digs, labs, shapes = [], [], []
+  for data, label in ds.mini_batches(**mb_kw):
+    arr = np.ascontiguousarray(data.numpy())
+    digs.append(digest(arr)); shapes.append(list(arr.shape)); labs.append(label.numpy().reshape(-1).astype(np.int64))
+  rec["batch_digest"] = np.stack(digs)
+  rec["batch_shape"] = np.array(shapes, dtype=np.int64)
+  rec["batch_labels"] = np.concatenate(labs)
+  rec["split"] = np.array([len(b) for n, bs in ((17, 5), (12, 4), (3, 8), (8, 8)) for b in D.split_array(np.arange(n), bs)])
+  return rec
+
+
 def make_system(kw):
   from nearl_b200 import io as bio
   return bio.synthetic_trajectory(kw["n_atoms"], kw["n_frames"], seed=kw["seed"], pin=False)
@@ -136,6 +229,15 @@ class Recorder:
     return self._grid(grid_dims)
   def frame_observation(self, *a, **k):
     raise AssertionError("not on the recorded path")
+
+
+class FakeKernels(Recorder):
+  """Deterministic stand-in results (a ramp that depends on the call number, with NaNs the sink has to scrub)."""
+  def _grid(self, dims):
+    n = int(np.prod([int(v) for v in dims]))
+    out = (np.arange(n, dtype=np.float32) % 17) * np.float32(0.25) + np.float32(len(self.calls))
+    out[len(self.calls) % 5::23] = np.nan
+    return out
 
 
 def digest(a):
@@ -217,6 +319,37 @@ def main(path):
     pack(name, np.zeros((0, 0, 3), dtype=np.float32), rec.calls, dumps, out)
     out[f"{name}/labels"] = np.concatenate(labels) if labels else np.zeros(0, dtype=int)
     print(name, "recorded", len(rec.calls), "kernel calls,", len(dumps), "dumps,", sum(len(l) for l in labels), "labels")
+  # ---- the reference's sink on this repo's self-contained HDF5 reader / writer standing in for h5py: dataset names,
+  # ---- shapes, chunking, append semantics, NaN scrub, the parameter group (not the bytes of the file: no libhdf5 here)
+  from nearl_b200 import hdf5_lite
+  import torch
+  sys.modules["h5py"].File = hdf5_lite.File
+  RU.h5py = sys.modules["h5py"]
+  import importlib
+  importlib.reload(RU)                      # drops the recorders put into nearl.utils above
+  RF.utils = RU; RFz.utils = RU
+  sink_path = "/tmp/nearl_golden_sink_ref.h5"
+  if os.path.exists(sink_path):
+    os.remove(sink_path)
+  sink_traj = make_system(SINK_SYSTEM)
+  RC.all_actions = FakeKernels()
+  fz = RFz.Featurizer(dict(SINK_PARMS, outfile=sink_path))
+  fz.register_features(sink_feature_set(RF, sink_path))
+  fz.register_focus([":ARG", "@CA"], "mask")
+  fz.register_trajloader([PtTrajectory(xyz=np.array(sink_traj.xyz), top=sink_traj.top, identity="sink")] * 2)
+  fz.run()
+  rows = file_manifest(sink_path)
+  pack_manifest("sink", rows, out)
+  print("sink recorded", len(rows), "datasets:", {k: v[0] for k, v in rows.items()})
+  # ---- the dataset consumer (nearl/io/dataset.py:40-393)
+  import nearl.io.dataset as RD
+  RD.h5py = sys.modules["h5py"]
+  files = write_dataset_files("/tmp")
+  for name, ds_kw, mb_kw, seed in DATASET_CASES:
+    rec = run_dataset_case(RD, torch, files, ds_kw, mb_kw, seed)
+    for k, v in rec.items():
+      out[f"{name}/{k}"] = v
+    print(name, "recorded", len(rec["batch_digest"]), "batches")
   np.savez_compressed(path, **out)
   print("wrote", path, os.path.getsize(path), "bytes")
 

@@ -133,3 +133,54 @@ def test_residue_loops_hand_over_the_reference_bits(name, restype, tag_limit):
   _, labels = host_ref.featurize_by_residue(pep.xyz, resids, workloads.describe(fz), blocks, fz.time_window, kernels=rec)
   compare(name, rec.calls, "oracle/host_ref.py residue loop")
   assert np.array_equal(labels, GOLD[f"{name}/labels"])
+
+
+@pytest.mark.parametrize("name,ds_kw,mb_kw,seed", G.DATASET_CASES)
+def test_dataset_consumer_yields_the_reference_batches(name, ds_kw, mb_kw, seed, tmp_path):
+  # /root/reference/nearl/io/dataset.py recorded with the reference's own code on the same files: sample reads, the
+  # three normalisations, split_array, shuffle order, and the augmentation's use of numpy's and torch's generators
+  import torch
+  from nearl_b200 import dataset
+  files = G.write_dataset_files(str(tmp_path))
+  rec = G.run_dataset_case(dataset, torch, files, ds_kw, mb_kw, seed)
+  for key, val in rec.items():
+    assert np.array_equal(val, GOLD[f"{name}/{key}"]), (name, key, val, GOLD[f"{name}/{key}"])
+
+
+def test_result_sink_writes_what_the_reference_sink_writes(tmp_path, monkeypatch):
+  # The reference's Featurizer.__init__ (parameter group) + Feature.dump + utils.append_hdf_data
+  # (/root/reference/nearl/featurizer.py:159-162, features.py:510-534, utils.py:491-570) were run on this repo's HDF5
+  # writer standing in for h5py; the same run through nearl_b200 must leave the same datasets: names (nested keys
+  # included), shapes, dtypes, chunking, extensibility, NaN scrub, append order, parameter group.
+  path = str(tmp_path / "sink.h5")
+  traj = G.make_system(G.SINK_SYSTEM)
+  traj.identity = "sink"
+  monkeypatch.setattr(commands, "all_actions", G.FakeKernels())
+  fz = featurizer.Featurizer(dict(G.SINK_PARMS, outfile=path))
+  fz.register_features(G.sink_feature_set(features, path))
+  fz.register_focus([":ARG", "@CA"], "mask")
+  for tid in range(2):
+    fz.traj = traj
+    assert fz.parse_focus()
+    for f in fz.FEATURESPACE:
+      f.cache(traj)
+    results = []
+    for bid in range(fz.SLICENUMBER):
+      frames = traj.xyz[fz.FRAMESLICES[bid]]
+      for pid in range(fz.FOCALNUMBER):
+        for feat in fz.FEATURESPACE:
+          results.append((feat, feat.run(*feat.query(traj.top, frames, fz.FOCALPOINTS[bid, pid]))))
+    for feat, res in results:
+      feat.dump(res)
+  rows = G.file_manifest(path)
+  assert sorted(rows) == [str(k) for k in GOLD["sink/keys"]]
+  for key, (shape, dtype, chunks, maxshape, compression, dig, val) in rows.items():
+    meta = [str(m) for m in GOLD[f"sink/{key}/meta"]]
+    if key == "featurizer_parms/outfile":               # the path itself: a string scalar of another length
+      assert dtype.startswith("<U") and meta[1].startswith("<U") and repr(shape) == meta[0]
+      continue
+    assert [repr(shape), dtype, repr(chunks), repr(maxshape), repr(compression)] == meta, (key, meta)
+    if dig is not None:
+      assert np.array_equal(dig, GOLD[f"sink/{key}/digest"]), key
+    else:
+      assert [str(v) for v in np.asarray(val).reshape(-1)] == [str(t) for t in GOLD[f"sink/{key}/text"]], key
