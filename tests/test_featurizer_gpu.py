@@ -325,3 +325,32 @@ def test_single_frame_systems_grouped_per_call(tmp_path):
     assert grouped[key].shape == want.shape == (26, 20, 20, 20)
     assert np.array_equal(grouped[key], want), key
   assert grouped["mass"].sum() > 0 and grouped["sel"].sum() > 0
+
+
+def test_recorded_reference_feature_set_on_the_device_path(tmp_path):
+  # The systems and the 15-feature set whose FFI-boundary vectors were recorded from the reference's own Python
+  # (tests/golden/make_host_golden.py; non-cubic 12 x 14 x 16 grid, per-feature cutoff / sigma / padding, by-residue,
+  # selections, frame offset, three focal masks): the device path (crop, cell lists, fused sweeps, fused reducers)
+  # against oracle/host_ref.py -- which tests/test_host_golden.py pins to that record -- feeding the C oracle.
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+  import make_host_golden as G
+  gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "host_vectors.npz"))
+  for name, kw in G.systems():
+    traj = G.make_system(kw)
+    (tmp_path / name).mkdir()
+    got, fz = build(traj, tmp_path / name, lambda: G.feature_set(features), dict(G.FEATURIZER_PARMS), focus=G.FOCUS)
+    assert np.array_equal(fz.FOCALPOINTS.view(np.int32), gold[f"{name}/focal"].view(np.int32))
+    ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, fz.time_window, buff_dim=_lib.buff_dim)
+    for f in fz.FEATURESPACE:
+      key = f.outkey
+      assert got[key].shape == ref[key].shape, key
+      if isinstance(f, features.MarchingObservers) and f.obs in (1, 2, 3) and f.agg in (3, 5, 6):
+        assert np.array_equal(got[key], ref[key]), key                                   # integer observable, order statistic
+      elif getattr(f, "agg", 0) in (2, 4, 8):
+        peak = max(float(np.abs(ref[key]).max()), 1e-30)
+        assert rel_bad(got[key], ref[key], atol=2e-5 * peak) == 0, key                    # cancelling reducers
+      elif getattr(f, "agg", 0) == 7:
+        assert np.count_nonzero(~np.isclose(got[key], ref[key], atol=1e-3)) <= max(2, got[key].size // 3000), key
+      else:
+        assert rel_bad(got[key], ref[key]) == 0, (key, np.abs(got[key] - ref[key]).max())
