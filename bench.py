@@ -326,6 +326,23 @@ def run_native(args):
               "step_warp_instructions": step_inst or None,
               "step_issue_frac": (step_inst / (ms_dev / args.steps * 1e-3) / issue_peak) if step_inst else None,
               "kernel_issue_active_pct_ncu": table.get(top, {}).get("issue_active_pct")}
+    # algorithmic pair tests of one observer task = F * G * n_c with n_c = rho * (4/3) pi c^3 atoms truly
+    # in range of a voxel, 9 flop each; a fused launch sweeps once for all observer channels of its work items
+    n_obs = sum(isinstance(f, _features.MarchingObservers) for f in fz.FEATURESPACE)
+    if top.startswith("tile_") and top != "tile_voxelize" and n_obs:
+      c = float(f0.cutoff)
+      box = float(np.prod(np.asarray(f0.dims) * f0.spacing + 2 * c))
+      n_c = n_in / box * (4.0 / 3.0) * np.pi * c ** 3
+      per_task = fz.time_window * G * n_c * 9.0
+      tasks_per_launch = windows * (n_obs if top == "tile_fused" else 1)
+      fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
+      roof_c.update({"algorithmic_flop_per_task": per_task, "atoms_in_range_per_voxel": n_c,
+                     "algorithmic_flop_per_launch": per_task * tasks_per_launch,
+                     "achieved_tflops": per_task * tasks_per_launch / t_launch / 1e12,
+                     "fp32_peak_tflops": fp32_peak / 1e12,
+                     "frac_of_fp32_peak": per_task * tasks_per_launch / t_launch / fp32_peak,
+                     "note": "launch_ms is the launch's span while it shares the SMs with the voxeliser launch of the same step; "
+                             "alone (ncu, profiles/kernel_table.json) the fused sweep takes %.0f us" % table.get(top, {}).get("duration_us", float("nan"))})
   else:
     roof_c = None
 

@@ -72,6 +72,10 @@ RES_PATCH = {
 RES2LAB_DUAL = {a + b: i * len(RES) + j for i, a in enumerate(RES) for j, b in enumerate(RES)}
 LAB2RES_DUAL = {lab: name for name, lab in RES2LAB_DUAL.items()}
 
+# superseded PDB entries (constants.py:327)
+PDBCODE_SUPERCEDES = {"4dgo": "6qs5", "4otw": "6op9", "4v1c": "6iso", "5v8h": "6nfg", "5v8j": "6nfo", "6fim": "6fex", "6h7k": "6ibl",
+                      "3m8t": "5wcm", "4n3l": "6eo8"}
+
 # parameters a Feature inherits from the Featurizer when it does not set them itself
 COMMON_FEATURE_PARMS = [
   "outfile",

@@ -27,6 +27,7 @@ logger = logging.getLogger(__name__)
 __all__ = [
   "Feature", "AtomicNumber", "Mass", "HeavyAtom", "Selection", "Backbone", "AtomType", "Electronegativity",
   "Hydrophobicity", "DynamicFeature", "DensityFlow", "MarchingObservers", "cache_properties", "crop",
+  "LabelIdentity", "LabelAffinity", "LabelStepping", "LabelRMSD", "LabelPCDT",
   "SUPPORTED_FEATURES", "SUPPORTED_AGGREGATION", "SUPPORTED_OBSERVATION",
 ]
 
@@ -669,3 +670,145 @@ class MarchingObservers(DynamicFeature):
 
   def _native_spec(self):
     return self._dynamic_spec(self.obs, 0.0)
+
+
+# ---- label features: per-task scalars written next to the grids (features.py:1529-1775) --------------------------
+class _Label(Feature):
+  """A feature whose task result is a scalar, not a grid: always the host protocol, dumped as rows of a 1-D
+  dataset (``outshape=(None,)``)."""
+  _native_kind = "label"
+
+  def _native_spec(self):
+    return None
+
+
+class LabelIdentity(_Label):
+  """The identity of the trajectory as meta-data (features.py:1529-1556)."""
+
+  def cache(self, trajectory):
+    super().cache(trajectory)
+    self.identity = trajectory.identity
+
+  def query(self, *args):
+    return (self.identity, )
+
+  def run(self, identity):
+    return identity
+
+
+class LabelAffinity(_Label):
+  """The affinity of the complex (trajectory identity -> PDB code -> column `colname` of a PDBBind-style csv
+  table with a `pdbcode` column), features.py:1559-1634."""
+
+  def __init__(self, baseline_map, colname="pK", **kwargs):
+    kwargs.setdefault("outshape", (None,))
+    super().__init__(**kwargs)
+    import pandas as pd
+    self.baseline_table = pd.read_csv(baseline_map, header=0, delimiter=",")
+    self.base_value = None
+    self.colname = colname
+    if self.colname not in self.baseline_table.columns:
+      raise ValueError(f"The column name {self.colname} is not found in the baseline table")
+    self._lookup = None
+
+  def search_baseline(self, pdbcode):
+    pdbcode = utils.get_pdbcode(pdbcode)
+    if self._lookup is None:       # first match wins, as row[...].values[0] does
+      codes, values = self.baseline_table["pdbcode"].values, self.baseline_table[self.colname].values
+      self._lookup = {}
+      for code, value in zip(codes, values):
+        self._lookup.setdefault(code, value)
+    if pdbcode in self._lookup:
+      return self._lookup[pdbcode]
+    raise ValueError(f"Cannot find the baseline value for {pdbcode}")
+
+  def cache(self, trajectory):
+    self.base_value = self.search_baseline(trajectory.identity)
+    if config.verbose():
+      printit(f"{self.classname}: Affinity value of {trajectory.identity} is {self.base_value}")
+
+  def query(self, *args):
+    return (self.base_value, )
+
+  def run(self, affinity_val):
+    return affinity_val
+
+
+class LabelStepping(LabelAffinity):
+  """Affinity as a class: floor(pK / 2) capped at 5 (features.py:1637-1645)."""
+
+  def query(self, *args):
+    assert self.base_value is not None, "The base value should be set before the query"
+    return (min(self.base_value // 2, 5), )
+
+
+class LabelRMSD(_Label):
+  """base_value scaled down by the mean no-fit RMSD of the window against the first frame of the trajectory
+  (features.py:1648-1676).  As in the reference the class needs a `selection`."""
+
+  def __init__(self, base_value=0, outshape=(None,), **kwargs):
+    if "selection" not in kwargs:
+      raise ValueError("The selection should be set for the RMSD label feature")
+    super().__init__(outshape=outshape, **kwargs)
+    self.base_value = float(base_value)
+
+  def cache(self, trajectory):
+    super().cache(trajectory)
+    self.refframe = trajectory[0]
+    self._index = np.flatnonzero(self.selected)
+    self.cached_array = np.minimum(utils.rmsd_nofit(trajectory.xyz, self._index, self.refframe.xyz), 8)
+
+  def query(self, topology, frames, focus):
+    rmsd = np.mean(utils.rmsd_nofit(frames, self._index, self.refframe.xyz))
+    return (self.base_value * (1 - 0.1 * (rmsd / 8.0)), )
+
+  def run(self, value):
+    return value
+
+
+class LabelPCDT(LabelAffinity):
+  """Affinity with a conformation penalty: the z-score of the window's pairwise-closest-distance profile against the
+  whole trajectory's (features.py:1679-1775)."""
+
+  def __init__(self, selection=None, search_cutoff=None, **kwargs):
+    super().__init__(**kwargs)
+    self.selection_prototype = selection
+    self.selected = None
+    self.selected_counterpart = None
+    self.refframe = None
+    self.cached_array = None
+    self.search_cutoff = search_cutoff
+
+  def cache(self, trajectory):
+    super().cache(trajectory)
+    if isinstance(self.selection_prototype, str):
+      selected = trajectory.top.select(self.selection_prototype)
+    elif isinstance(self.selection_prototype, (list, tuple, np.ndarray)):
+      selected = np.array([int(i) for i in self.selection_prototype])
+    else:
+      raise ValueError("The selection should be either a string or a list of atom indices")
+    self.refframe = trajectory[0]
+    self.selected = selected
+    self.selected_counterpart = np.full(len(selected), 0, dtype=int)
+    backbone_cb = trajectory.top.select("@C, @N, @CA, @O, @CB")
+    ref = self.refframe.xyz
+    for i in range(len(selected)):
+      dist = np.linalg.norm(ref[selected[i]] - ref[backbone_cb], axis=1)
+      self.selected_counterpart[i] = backbone_cb[np.argmin(dist)]
+    self.cached_array = utils.compute_pcdt(trajectory, self.selected, self.selected_counterpart, ref=self.refframe)
+    if self.search_cutoff is not None:
+      self.cached_array = np.minimum(self.cached_array, self.search_cutoff)
+
+  def query(self, topology, frames, focus):
+    from . import io
+    window = io.Trajectory(np.asarray(frames), topology)
+    pdist_arr = utils.compute_pcdt(window, self.selected, self.selected_counterpart, ref=self.refframe)
+    if self.search_cutoff is not None:
+      pdist_arr = np.minimum(pdist_arr, self.search_cutoff)
+    mean_0 = np.mean(self.cached_array, axis=1)
+    mean_1 = np.mean(pdist_arr, axis=1)
+    std_0 = np.std(self.cached_array, axis=1)
+    if np.any(std_0 == 0):
+      std_0[std_0 == 0] = self.search_cutoff if self.search_cutoff is not None else 6.0
+    penalty = abs(np.mean((mean_0 - mean_1) / std_0))
+    return (self.base_value * (1 - 0.1 * penalty), )

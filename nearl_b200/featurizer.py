@@ -245,12 +245,7 @@ class Featurizer:
       job = self._submit(tid, lane=count % depth)
       if job is None:
         continue
-      if job["generic_ids"]:
-        while pending:
-          self._finish(pending.pop(0), stats)
-        self._finish(job, stats)        # host-protocol features read self.traj: no overlap with the next trajectory
-      else:
-        pending.append(job)
+      pending.append(job)              # host-protocol tasks were evaluated inside _submit
     while pending:
       self._finish(pending.pop(0), stats)
     stats["seconds"] = time.perf_counter() - t_run
@@ -264,14 +259,18 @@ class Featurizer:
     are concatenated into one pseudo-system per native call, each a slice of its atoms with its own focus box."""
     if not (self.use_native_batch and self.time_window == 1 and int(self.static_group) > 1 and self.FEATURENUMBER > 0):
       return False
+    n_static = 0
     for feat in self.FEATURESPACE:
+      if getattr(feat, "_native_kind", None) == "label":
+        continue                      # per-system scalars (affinity labels ...): evaluated on the host, member by member
       if getattr(feat, "_native_kind", None) != "static" or not feat._is_builtin("query", "run", "cache"):
         return False
       if feat.selection is not None and not isinstance(feat.selection, str):
         return False
       if int(feat.frame_offset or 0) != 0:
         return False
-    return True
+      n_static += 1
+    return n_static > 0
 
   def _run_static_groups(self, indices, depth, stats):
     group = max(2, int(self.static_group))
@@ -321,7 +320,8 @@ class Featurizer:
       for feat in self.FEATURESPACE:
         feat.cache(traj)
       specs = [feat._native_spec() for feat in self.FEATURESPACE]
-      if any(sp is None for sp in specs):
+      label_feats = [f for f, feat in enumerate(self.FEATURESPACE) if feat._native_kind == "label"]
+      if any(sp is None for f, sp in enumerate(specs) if f not in label_feats):
         return None
       if n_focal is None:
         n_focal = len(focal)
@@ -330,8 +330,10 @@ class Featurizer:
       xyz = traj.xyz
       if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64):
         xyz = np.asarray(xyz, dtype=np.float32)
-      members.append({"tid": tid, "identity": traj.identity, "xyz": xyz, "focal": focal, "specs": specs,
-                      "resids": self.FEATURESPACE[0].resids})
+      labels = {(pid, f): self.FEATURESPACE[f].run(*self.FEATURESPACE[f].query(traj.top, traj.xyz[0:1], focal[pid]))
+                for pid in range(len(focal)) for f in label_feats}
+      members.append({"tid": tid, "identity": traj.identity, "xyz": xyz, "focal": focal, "specs": specs, "labels": labels,
+                      "resids": next(feat.resids for feat in self.FEATURESPACE if feat._native_kind != "label")})
     if not members:
       return {"members": [], "batch": None, "lane": lane}
     dtype = members[0]["xyz"].dtype
@@ -343,14 +345,14 @@ class Featurizer:
     cat = self._table_buffer(lane, "group_xyz_" + dtype.name, (1, n_total, 3), dtype)
     for m, o in zip(members, offsets):
       cat[0, o:o + m["xyz"].shape[1]] = m["xyz"][0]
-    nf = self.FEATURENUMBER
-    specs_cat = []
-    for f in range(nf):
+    native_feats = [f for f, feat in enumerate(self.FEATURESPACE) if feat._native_kind != "label"]
+    specs_cat = [None] * self.FEATURENUMBER
+    for f in native_feats:
       sp = dict(members[0]["specs"][f])
       sp["weights"] = np.concatenate([np.asarray(m["specs"][f]["weights"], dtype=np.float32) for m in members])
-      specs_cat.append(sp)
+      specs_cat[f] = sp
     residue_index = None
-    if any(feat.byres for feat in self.FEATURESPACE):
+    if any(self.FEATURESPACE[f].byres for f in native_feats):
       dense, most = [], 1
       for m in members:
         _, inv = np.unique(m["resids"], return_inverse=True)
@@ -360,7 +362,7 @@ class Featurizer:
     starts = np.repeat(offsets[:-1], n_focal)
     stops = np.repeat(offsets[1:], n_focal)
     focal = np.concatenate([m["focal"] for m in members], axis=0)
-    batch = self._lower_residue_batch(list(range(nf)), specs_cat, dtype == np.float64, 0, starts, stops, np.zeros(len(starts), dtype=np.int64),
+    batch = self._lower_residue_batch(native_feats, specs_cat, dtype == np.float64, 0, starts, stops, np.zeros(len(starts), dtype=np.int64),
                                       focal, n_total, lane, residue_index=residue_index)
     buffers = self.__dict__.setdefault("_out_buffers", {})
     if lane not in buffers or buffers[lane].size < batch.out_floats:
@@ -380,9 +382,12 @@ class Featurizer:
       for m in job["members"]:
         for pid in range(n_focal):
           for fidx in range(nf):
-            result = grids[k]
-            k += 1
             feat = self.FEATURESPACE[fidx]
+            if (pid, fidx) in m["labels"]:
+              result = m["labels"][(pid, fidx)]
+            else:
+              result = grids[k]
+              k += 1
             if self.result_sink is not None:
               self.result_sink(feat.outkey, m["tid"], 0, pid, result)
             if self.keep_results:
@@ -391,7 +396,7 @@ class Featurizer:
               feat.dump(result)
         stats["trajectories"] += 1
         stats["tasks"] += n_focal * nf
-        stats["native_tasks"] += n_focal * nf
+        stats["native_tasks"] += n_focal * nf - len(m["labels"])
         stats["frames"] += 1
 
   def main_loop(self, *args, **kwargs):
@@ -421,6 +426,7 @@ class Featurizer:
     native_ids = [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is not None]
     job = {"tid": tid, "traj": self.traj, "task_keys": task_keys, "native_ids": native_ids, "lane": lane, "start": st,
            "generic_ids": [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is None], "batch": None}
+    job["generic_results"] = self._run_generic_tasks(job)
     if native_ids:
       xyz = self.traj.xyz
       if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
@@ -434,15 +440,13 @@ class Featurizer:
       job.update(batch=batch, out=out, xyz=xyz)
     return job
 
-  def _finish(self, job, stats):
-    """Wait for the native results of `job`, run its host-protocol tasks, dump in order."""
-    task_keys = job["task_keys"]
-    results = [None] * len(task_keys)
-    if job["batch"] is not None:
-      _lib.check(_lib.lib().nrl_lane_synchronize(job["lane"]))
-      for i, arr in zip(job["native_ids"], job["batch"].split(job["out"], copy=self.keep_results)):
-        results[i] = arr
+  def _run_generic_tasks(self, job):
+    """The host-protocol tasks of `job` (label features, user subclasses that override query / run), evaluated at
+    submit time -- while `self.traj`, the focal points and the features' caches are this trajectory's -- so that
+    they do not stop the pipeline: {task index: result}."""
+    out = {}
     frames_cache = {}
+    task_keys = job["task_keys"]
     for i in job["generic_ids"]:
       bid, pid, fidx = task_keys[i]
       self.frame_slice = self.FRAMESLICES[bid]
@@ -450,7 +454,19 @@ class Featurizer:
         frames_cache = {bid: self.traj.xyz[self.FRAMESLICES[bid]]}
       focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else np.zeros(3, dtype=np.float32)
       feat = self.FEATURESPACE[fidx]
-      results[i] = feat.run(*feat.query(self.top, frames_cache[bid], focal))
+      out[i] = feat.run(*feat.query(self.top, frames_cache[bid], focal))
+    return out
+
+  def _finish(self, job, stats):
+    """Wait for the native results of `job`, merge its host-protocol results, dump in order."""
+    task_keys = job["task_keys"]
+    results = [None] * len(task_keys)
+    if job["batch"] is not None:
+      _lib.check(_lib.lib().nrl_lane_synchronize(job["lane"]))
+      for i, arr in zip(job["native_ids"], job["batch"].split(job["out"], copy=self.keep_results)):
+        results[i] = arr
+    for i, res in job["generic_results"].items():
+      results[i] = res
     tid = job["tid"]
     printit(f"{self.classname}: Trajectory {tid + 1} yields {len(task_keys)} frame-slices (tasks) for the featurization. ")
     with utils.batched_output():

@@ -103,6 +103,11 @@ class Topology:
     idx = np.arange(self.n_atoms)[key]
     return Topology(self.names[idx], self.resids[idx], self.resnames[idx], self.atomic_numbers[idx])
 
+  def set_reference(self, frame):
+    """pytraj's Topology.set_reference (the frame distance-based masks refer to; /root/reference/nearl/utils.py:97-100
+    sets it before selecting).  Distance-based masks are outside the supported subset: the frame is only kept."""
+    self._reference = frame
+
   def strip(self, mask):
     """Remove the atoms selected by `mask`, in place (pytraj's Topology.strip; MisatoTraj drops water and
     ions this way, /root/reference/nearl/io/traj.py:362-369)."""
@@ -124,6 +129,7 @@ class Topology:
 
   def _select(self, mask):
     mask = mask.strip()
+    mask = re.sub(r",\s*(?=[:@])", "|", mask)       # '@C, @N, @CA' (features.py:1725): a list of masks is their union
     tokens = re.findall(r"[()!&|]|[:@][^()!&|:@\s]+", mask)
     if "".join(tokens) != re.sub(r"\s+", "", mask) or any(
         t[0] in ":@" and not re.fullmatch(r"[:@][A-Za-z0-9*=?,\-+'/_]+", t) for t in tokens):
@@ -213,6 +219,17 @@ class Topology:
     return np.array([rx.fullmatch(str(u)) is not None for u in uniq], dtype=bool)[inverse]
 
 
+class Frame:
+  """One frame of a trajectory (pytraj.Frame as far as the label features read it: ``xyz [N, 3]``)."""
+
+  def __init__(self, xyz):
+    self.xyz = np.asarray(xyz)
+
+  @property
+  def n_atoms(self):
+    return self.xyz.shape[0]
+
+
 class Trajectory:
   """Coordinates ``xyz [F, N, 3]`` (float32 or float64) + topology + identity."""
 
@@ -235,6 +252,13 @@ class Trajectory:
 
   def __len__(self):
     return self.n_frames
+
+  def __getitem__(self, index):
+    """`traj[i]` -> Frame (copy), `traj[slice]` -> Trajectory of those frames (pytraj's indexing, as far as the
+    label features and scripts use it)."""
+    if isinstance(index, (int, np.integer)):
+      return Frame(np.array(self.xyz[int(index)]))
+    return Trajectory(np.ascontiguousarray(self.xyz[index]), self.top, identity=self.identity)
 
 
 _ELEMENTS = np.array([1, 6, 7, 8, 16])

@@ -93,6 +93,65 @@ def dump_dict(outfile, groupname, dic):
 
 
 # ---- residue blocks of Featurizer.loop_by_residue ---------------------------------------------------
+def get_pdbcode(pdbcode):
+  """Lower-case PDB code, superseded entries replaced (utils.py:196-214)."""
+  pdbcode = pdbcode.lower()
+  return constants.PDBCODE_SUPERCEDES.get(pdbcode, pdbcode)
+
+
+def _pair_distances(a, b):
+  """[len(a), len(b)] Euclidean distances in the input dtype (the quantity scipy.spatial.distance_matrix returns,
+  which the reference calls at utils.py:118-136; only its row-wise argmin is used)."""
+  d = np.asarray(a)[:, None, :] - np.asarray(b)[None, :, :]
+  return np.sqrt(np.sum(d * d, axis=-1))
+
+
+def compute_pcdt(traj, mask1, mask2, use_mean=False, ref=None, return_info=False):
+  """Pairwise Closest DisTance (utils.py:70-166): every atom of `mask1` is paired with the atom of `mask2`
+  closest to it in the reference frame (a frame index, a Frame, the mean structure, or frame 0); returns the
+  distance of each pair in every frame, ``[len(mask1), n_frames]`` float64."""
+  from . import io
+  is_number = isinstance(ref, (int, float, np.int32, np.int64, np.float32, np.float64)) and not isinstance(ref, bool)
+  if ref is not None and is_number:
+    traj.top.set_reference(traj[int(ref)])
+  elif ref is not None and isinstance(ref, io.Frame):
+    traj.top.set_reference(ref)
+  selmask1 = traj.top.select(mask1) if isinstance(mask1, str) else np.asarray(mask1)
+  selmask2 = traj.top.select(mask2) if isinstance(mask2, str) else np.asarray(mask2)
+  if len(selmask1) == 0:
+    print("No target atom selected, please check the mask")
+    return None, None
+  if len(selmask2) == 0:
+    print("No counter part atom selected, please check the mask")
+    return None, None
+  if use_mean is True:
+    base = np.mean(traj.xyz, axis=0)
+  elif isinstance(ref, io.Frame):
+    base = ref.xyz
+  elif ref is not None and is_number:
+    base = traj.xyz[int(ref)]
+  else:
+    base = traj.xyz[0]
+  ref_frame = _pair_distances(base[selmask1], base[selmask2])
+  selclosest = selmask2[np.argmin(ref_frame, axis=1)]
+  diff = traj.xyz[:, selmask1, :] - traj.xyz[:, selclosest, :]                  # [F, n1, 3], in the trajectory's dtype
+  distarr = np.zeros((len(selmask1), traj.n_frames))
+  distarr[:, :] = np.sqrt(np.sum(diff ** 2, axis=2)).T
+  if return_info:
+    atoms = traj.atoms if hasattr(traj, "atoms") else list(traj.top.atoms)
+    info = {"atom_name_group1": [atoms[i].name for i in selmask1], "indices_group1": [atoms[i].index for i in selmask1],
+            "atom_name_group2": [atoms[i].name for i in selclosest], "indices_group2": [atoms[i].index for i in selclosest]}
+    return distarr, info
+  return distarr
+
+
+def rmsd_nofit(xyz, index, ref_xyz):
+  """Per-frame RMSD of the atoms `index` against `ref_xyz [N, 3]` without fitting and without mass weighting
+  (what pytraj.rmsd_nofit returns for `mask=`, `ref=`; features.py:1664,1672)."""
+  d = np.asarray(xyz, dtype=np.float64)[:, index, :] - np.asarray(ref_xyz, dtype=np.float64)[index][None]
+  return np.sqrt(np.mean(np.sum(d * d, axis=2), axis=1))
+
+
 def _known_residue(name):
   return name in constants.RES or name in constants.RES_PATCH
 

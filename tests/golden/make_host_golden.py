@@ -115,6 +115,29 @@ def pack_manifest(prefix, rows, out):
       out[f"{prefix}/{key}/text"] = np.array([str(v) for v in np.asarray(val).reshape(-1)])
 
 
+# ---- label features (features.py:1559-1775, utils.py:70-166,196-214) ---------------------------------------------------
+LABEL_TABLE = "pdbcode,pK,resolution\n1abc,7.25,2.0\n6qs5,4.5,1.9\n2xyz,3.1,1.5\n1abc,9.99,3.0\n"
+LABEL_SYSTEMS = [("1ABC", dict(n_atoms=700, n_frames=13, seed=4242)), ("4dgo", dict(n_atoms=520, n_frames=8, seed=977))]
+LABEL_PARMS = {"dimensions": [8, 8, 8], "lengths": [8.0, 8.0, 8.0], "time_window": 4, "sigma": 1.0, "cutoff": 2.0}
+
+
+def write_label_table(folder):
+  path = os.path.join(folder, "nearl_golden_labels.csv")
+  with open(path, "w") as f:
+    f.write(LABEL_TABLE)
+  return path
+
+
+def label_feature_set(F, table):
+  return [
+    F.LabelAffinity(baseline_map=table, outkey="pk"),
+    F.LabelStepping(baseline_map=table, outkey="step"),
+    F.LabelAffinity(baseline_map=table, colname="resolution", outkey="res"),
+    F.LabelPCDT(selection=":LYS&!@H=", baseline_map=table, outkey="pcdt"),
+    F.LabelPCDT(selection=":ARG@CA", search_cutoff=5.5, baseline_map=table, outkey="pcdt_cut"),
+  ]
+
+
 # ---- dataset consumer (nearl/io/dataset.py) ----------------------------------------------------------------
 DATASET_KEYS = ["mass", "obs"]
 DATASET_CASES = [       # (name, Dataset kwargs, mini_batches kwargs, numpy / torch seed)
@@ -186,8 +209,14 @@ def _module(name, **attrs):
   return m
 
 
+class PtFrame:
+  """pytraj.Frame as far as the label features read it."""
+  def __init__(self, xyz=None):
+    self.xyz = np.asarray(xyz)
+
+
 class PtTrajectory:
-  """pytraj.Trajectory as far as the recorded path reads it: xyz, top, n_frames, n_atoms, identity."""
+  """pytraj.Trajectory as far as the recorded path reads it: xyz, top, n_frames, n_atoms, identity, traj[i]."""
   def __init__(self, xyz=None, top=None, identity="stub", **kw):
     self.xyz = np.asarray(xyz)
     self.top = top
@@ -197,11 +226,12 @@ class PtTrajectory:
   @property
   def n_atoms(self): return self.xyz.shape[1]
   def __len__(self): return self.xyz.shape[0]
+  def __getitem__(self, i): return PtFrame(np.array(self.xyz[int(i)]))
 
 
 def install_stubs():
   _module("h5py", File=_Inert, Dataset=_Inert, Group=_Inert)
-  _module("pytraj", Trajectory=PtTrajectory, Topology=type("Topology", (), {}), Frame=type("Frame", (), {}), Atom=_Inert, Residue=_Inert)
+  _module("pytraj", Trajectory=PtTrajectory, Topology=type("Topology", (), {}), Frame=PtFrame, Atom=_Inert, Residue=_Inert)
   rd = _module("rdkit")
   rd.Chem = _module("rdkit.Chem", AllChem=_Inert(), rdFMCS=_Inert(), rdMolTransforms=_Inert())
   for sub in ("AllChem", "rdFMCS", "rdMolTransforms"):
@@ -319,6 +349,22 @@ def main(path):
     pack(name, np.zeros((0, 0, 3), dtype=np.float32), rec.calls, dumps, out)
     out[f"{name}/labels"] = np.concatenate(labels) if labels else np.zeros(0, dtype=int)
     print(name, "recorded", len(rec.calls), "kernel calls,", len(dumps), "dumps,", sum(len(l) for l in labels), "labels")
+  # ---- label features: values dumped per (window, focal point) task, in task order
+  table = write_label_table("/tmp")
+  for ident, kw in LABEL_SYSTEMS:
+    ltraj = make_system(kw)
+    vals = []
+    feats = label_feature_set(RF, table)
+    for f in feats:
+      f.dump = (lambda key: (lambda result: vals.append((key, float(result)))))(f.outkey)
+    fz = RFz.Featurizer(dict(LABEL_PARMS))
+    fz.register_features(feats)
+    fz.register_focus([":ARG", "@CA"], "mask")
+    fz.register_trajloader([PtTrajectory(xyz=np.array(ltraj.xyz), top=ltraj.top, identity=ident)])
+    fz.run()
+    out[f"labels_{ident}/keys"] = np.array([k for k, _ in vals])
+    out[f"labels_{ident}/values"] = np.array([v for _, v in vals], dtype=np.float64)
+    print("labels", ident, len(vals), "values", vals[:5])
   # ---- the reference's sink on this repo's self-contained HDF5 reader / writer standing in for h5py: dataset names,
   # ---- shapes, chunking, append semantics, NaN scrub, the parameter group (not the bytes of the file: no libhdf5 here)
   from nearl_b200 import hdf5_lite

@@ -354,3 +354,76 @@ def test_recorded_reference_feature_set_on_the_device_path(tmp_path):
         assert np.count_nonzero(~np.isclose(got[key], ref[key], atol=1e-3)) <= max(2, got[key].size // 3000), key
       else:
         assert rel_bad(got[key], ref[key]) == 0, (key, np.abs(got[key] - ref[key]).max())
+
+
+def test_label_features_ride_along_pipelined_and_grouped(tmp_path):
+  # The reference's production scripts register LabelAffinity / LabelStepping / LabelPCDT next to the voxel features
+  # (scripts/featurize_misato.py:214-217, featurize_pdbbind.py:92).  Labels are host-protocol tasks: they must not stop
+  # the trajectory pipeline nor the grouping of single-frame systems, must land in task order, and must leave the grids
+  # exactly as a run without them.
+  table = str(tmp_path / "table.csv")
+  codes = [f"{i:d}abc" for i in range(1, 10)]
+  with open(table, "w") as f:
+    f.write("pdbcode,pK\n" + "".join(f"{c},{2.0 + 0.75 * i}\n" for i, c in enumerate(codes)))
+
+  def run(trajs, parms, with_labels, group=32, depth=3):
+    fz = featurizer.Featurizer(parms)
+    feats = [features.Mass(outkey="mass"), features.HeavyAtom(outkey="heavy", byres=True)]
+    if parms["time_window"] > 1:
+      feats.append(features.MarchingObservers(obs="existence", agg="mean", weight_type="mass", outkey="obs"))
+    if with_labels:
+      feats.insert(1, features.LabelAffinity(baseline_map=table, outkey="pk"))
+      feats.append(features.LabelStepping(baseline_map=table, outkey="step"))
+      if parms["time_window"] > 1:
+        feats.append(features.LabelPCDT(selection=":LYS&!@H=", baseline_map=table, outkey="pcdt"))
+    fz.register_features(feats)
+    fz.register_focus([":ARG", "@CA"], "mask")
+    fz.register_trajloader(trajs)
+    fz.static_group, fz.pipeline_depth = group, depth
+    rows = []
+    fz.result_sink = lambda outkey, tid, bid, pid, result: rows.append((outkey, tid, bid, pid, np.array(result)))
+    fz.run()
+    return rows, fz
+
+  # multi-frame trajectories: pipelined over three lanes
+  trajs = [io.synthetic_trajectory(1500 + 100 * i, 12, seed=50 + i) for i in range(5)]
+  for t, c in zip(trajs, codes):
+    t.identity = c.upper()
+  parms = {"dimensions": 16, "lengths": 12, "time_window": 4, "cutoff": 3.0, "sigma": 1.2}
+  plain, _ = run(trajs, parms, False)
+  mixed, fz = run(trajs, parms, True)
+  assert fz.last_run_stats["native_tasks"] == len(plain)
+  grids = [r for r in mixed if r[0] in ("mass", "heavy", "obs")]
+  assert len(grids) == len(plain)
+  for a, b in zip(grids, plain):
+    assert a[:4] == b[:4] and np.array_equal(a[4], b[4])
+  order = [r[0] for r in mixed[:6]]
+  assert order == ["mass", "pk", "heavy", "obs", "step", "pcdt"]                      # registration order inside a task group
+  for r in mixed:
+    if r[0] == "pk":
+      assert float(r[4]) == 2.0 + 0.75 * r[1]
+    if r[0] == "step":
+      assert float(r[4]) == min((2.0 + 0.75 * r[1]) // 2, 5)
+  # PCDT against a serial, unpipelined run of the same featuriser
+  serial, _ = run(trajs, parms, True, depth=1)
+  assert [float(r[4]) for r in mixed if r[0] == "pcdt"] == [float(r[4]) for r in serial if r[0] == "pcdt"]
+
+  # single-frame systems: grouped per native call
+  systems = [io.synthetic_complex(900 + 50 * i, seed=70 + i) for i in range(9)]
+  for t, c in zip(systems, codes):
+    t.identity = c
+  sparms = {"dimensions": 12, "lengths": 10, "time_window": 1, "cutoff": 2.5, "sigma": 1.0}
+  launches0 = _lib.kernel_launches()
+  plain, _ = run(systems, sparms, False, group=4)
+  launches_plain = _lib.kernel_launches() - launches0
+  launches0 = _lib.kernel_launches()
+  mixed, fz = run(systems, sparms, True, group=4)
+  launches_mixed = _lib.kernel_launches() - launches0
+  assert launches_mixed == launches_plain                                             # labels did not break the grouping
+  one_by_one, _ = run(systems, sparms, True, group=1)
+  assert [(r[0], r[1], r[2], r[3]) for r in mixed] == [(r[0], r[1], r[2], r[3]) for r in one_by_one]
+  for a, b in zip(mixed, one_by_one):
+    assert np.array_equal(a[4], b[4]), a[:4]
+  grids = [r for r in mixed if r[0] in ("mass", "heavy")]
+  for a, b in zip(grids, plain):
+    assert a[:4] == b[:4] and np.array_equal(a[4], b[4])

@@ -184,3 +184,22 @@ def test_result_sink_writes_what_the_reference_sink_writes(tmp_path, monkeypatch
       assert np.array_equal(dig, GOLD[f"sink/{key}/digest"]), key
     else:
       assert [str(v) for v in np.asarray(val).reshape(-1)] == [str(t) for t in GOLD[f"sink/{key}/text"]], key
+
+
+@pytest.mark.parametrize("ident,kw", G.LABEL_SYSTEMS)
+def test_label_features_give_the_reference_values(ident, kw, tmp_path):
+  # LabelAffinity / LabelStepping / LabelPCDT (features.py:1559-1775, utils.compute_pcdt, utils.get_pdbcode incl. a superseded
+  # PDB code and a duplicated table row) recorded from the reference; here through Featurizer.run() itself, which needs no
+  # GPU when every registered feature is a label
+  table = G.write_label_table(str(tmp_path))
+  traj = G.make_system(kw)
+  traj.identity = ident
+  got = []
+  fz = featurizer.Featurizer(dict(G.LABEL_PARMS))
+  fz.register_features(G.label_feature_set(features, table))
+  fz.register_focus([":ARG", "@CA"], "mask")
+  fz.register_trajloader([traj])
+  fz.result_sink = lambda outkey, tid, bid, pid, result: got.append((outkey, float(result)))
+  fz.run()
+  assert [k for k, _ in got] == [str(k) for k in GOLD[f"labels_{ident}/keys"]]
+  assert np.allclose([v for _, v in got], GOLD[f"labels_{ident}/values"], rtol=1e-12, atol=0)
