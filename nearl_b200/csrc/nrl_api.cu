@@ -350,10 +350,13 @@ int bin_frames(Ctx &c, const NrlFrames &packed, std::vector<NrlCellGrid> &hgrids
   NRL_TRY(c.batoms.reserve(std::max<size_t>(atoms_capacity, 1) * sizeof(float4)));
   NRL_TRY(c.bcnt.reserve(hgrids.size() * sizeof(int)));
   NRL_TRY(c.cstart.reserve((size_t)cs_total * sizeof(int)));
-  NRL_TRY(c.grids.reserve(hgrids.size() * sizeof(NrlCellGrid)));
-  NRL_TRY(c.blist.reserve(frame_list.size() * sizeof(int)));
-  NRL_CUDA(cudaMemcpyAsync(c.grids.p, hgrids.data(), hgrids.size() * sizeof(NrlCellGrid), cudaMemcpyHostToDevice, st));
-  NRL_CUDA(cudaMemcpyAsync(c.blist.p, frame_list.data(), frame_list.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  // grids | frame list in one blob, one upload
+  const size_t grids_bytes = (hgrids.size() * sizeof(NrlCellGrid) + 15) & ~(size_t)15;
+  std::vector<unsigned char> blob(grids_bytes + frame_list.size() * sizeof(int));
+  memcpy(blob.data(), hgrids.data(), hgrids.size() * sizeof(NrlCellGrid));
+  memcpy(blob.data() + grids_bytes, frame_list.data(), frame_list.size() * sizeof(int));
+  NRL_TRY(c.grids.reserve(blob.size()));
+  NRL_CUDA(cudaMemcpyAsync(c.grids.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
   const size_t smem = (size_t)(max_ncell + 2) * sizeof(int);
   if (!c.attr_set[kAttrBin]) {
     NRL_CUDA(cudaFuncSetAttribute(nrl_bin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c.smem_optin - 2048)));
@@ -362,7 +365,7 @@ int bin_frames(Ctx &c, const NrlFrames &packed, std::vector<NrlCellGrid> &hgrids
   NrlBinParams bp;
   bp.in = packed;
   bp.grids = c.grids.as<NrlCellGrid>();
-  bp.frame_list = c.blist.as<int>();
+  bp.frame_list = reinterpret_cast<const int *>((const char *)c.grids.p + grids_bytes);
   bp.atoms_out = c.batoms.as<float4>();
   bp.cnt_out = c.bcnt.as<int>();
   bp.cell_start = c.cstart.as<int>();
