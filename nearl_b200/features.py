@@ -789,26 +789,27 @@ class LabelPCDT(LabelAffinity):
       raise ValueError("The selection should be either a string or a list of atom indices")
     self.refframe = trajectory[0]
     self.selected = selected
-    self.selected_counterpart = np.full(len(selected), 0, dtype=int)
     backbone_cb = trajectory.top.select("@C, @N, @CA, @O, @CB")
     ref = self.refframe.xyz
-    for i in range(len(selected)):
-      dist = np.linalg.norm(ref[selected[i]] - ref[backbone_cb], axis=1)
-      self.selected_counterpart[i] = backbone_cb[np.argmin(dist)]
+    # counterpart of every selected atom: the closest backbone / CB atom in the reference frame (one distance matrix
+    # instead of the reference's loop over atoms; the same differences, squares, sums and square roots)
+    self.selected_counterpart = backbone_cb[np.argmin(utils._pair_distances(ref[selected], ref[backbone_cb]), axis=1)]
     self.cached_array = utils.compute_pcdt(trajectory, self.selected, self.selected_counterpart, ref=self.refframe)
+    # compute_pcdt pairs atom i with the member of the counterpart LIST closest to it in the reference frame: the pairs do
+    # not depend on the window, so query() re-uses them
+    self._closest = self.selected_counterpart[np.argmin(utils._pair_distances(ref[self.selected], ref[self.selected_counterpart]), axis=1)]
     if self.search_cutoff is not None:
       self.cached_array = np.minimum(self.cached_array, self.search_cutoff)
-
-  def query(self, topology, frames, focus):
-    from . import io
-    window = io.Trajectory(np.asarray(frames), topology)
-    pdist_arr = utils.compute_pcdt(window, self.selected, self.selected_counterpart, ref=self.refframe)
-    if self.search_cutoff is not None:
-      pdist_arr = np.minimum(pdist_arr, self.search_cutoff)
-    mean_0 = np.mean(self.cached_array, axis=1)
-    mean_1 = np.mean(pdist_arr, axis=1)
+    self._mean_0 = np.mean(self.cached_array, axis=1)
     std_0 = np.std(self.cached_array, axis=1)
     if np.any(std_0 == 0):
       std_0[std_0 == 0] = self.search_cutoff if self.search_cutoff is not None else 6.0
-    penalty = abs(np.mean((mean_0 - mean_1) / std_0))
+    self._std_0 = std_0
+
+  def query(self, topology, frames, focus):
+    pdist_arr = utils.pair_track(np.asarray(frames), self.selected, self._closest).astype(np.float64)    # compute_pcdt on the window
+    if self.search_cutoff is not None:
+      pdist_arr = np.minimum(pdist_arr, self.search_cutoff)
+    mean_1 = np.mean(pdist_arr, axis=1)
+    penalty = abs(np.mean((self._mean_0 - mean_1) / self._std_0))
     return (self.base_value * (1 - 0.1 * penalty), )

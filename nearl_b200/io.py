@@ -289,13 +289,16 @@ def _synthetic_topology(rng, n_atoms, ligand_atoms=0):
   return Topology(names, resids, resnames, z)
 
 
-def synthetic_trajectory(n_atoms, n_frames, seed, dtype=np.float32, identity=None, pin=True, step=0.3):
-  """Uniform-density (0.1 atoms/A^3) cube, random-walk dynamics of `step` A per frame."""
+def synthetic_trajectory(n_atoms, n_frames, seed, dtype=np.float32, identity=None, pin=True, step=0.3, ligand_atoms=0):
+  """Uniform-density (0.1 atoms/A^3) cube, random-walk dynamics of `step` A per frame; optionally the last
+  `ligand_atoms` atoms are a ligand (residue LIG) at the cube centre."""
   rng = np.random.default_rng(seed)
-  top = _synthetic_topology(rng, n_atoms)
+  top = _synthetic_topology(rng, n_atoms, ligand_atoms=ligand_atoms)
   side = (n_atoms / 0.1) ** (1.0 / 3.0)
   xyz = pinned_empty((n_frames, n_atoms, 3), dtype) if pin else np.empty((n_frames, n_atoms, 3), dtype=dtype)
   frame = rng.uniform(0.0, side, size=(n_atoms, 3))
+  if ligand_atoms:
+    frame[n_atoms - ligand_atoms:] = side / 2 + rng.normal(0.0, 2.0, size=(ligand_atoms, 3))
   for t in range(n_frames):
     if t:
       frame = frame + rng.normal(0.0, step, size=(n_atoms, 3))

@@ -100,10 +100,23 @@ def get_pdbcode(pdbcode):
 
 
 def _pair_distances(a, b):
-  """[len(a), len(b)] Euclidean distances in the input dtype (the quantity scipy.spatial.distance_matrix returns,
-  which the reference calls at utils.py:118-136; only its row-wise argmin is used)."""
-  d = np.asarray(a)[:, None, :] - np.asarray(b)[None, :, :]
-  return np.sqrt(np.sum(d * d, axis=-1))
+  """[len(a), len(b)] Euclidean distances in the input dtype: sqrt((dx^2 + dy^2) + dz^2), the quantity (and the order of
+  additions) of np.linalg.norm(a[i] - b, axis=1) and of scipy.spatial.distance_matrix, which the reference calls at
+  features.py:1727 and utils.py:118-136; only row-wise argmins are taken from it.  Column by column: a reduction over an
+  axis of length 3 is the slow way to say this in numpy."""
+  a, b = np.asarray(a), np.asarray(b)
+  dx = a[:, None, 0] - b[None, :, 0]
+  dy = a[:, None, 1] - b[None, :, 1]
+  dz = a[:, None, 2] - b[None, :, 2]
+  return np.sqrt((dx * dx + dy * dy) + dz * dz)
+
+
+def pair_track(xyz, first, second):
+  """[len(first), n_frames] distance of atom first[i] to atom second[i] in every frame, in the dtype of `xyz`:
+  sqrt((dx^2 + dy^2) + dz^2), the arithmetic of np.sqrt(np.sum((a - b) ** 2, axis=1)) at utils.py:146-147."""
+  d = xyz[:, first, :] - xyz[:, second, :]
+  dx, dy, dz = d[:, :, 0], d[:, :, 1], d[:, :, 2]
+  return np.sqrt((dx * dx + dy * dy) + dz * dz).T
 
 
 def compute_pcdt(traj, mask1, mask2, use_mean=False, ref=None, return_info=False):
@@ -134,9 +147,8 @@ def compute_pcdt(traj, mask1, mask2, use_mean=False, ref=None, return_info=False
     base = traj.xyz[0]
   ref_frame = _pair_distances(base[selmask1], base[selmask2])
   selclosest = selmask2[np.argmin(ref_frame, axis=1)]
-  diff = traj.xyz[:, selmask1, :] - traj.xyz[:, selclosest, :]                  # [F, n1, 3], in the trajectory's dtype
   distarr = np.zeros((len(selmask1), traj.n_frames))
-  distarr[:, :] = np.sqrt(np.sum(diff ** 2, axis=2)).T
+  distarr[:, :] = pair_track(traj.xyz, selmask1, selclosest)
   if return_info:
     atoms = traj.atoms if hasattr(traj, "atoms") else list(traj.top.atoms)
     info = {"atom_name_group1": [atoms[i].name for i in selmask1], "indices_group1": [atoms[i].index for i in selmask1],

@@ -124,3 +124,32 @@ def residue_classification(n_traj=1, n_residues=300, n_frames=100, seed_offset=0
   ])
   fz.register_trajloader(trajs)
   return fz, trajs
+
+
+def misato_production(n_traj=1, n_atoms=6000, n_frames=100, seed_offset=0, outfile=None, pin=True, label_table=None):
+  """The feature set the reference's MISATO production script registers (/root/reference/scripts/featurize_misato.py:107-217):
+  10 static atom-type channels (H/C/N/O/S x protein / ligand selection), 2 distinct_count observers and 4 density flows with
+  uniformed weights on the protein / ligand selections (mean and standard deviation), and -- with `label_table`, a csv with
+  `pdbcode` and `pK` columns holding the trajectories' identities -- the three labels; 32^3 over 20 A, window 10, focus on the
+  ligand, 6 000 atoms x 100 frames with a 30-atom ligand."""
+  trajs = [io.synthetic_trajectory(n_atoms, n_frames, seed=BASE_SEED + 7 + 1000 * (i + seed_offset), pin=pin, ligand_atoms=30,
+                                   identity=f"{(i + seed_offset) % 9 + 1}syn")
+           for i in range(n_traj)]
+  kw = dict(cutoff=2.5, sigma=1.5, outfile=outfile)
+  fz = featurizer.Featurizer({"dimensions": 32, "lengths": 20, "time_window": 10})
+  feats = []
+  for sel, tag in (("!:LIG", "prot"), (":LIG", "lig")):
+    feats += [features.AtomType(selection=sel, focus_element=z, outkey=f"static_{sym}_{tag}", **kw)
+              for z, sym in ((1, "H"), (6, "C"), (7, "N"), (8, "O"), (16, "S"))]
+  feats += [features.MarchingObservers(selection=sel, weight_type="uniformed", obs="distinct_count", agg="standard_deviation",
+                                       outkey=f"mo_PCount_{tag}", **kw) for sel, tag in ((":LIG", "lig"), ("!:LIG", "prot"))]
+  feats += [features.DensityFlow(selection=sel, weight_type="uniformed", agg=agg, outkey=f"pdf_P{a}_{tag}", **kw)
+            for sel, tag in ((":LIG", "lig"), ("!:LIG", "prot")) for agg, a in (("mean", "M"), ("standard_deviation", "S"))]
+  if label_table is not None:
+    feats += [features.LabelAffinity(baseline_map=label_table, outkey="pk_original", outfile=outfile),
+              features.LabelStepping(baseline_map=label_table, outkey="pk_stepping", outfile=outfile),
+              features.LabelPCDT(selection=":LIG", baseline_map=label_table, outkey="label_pcdt", outfile=outfile)]
+  fz.register_features(feats)
+  fz.register_focus([":LIG"], "mask")
+  fz.register_trajloader(trajs)
+  return fz, trajs

@@ -1,5 +1,5 @@
 """Wall time and per-kernel breakdown of one workload through Featurizer.run():
-  python scripts/time_workload.py misato|stress|stress_native|dynamic|readme|pdbbind [n_traj] [reps]"""
+  python scripts/time_workload.py misato|misato_production[_labels]|stress|stress_native|dynamic|readme|pdbbind|residue_single|residue_dual [n_traj] [reps]"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -16,6 +16,14 @@ loop = "run"
 if name in ("residue_single", "residue_dual"):
   fz, trajs = workloads.residue_classification(n_traj=n_traj)
   loop = name.split("_")[1]
+elif name in ("misato_production", "misato_production_labels"):
+  table = None
+  if name.endswith("labels"):
+    import tempfile
+    table = os.path.join(tempfile.mkdtemp(), "table.csv")
+    with open(table, "w") as f:
+      f.write("pdbcode,pK\n" + "".join(f"{i}syn,{3.0 + 0.5 * i}\n" for i in range(1, 10)))
+  fz, trajs = workloads.misato_production(n_traj=n_traj, label_table=table)
 elif name == "pdbbind":
   fz, trajs = workloads.pdbbind_static(n_complex=n_traj)
 else:
