@@ -46,6 +46,10 @@ WORKLOADS = {
               "focus ':LIG', synthetic 3k-atom complexes (one frame each; a step = one complex)"),
   "misato": ("configs[3]: MISATO-style batch, 3 static + 2 marching-observer + 2 density-flow channels at 32^3 over 20 A, window 10, "
              "cutoff 2.5 static / 5.0 dynamic, sigma 1.5, focus ':ARG', synthetic 6k-atom x 100-frame trajectories"),
+  "misato_production": ("the feature set of the reference's MISATO production script (scripts/featurize_misato.py:107-217, labels left "
+                        "out): 10 static atom-type channels on protein / ligand selections, 2 distinct_count observers and 4 density "
+                        "flows (uniformed weights, mean / standard deviation), 32^3 over 20 A, window 10, cutoff 2.5, sigma 1.5, focus on "
+                        "the ligand, synthetic 6k-atom x 100-frame trajectories"),
   "stress": ("configs[4]: 128^3 grid at 0.5 A, synthetic 200k-atom x 200-frame trajectory, time_window=100, cutoff 5.0, observers existence / "
              "distinct_count / mean_distance + 2 density flows, mean and standard deviation (reference's 9999-atom cap kept)"),
 }
@@ -62,6 +66,8 @@ def make_workload(name, n_traj, seed_offset=0, pin=True):
     return workloads.pdbbind_static(n_complex=n_traj * 8, seed_offset=seed_offset, pin=pin)
   if name == "misato":
     return workloads.misato_mixed(n_traj=n_traj, seed_offset=seed_offset, pin=pin)
+  if name == "misato_production":
+    return workloads.misato_production(n_traj=n_traj, seed_offset=seed_offset, pin=pin)
   if name == "stress":
     return workloads.stress_large(n_traj=min(n_traj, 2), seed_offset=seed_offset, pin=pin)
   raise SystemExit(f"unknown workload {name}")

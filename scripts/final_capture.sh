@@ -1,9 +1,9 @@
 set -x
-D=gpurun_out/r1w; mkdir -p $D
+D=gpurun_out/${1:-r1y}; mkdir -p $D
 timeout 900 python -m pytest tests -m gpu -x -q > $D/pytest.log 2>&1; tail -2 $D/pytest.log
 python bench.py > $D/bench_n1.json 2> $D/bench_n1.err
 python bench.py --impl reference > $D/bench_ref.json 2> $D/bench_ref.err
-for w in readme pdbbind misato stress; do python bench.py --workload $w > $D/bench_$w.json 2> $D/bench_$w.err; done
+for w in readme pdbbind misato misato_production stress; do python bench.py --workload $w > $D/bench_$w.json 2> $D/bench_$w.err; done
 python scripts/profile_step.py 2 > $D/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $D/launches.csv python bench.py --steps 2 --warmup 1 > $D/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -c 6 -o $D/prof_full -f python scripts/profile_step.py 1 > $D/ncu2.log 2>&1
 ncu -i $D/prof_full.ncu-rep --page raw --csv > $D/prof_full_raw.csv 2>/dev/null
