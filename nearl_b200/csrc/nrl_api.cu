@@ -74,10 +74,11 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   std::mutex mu;
   DevBuf coords, weights, perm, atoms, inv, off, cnt, out, tasks, flist, cand_scr, ser_scr, misc, series;
-  DevBuf xyz, wtabs, sels, resid, orders, crops, fcrop, fsrc, keep, resflags;
-  DevBuf foff, pbase;                            // per crop frame: first packed atom, payload base
+  DevBuf xyz, wtabs, sels, resid, orders, resflags;
+  DevBuf crops;                                  // descriptor blob of a batch: crops | frame offsets | frame -> crop | frame -> source frame
+  DevBuf pbase;                                  // per crop frame: payload base
   DevBuf sup_idx, sup_ref, sup_rmsd;             // superposition: fitted atom indices, reference set, per-frame RMSD
-  DevBuf batoms, bcnt, cstart, grids, blist;     // cell lists: binned frames, cell prefixes, per-frame cell grids
+  DevBuf batoms, bcnt, cstart, grids;            // cell lists: binned frames, cell prefixes, per-frame cell grids | frame list
   bool attr_set[64] = {false};          // "dynamic shared memory opt-in done" per kernel family, indexed by kAttr*
   cudaStream_t user_stream = nullptr;   // nrl_set_stream: run on the caller's stream instead of our own
   bool use_user_stream = false;
