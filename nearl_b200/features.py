@@ -608,8 +608,19 @@ class DynamicFeature(Feature):
       return None
     if self.cached_array is None or self.center is None or self.padding is None or self.cutoff is None:
       return None
+    weights = np.asarray(self.cached_array, dtype=np.float32)
+    folded = False
+    if int(mode) == 0 and self.selection is not None and (self.MAX_ALLOWED_ATOMS == 0 or len(weights) <= self.MAX_ALLOWED_ATOMS):
+      # A density flow deposits weight x Gaussian: an unselected atom and a zero-weight atom (skipped by the kernel,
+      # voxelize.cu:63) are the same thing, as for the static channels -- fold the selection into the weights so that
+      # the flows of several selections share ONE focus box and ONE sweep.  Only while the atom cap of the dynamic
+      # query (features.py:1353-1359) cannot bite: beyond it the cap counts selected atoms only.
+      memo = getattr(self, "_masked_weights", None)
+      if memo is None or memo[0] is not self.cached_array or memo[1] is not self.selected:
+        self._masked_weights = memo = (self.cached_array, self.selected, np.where(self.selected, weights, np.float32(0.0)).astype(np.float32))
+      weights, folded = memo[2], True
     spec = {
-      "kind": "dynamic", "mode": int(mode), "agg": int(self.agg), "weights": np.asarray(self.cached_array, dtype=np.float32),
+      "kind": "dynamic", "mode": int(mode), "agg": int(self.agg), "weights": weights, "selection_folded": folded,
       "frame_offset": 0, "max_atoms": int(self.MAX_ALLOWED_ATOMS), "sigma": float(sigma),
     }
     if self._is_builtin("cache") and self.selection is None:

@@ -427,3 +427,36 @@ def test_label_features_ride_along_pipelined_and_grouped(tmp_path):
   grids = [r for r in mixed if r[0] in ("mass", "heavy")]
   for a, b in zip(grids, plain):
     assert a[:4] == b[:4] and np.array_equal(a[4], b[4])
+
+
+def test_density_flow_selections_share_one_sweep(tmp_path):
+  # scripts/featurize_misato.py:163-166: density flows on the ligand and on the protein selection, mean and standard deviation.
+  # Their selections are folded into the weights (an unselected atom = a zero-weight atom for the voxeliser), so the four
+  # channels share one focus box and one multi-channel sweep; by-residue flows and systems above the 9 999-atom cap of the
+  # dynamic query (no folding there) take the separate-crop path.  All against the host pipeline feeding the C oracle.
+  def feats():
+    out = []
+    for sel, tag in ((":LIG", "lig"), ("!:LIG", "prot")):
+      for agg in ("mean", "standard_deviation"):
+        out.append(features.DensityFlow(selection=sel, weight_type="uniformed", agg=agg, outkey=f"pdf_{agg[:2]}_{tag}"))
+    out.append(features.DensityFlow(selection=":ARG,LYS", weight_type="mass", agg="max", byres=True, outkey="pdf_byres"))
+    out.append(features.MarchingObservers(selection=":LIG", weight_type="uniformed", obs="distinct_count", agg="standard_deviation", outkey="mo_lig"))
+    return out
+  parms = {"dimensions": 20, "lengths": 15, "time_window": 4, "cutoff": 2.5, "sigma": 1.5}
+  for n_atoms, expect_folded in ((2500, True), (10400, False)):
+    traj = io.synthetic_trajectory(n_atoms, 8, seed=300 + n_atoms, ligand_atoms=30)
+    (tmp_path / str(n_atoms)).mkdir()
+    launches0 = _lib.kernel_launches()
+    got, fz = build(traj, tmp_path / str(n_atoms), feats, parms, focus=(":LIG",))
+    launches = _lib.kernel_launches() - launches0
+    spec = fz.FEATURESPACE[0]._native_spec()
+    assert spec["selection_folded"] is expect_folded
+    ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 4, buff_dim=_lib.buff_dim)
+    for f in fz.FEATURESPACE:
+      key = f.outkey
+      if f.agg == 2:
+        peak = max(float(np.abs(ref[key]).max()), 1e-30)
+        assert rel_bad(got[key], ref[key], atol=2e-5 * peak) == 0, (n_atoms, key)
+      else:
+        assert rel_bad(got[key], ref[key]) == 0, (n_atoms, key, np.abs(got[key] - ref[key]).max())
+    assert launches > 0
