@@ -811,16 +811,36 @@ class LabelPCDT(LabelAffinity):
     self._closest = self.selected_counterpart[np.argmin(utils._pair_distances(ref[self.selected], ref[self.selected_counterpart]), axis=1)]
     if self.search_cutoff is not None:
       self.cached_array = np.minimum(self.cached_array, self.search_cutoff)
+    self._xyz = trajectory.xyz
     self._mean_0 = np.mean(self.cached_array, axis=1)
     std_0 = np.std(self.cached_array, axis=1)
     if np.any(std_0 == 0):
       std_0[std_0 == 0] = self.search_cutoff if self.search_cutoff is not None else 6.0
     self._std_0 = std_0
 
+  def _window_start(self, frames):
+    """Index of the first frame when `frames` is a view of consecutive frames of the cached trajectory, else None."""
+    xyz = getattr(self, "_xyz", None)
+    if not (isinstance(frames, np.ndarray) and isinstance(xyz, np.ndarray)) or frames.ndim != 3 or frames.dtype != xyz.dtype:
+      return None
+    if frames.shape[1:] != xyz.shape[1:] or frames.strides != xyz.strides or len(frames) == 0:
+      return None
+    offset = frames.__array_interface__["data"][0] - xyz.__array_interface__["data"][0]
+    if offset < 0 or offset % xyz.strides[0]:
+      return None
+    first = offset // xyz.strides[0]
+    return int(first) if first + len(frames) <= len(xyz) else None
+
   def query(self, topology, frames, focus):
-    pdist_arr = utils.pair_track(np.asarray(frames), self.selected, self._closest).astype(np.float64)    # compute_pcdt on the window
-    if self.search_cutoff is not None:
-      pdist_arr = np.minimum(pdist_arr, self.search_cutoff)
+    first = self._window_start(frames)
+    if first is not None:
+      # the window is a run of frames of the cached trajectory: its pair distances are columns of the cached profile
+      # (same pairs, same arithmetic, cutoff already applied)
+      pdist_arr = self.cached_array[:, first:first + len(frames)]
+    else:
+      pdist_arr = utils.pair_track(np.asarray(frames), self.selected, self._closest).astype(np.float64)    # compute_pcdt on the window
+      if self.search_cutoff is not None:
+        pdist_arr = np.minimum(pdist_arr, self.search_cutoff)
     mean_1 = np.mean(pdist_arr, axis=1)
     penalty = abs(np.mean((self._mean_0 - mean_1) / self._std_0))
     return (self.base_value * (1 - 0.1 * penalty), )

@@ -104,17 +104,22 @@ def _pair_distances(a, b):
   additions) of np.linalg.norm(a[i] - b, axis=1) and of scipy.spatial.distance_matrix, which the reference calls at
   features.py:1727 and utils.py:118-136; only row-wise argmins are taken from it.  Column by column: a reduction over an
   axis of length 3 is the slow way to say this in numpy."""
-  a, b = np.asarray(a), np.asarray(b)
-  dx = a[:, None, 0] - b[None, :, 0]
-  dy = a[:, None, 1] - b[None, :, 1]
-  dz = a[:, None, 2] - b[None, :, 2]
-  return np.sqrt((dx * dx + dy * dy) + dz * dz)
+  at, bt = np.ascontiguousarray(np.asarray(a).T), np.ascontiguousarray(np.asarray(b).T)     # contiguous coordinate columns
+  dx = at[0][:, None] - bt[0][None, :]
+  dy = at[1][:, None] - bt[1][None, :]
+  dz = at[2][:, None] - bt[2][None, :]
+  dx *= dx
+  dy *= dy
+  dz *= dz
+  dx += dy
+  dx += dz
+  return np.sqrt(dx, out=dx)
 
 
 def pair_track(xyz, first, second):
   """[len(first), n_frames] distance of atom first[i] to atom second[i] in every frame, in the dtype of `xyz`:
   sqrt((dx^2 + dy^2) + dz^2), the arithmetic of np.sqrt(np.sum((a - b) ** 2, axis=1)) at utils.py:146-147."""
-  d = xyz[:, first, :] - xyz[:, second, :]
+  d = np.take(xyz, first, axis=1) - np.take(xyz, second, axis=1)
   dx, dy, dz = d[:, :, 0], d[:, :, 1], d[:, :, 2]
   return np.sqrt((dx * dx + dy * dy) + dz * dz).T
 
