@@ -45,6 +45,7 @@ __device__ __forceinline__ void nrl_mbar_wait(uint64_t *bar, uint32_t parity) {
 // median_device, gpuutils.cuh:227-245 -- the tile column is overwritten) and information entropy
 // (information_entropy_histogram_device, gpuutils.cuh:140-173).
 #define NRL_AGG_BLOCK 16
+#define NRL_AGG_LEGACY_ENTROPY 107
 __device__ __forceinline__ float nrl_agg_voxel(float *fb, const int W, const int v, const int n, const int agg) {
   const float fn = (float)n;
   if (agg == 2 || agg == 4) {
@@ -86,30 +87,52 @@ __device__ __forceinline__ float nrl_agg_voxel(float *fb, const int W, const int
     return (n & 1) ? fb[(size_t)(n / 2) * W + v]
                    : nrl_div_approx(fb[(size_t)(n / 2 - 1) * W + v] + fb[(size_t)(n / 2) * W + v], 2.0f);
   }
-  // information entropy: the histogram is ALU work
+  // information entropy: the histogram is ALU work.  Sixteen 4-bit counters in one 64-bit word take the increments
+  // (one shifted add per sample); every 15 samples they are spilled into 16-bit counters (bin b -> word b & 3, lane b >> 2,
+  // so that a spill is four masked adds).  NRL_AGG_LEGACY_ENTROPY (agg = 107, tests only) keeps the former form -- four
+  // predicated 64-bit adds per sample -- to check the counts bit for bit.
+  const bool legacy = agg == NRL_AGG_LEGACY_ENTROPY;
   float r = 0.0f;
   if (n > 1) {
-    float mn = fb[v], mx = fb[v];
+    const float *col = fb + v;
+    float mn = col[0], mx = col[0];
 #pragma unroll 8
-    for (int i = 1; i < n; ++i) { const float x = fb[(size_t)i * W + v]; if (x < mn) mn = x; if (x > mx) mx = x; }
+    for (int i = 1; i < n; ++i) { const float x = col[i * W]; if (x < mn) mn = x; if (x > mx) mx = x; }
     const float range = mx - mn;
     unsigned long long h0 = 0ull, h1 = 0ull, h2 = 0ull, h3 = 0ull;      // 16 counters of 16 bits
+    if (legacy) {
 #pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-      const float sc = nrl_div_approx(fb[(size_t)i * W + v] - mn, range) * 16.0f;
-      int bin;
-      asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
-      bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
-      const unsigned long long inc = 1ull << ((bin & 3) * 16);
-      const int word = bin >> 2;
-      h0 += (word == 0) ? inc : 0ull; h1 += (word == 1) ? inc : 0ull;
-      h2 += (word == 2) ? inc : 0ull; h3 += (word == 3) ? inc : 0ull;
+      for (int i = 0; i < n; ++i) {
+        const float sc = nrl_div_approx(col[i * W] - mn, range) * 16.0f;
+        int bin;
+        asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
+        bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
+        const unsigned long long inc = 1ull << ((bin >> 2) * 16);
+        const int word = bin & 3;
+        h0 += (word == 0) ? inc : 0ull; h1 += (word == 1) ? inc : 0ull;
+        h2 += (word == 2) ? inc : 0ull; h3 += (word == 3) ? inc : 0ull;
+      }
+    } else {
+      const unsigned long long lanes = 0x000F000F000F000Full;
+      for (int i0 = 0; i0 < n; i0 += 15) {
+        unsigned long long acc = 0ull;
+        const int i1 = min(i0 + 15, n);
+#pragma unroll 5
+        for (int i = i0; i < i1; ++i) {
+          const float sc = nrl_div_approx(col[i * W] - mn, range) * 16.0f;
+          int bin;
+          asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
+          bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
+          acc += 1ull << (4 * bin);
+        }
+        h0 += acc & lanes; h1 += (acc >> 4) & lanes; h2 += (acc >> 8) & lanes; h3 += (acc >> 12) & lanes;
+      }
     }
     if (range != 0.0f) {
       const unsigned long long h[4] = {h0, h1, h2, h3};
 #pragma unroll
       for (int b = 0; b < NRL_ENTROPY_BINS; ++b) {
-        const int cnt = (int)((h[b >> 2] >> ((b & 3) * 16)) & 0xffffull);
+        const int cnt = (int)((h[b & 3] >> ((b >> 2) * 16)) & 0xffffull);
         if (cnt > 0) {
           const float pr = nrl_div_approx((float)cnt, fn);
           r = fmaf(-pr, nrl_lg2_approx(pr), r);
@@ -148,7 +171,7 @@ __global__ void __launch_bounds__(NRL_AGG_NT) nrl_aggregate_kernel(const float *
       for (int v = tid; v < W; v += NRL_AGG_NT) fb[(size_t)i * W + v] = v < w ? series[(long long)i * G + g0 + v] : 0.0f;
     __syncthreads();
   }
-  if (agg == 2 || agg == 4 || agg == 7 || (agg == 3 && W <= NRL_AGG_NT)) {
+  if (agg == 2 || agg == 4 || agg == 7 || agg == NRL_AGG_LEGACY_ENTROPY || (agg == 3 && W <= NRL_AGG_NT)) {
     // one voxel per thread keeps all 128 threads busy (a float4 column per thread leaves three warps of a narrow
     // tile idle); the median does so only for narrow tiles, i.e. long series
     float *fb = reinterpret_cast<float *>(buf);

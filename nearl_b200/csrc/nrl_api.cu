@@ -30,7 +30,8 @@ thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_force_scan{0};    // nrl_set_option("force_scan", 1): never use the cell-list kernels
 std::atomic<int> g_agg_pipe_w{0};    // nrl_set_option("agg_pipe_w" / "agg_pipe_stages"): tile width / ring depth of the pipelined K3
-std::atomic<int> g_agg_pipe_stages{0};  // (0 = chosen from the series length; -1 stages = staged one-shot kernel instead)
+std::atomic<int> g_agg_pipe_stages{0};
+std::atomic<int> g_agg_entropy_legacy{0};   // nrl_set_option("agg_entropy_legacy"): former histogram form in the staged / pipelined K3 (tests)  // (0 = chosen from the series length; -1 stages = staged one-shot kernel instead)
 std::atomic<int> g_no_fuse{0};       // nrl_set_option("no_fuse", 1): one sweep per observable (tests / A-B timing)
 
 int fail(int code, const std::string &msg) {
@@ -890,7 +891,7 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
     const long long grid = std::min<long long>(n_tiles, c.sms);
     {
       ScopedProf sp(c, st, CAT_AGGREGATE);
-      nrl_aggregate_pipe_kernel<<<(unsigned)grid, NRL_AGG_PIPE_NT, smem, st>>>(map, n, G, agg, W, stages, n_tiles, rows, n_boxes, d_out);
+      nrl_aggregate_pipe_kernel<<<(unsigned)grid, NRL_AGG_PIPE_NT, smem, st>>>(map, n, G, (agg == 7 && g_agg_entropy_legacy.load()) ? NRL_AGG_LEGACY_ENTROPY : agg, W, stages, n_tiles, rows, n_boxes, d_out);
     }
     g_launches.fetch_add(1);
     NRL_CUDA(cudaGetLastError());
@@ -910,7 +911,7 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
     const long long grid = (G + W - 1) / W;
     {
       ScopedProf sp(c, st, CAT_AGGREGATE);
-      nrl_aggregate_kernel<<<(unsigned)grid, NRL_AGG_NT, smem, st>>>(d_in, n, G, agg, W, bulk, d_out);
+      nrl_aggregate_kernel<<<(unsigned)grid, NRL_AGG_NT, smem, st>>>(d_in, n, G, (agg == 7 && g_agg_entropy_legacy.load()) ? NRL_AGG_LEGACY_ENTROPY : agg, W, bulk, d_out);
     }
     g_launches.fetch_add(1);
     NRL_CUDA(cudaGetLastError());
@@ -1027,6 +1028,7 @@ int nrl_set_option(const char *name, int value) {
   if (!name) return fail(NRL_ERR_ARGUMENT, "option name is NULL");
   if (strcmp(name, "force_scan") == 0) { g_force_scan.store(value != 0); return NRL_OK; }
   if (strcmp(name, "no_fuse") == 0) { g_no_fuse.store(value != 0); return NRL_OK; }
+  if (strcmp(name, "agg_entropy_legacy") == 0) { g_agg_entropy_legacy.store(value != 0); return NRL_OK; }
   if (strcmp(name, "agg_pipe_w") == 0) { g_agg_pipe_w.store((int)value); return NRL_OK; }
   if (strcmp(name, "agg_pipe_stages") == 0) { g_agg_pipe_stages.store((int)value); return NRL_OK; }
   return fail(NRL_ERR_ARGUMENT, std::string("unknown option ") + name);

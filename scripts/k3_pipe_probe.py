@@ -45,4 +45,12 @@ for F, D in ((100, 128), (200, 96), (300, 64), (512, 64), (100, 30), (65, 34)):
       same = bool(torch.equal(out.view(torch.int32), out_ref.view(torch.int32)))
       row[f"W{W}S{S}"] = round(nbytes / t / 1e9) if same else "MISMATCH"
     _lib.set_option("agg_pipe_w", 0); _lib.set_option("agg_pipe_stages", 0)
+    if agg == 7:
+      _lib.set_option("agg_entropy_legacy", 1)
+      out.zero_()
+      t = timed(lambda: run(out))
+      _lib.set_option("agg_entropy_legacy", 0)
+      row["legacy_histogram_GBs"] = round(nbytes / t / 1e9)
+      out2 = torch.empty_like(out); run(out2); torch.cuda.synchronize()
+      row["legacy_histogram_same_bits"] = bool(torch.equal(out.view(torch.int32), out2.view(torch.int32)))
     res.append(row); print(json.dumps(row), flush=True)

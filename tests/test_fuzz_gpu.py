@@ -1,0 +1,141 @@
+"""Seeded random configurations of the whole path -- grid shape and spacing, cutoff, sigma, padding, window, selections,
+by-residue crops, frame offsets, every observable and reducer, focal points on atoms / in empty space / at the edge of the
+system, float32 and float64 trajectories -- through Featurizer.run (device crop, cell lists or full-frame scan, fused
+sweeps, fused reducers) against oracle/host_ref.py feeding the C oracle.  Each case is small enough for the oracle to
+finish in about a second; the seeds are fixed, so a failure names a reproducible case."""
+import numpy as np
+import pytest
+
+import nearl_b200
+from nearl_b200 import _lib, features, featurizer, io
+from oracle import host_ref
+
+pytestmark = pytest.mark.gpu
+nearl_b200.update_config(quiet=True)
+
+OBS = ["existence", "direct_count", "distinct_count", "mean_distance", "cumulative_weight", "density", "dispersion",
+       "eccentricity", "radius_of_gyration"]
+AGG = ["mean", "standard_deviation", "median", "variance", "max", "min", "information_entropy", "drift"]
+WEIGHTS = ["mass", "atomic_number", "electronegativity", "hydrophobicity", "heavy_atom", "uniformed", "residue_id", "sidechainness"]
+SELECTIONS = [None, None, "!@H=", ":ARG,LYS,GLU", ":LIG", "!:LIG", "@CA,C,N,O"]
+INTEGER_OBS = (1, 2, 3)
+
+
+def random_case(seed):
+  rng = np.random.default_rng(seed)
+  n_atoms = int(rng.integers(300, 2200))
+  window = int(rng.choice([1, 2, 3, 5, 8]))
+  n_frames = window * int(rng.integers(1, 4)) + int(rng.integers(0, 2))
+  dtype = np.float64 if rng.random() < 0.25 else np.float32
+  traj = io.synthetic_trajectory(n_atoms, n_frames, seed=seed * 7 + 1, dtype=dtype, pin=False, ligand_atoms=int(rng.choice([0, 12, 30])),
+                                 step=float(rng.choice([0.1, 0.3, 0.8])))
+  dims = [int(v) for v in rng.integers(6, 21, size=3)] if rng.random() < 0.5 else [int(rng.integers(6, 21))] * 3
+  spacing = float(rng.choice([0.5, 0.75, 1.0, 1.3]))
+  lengths = [d * spacing for d in dims]
+  cutoff = float(rng.choice([1.5, 2.5, 3.25, 4.0, 5.0]))
+  sigma = float(rng.choice([0.7, 1.0, 1.5, 2.2]))
+  parms = {"dimensions": dims, "lengths": lengths, "time_window": window, "cutoff": cutoff, "sigma": sigma}
+
+  def kw():
+    out = {}
+    sel = SELECTIONS[int(rng.integers(0, len(SELECTIONS)))]
+    if sel is not None:
+      out["selection"] = sel
+    if rng.random() < 0.2:
+      out["byres"] = True
+    if rng.random() < 0.2:
+      out["padding"] = float(rng.choice([0.0, 1.0, cutoff + 1.5]))
+    if rng.random() < 0.2:
+      out["cutoff"] = float(rng.choice([2.0, 3.0, 4.5]))
+    return out
+
+  specs = []
+  for i in range(int(rng.integers(3, 8))):
+    kind = rng.random()
+    k = kw()
+    if kind < 0.3:
+      cls = [features.Mass, features.HeavyAtom, features.AtomicNumber, features.Electronegativity, features.Hydrophobicity][int(rng.integers(0, 5))]
+      if window > 1 and rng.random() < 0.3:
+        k["frame_offset"] = int(rng.integers(0, window))
+      if rng.random() < 0.2:
+        k["sigma"] = float(rng.choice([0.8, 1.8]))
+      specs.append((cls, dict(k, outkey=f"f{i}")))
+    elif kind < 0.75:
+      k.update(obs=OBS[int(rng.integers(0, len(OBS)))], agg=AGG[int(rng.integers(0, len(AGG)))],
+               weight_type=WEIGHTS[int(rng.integers(0, len(WEIGHTS)))], outkey=f"f{i}")
+      specs.append((features.MarchingObservers, k))
+    else:
+      k.update(agg=AGG[int(rng.integers(0, len(AGG)))], weight_type=WEIGHTS[int(rng.integers(0, len(WEIGHTS)))], outkey=f"f{i}")
+      specs.append((features.DensityFlow, k))
+  # focal points: a mask, an atom index list, or absolute points (one of them far outside the system)
+  choice = rng.random()
+  side = (n_atoms / 0.1) ** (1.0 / 3.0)
+  if choice < 0.4:
+    focus, fmt = [":ARG", "@CA"][: int(rng.integers(1, 3))], "mask"
+  elif choice < 0.7:
+    focus, fmt = [rng.choice(n_atoms, size=int(rng.integers(1, 6)), replace=False) for _ in range(int(rng.integers(1, 3)))], "index"
+  else:
+    pts = rng.uniform(0.0, side, size=(int(rng.integers(1, 3)), 3))
+    if rng.random() < 0.5:
+      pts = np.concatenate([pts, [[side + 40.0, -25.0, side / 2]]])
+    focus, fmt = pts.astype(np.float32), "absolute"
+  return traj, parms, specs, focus, fmt
+
+
+def descs_from(fz):
+  descs = []
+  for f in fz.FEATURESPACE:
+    d = {"outkey": f.outkey, "dims": f.dims, "spacing": f.spacing, "cutoff": f.cutoff, "sigma": f.sigma, "padding": f.padding,
+         "byres": f.byres, "selection": (f.selected if f.selection is not None else None), "weights": f.cached_array,
+         "frame_offset": f.frame_offset}
+    if isinstance(f, features.MarchingObservers):
+      d.update(kind="marching_observers", obs=f.obs, agg=f.agg)
+    elif isinstance(f, features.DensityFlow):
+      d.update(kind="density_flow", agg=f.agg)
+    else:
+      d.update(kind="static")
+    descs.append(d)
+  return descs
+
+
+@pytest.mark.parametrize("seed", list(range(1, 49)))
+def test_random_configuration_against_the_oracle(seed):
+  traj, parms, specs, focus, fmt = random_case(seed)
+  fz = featurizer.Featurizer(parms)
+  fz.register_features([cls(**k) for cls, k in specs])
+  fz.register_focus(focus, fmt)
+  fz.register_trajloader([traj])
+  fz.keep_results = True
+  if seed % 5 == 0:
+    _lib.set_option("force_scan", 1)             # every fifth case on the full-frame scan kernels
+  try:
+    fz.run()
+  finally:
+    _lib.set_option("force_scan", 0)
+  got = {k: np.array(v) for k, v in fz.RESULTS.items()}
+  ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, fz.time_window, buff_dim=_lib.buff_dim)
+  for f in fz.FEATURESPACE:
+    key, where = f.outkey, (seed, f.outkey, str(f))
+    g, r = got[key].reshape(ref[key].shape), ref[key]
+    obs, agg = getattr(f, "obs", 0) if isinstance(f, features.MarchingObservers) else 0, getattr(f, "agg", 0) if isinstance(f, features.DynamicFeature) else 0
+    scale = max(float(np.abs(r).max()), 1e-30)
+    if obs in INTEGER_OBS and agg in (3, 5, 6):
+      if agg == 3 and fz.time_window % 2 == 0:
+        assert np.allclose(g, r, rtol=3e-7, atol=0), where                  # even window: the median halves a sum (div.approx)
+      else:
+        assert np.array_equal(g, r), where                                  # integers, order statistics: bit-exact
+    elif agg == 7:
+      # the reference's own criterion (a few voxels of 32 768 off, test_features.py:119-125) for float-valued series; series of
+      # integers (counts, sums of integer weights) put samples exactly on bin edges, where the device follows the reference's
+      # fast-math division and the IEEE oracle cannot (tests/test_parity_actions_gpu.py checks those against the reference's
+      # own kernels): up to 0.5 % of the voxels may land in the neighbouring bin
+      bad = np.count_nonzero(~np.isclose(g, r, atol=1e-3))
+      assert bad <= max(2, r.size // 200), (where, bad)
+    elif agg in (2, 4, 8) or obs in (14, 15, 16):
+      # reducers that cancel (std, variance, drift) and observables that subtract positions (dispersion, eccentricity,
+      # radius of gyration): error relative to the magnitude of what is subtracted
+      tol = 2e-5 * scale + (8 * np.finfo(np.float32).eps * (max(fz.FEATURESPACE[0].lengths) + f.cutoff) if obs in (14, 15, 16) else 0.0)
+      assert np.count_nonzero(np.abs(g.astype(np.float64) - r) > 1e-5 * np.abs(r) + tol) == 0, (where, np.abs(g - r).max())
+    else:
+      bad = np.abs(g.astype(np.float64) - r) > 1e-5 * np.maximum(np.abs(r), 1e-5 * scale)
+      assert bad.sum() == 0, (where, int(bad.sum()), float(np.abs(g - r).max()))

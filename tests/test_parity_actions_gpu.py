@@ -271,6 +271,21 @@ def test_vs_reference_kernels(ref_actions):
     r = ref_actions.aggregate(x, agg)
     g = nb.aggregate(x, agg)
     assert np.count_nonzero(~np.isclose(g, r, rtol=1e-5, atol=1e-6)) == 0, agg
+  # integer-valued series (counts, sums of integer weights) put many samples EXACTLY on a histogram bin edge, where the
+  # reference's fast-math division decides the bin: the entropy must follow the reference's kernels there, short
+  # series (register kernel), long series (pipelined kernel) and the one-shot staged kernel alike
+  for F in (9, 50, 100, 130):
+    xi = rng.integers(0, 9, size=(F, 8192)).astype(np.float32)
+    xi[:, ::3] = rng.integers(0, 17, size=(F, xi[:, ::3].shape[1])).astype(np.float32)
+    r = ref_actions.aggregate(xi, 7)
+    g = nb.aggregate(xi, 7)
+    assert np.count_nonzero(~np.isclose(g, r, rtol=1e-5, atol=1e-6)) == 0, (F, np.count_nonzero(~np.isclose(g, r, rtol=1e-5, atol=1e-6)))
+    _lib.set_option("agg_pipe_stages", -1)
+    try:
+      g1 = nb.aggregate(xi, 7)
+    finally:
+      _lib.set_option("agg_pipe_stages", 0)
+    assert np.array_equal(g.view(np.int32), g1.view(np.int32)), F
 
 
 def test_buff_dim_probe(ref_actions):
