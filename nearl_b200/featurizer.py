@@ -814,13 +814,25 @@ class Featurizer:
     tpl = self._template(native_feats, specs, n_atoms, is_f64)
     batch = LoweredBatch()
     batch.n_atoms, batch.is_f64 = n_atoms, bool(is_f64)
-    crops = (_lib.CropStruct * len(tpl["crops"]))(*tpl["crops"])     # copies: focal points are per trajectory
-    zero = np.zeros(3, dtype=np.float32)
-    for ci, (bid, pid) in enumerate(tpl["crop_slots"]):
-      focal = self.FOCALPOINTS[bid, pid] if self.FOCALNUMBER > 0 else zero
-      crops[ci].focal[0], crops[ci].focal[1], crops[ci].focal[2] = float(focal[0]), float(focal[1]), float(focal[2])
-      crops[ci].focal_f64[0], crops[ci].focal_f64[1], crops[ci].focal_f64[2] = float(focal[0]), float(focal[1]), float(focal[2])
-    batch.crops, batch.tasks, batch.shapes, batch.out_floats = crops, tpl["tasks"], tpl["shapes"], tpl["out_floats"]
+    # the crop table of the template as a numpy record array (a ctypes array costs microseconds per element to copy and
+    # to fill); only the focal points are per trajectory
+    crops_np = tpl.get("crops_np")
+    if crops_np is None:
+      n = len(tpl["crops"])
+      crops_np = tpl["crops_np"] = np.frombuffer((_lib.CropStruct * n)(*tpl["crops"]), dtype=np.dtype(_lib.CropStruct, align=True)).copy()
+      tpl["crop_bid"] = np.array([bid for bid, _ in tpl["crop_slots"]], dtype=np.int64)
+      tpl["crop_pid"] = np.array([pid for _, pid in tpl["crop_slots"]], dtype=np.int64)
+    crops = crops_np.copy()
+    if self.FOCALNUMBER > 0 and len(crops):
+      focal = self.FOCALPOINTS[tpl["crop_bid"], tpl["crop_pid"]]
+      crops["focal"] = focal
+      crops["focal_f64"] = focal
+    else:
+      crops["focal"] = 0.0
+      crops["focal_f64"] = 0.0
+    batch._keep = crops                # the ctypes view below borrows this array
+    batch.crops, batch.n_crops = crops.ctypes.data_as(ctypes.POINTER(_lib.CropStruct)), len(crops)
+    batch.tasks, batch.shapes, batch.out_floats = tpl["tasks"], tpl["shapes"], tpl["out_floats"]
     rows = [specs[f]["weights"] for f in tpl["table_feats"]] + [specs[f]["ranks"] for f in tpl["rank_feats"]]
     batch.weight_tables = self._table_buffer(lane, "weights", (len(rows), n_atoms), np.float32)
     for i, row in enumerate(rows):
