@@ -246,7 +246,9 @@ __device__ __forceinline__ bool nrl_rec_sweep(const float4 *rec, const int nrec,
           const float dz = pz[k] - a.z;
           const float d2 = fmaf(dz, dz, part);
           if (!(d2 > c2)) {
-            A.n[k] += 1;
+            // with a rank mask in the group, its presence bit (bit 31, set for every atom) is the "some atom in range"
+            // flag and the counter is not kept (a direct count never shares a group with a rank mask)
+            if constexpr ((NWT & NRL_FUSE_SEEN) == 0) A.n[k] += 1;
             if constexpr ((NWT & NRL_FUSE_SEEN) != 0) A.seen[k] |= mask;
             if constexpr ((NWT & NRL_FUSE_R) != 0) A.f0[0][k] = fmaf(nrl_sqrt_approx(d2), a.w, A.f0[0][k]);
             if constexpr ((NWT & NRL_FUSE_WS) != 0) A.f1[k] = A.f1[k] + a.w;
@@ -302,14 +304,16 @@ __device__ __forceinline__ void nrl_rec_finish(const NrlAcc<MODE, NWT> &A, const
 #pragma unroll
       for (int k = 0; k < NRL_VPT; ++k) {
         float v = 0.0f;
-        if (m == NRL_OBS_EXISTENCE) v = A.n[k] > 0 ? 1.0f : 0.0f;
+        bool any;
+        if constexpr ((NWT & NRL_FUSE_SEEN) != 0) any = A.seen[k] != 0u; else any = A.n[k] > 0;
+        if (m == NRL_OBS_EXISTENCE) v = any ? 1.0f : 0.0f;
         else if (m == NRL_OBS_DIRECT_COUNT) v = (float)A.n[k];
-        else if (m == NRL_OBS_DISTINCT_COUNT) v = fminf((float)__popc(A.seen[k]), NRL_DISTINCT_LIMIT);
-        else if (m == NRL_OBS_MEAN_DISTANCE) v = A.n[k] > 0 ? nrl_div_approx(A.f0[0][k], A.f1[k]) : 0.0f;
+        else if (m == NRL_OBS_DISTINCT_COUNT) v = fminf((float)__popc(A.seen[k] & 0x7fffffffu), NRL_DISTINCT_LIMIT);
+        else if (m == NRL_OBS_MEAN_DISTANCE) v = any ? nrl_div_approx(A.f0[0][k], A.f1[k]) : 0.0f;
         else if (m == NRL_OBS_CUMULATIVE_WEIGHT) v = A.f1[k];
         else if (m == NRL_OBS_DENSITY) v = (float)((double)A.f1[k] / t.sphere_volume);
         else if (m == NRL_OBS_ECCENTRICITY) {
-          if (A.n[k] > 0 && A.f1[k] != 0.0f) {
+          if (any && A.f1[k] != 0.0f) {
             const float m0 = nrl_div_approx(A.f2[k], A.f1[k]), m1 = nrl_div_approx(A.f3[k], A.f1[k]), m2 = nrl_div_approx(A.f4[k], A.f1[k]);
             v = nrl_sqrt_approx(nrl_obs_d2(px, py, pz[k], m0, m1, m2));
           } else {
@@ -538,7 +542,8 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
                 slot[0] = a[u];
                 if constexpr ((NWT & NRL_FUSE_SEEN) != 0) {
                   const int rank = (int)rk[u];
-                  slot[1] = make_float4(__int_as_float(rank >= 0 ? (int)(1u << (rank & 31)) : 0), 0.f, 0.f, 0.f);
+                  // bit 31: "an atom" (ranks of a fused group are <= 30, checked by the host side of the call)
+                  slot[1] = make_float4(__int_as_float((int)((rank >= 0 ? (1u << (rank & 31)) : 0u) | 0x80000000u)), 0.f, 0.f, 0.f);
                 }
               }
             }

@@ -460,3 +460,50 @@ def test_density_flow_selections_share_one_sweep(tmp_path):
       else:
         assert rel_bad(got[key], ref[key]) == 0, (n_atoms, key, np.abs(got[key] - ref[key]).max())
     assert launches > 0
+
+
+def test_fused_presence_bit_and_its_exclusions(tmp_path):
+  # A fused sweep with a distinct_count channel keeps no in-range counter: bit 31 of every atom's rank mask says "an atom
+  # is in range".  So (1) a rank table that uses all 32 ranks stays on the single-observable kernel, (2) a direct count
+  # never shares a group with a rank mask, (3) atoms whose value distinct_count hides (99999.0) still count for existence.
+  # All three against the host pipeline feeding the C oracle; integer observables with max: bit-exact.
+  traj = io.synthetic_trajectory(2400, 6, seed=91)
+  parms = {"dimensions": 16, "lengths": 12, "time_window": 3, "cutoff": 3.5, "sigma": 1.0}
+
+  class Ranks32(features.MarchingObservers):          # 32 distinct weight values: ranks 0..31
+    def cache(self, trajectory):
+      super().cache(trajectory)
+      self.cached_array = (np.arange(len(self.resids)) % 32).astype(np.float32)
+
+  class Hidden(features.MarchingObservers):           # every third atom carries the placeholder distinct_count skips
+    def cache(self, trajectory):
+      super().cache(trajectory)
+      w = (np.arange(len(self.resids)) % 7).astype(np.float32)
+      w[::3] = 99999.0
+      self.cached_array = w
+
+  def feats():
+    return [
+      features.MarchingObservers(obs="existence", agg="max", outkey="exist"),
+      Ranks32(obs="distinct_count", agg="max", weight_type="atomic_number", outkey="d32"),
+      Hidden(obs="distinct_count", agg="max", weight_type="atomic_number", outkey="dhid"),
+      features.MarchingObservers(obs="direct_count", agg="max", outkey="count"),
+      features.MarchingObservers(obs="distinct_count", agg="min", weight_type="atomic_number", outkey="dz"),
+      features.MarchingObservers(obs="mean_distance", agg="mean", weight_type="mass", outkey="md"),
+    ]
+  got, fz = build(traj, tmp_path, feats, parms, focus=(":ARG", "@CA"))
+  assert fz.FEATURESPACE[1].value_ranks().max() == 31
+  ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, 3, buff_dim=_lib.buff_dim)
+  for key in ("exist", "d32", "dhid", "count", "dz"):
+    assert np.array_equal(got[key], ref[key]), key
+  assert got["d32"].max() > 20 and got["dhid"].max() <= 7 and got["exist"].max() == 1.0
+  assert rel_bad(got["md"], ref["md"]) == 0
+  # and the same bits as one sweep per observable
+  _lib.set_option("no_fuse", 1)
+  try:
+    (tmp_path / "nofuse").mkdir()
+    sep, _ = build(traj, tmp_path / "nofuse", feats, parms, focus=(":ARG", "@CA"))
+  finally:
+    _lib.set_option("no_fuse", 0)
+  for key in got:
+    assert np.array_equal(got[key].view(np.int32), sep[key].view(np.int32)), key
