@@ -133,12 +133,14 @@ def test_random_configuration_against_the_oracle(seed):
       # integers (counts, sums of integer weights) put samples exactly on bin edges, where the device follows the reference's
       # fast-math division and the IEEE oracle cannot (tests/test_parity_actions_gpu.py checks those against the reference's
       # own kernels): up to 0.5 % of the voxels may land in the neighbouring bin
-      # Not compared: the entropy of observables whose samples can be EQUAL up to the order of a float sum -- cumulative
-      # weight and density depend only on WHICH atoms are in range, so a voxel whose neighbourhood does not change over the
-      # window has exactly equal samples in the reference (atom order in every frame: range 0, entropy 0) and samples one ulp
-      # apart here when an atom changed cell (cell order: range 1 ulp, entropy up to 1); dispersion, eccentricity and radius of
-      # gyration degenerate the same way around a single weighted atom.  The reducer is discontinuous exactly there
-      # (DESIGN.md section 4); integer observables, mean distance and the density flows are compared.
+      # Not compared: the entropy of cumulative weight and density.  Their samples are sums of discrete per-atom weights over
+      # the atoms in range, so series like {A - m, A, A, A + m} put the repeated value exactly ON a histogram bin edge, and
+      # two frames whose totals are "the same" differ by an ulp or not depending on the order of the float additions --
+      # atom order in the reference (whose own samples carry such ulps: its entropy there is decided by them), cell order
+      # here.  scripts/debug_fuzz_case.py shows the per-frame values equal to the reference's to the last bit on the
+      # single-frame path and the entropy of 1-4 % of such voxels different.  Dispersion, eccentricity
+      # and radius of gyration degenerate the same way around a single weighted atom.  Integer observables, mean distance and
+      # the density flows are compared.
       if obs in (12, 13, 14, 15, 16) or (fz.time_window < 4 and obs not in INTEGER_OBS):
         continue
       bad = np.count_nonzero(~np.isclose(g, r, atol=1e-3))
