@@ -311,7 +311,7 @@ __device__ __forceinline__ void nrl_rec_finish(const NrlAcc<MODE, NWT> &A, const
         else if (m == NRL_OBS_DISTINCT_COUNT) v = fminf((float)__popc(A.seen[k] & 0x7fffffffu), NRL_DISTINCT_LIMIT);
         else if (m == NRL_OBS_MEAN_DISTANCE) v = any ? nrl_div_approx(A.f0[0][k], A.f1[k]) : 0.0f;
         else if (m == NRL_OBS_CUMULATIVE_WEIGHT) v = A.f1[k];
-        else if (m == NRL_OBS_DENSITY) v = (float)((double)A.f1[k] / t.sphere_volume);
+        else if (m == NRL_OBS_DENSITY) v = nrl_div_approx(A.f1[k], (float)t.sphere_volume);      // float volume, fast-math division (:199-201)
         else if (m == NRL_OBS_ECCENTRICITY) {
           if (any && A.f1[k] != 0.0f) {
             const float m0 = nrl_div_approx(A.f2[k], A.f1[k]), m1 = nrl_div_approx(A.f3[k], A.f1[k]), m2 = nrl_div_approx(A.f4[k], A.f1[k]);
@@ -335,7 +335,7 @@ __device__ __forceinline__ void nrl_rec_finish(const NrlAcc<MODE, NWT> &A, const
     } else if constexpr (MODE == NRL_OBS_MEAN_DISTANCE) {
       val[0][k] = A.n[k] > 0 ? nrl_div_approx(A.f0[0][k], A.f1[k]) : 0.0f;
     } else if constexpr (MODE == NRL_OBS_DENSITY) {
-      val[0][k] = (float)((double)A.f0[0][k] / t.sphere_volume);        // :199-201
+      val[0][k] = nrl_div_approx(A.f0[0][k], (float)t.sphere_volume);        // float volume, fast-math division (:199-201)
     } else if constexpr (MODE == NRL_OBS_ECCENTRICITY) {
       if (A.n[k] > 0 && A.f3[k] != 0.0f) {                               // :289-298
         const float m0 = nrl_div_approx(A.f0[0][k], A.f3[k]), m1 = nrl_div_approx(A.f1[k], A.f3[k]),

@@ -102,7 +102,7 @@ struct NrlTask {
   float cutoff;
   float k2;                 // voxelize: -0.5*log2(e)/sigma^2
   float sigma;
-  double sphere_volume;     // density: (4/3) pi cutoff^3 in double (marching_observers.cu:200)
+  double sphere_volume;     // density: (4/3) pi cutoff^3 evaluated in double, used as a float (marching_observers.cu:200-201)
   long long frame0;         // first frame descriptor
   const float *wtab[NRL_MAX_CH];   // per weight slot: table addressed by the atom's index payload
   const float *inv_norm;    // voxelize: 1/S per packed atom (parallel to atoms), else null

@@ -238,6 +238,13 @@ bool cell_mode(int mode) {
          mode == NRL_OBS_ECCENTRICITY;      // + distinct_count when its values have <= 32 ranks (decided by the caller)
 }
 
+// The entropy of cumulative weight / density is decided by the last bit of its samples (sums of discrete per-atom weights
+// land exactly on histogram bin edges; two "equal" totals differ by an ulp or not with the order of the additions): these
+// tasks take the scan kernel, which adds the atoms in index order like the reference, whatever the grid.
+bool index_order_matters(int mode, int agg) {
+  return agg == 7 && (mode == NRL_OBS_CUMULATIVE_WEIGHT || mode == NRL_OBS_DENSITY);
+}
+
 template <int MODE, int NWT>
 int launch_cell_tiles_mode(Ctx &c, const NrlCellTileParams &p, int grid, size_t smem, cudaStream_t st, int slot) {
   const int attr = kAttrCell + (NWT > 1 ? kAttrMultiTable : slot);
@@ -760,7 +767,8 @@ int legacy_run(const LegacyArgs &a) {
     CellSetup cells;
     // (a single short frame is cheaper on the scan kernel: nothing to amortise the binning launch over;
     //  rank-based distinct_count exists on the cell-list kernel only)
-    if ((cell_mode(a.mode) || d_ranks) && !g_force_scan && n_atoms > 0 && (d_ranks || !(nF == 1 && a.N <= 4096))) {
+    if ((cell_mode(a.mode) || d_ranks) && !g_force_scan && !index_order_matters(a.mode, a.agg) && n_atoms > 0 &&
+        (d_ranks || !(nF == 1 && a.N <= 4096))) {
       if (grid_ok) {
         std::vector<NrlCellGrid> hgrids((size_t)nF, cell_grid);
         std::vector<int> fl(nF);

@@ -242,7 +242,7 @@ _Pragma("unroll")
     )
 #pragma unroll
     for (int k = 0; k < NRL_VPT; ++k) {
-      if constexpr (MODE == NRL_OBS_DENSITY) val[k] = (float)((double)ws[k] / t.sphere_volume);  // :199-201
+      if constexpr (MODE == NRL_OBS_DENSITY) val[k] = nrl_div_approx(ws[k], (float)t.sphere_volume);  // float volume, fast-math division (:199-201)
       else val[k] = ws[k];
     }
   } else if constexpr (MODE == NRL_OBS_ECCENTRICITY || MODE == NRL_OBS_RADIUS_OF_GYRATION) {

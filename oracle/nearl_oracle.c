@@ -232,11 +232,12 @@ static float orc_cumulative_weight(const float *o, const orc_frame_t *f) {
   }
   return r;
 }
-/* :197-202  volume = (4.0/3.0)*M_PI*cutoff^3 in double, float / double -> float */
+/* :197-202  `float volume = (4.0/3.0)*M_PI*cutoff^3`: evaluated in double, stored as a float; float / float (the
+ * reference binary divides with div.approx under -use_fast_math: <= 2 ulp from this IEEE quotient) */
 static float orc_density(const float *o, const orc_frame_t *f) {
   float ws = orc_cumulative_weight(o, f);
-  double vol = (4.0 / 3.0) * M_PI * (double)f->c * (double)f->c * (double)f->c;
-  return (float)((double)ws / vol);
+  float vol = (float)((4.0 / 3.0) * M_PI * (double)f->c * (double)f->c * (double)f->c);
+  return ws / vol;
 }
 /* :219-249 */
 static float orc_dispersion(const float *o, const orc_frame_t *f) {
