@@ -24,13 +24,15 @@ INTEGER_OBS = (1, 2, 3)
 def random_case(seed):
   rng = np.random.default_rng(seed)
   n_atoms = int(rng.integers(300, 2200))
-  window = int(rng.choice([1, 2, 3, 5, 8]))
-  n_frames = window * int(rng.integers(1, 4)) + int(rng.integers(0, 2))
+  window = int(rng.choice([1, 2, 3, 5, 8, 17, 24]))           # > 16 frames: the series leaves shared memory
+  n_frames = window * int(rng.integers(1, 4 if window < 17 else 2)) + int(rng.integers(0, 2))
   dtype = np.float64 if rng.random() < 0.25 else np.float32
   traj = io.synthetic_trajectory(n_atoms, n_frames, seed=seed * 7 + 1, dtype=dtype, pin=False, ligand_atoms=int(rng.choice([0, 12, 30])),
                                  step=float(rng.choice([0.1, 0.3, 0.8])))
   dims = [int(v) for v in rng.integers(6, 21, size=3)] if rng.random() < 0.5 else [int(rng.integers(6, 21))] * 3
-  spacing = float(rng.choice([0.5, 0.75, 1.0, 1.3]))
+  if rng.random() < 0.1:
+    dims = [int(rng.integers(24, 41))] * 3                    # several tiles per axis
+  spacing = float(rng.choice([0.35, 0.5, 0.75, 1.0, 1.3]))
   lengths = [d * spacing for d in dims]
   cutoff = float(rng.choice([1.5, 2.5, 3.25, 4.0, 5.0]))
   sigma = float(rng.choice([0.7, 1.0, 1.5, 2.2]))
@@ -174,3 +176,54 @@ def test_random_configuration_against_the_oracle(seed):
     else:
       bad = np.abs(g.astype(np.float64) - r) > 1e-5 * np.maximum(np.abs(r), 1e-5 * scale)
       assert bad.sum() == 0, (where, int(bad.sum()), float(np.abs(g - r).max()))
+
+
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_random_single_frame_systems_grouped(seed):
+  """Static channels over a list of single-frame systems of different sizes: the grouped path (several systems per native
+  call, each a slice of one pseudo-system with its own focal points and residue numbering) against the oracle, system by
+  system."""
+  rng = np.random.default_rng(1000 + seed)
+  systems = [io.synthetic_complex(int(rng.integers(200, 1500)), seed=seed * 31 + i, ligand_atoms=int(rng.choice([8, 30])),
+                                  dtype=(np.float64 if seed % 4 == 0 else np.float32)) for i in range(int(rng.integers(3, 8)))]
+  dims = [int(v) for v in rng.integers(6, 19, size=3)]
+  spacing = float(rng.choice([0.5, 0.8, 1.0]))
+  parms = {"dimensions": dims, "lengths": [d * spacing for d in dims], "time_window": 1,
+           "cutoff": float(rng.choice([1.5, 2.5, 4.0])), "sigma": float(rng.choice([0.8, 1.5]))}
+  classes = [features.Mass, features.HeavyAtom, features.AtomicNumber, features.Electronegativity, features.Hydrophobicity]
+  specs = []
+  for i in range(int(rng.integers(2, 7))):
+    k = {"outkey": f"s{i}"}
+    sel = SELECTIONS[int(rng.integers(0, len(SELECTIONS)))]
+    if sel is not None:
+      k["selection"] = sel
+    if rng.random() < 0.3:
+      k["byres"] = True
+    if rng.random() < 0.3:
+      k["cutoff"] = float(rng.choice([2.0, 3.0]))
+    if rng.random() < 0.2:
+      k["padding"] = float(rng.choice([0.0, 5.0]))
+    specs.append((classes[int(rng.integers(0, len(classes)))], k))
+  specs.append((features.AtomType, {"focus_element": int(rng.choice([1, 6, 7, 8])), "outkey": "type"}))
+  fz = featurizer.Featurizer(parms)
+  fz.register_features([cls(**k) for cls, k in specs])
+  fz.register_focus([":LIG", ":ARG"][: int(rng.integers(1, 3))], "mask")
+  fz.register_trajloader(systems)
+  fz.static_group = int(rng.choice([2, 3, 32]))
+  rows = {}
+  fz.result_sink = lambda outkey, tid, bid, pid, grid: rows.setdefault((tid, outkey), []).append(np.array(grid))
+  fz.run()
+  for tid, traj in enumerate(systems):
+    one = featurizer.Featurizer(parms)
+    one.register_features([cls(**k) for cls, k in specs])
+    one.register_focus(fz.FOCALPOINTS_PROTOTYPE, "mask")
+    one.traj = traj
+    assert one.parse_focus()
+    for f in one.FEATURESPACE:
+      f.cache(traj)
+    ref = host_ref.featurize(traj.xyz, one.FEATURESPACE[0].resids, descs_from(one), one.FOCALPOINTS, 1, buff_dim=_lib.buff_dim)
+    for f in one.FEATURESPACE:
+      g, r = np.array(rows[(tid, f.outkey)]).reshape(ref[f.outkey].shape), ref[f.outkey]
+      scale = max(float(np.abs(r).max()), 1e-30)
+      bad = np.abs(g.astype(np.float64) - r) > 1e-5 * np.maximum(np.abs(r), 1e-5 * scale)
+      assert bad.sum() == 0, (seed, tid, f.outkey, int(bad.sum()), float(np.abs(g - r).max()))
