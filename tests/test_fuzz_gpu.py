@@ -227,3 +227,60 @@ def test_random_single_frame_systems_grouped(seed):
       scale = max(float(np.abs(r).max()), 1e-30)
       bad = np.abs(g.astype(np.float64) - r) > 1e-5 * np.maximum(np.abs(r), 1e-5 * scale)
       assert bad.sum() == 0, (seed, tid, f.outkey, int(bad.sum()), float(np.abs(g - r).max()))
+
+
+@pytest.mark.parametrize("seed", list(range(1, 1 + max(40, int(os.environ.get("NRL_FUZZ_CASES", "40"))))))
+def test_random_calls_against_the_reference_kernels(seed):
+  """The six FFI twins on random shapes against the REFERENCE'S OWN KERNELS (oracle/_ref, built unmodified from the
+  reference's sources): the arbiter that shares the reference's fast-math arithmetic, which the IEEE oracle cannot."""
+  ref = reference_module()
+  if ref is None:
+    pytest.skip("oracle/_ref not built")
+  from nearl_b200 import all_actions as nb
+  rng = np.random.default_rng(5000 + seed)
+  D = int(rng.integers(8, 25))
+  dims = np.array([D, D, D], dtype=np.int32)                  # the reference's index math needs cubic grids
+  s = float(rng.choice([0.5, 0.75, 1.0]))
+  c = float(rng.choice([1.5, 2.5, 3.5, 5.0]))
+  sig = float(rng.choice([0.8, 1.5, 2.0]))
+  F = int(rng.choice([1, 2, 5, 10, 17]))
+  N = int(rng.integers(1, 700))
+  coords = rng.uniform(-c, D * s + c, size=(F, N, 3)).astype(np.float32)
+  if rng.random() < 0.3:
+    coords[:, N - N // 5:] = 99999.0                          # the padding of DynamicFeature.query
+  integer_w = rng.random() < 0.5
+  w = (rng.integers(0, 9, size=F * N) if integer_w else rng.uniform(0.0, 16.0, size=F * N)).astype(np.float32)
+  if rng.random() < 0.3:
+    w[rng.random(F * N) < 0.2] = 0.0
+  obs = int(rng.choice([1, 2, 3, 11, 12, 13, 14, 15, 16]))
+  agg = int(rng.integers(1, 9))
+  where = (seed, D, s, c, F, N, obs, agg, integer_w)
+  g = nb.marching_observer(coords, w, dims, s, c, obs, agg)
+  r = ref.marching_observer(coords, w, np.array(dims, dtype=int), s, c, obs, agg)
+  scale = max(float(np.abs(r).max()), 1e-30)
+  if obs in INTEGER_OBS and agg in (5, 6):
+    assert np.array_equal(g, r), where
+  elif agg == 7:
+    bad = np.count_nonzero(~np.isclose(g, r, rtol=1e-5, atol=1e-5))
+    # integers and set sums: every voxel; position-dependent floats: the order of the additions may move a sample across a
+    # bin edge in a few voxels
+    assert bad <= (0 if (obs in INTEGER_OBS or obs in (12, 13)) else max(2, r.size // 500)), (where, bad)
+  elif agg in (2, 4, 8) or obs in (14, 15, 16):
+    tol = 2e-5 * scale + (8 * np.finfo(np.float32).eps * (D * s + c) if obs in (14, 15, 16) else 0.0)
+    assert np.count_nonzero(np.abs(g.astype(np.float64) - r) > 1e-5 * np.abs(r) + tol) == 0, (where, float(np.abs(g - r).max()))
+  else:
+    assert np.count_nonzero(np.abs(g.astype(np.float64) - r) > 1e-5 * np.maximum(np.abs(r), 1e-5 * scale)) == 0, (where, float(np.abs(g - r).max()))
+  # single frame, voxeliser and flow
+  g1 = nb.frame_observation(coords[0], w[:N], dims, s, c, obs)
+  r1 = ref.frame_observation(coords[0], w[:N], np.array(dims, dtype=int), s, c, obs)
+  tol1 = 8 * np.finfo(np.float32).eps * (D * s + c) if obs in (14, 15, 16) else 0.0
+  assert np.count_nonzero(np.abs(g1.astype(np.float64) - r1) > 1e-5 * np.abs(r1) + tol1) == 0, (where, "frame_observation")
+  gv = nb.frame_voxelize(coords[0], w[:N], dims, s, c, sig, 0)
+  rv = ref.frame_voxelize(coords[0], w[:N], np.array(dims, dtype=int), s, c, sig, 0)
+  sv = max(float(np.abs(rv).max()), 1e-30)
+  assert np.count_nonzero(np.abs(gv.astype(np.float64) - rv) > 1e-5 * np.maximum(np.abs(rv), 1e-5 * sv)) == 0, (where, "frame_voxelize")
+  if agg in (1, 2, 5, 6):
+    gf = nb.density_flow(coords, w, dims, s, c, sig, agg)
+    rf = ref.density_flow(coords, w, np.array(dims, dtype=int), s, c, sig, agg)
+    sf = max(float(np.abs(rf).max()), 1e-30)
+    assert np.count_nonzero(np.abs(gf.astype(np.float64) - rf) > 1e-5 * np.abs(rf) + (2e-5 * sf if agg == 2 else 1e-10 * sf)) == 0, (where, "density_flow")
