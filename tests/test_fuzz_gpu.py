@@ -284,3 +284,34 @@ def test_random_calls_against_the_reference_kernels(seed):
     rf = ref.density_flow(coords, w, np.array(dims, dtype=int), s, c, sig, agg)
     sf = max(float(np.abs(rf).max()), 1e-30)
     assert np.count_nonzero(np.abs(gf.astype(np.float64) - rf) > 1e-5 * np.abs(rf) + (2e-5 * sf if agg == 2 else 1e-10 * sf)) == 0, (where, "density_flow")
+
+
+@pytest.mark.parametrize("seed", list(range(1, 1 + max(24, int(os.environ.get("NRL_FUZZ_CASES", "24"))))))
+def test_random_series_against_the_reference_aggregate(seed):
+  """Standalone K3 on random series shapes (1..512 frames, ragged voxel counts, integer / float / constant / negative series)
+  against the reference's own `aggregate`: streaming, register, pipelined (tiled TMA) and one-shot staged kernels."""
+  ref = reference_module()
+  if ref is None:
+    pytest.skip("oracle/_ref not built")
+  from nearl_b200 import all_actions as nb
+  rng = np.random.default_rng(9000 + seed)
+  F = int(rng.choice([1, 2, 3, 7, 10, 33, 64, 65, 100, 129, 257, 300, 512]))
+  G = int(rng.choice([1, 5, 64, 1000, 1003, 4096, 4 * 3001, 20000]))
+  kind = rng.random()
+  if kind < 0.35:
+    x = rng.integers(-3, 12, size=(F, G)).astype(np.float32)
+  elif kind < 0.8:
+    x = (rng.random((F, G)) * float(rng.choice([1.0, 50.0, 1e-3]))).astype(np.float32)
+  else:
+    x = (rng.standard_normal((F, G)) * 4).astype(np.float32)
+  if G > 4:
+    x[:, ::5] = float(rng.choice([0.0, 1.25, -2.0]))            # constant columns
+  for agg in range(1, 9):
+    g = nb.aggregate(x, agg)
+    r = ref.aggregate(x, agg)
+    where = (seed, F, G, agg, round(kind, 2))
+    if agg in (3, 5, 6):
+      assert np.array_equal(g, r), where
+    else:
+      scale = max(float(np.abs(x).max()), 1e-30)
+      assert np.count_nonzero(np.abs(g.astype(np.float64) - r) > 1e-5 * np.abs(r) + 1e-6 * scale) == 0, (where, float(np.abs(g - r).max()))
