@@ -314,8 +314,7 @@ __device__ __forceinline__ void nrl_rec_finish(const NrlAcc<MODE, NWT> &A, const
         else if (m == NRL_OBS_DENSITY) v = nrl_div_approx(A.f1[k], (float)t.sphere_volume);      // float volume, fast-math division (:199-201)
         else if (m == NRL_OBS_ECCENTRICITY) {
           if (any && A.f1[k] != 0.0f) {
-            const float m0 = nrl_div_approx(A.f2[k], A.f1[k]), m1 = nrl_div_approx(A.f3[k], A.f1[k]), m2 = nrl_div_approx(A.f4[k], A.f1[k]);
-            v = nrl_sqrt_approx(nrl_obs_d2(px, py, pz[k], m0, m1, m2));
+            v = nrl_eccentricity(px, py, pz[k], A.f2[k], A.f3[k], A.f4[k], A.f1[k]);
           } else {
             v = t.cutoff;
           }
@@ -338,9 +337,7 @@ __device__ __forceinline__ void nrl_rec_finish(const NrlAcc<MODE, NWT> &A, const
       val[0][k] = nrl_div_approx(A.f0[0][k], (float)t.sphere_volume);        // float volume, fast-math division (:199-201)
     } else if constexpr (MODE == NRL_OBS_ECCENTRICITY) {
       if (A.n[k] > 0 && A.f3[k] != 0.0f) {                               // :289-298
-        const float m0 = nrl_div_approx(A.f0[0][k], A.f3[k]), m1 = nrl_div_approx(A.f1[k], A.f3[k]),
-                    m2 = nrl_div_approx(A.f2[k], A.f3[k]);
-        val[0][k] = nrl_sqrt_approx(nrl_obs_d2(px, py, pz[k], m0, m1, m2));
+        val[0][k] = nrl_eccentricity(px, py, pz[k], A.f0[0][k], A.f1[k], A.f2[k], A.f3[k]);
       } else {
         val[0][k] = t.cutoff;
       }

@@ -52,10 +52,24 @@ __device__ __forceinline__ float nrl_div_approx(float a, float b) {
   asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
   return r;
 }
+__device__ __forceinline__ float nrl_rcp_approx(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+// eccentricity_device (marching_observers.cu:289-298) as the reference binary evaluates it: ONE reciprocal of the weight
+// sum, each centre-of-mass division fused with the subtraction from the observer (d = fma(rcp, -com, o), no rounded
+// quotient in between), squares summed x, y, z, approximate square root
+__device__ __forceinline__ float nrl_eccentricity(float ox, float oy, float oz, float cx, float cy, float cz, float ws);
 __device__ __forceinline__ float nrl_sqrt_approx(float a) {
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
+}
+__device__ __forceinline__ float nrl_eccentricity(float ox, float oy, float oz, float cx, float cy, float cz, float ws) {
+  const float rcp = nrl_rcp_approx(ws);
+  const float dx = fmaf(rcp, -cx, ox), dy = fmaf(rcp, -cy, oy), dz = fmaf(rcp, -cz, oz);
+  return nrl_sqrt_approx(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
 }
 __device__ __forceinline__ float nrl_lg2_approx(float a) {
   float r;

@@ -270,9 +270,7 @@ _Pragma("unroll")
 #pragma unroll
       for (int k = 0; k < NRL_VPT; ++k) {
         if (n[k] > 0 && ws[k] != 0.0f) {                                // :289-298
-          const float m0 = nrl_div_approx(cx[k], ws[k]), m1 = nrl_div_approx(cy[k], ws[k]),
-                      m2 = nrl_div_approx(cz[k], ws[k]);
-          val[k] = nrl_sqrt_approx(nrl_obs_d2(px, py, pz[k], m0, m1, m2));
+          val[k] = nrl_eccentricity(px, py, pz[k], cx[k], cy[k], cz[k], ws[k]);
         } else {
           val[k] = t.cutoff;
         }

@@ -274,8 +274,10 @@ static float orc_eccentricity(const float *o, const orc_frame_t *f) {
     ws = ws + f->w[j];
   }
   if (count > 0 && ws != 0.0f) {
-    float com0 = cx / ws, com1 = cy / ws, com2 = cz / ws;
-    return sqrtf(orc_d2_obs(o[0], o[1], o[2], com0, com1, com2));
+    /* the reference binary: one reciprocal, each quotient fused with the subtraction (FFMA rcp, -com, o) */
+    float rcp = 1.0f / ws;
+    float dx = fmaf(rcp, -cx, o[0]), dy = fmaf(rcp, -cy, o[1]), dz = fmaf(rcp, -cz, o[2]);
+    return sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
   }
   return f->c;
 }

@@ -353,3 +353,27 @@ def test_max_frames_boundary():
   big = np.concatenate([coords, coords[:8]], axis=0)                   # density_flow: frames beyond 512 are ignored
   wb = np.ones(520 * 20, dtype=np.float32)
   assert np.array_equal(nb.density_flow(big, wb, dims, 1.0, 2.0, 1.0, 5), nb.density_flow(coords, w, dims, 1.0, 2.0, 1.0, 5))
+
+
+def test_single_frame_observables_and_reducers_bit_identical_to_the_reference(ref_actions):
+  # On the index-ordered path (frame_observation: the scan kernel adds the atoms in the reference's order) the arithmetic is
+  # the reference binary's op for op: all nine observables, and all eight reducers of `aggregate`, to the last bit
+  # (scripts/bitwise_vs_reference.py prints the rates).  The voxeliser is excluded: the reference deposits with float
+  # atomics, its own result varies from run to run.
+  rng = np.random.default_rng(77)
+  D, s, c = 20, 0.75, 3.5
+  dims = np.array([D, D, D], dtype=np.int32)
+  for N in (300, 2500):
+    coords = rng.uniform(-c, D * s + c, size=(N, 3)).astype(np.float32)
+    w = rng.uniform(0.5, 16.0, size=N).astype(np.float32)
+    for obs in (1, 2, 3, 11, 12, 13, 14, 15, 16):
+      g = nb.frame_observation(coords, w, dims, s, c, obs)
+      r = ref_actions.frame_observation(coords, w, np.array(dims, dtype=int), s, c, obs)
+      assert np.array_equal(g.view(np.int32), r.view(np.int32)), (N, obs, int(np.count_nonzero(g.view(np.int32) != r.view(np.int32))))
+  coords = rng.uniform(-c, D * s + c, size=(10, 600, 3)).astype(np.float32)
+  w = rng.uniform(0.5, 16.0, size=10 * 600).astype(np.float32)
+  series = np.stack([ref_actions.frame_observation(coords[i], w[i * 600:(i + 1) * 600], np.array(dims, dtype=int), s, c, 11) for i in range(10)])
+  for agg in range(1, 9):
+    g = nb.aggregate(series, agg)
+    r = ref_actions.aggregate(series, agg)
+    assert np.array_equal(g.view(np.int32), r.view(np.int32)), agg
