@@ -3,6 +3,8 @@ by-residue crops, frame offsets, every observable and reducer, focal points on a
 system, float32 and float64 trajectories -- through Featurizer.run (device crop, cell lists or full-frame scan, fused
 sweeps, fused reducers) against oracle/host_ref.py feeding the C oracle.  Each case is small enough for the oracle to
 finish in about a second; the seeds are fixed, so a failure names a reproducible case."""
+import os
+
 import numpy as np
 import pytest
 
@@ -100,7 +102,6 @@ def descs_from(fz):
   return descs
 
 
-import os
 SEEDS = list(range(1, 1 + int(os.environ.get("NRL_FUZZ_CASES", "48"))))      # NRL_FUZZ_CASES=600 for a soak run
 
 
