@@ -45,6 +45,7 @@ __device__ __forceinline__ void nrl_mbar_wait(uint64_t *bar, uint32_t parity) {
 // median_device, gpuutils.cuh:227-245 -- the tile column is overwritten) and information entropy
 // (information_entropy_histogram_device, gpuutils.cuh:140-173).
 #define NRL_AGG_BLOCK 16
+#define NRL_MEDIAN_SELECT_MIN 24
 #define NRL_AGG_LEGACY_ENTROPY 107
 __device__ __forceinline__ float nrl_agg_voxel(float *fb, const int W, const int v, const int n, const int agg) {
   const float fn = (float)n;
@@ -76,6 +77,77 @@ __device__ __forceinline__ float nrl_agg_voxel(float *fb, const int W, const int
     return agg == 2 ? nrl_sqrt_approx(nrl_div_approx(acc, fn)) : nrl_div_approx(acc, fn);
   }
   if (agg == 3) {
+    // The median is an order statistic: any exact selection returns the value the reference's exchange sort
+    // (median_device, gpuutils.cuh:227-245) leaves in the middle.  Series longer than NRL_MEDIAN_SELECT_MIN without a NaN
+    // are selected by radix (4-bit digits of the order-preserving integer image of the floats, most significant first,
+    // counted in packed 4-bit counters like the entropy histogram): ~60-100 operations per sample instead of n / 2
+    // compare-exchanges.  A NaN compares false with everything, so where it ends up depends on the sort itself: those series
+    // keep the reference's sort, as do short ones.
+    unsigned *key = reinterpret_cast<unsigned *>(fb) + v;
+    bool select = n >= NRL_MEDIAN_SELECT_MIN;
+    if (select) {
+      for (int i = 0; i < n; ++i) { const float x = fb[(size_t)i * W + v]; if (x != x) select = false; }
+    }
+    if (select) {
+      for (int i = 0; i < n; ++i) {            // float -> unsigned with the same order (-0.0 sorts before +0.0: equal anyway)
+        const unsigned u = key[(size_t)i * W];
+        key[(size_t)i * W] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      }
+      const unsigned long long lanes = 0x000F000F000F000Full;
+      unsigned sel[2];
+      int n_sel = 0;
+      const int k0 = (n & 1) ? n / 2 : n / 2 - 1;
+      unsigned prefix = 0u;
+      int kk = k0, group = n;                   // rank wanted inside the candidate group, size of the group
+      for (int shift = 28; shift >= 0 && group > 1; shift -= 4) {
+        const unsigned himask = shift == 28 ? 0u : ~((1u << (shift + 4)) - 1u);
+        unsigned long long h0 = 0ull, h1 = 0ull, h2 = 0ull, h3 = 0ull;
+        for (int i0 = 0; i0 < n; i0 += 15) {
+          unsigned long long acc = 0ull;
+          const int i1 = min(i0 + 15, n);
+          for (int i = i0; i < i1; ++i) {
+            const unsigned u = key[(size_t)i * W];
+            if (((u ^ prefix) & himask) == 0u) acc += 1ull << (4 * ((u >> shift) & 15u));
+          }
+          h0 += acc & lanes; h1 += (acc >> 4) & lanes; h2 += (acc >> 8) & lanes; h3 += (acc >> 12) & lanes;
+        }
+        const unsigned long long h[4] = {h0, h1, h2, h3};
+        int below = 0, d = 0, cnt = 0;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          const int cb = (int)((h[b & 3] >> ((b >> 2) * 16)) & 0xffffull);
+          if (cnt == 0 && kk < below + cb) { d = b; cnt = cb; } else if (cnt == 0) below += cb;
+        }
+        kk -= below;
+        group = cnt;
+        prefix |= (unsigned)d << shift;
+        if (shift == 0) break;
+        if (group == 1) {                       // one candidate left: fetch it
+          const unsigned hm = ~((1u << shift) - 1u);
+          for (int i = 0; i < n; ++i) { const unsigned u = key[(size_t)i * W]; if (((u ^ prefix) & hm) == 0u) prefix = u; }
+        }
+      }
+      sel[n_sel++] = prefix;
+      if ((n & 1) == 0) {
+        // the next order statistic: the same value when the group of equals reaches past rank kk, else the smallest larger key
+        unsigned next = 0xffffffffu;
+        int equal = 0;
+        for (int i = 0; i < n; ++i) {
+          const unsigned u = key[(size_t)i * W];
+          equal += u == prefix;
+          if (u > prefix && u < next) next = u;
+        }
+        int smaller = 0;
+        for (int i = 0; i < n; ++i) smaller += key[(size_t)i * W] < prefix;
+        sel[n_sel++] = (k0 + 1 < smaller + equal) ? prefix : next;
+      }
+      float val[2];
+      for (int q = 0; q < n_sel; ++q) {
+        const unsigned u = sel[q];
+        val[q] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+      }
+      return (n & 1) ? val[0] : nrl_div_approx(val[0] + val[1], 2.0f);
+    }
     for (int i = 0; i < n; ++i) {
       float a = fb[(size_t)i * W + v];
       for (int j = i + 1; j < n; ++j) {
