@@ -238,11 +238,13 @@ bool cell_mode(int mode) {
          mode == NRL_OBS_ECCENTRICITY;      // + distinct_count when its values have <= 32 ranks (decided by the caller)
 }
 
-// The entropy of cumulative weight / density is decided by the last bit of its samples (sums of discrete per-atom weights
-// land exactly on histogram bin edges; two "equal" totals differ by an ulp or not with the order of the additions): these
-// tasks take the scan kernel, which adds the atoms in index order like the reference, whatever the grid.
+// The information entropy is discontinuous in its samples (a histogram): where a sample sits on a bin edge -- always the
+// case for sums of discrete per-atom weights, {A - m, A, A, A + m} puts A exactly on one -- the last bit decides, and the last
+// bit of a float sum depends on the order of the additions.  Entropy tasks over float observables therefore take the scan
+// kernel, which adds the atoms in index order like the reference and is bit-identical to it, whatever the grid.
 bool index_order_matters(int mode, int agg) {
-  return agg == 7 && (mode == NRL_OBS_CUMULATIVE_WEIGHT || mode == NRL_OBS_DENSITY);
+  return agg == 7 && (mode == NRL_OBS_MEAN_DISTANCE || mode == NRL_OBS_CUMULATIVE_WEIGHT || mode == NRL_OBS_DENSITY ||
+                      mode == NRL_OBS_ECCENTRICITY);
 }
 
 template <int MODE, int NWT>
