@@ -227,31 +227,41 @@ class Featurizer:
     Trajectories are software-pipelined over `pipeline_depth` lanes of the native library: while
     the kernels of trajectory i run, the host lowers the next ones and their frames upload;
     results are dumped in trajectory order."""
-    indices = range(self.TRAJECTORYNUMBER) if trajectory_indices is None else trajectory_indices
+    indices = list(range(self.TRAJECTORYNUMBER) if trajectory_indices is None else trajectory_indices)
     stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "frames": 0, "seconds": 0.0}
     t_run = time.perf_counter()
     depth = max(1, min(int(self.pipeline_depth), 4))        # lanes of the native library (NRL_MAX_LANES)
     self.__dict__.pop("_fingerprint_memo", None)
-    if self._static_groupable():
-      self._run_static_groups(list(indices), depth, stats)
-      stats["seconds"] = time.perf_counter() - t_run
-      self.last_run_stats = stats
-      printit(f"{self.classname}: All trajectories and tasks are finished. \n")
-      return stats
-    pending = []                                             # submitted, not yet finished, oldest first
-    for count, tid in enumerate(indices):
-      if len(pending) >= depth:
-        self._finish(pending.pop(0), stats)                  # frees the lane (and its buffers) about to be reused
-      job = self._submit(tid, lane=count % depth)
-      if job is None:
-        continue
-      pending.append(job)              # host-protocol tasks were evaluated inside _submit
-    while pending:
-      self._finish(pending.pop(0), stats)
+    with utils.hdf_session():                                # output files stay open until the run is over
+      done = self._run_static_groups(indices, depth, stats) if self._static_groupable() else 0
+      self._run_pipelined(indices[done:], depth, stats)
     stats["seconds"] = time.perf_counter() - t_run
     self.last_run_stats = stats
     printit(f"{self.classname}: All trajectories and tasks are finished. \n")
     return stats
+
+  def _run_pipelined(self, indices, depth, stats, loaded=None):
+    """One native call per trajectory, `depth` of them in flight.  A lane (its page-locked result buffer and table
+    buffers) belongs to a job from submission until `_finish`: the lane number advances with the jobs actually
+    submitted -- a skipped trajectory takes none -- and the job `depth` submissions back, the lane's previous owner,
+    is finished before the lane is handed out again."""
+    pending = []                                             # submitted, not yet finished, oldest first
+    submitted = 0
+    multi_frame = False
+    for tid in indices:
+      if len(pending) >= depth:
+        self._finish(pending.pop(0), stats)                  # frees the lane (and its buffers) about to be reused
+      lane = submitted % depth
+      assert all(job["lane"] != lane for job in pending), "pipeline lane handed out while its job is pending"
+      job = self._submit(tid, lane=lane, traj=None if loaded is None else loaded.get(tid))
+      multi_frame |= self.traj.n_frames != 1
+      if job is None:
+        continue                                             # skipped (no focal point): the lane stays free
+      submitted += 1
+      pending.append(job)              # host-protocol tasks were evaluated inside _submit
+    while pending:
+      self._finish(pending.pop(0), stats)
+    return multi_frame
 
   # ---- single-frame systems (PDBBind-style): many systems per native call ------------------------------
   def _static_groupable(self):
@@ -273,32 +283,35 @@ class Featurizer:
     return n_static > 0
 
   def _run_static_groups(self, indices, depth, stats):
+    """Groups of `static_group` single-frame systems per native call, `depth` calls in flight.  Returns how many of
+    `indices` were featurised: a multi-frame trajectory switches grouping off, and run() takes the rest of the list
+    through the pipelined one-call-per-trajectory loop (trajectory lists are homogeneous in practice)."""
     group = max(2, int(self.static_group))
     pending = []
-    grouping_off = False
-    count = 0
+    submitted = 0
     for g0 in range(0, len(indices), group):
       tids = indices[g0:g0 + group]
       if len(pending) >= depth:
         self._finish_static_group(pending.pop(0), stats)
       loaded = {}
-      job = None if grouping_off else self._submit_static_group(tids, lane=count % depth, loaded=loaded)
-      count += 1
+      lane = submitted % depth
+      assert all(job["lane"] != lane for job in pending), "pipeline lane handed out while its job is pending"
+      job = self._submit_static_group(tids, lane=lane, loaded=loaded)
       if job is None:
-        # a multi-frame trajectory (or a feature without weights) in this group: one by one, reference order kept,
-        # re-using the trajectories the attempt already loaded; a multi-frame trajectory switches grouping off for
-        # the rest of the run (trajectory lists are homogeneous in practice)
+        # a multi-frame trajectory (or a feature without weights) in this group: one call per trajectory, reference
+        # order kept, re-using the trajectories the attempt already loaded
         while pending:
           self._finish_static_group(pending.pop(0), stats)
-        for tid in tids:
-          single = self._submit(tid, lane=0, traj=loaded.get(tid))
-          if single is not None:
-            self._finish(single, stats)
-          grouping_off |= self.traj.n_frames != 1
+        if self._run_pipelined(tids, depth, stats, loaded=loaded):
+          return g0 + len(tids)
         continue
+      if job["batch"] is None:
+        continue                        # every member was skipped: nothing was submitted, the lane stays free
+      submitted += 1
       pending.append(job)
     while pending:
       self._finish_static_group(pending.pop(0), stats)
+    return len(indices)
 
   def _submit_static_group(self, tids, lane, loaded=None):
     members = []
@@ -522,6 +535,10 @@ class Featurizer:
     with the per-atom tables of the last block of a different length that preceded one of its own length;
     and ``label`` receives the first n_blocks entries of the per-TASK label list (featurizer.py:545-549).
     `process_nr` (some scripts pass a worker count) is accepted and ignored."""
+    with utils.hdf_session():                                # output files stay open until the loop is over
+      return self._loop_by_residue(restype, tag_limit, chunk_floats)
+
+  def _loop_by_residue(self, restype, tag_limit, chunk_floats):
     stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "blocks": 0, "seconds": 0.0}
     t_run = time.perf_counter()
     for tid in range(self.TRAJECTORYNUMBER):
@@ -545,6 +562,7 @@ class Featurizer:
       # the reference's cache state: length of the slice the features were last cached on, and where it starts
       cached_len, src_first = n_all, 0
       pending = None
+      submitted = 0                     # native chunks sent so far: with one job pending, alternate lanes never alias
       with utils.batched_output():
         for bid in range(self.SLICENUMBER):
           first = bid * self.time_window
@@ -573,7 +591,8 @@ class Featurizer:
             c1 = min(c0 + step, len(blocks))
             job = {"bid": bid, "c0": c0, "c1": c1, "generic": generic, "native": None}
             if native_feats:
-              lane = (c0 // step + bid) % 2
+              lane = submitted % 2      # the pending job (if any) holds the other lane
+              submitted += 1
               batch = self._lower_residue_batch(native_feats, specs, xyz.dtype == np.float64, first, starts[c0:c1], stops[c0:c1],
                                                 shifts[c0:c1], focal[c0:c1], n_all, lane)
               buffers = self.__dict__.setdefault("_out_buffers", {})

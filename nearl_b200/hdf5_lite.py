@@ -1,31 +1,40 @@
-"""A small, dependency-free HDF5 writer/reader for the output layout of the hot path.
+"""A small, dependency-free HDF5 writer/reader for the files on either side of the hot path.
 
-The image this package is built on has neither h5py nor libhdf5, yet the path's product is
-an HDF5 file (/root/reference/nearl/utils.py:491-570, /root/reference/nearl/features.py:510-534).
-This module writes real HDF5 (version-2 superblock, version-2 object headers with compact
-link storage, version-3 layout messages, version-1 chunk B-trees, a global heap for
-variable-length strings) for exactly the objects that layout needs:
+The image this package is built on has neither h5py nor libhdf5, yet the path's product is an HDF5 file
+(/root/reference/nearl/utils.py:491-570, /root/reference/nearl/features.py:510-534) and one of its inputs is one
+(MISATO's ``MD.hdf5``, /root/reference/nearl/io/traj.py:287-423).
+
+**Writing** -- real HDF5 (version-2 superblock, version-2 object headers with compact link storage, version-3
+layout messages, version-1 chunk B-trees, a global heap for variable-length strings) for exactly the objects
+the output layout needs:
 
   * groups,
-  * scalar and 1-D datasets of float64 / int64 / float32 / int32 / variable-length UTF-8
-    strings (``featurizer_parms/*``, contiguous layout),
-  * N-D float32 / int / float datasets extensible along axis 0 with chunks that span the
-    trailing axes (``chunks=(c0, *shape[1:])``, ``maxshape=(None, ...)``), optionally gzip
-    compressed (one feature dataset per ``outkey``).
+  * scalar and 1-D datasets of float64 / int64 / float32 / int32 / variable-length UTF-8 strings
+    (``featurizer_parms/*``, contiguous layout),
+  * N-D float / int datasets extensible along axis 0 with chunks that span the trailing axes
+    (``chunks=(c0, *shape[1:])``, ``maxshape=(None, ...)``), optionally gzip compressed (one per ``outkey``).
 
-and reads the same subset back (enough for tests and for appending to a file it wrote).
-The API is the slice of h5py's that nearl uses: ``File(path, mode)`` as a context manager,
-``in`` / ``[]`` / ``del`` / ``create_group`` / ``create_dataset`` / item assignment, and on
-datasets ``shape`` / ``dtype`` / ``maxshape`` / ``chunks`` / ``resize`` / slicing on axis 0.
+Appending is O(log rows): chunk data goes to the end of the file and never moves; every piece of metadata has a
+fixed size and a fixed address once allocated and is UPDATED IN PLACE -- the dataset's object header (its shape),
+the nodes on the right edge of its chunk B-tree (full nodes never change again except for their right-sibling
+pointer), group headers (allocated with room for more links) and the superblock.  Re-opening a file reads the
+group / dataset headers only; B-tree nodes are read when a chunk is looked up or appended (the right edge).
 
-Appending never moves chunk data: new chunks go to the end of the file and the (small)
-metadata -- object headers, B-tree nodes, heap -- is written afresh behind them, after which
-the superblock is pointed at the new root header.  Format reference: "HDF5 File Format
-Specification Version 3.0" (sections II.A superblock, III.A.1 v1 B-trees, III.E global heap,
-IV.A.1.b / IV.A.2 object headers and messages).  Compatibility with libhdf5 could not be
-exercised on this image (no HDF5 library available); the structures follow the
-specification field by field and are checked by the module's own independent reader.
+**Reading** -- besides its own files, the classic layout stock h5py / libhdf5 write by default: version-0/1
+superblocks (with a user block), version-1 object headers with continuation blocks, symbol-table groups (group
+B-trees, local heaps), contiguous / compact / chunked datasets with arbitrary N-D chunk shapes, the deflate,
+shuffle and Fletcher-32 filters, fixed-point / floating-point / fixed- and variable-length string types of either
+byte order, and attributes of those types.  Datasets are read lazily, hyperslab by hyperslab along axis 0.
+This half is pinned on a file written by libhdf5 itself (tests/test_hdf5_classic.py).
+
+The API is the slice of h5py's that nearl uses: ``File(path, mode)`` as a context manager, ``in`` / ``[]`` / ``del``
+/ ``create_group`` / ``create_dataset`` / item assignment, and on datasets ``shape`` / ``dtype`` / ``maxshape`` /
+``chunks`` / ``attrs`` / ``resize`` / slicing.  Format reference: "HDF5 File Format Specification Version 3.0"
+(II.A superblock, III.A.1 v1 B-trees, III.B symbol-table nodes, III.D local heaps, III.E global heap, IV.A object
+headers and messages).  The WRITER's compatibility with libhdf5 could not be exercised on this image (no HDF5
+library); it shares the message / B-tree / datatype code with the reader that is pinned on libhdf5's own output.
 """
+import bisect
 import os
 import struct
 import zlib
@@ -39,8 +48,10 @@ UNDEF = 0xFFFFFFFFFFFFFFFF
 UNLIMITED = 0xFFFFFFFFFFFFFFFF
 BTREE_K = 32      # default "indexed storage internal node K": at most 2K = 64 children per chunk B-tree node
 
-MSG_DATASPACE, MSG_LINKINFO, MSG_DATATYPE, MSG_FILLVALUE, MSG_LINK = 0x01, 0x02, 0x03, 0x05, 0x06
-MSG_LAYOUT, MSG_GROUPINFO, MSG_FILTERS = 0x08, 0x0A, 0x0B
+MSG_NIL, MSG_DATASPACE, MSG_LINKINFO, MSG_DATATYPE, MSG_FILLVALUE_OLD, MSG_FILLVALUE, MSG_LINK = 0, 1, 2, 3, 4, 5, 6
+MSG_LAYOUT, MSG_GROUPINFO, MSG_FILTERS, MSG_ATTRIBUTE, MSG_CONTINUATION, MSG_SYMBOLTABLE = 0x08, 0x0A, 0x0B, 0x0C, 0x10, 0x11
+
+GROUP_HEADER_SLACK = 512      # a group header is allocated with room for more links before it has to move
 
 
 # ---- Jenkins lookup3 (hashlittle), the metadata checksum of HDF5 -------------------------------
@@ -113,39 +124,254 @@ def _encode_dtype(dt):
 
 
 def _decode_dtype(buf):
+  """numpy dtype (or VLEN_STR) of a datatype message: classes 0 fixed-point, 1 floating-point, 3 fixed-length
+  string, 9 variable-length string; either byte order."""
   cls = buf[0] & 0x0F
   size = struct.unpack_from("<I", buf, 4)[0]
+  order = ">" if buf[1] & 0x01 else "<"
   if cls == 1:
-    return np.dtype("<f%d" % size)
+    return np.dtype("%sf%d" % (order, size))
   if cls == 0:
-    return np.dtype(("<i%d" if buf[1] & 0x08 else "<u%d") % size)
+    return np.dtype(("%si%d" if buf[1] & 0x08 else "%su%d") % (order, size))
+  if cls == 3:
+    return np.dtype("S%d" % size)
   if cls == 9 and (buf[1] & 0x0F) == 1:
     return VLEN_STR
   raise TypeError(f"hdf5_lite: unsupported datatype class {cls}")
 
 
+# ---- version-1 B-tree over the chunks of a dataset (node type 1) ----------------------------------------
+class _Node:
+  __slots__ = ("addr", "level", "entries", "left", "right", "dirty")
+
+  def __init__(self, addr, level):
+    self.addr, self.level = addr, level
+    self.entries = []          # [offset tuple, stored size, child address, filter mask], ordered by offset
+    self.left = self.right = UNDEF
+    self.dirty = True
+
+
+class _ChunkIndex:
+  """Chunk offsets -> (address, stored size, filter mask).  Nodes have a fixed size (2K children) and a fixed
+  address; appending a chunk beyond the last one touches the nodes of the right edge only, and those are
+  rewritten in place by `flush`.  Reading descends from the root, one node per level."""
+
+  def __init__(self, dset, root=None):
+    self.d = dset
+    self.f = dset._file
+    self.rank = len(dset.chunks)
+    self.nkey = self.rank + 1   # offsets per key: one per axis and a last one for the element (always 0)
+    self.key_len = 8 + 8 * self.nkey
+    self.node_len = 24 + (2 * self.f._btree_k + 1) * self.key_len + 2 * self.f._btree_k * 8
+    self.root = root            # file address of the root node; None: tree not allocated yet
+    self.nodes = {}
+    self.edge = None            # nodes from the root to the rightmost leaf
+    self.last = None            # offsets of the last chunk
+    self.root_moved = False
+
+  # -- reading
+  def _node(self, addr):
+    node = self.nodes.get(addr)
+    if node is not None:
+      return node
+    f = self.f
+    raw = f._read(addr, self.node_len)
+    if raw[:4] != b"TREE" or raw[4] != 1:
+      raise OSError("hdf5_lite: bad chunk B-tree node")
+    node = _Node(addr, raw[5])
+    used = struct.unpack_from("<H", raw, 6)[0]
+    node.left, node.right = (f._addr_in(a) for a in struct.unpack_from("<QQ", raw, 8))
+    pos = 24
+    for _ in range(used):
+      size, mask = struct.unpack_from("<II", raw, pos)
+      offs = struct.unpack_from("<%dQ" % self.nkey, raw, pos + 8)
+      child = f._addr_in(struct.unpack_from("<Q", raw, pos + self.key_len)[0])
+      node.entries.append([offs, size, child, mask])
+      pos += self.key_len + 8
+    node.dirty = False
+    if len(self.nodes) > 512:
+      self.nodes = {a: n for a, n in self.nodes.items() if n.dirty or (self.edge and n in self.edge)}
+    self.nodes[addr] = node
+    return node
+
+  def find(self, offsets):
+    """(address, stored size, filter mask) of the chunk at `offsets`, or None."""
+    if self.root is None or self.root == UNDEF:
+      return None
+    offsets = tuple(offsets)
+    node = self._node(self.root)
+    while True:
+      keys = [e[0] for e in node.entries]
+      i = bisect.bisect_right(keys, offsets) - 1
+      if i < 0:
+        return None
+      if node.level == 0:
+        e = node.entries[i]
+        return (e[2], e[1], e[3]) if e[0] == offsets else None
+      node = self._node(node.entries[i][2])
+
+  def _leaf_of(self, offsets):
+    node = self._node(self.root)
+    while node.level > 0:
+      keys = [e[0] for e in node.entries]
+      node = self._node(node.entries[max(bisect.bisect_right(keys, offsets) - 1, 0)][2])
+    return node
+
+  def walk(self, addr=None):
+    """Every (offsets, address, stored size, filter mask), in order."""
+    if self.root is None or self.root == UNDEF:
+      return
+    node = self._node(self.root if addr is None else addr)
+    for offs, size, child, mask in list(node.entries):
+      if node.level == 0:
+        yield offs, child, size, mask
+      else:
+        yield from self.walk(child)
+
+  # -- writing
+  def _right_edge(self):
+    if self.edge is not None:
+      return
+    if self.root is None:
+      self.root = self.f._alloc(self.node_len)
+      self.root_moved = True
+      self.nodes[self.root] = _Node(self.root, 0)
+    node = self._node(self.root)
+    self.edge = [node]
+    while node.level > 0:
+      node = self._node(node.entries[-1][2])
+      self.edge.append(node)
+    self.last = node.entries[-1][0] if node.entries else None
+
+  def set(self, offsets, addr, size, mask=0):
+    offsets = tuple(offsets)
+    self._right_edge()
+    if self.last is None or offsets > self.last:
+      self._append(offsets, addr, size, mask)
+      return
+    leaf = self._leaf_of(offsets)
+    for e in leaf.entries:
+      if e[0] == offsets:
+        e[1], e[2], e[3] = size, addr, mask
+        leaf.dirty = True
+        return
+    # a chunk in a gap left behind by out-of-order writes: rare -- rebuild the tree around the sorted entry list
+    entries = [[o, s, a, m] for o, a, s, m in self.walk()] + [[offsets, size, addr, mask]]
+    entries.sort(key=lambda e: e[0])
+    self.nodes, self.edge, self.last, self.root = {}, None, None, None
+    self._right_edge()
+    for o, s, a, m in entries:
+      self._append(o, a, s, m)
+
+  def _append(self, offsets, addr, size, mask):
+    cap = 2 * self.f._btree_k
+    entry = [offsets, size, addr, mask]
+    i = len(self.edge) - 1                                   # from the leaf upwards
+    split = None
+    while True:
+      if i < 0:                                              # the root itself was split: one more level
+        root = _Node(self.f._alloc(self.node_len), split.level + 1)
+        root.entries.append([split.entries[0][0], split.entries[0][1], split.addr, 0])
+        root.entries.append(entry)
+        self.nodes[root.addr] = root
+        self.edge.insert(0, root)
+        self.root, self.root_moved = root.addr, True
+        break
+      node = self.edge[i]
+      if len(node.entries) < cap:
+        node.entries.append(entry)
+        node.dirty = True
+        break
+      sibling = _Node(self.f._alloc(self.node_len), node.level)   # full: open a right sibling, push it into the parent
+      sibling.left, node.right = node.addr, sibling.addr
+      sibling.entries.append(entry)
+      node.dirty = True
+      self.nodes[sibling.addr] = sibling
+      self.edge[i] = sibling
+      split = node
+      entry = [offsets, size, sibling.addr, 0]
+      i -= 1
+    self.last = offsets
+
+  def _key(self, size, mask, offsets):
+    return struct.pack("<II", size, mask) + struct.pack("<%dQ" % self.nkey, *offsets)
+
+  def flush(self):
+    """Write the nodes that changed, each at its own address."""
+    if self.root is not None and self.edge is None:
+      return                                                 # loaded and never modified
+    self._right_edge()
+    f = self.f
+    # the key behind the last child of a node is the first key of its right sibling; on the right edge the corner
+    # beyond the last chunk (every offset advanced by the chunk's extent, as libhdf5 leaves it)
+    extent = tuple(self.d.chunks) + (self.d._itemsize(),)
+    beyond = tuple(o + c for o, c in zip(self.last, extent)) if self.last is not None else None
+    for node in [n for n in self.nodes.values() if n.dirty]:
+      blob = b"TREE" + bytes([1, node.level]) + struct.pack("<HQQ", len(node.entries), f._addr_out(node.left), f._addr_out(node.right))
+      for offs, size, child, mask in node.entries:
+        blob += self._key(size, mask, offs) + struct.pack("<Q", f._addr_out(child))
+      if node.entries:
+        if node.right != UNDEF:
+          first = self._node(node.right).entries[0]
+          blob += self._key(first[1], first[3], first[0])
+        else:
+          blob += self._key(0, 0, beyond)
+      f._write(node.addr, blob + b"\x00" * (self.node_len - len(blob)))
+      node.dirty = False
+    self.nodes = {n.addr: n for n in self.edge}              # full nodes left behind are not needed again
+
+
 # ---- object model -----------------------------------------------------------------------------------
-class Dataset:
-  def __init__(self, file, shape, dtype, maxshape=None, chunks=None, compression=None, compression_opts=None):
+class _Object:
+  def __init__(self, file):
     self._file = file
+    self._addr = None          # address of the object header (None: not written yet)
+    self._cap = 0              # bytes allocated for it
+    self._dirty = True
+    self.attrs = {}
+
+
+def _unfilter(raw, filters, mask, itemsize):
+  for i in reversed(range(len(filters))):
+    fid, cdata = filters[i]
+    if mask & (1 << i):
+      continue
+    if fid == 1:
+      raw = zlib.decompress(raw)
+    elif fid == 2:                                             # shuffle: bytes of equal significance were grouped
+      n = len(raw) // itemsize
+      body = np.frombuffer(raw[:n * itemsize], dtype=np.uint8).reshape(itemsize, n).T.tobytes()
+      raw = body + raw[n * itemsize:]
+    elif fid == 3:                                             # Fletcher-32: checksum trails the data
+      raw = raw[:-4]
+    else:
+      raise OSError(f"hdf5_lite: unsupported filter {fid}")
+  return raw
+
+
+class Dataset(_Object):
+  def __init__(self, file, shape, dtype, maxshape=None, chunks=None, compression=None, compression_opts=None, _loaded=False):
+    _Object.__init__(self, file)
     self.shape = tuple(int(s) for s in shape)
     self.dtype = dtype if dtype is VLEN_STR else np.dtype(dtype)
     self.maxshape = tuple(maxshape) if maxshape is not None else self.shape
     self.compression = compression
     self.compression_opts = 4 if (compression == "gzip" and compression_opts is None) else compression_opts
+    self._filters = [(1, (int(self.compression_opts),))] if compression == "gzip" else []
     extensible = any(m is None for m in self.maxshape) or self.maxshape != self.shape
     if chunks is True or (chunks is None and (extensible or compression)):
       chunks = (1,) + self.shape[1:] if len(self.shape) > 0 else None
     self.chunks = tuple(int(c) for c in chunks) if chunks else None
+    self._value = None           # contiguous / compact data held in memory (None: still on disk)
+    self._data_addr, self._data_size = None, 0
+    self._heap_ref = None
     if self.chunks is not None:
-      if len(self.chunks) != len(self.shape) or self.chunks[1:] != self.shape[1:]:
+      if not _loaded and (len(self.chunks) != len(self.shape) or self.chunks[1:] != self.shape[1:]):
         raise ValueError("hdf5_lite: chunks must span the trailing axes: (c0, *shape[1:])")
-      self._disk_chunks = {}       # chunk index along axis 0 -> (address, stored size)
-      self._mem_chunks = {}        # chunk index -> ndarray [c0, *trailing] not yet on disk
-      self._value = None
-    else:
+      self._index = _ChunkIndex(self)
+      self._mem_chunks = {}        # chunk index along axis 0 -> ndarray [c0, *trailing] not yet on disk
+    elif not _loaded:
       self._value = None if self.dtype is VLEN_STR else np.zeros(self.shape, dtype=self.dtype)
-      self._contig_addr = None
 
   # -- h5py-like surface
   def __len__(self):
@@ -154,6 +380,10 @@ class Dataset:
   @property
   def ndim(self):
     return len(self.shape)
+
+  @property
+  def size(self):
+    return int(np.prod(self.shape, dtype=np.int64))
 
   def resize(self, size, axis=None):
     if self.chunks is None:
@@ -165,8 +395,9 @@ class Dataset:
       raise ValueError("hdf5_lite: only axis 0 can be resized")
     if self.maxshape[0] is not None and size[0] > self.maxshape[0]:
       raise ValueError("resize beyond maxshape")
+    self._file._writable()
     self.shape = size
-    self._file._dirty = True
+    self._dirty = self._file._dirty = True
 
   def _row_range(self, key):
     """Split an index into (row start, row stop, row-is-scalar, index for the trailing axes)."""
@@ -183,43 +414,86 @@ class Dataset:
       if not 0 <= k < self.shape[0]:
         raise IndexError("index out of range")
       return k, k + 1, True, rest
+    if not isinstance(key, slice):
+      raise IndexError("hdf5_lite: axis 0 takes an integer or a slice")
     start, stop, step = key.indices(self.shape[0])
     if step != 1:
       raise IndexError("hdf5_lite: step slicing is not supported")
     return start, max(stop, start), False, rest
 
+  def _decode(self, raw, count_shape):
+    if self.dtype is VLEN_STR:
+      n = int(np.prod(count_shape, dtype=np.int64))
+      vals = []
+      for i in range(n):
+        length, haddr, index = struct.unpack_from("<IQI", raw, 16 * i)
+        vals.append(self._file._heap_object(self._file._addr_in(haddr), index)[:length].decode("utf-8") if length else "")
+      return vals[0] if count_shape == () else np.array(vals, dtype=object).reshape(count_shape)
+    return np.frombuffer(raw, dtype=self.dtype).reshape(count_shape)
+
+  def _itemsize(self):
+    return 16 if self.dtype is VLEN_STR else self.dtype.itemsize
+
+  def _read_chunk(self, offsets):
+    """The chunk at `offsets` as an array of the chunk shape (zeros when it was never written)."""
+    hit = self._index.find(tuple(offsets) + (0,))
+    if hit is None:
+      return np.zeros(self.chunks, dtype=self.dtype)
+    addr, size, mask = hit
+    raw = _unfilter(self._file._read(addr, size), self._filters, mask, self._itemsize())
+    return self._decode(raw, self.chunks)
+
   def _load_chunk(self, ci):
     if ci in self._mem_chunks:
       return self._mem_chunks[ci]
-    if ci in self._disk_chunks:
-      addr, size = self._disk_chunks[ci]
-      raw = self._file._read(addr, size)
-      if self.compression == "gzip":
-        raw = zlib.decompress(raw)
-      return np.frombuffer(raw, dtype=self.dtype).reshape(self.chunks).copy()
-    return np.zeros(self.chunks, dtype=self.dtype)
+    return np.array(self._read_chunk((ci * self.chunks[0],) + (0,) * (len(self.chunks) - 1)))
 
   def __getitem__(self, key):
     if self.ndim == 0:
+      if self._value is None and self._data_addr is not None:
+        self._value = self._decode(self._file._read(self._data_addr, self._data_size), ())
+        if self.dtype is not VLEN_STR:
+          self._value = np.array(self._value)
       return self._value if self.dtype is VLEN_STR else self._value[()]
-    if self.chunks is None:
-      return self._value[key]
     r0, r1, scalar, rest = self._row_range(key)
-    out = np.zeros((r1 - r0,) + self.shape[1:], dtype=self.dtype)
-    c0 = self.chunks[0]
-    for ci in range(r0 // c0, (r1 + c0 - 1) // c0 if r1 > r0 else r0 // c0):
-      lo, hi = max(r0, ci * c0), min(r1, (ci + 1) * c0)
-      out[lo - r0:hi - r0] = self._load_chunk(ci)[lo - ci * c0:hi - ci * c0]
+    if self.chunks is None:
+      if self._value is not None:
+        out = self._value[r0:r1]
+      else:
+        row = int(np.prod(self.shape[1:], dtype=np.int64)) * self._itemsize()
+        raw = self._file._read(self._data_addr + r0 * row, (r1 - r0) * row) if self._data_addr is not None and r1 > r0 else b""
+        out = self._decode(raw, (r1 - r0,) + self.shape[1:])
+    else:
+      out = np.zeros((r1 - r0,) + self.shape[1:], dtype=self.dtype if self.dtype is not VLEN_STR else object)
+      c0 = self.chunks[0]
+      spans_rows = self.chunks[1:] == self.shape[1:]
+      for ci in range(r0 // c0, (r1 + c0 - 1) // c0 if r1 > r0 else r0 // c0):
+        lo, hi = max(r0, ci * c0), min(r1, (ci + 1) * c0)
+        if spans_rows:
+          out[lo - r0:hi - r0] = self._load_chunk(ci)[lo - ci * c0:hi - ci * c0]
+          continue
+        # general chunk grid: every chunk of this row block
+        grid = [range(0, s, c) for s, c in zip(self.shape[1:], self.chunks[1:])]
+        for offs in np.ndindex(*[len(g) for g in grid]):
+          corner = tuple(g[i] for g, i in zip(grid, offs))
+          chunk = self._read_chunk((ci * c0,) + corner)
+          ext = tuple(min(c, s - o) for c, s, o in zip(self.chunks[1:], self.shape[1:], corner))
+          dst = (slice(lo - r0, hi - r0),) + tuple(slice(o, o + e) for o, e in zip(corner, ext))
+          src = (slice(lo - ci * c0, hi - ci * c0),) + tuple(slice(0, e) for e in ext)
+          out[dst] = chunk[src]
     if scalar:
       return out[0][rest] if rest else out[0]
     return out[(slice(None),) + rest] if rest else out
 
   def __setitem__(self, key, value):
-    self._file._dirty = True
+    self._file._writable()
+    self._dirty = self._file._dirty = True
     if self.ndim == 0 or self.chunks is None:
       if self.dtype is VLEN_STR:
         self._value = value
       else:
+        if self._value is None:
+          self._value = np.array(self[...])
         self._value[key] = value
       return
     r0, r1, _, rest = self._row_range(key)
@@ -235,15 +509,15 @@ class Dataset:
         chunk = self._load_chunk(ci)
         chunk[lo - ci * c0:hi - ci * c0] = value[lo - r0:hi - r0]
       self._mem_chunks[ci] = chunk
-      self._disk_chunks.pop(ci, None)
     if len(self._mem_chunks) * int(np.prod(self.chunks)) * self.dtype.itemsize > (256 << 20):
       self._file._spill(self)
 
 
-class Group:
+class Group(_Object):
   def __init__(self, file):
-    self._file = file
+    _Object.__init__(self, file)
     self._members = {}
+    self._written_links = None    # {name: address} as serialised in the header on disk
 
   def _resolve(self, path, create=False):
     node = self
@@ -265,9 +539,10 @@ class Group:
 
   def __getitem__(self, path):
     node, leaf = self._resolve(path)
-    return node._members[leaf]
+    return node._members[leaf] if leaf else node
 
   def __delitem__(self, path):
+    self._file._writable()
     node, leaf = self._resolve(path)
     del node._members[leaf]
     self._file._dirty = True
@@ -278,10 +553,17 @@ class Group:
   def items(self):
     return self._members.items()
 
+  def values(self):
+    return self._members.values()
+
   def __iter__(self):
     return iter(self._members)
 
+  def __len__(self):
+    return len(self._members)
+
   def create_group(self, path):
+    self._file._writable()
     node, leaf = self._resolve(path, create=True)
     if leaf in node._members:
       raise ValueError(f"Unable to create group (name already exists): {path}")
@@ -291,6 +573,7 @@ class Group:
 
   def create_dataset(self, path, shape=None, dtype=None, data=None, maxshape=None, chunks=None, compression=None,
                      compression_opts=None, **_ignored):
+    self._file._writable()
     node, leaf = self._resolve(path, create=True)
     if leaf in node._members:
       raise ValueError(f"Unable to create dataset (name already exists): {path}")
@@ -310,6 +593,7 @@ class Group:
 
   def __setitem__(self, path, value):
     """h5py's implicit dataset creation: float -> f64, int -> i64, str -> vlen UTF-8, sequences -> arrays."""
+    self._file._writable()
     node, leaf = self._resolve(path, create=True)
     if isinstance(value, (str, bytes)):
       dset = Dataset(self._file, (), VLEN_STR)
@@ -336,6 +620,11 @@ class File(Group):
     self._dirty = False
     self._fh = None
     self._eof = 0
+    self._base = 0               # base address: every address in the file is relative to it (user block)
+    self._btree_k = BTREE_K
+    self._own_format = True      # version-2 superblock at offset 0: the layout this module can extend
+    self._heaps = {}
+    self.stats = {"bytes_written": 0, "bytes_read": 0}
     exists = os.path.exists(path) and os.path.getsize(path) > 0
     if mode == "r":
       if not exists:
@@ -346,6 +635,10 @@ class File(Group):
       if exists:
         self._fh = open(path, "r+b")
         _Reader(self).load()
+        if not self._own_format:
+          self._fh.close()
+          raise OSError("hdf5_lite can only append to files with a version-2 superblock (its own output); "
+                        "classic-layout files are read-only")
       elif mode == "r+":
         raise FileNotFoundError(path)
       else:
@@ -366,25 +659,70 @@ class File(Group):
     self.close()
     return False
 
+  def _writable(self):
+    if self.mode == "r":
+      raise OSError("hdf5_lite: file is open read-only")
+
+  # -- raw access: addresses handed around inside this module are ABSOLUTE file offsets
+  def _addr_in(self, addr):
+    return addr if addr == UNDEF else addr + self._base
+
+  def _addr_out(self, addr):
+    return addr if addr == UNDEF else addr - self._base
+
   def _read(self, addr, size):
     self._fh.seek(addr)
+    self.stats["bytes_read"] += size
     return self._fh.read(size)
 
-  def _append(self, blob, align=8):
-    """Write `blob` at the (aligned) end of file, return its address."""
-    addr = (max(self._eof, 48) + align - 1) // align * align
+  def _write(self, addr, blob):
     self._fh.seek(addr)
     self._fh.write(blob)
-    self._eof = addr + len(blob)
+    self.stats["bytes_written"] += len(blob)
+
+  def _alloc(self, size, align=8):
+    """Reserve `size` bytes at the (aligned) end of file."""
+    addr = (max(self._eof, 48) + align - 1) // align * align
+    self._eof = addr + size
     return addr
 
+  def _append(self, blob, align=8):
+    addr = self._alloc(len(blob), align)
+    self._write(addr, blob)
+    return addr
+
+  def _heap_object(self, addr, index):
+    if addr not in self._heaps:
+      head = self._read(addr, 16)
+      if head[:4] != b"GCOL":
+        raise OSError("bad global heap collection")
+      size = struct.unpack_from("<Q", head, 8)[0]
+      blob = self._read(addr, size)
+      objs, pos = {}, 16
+      while pos + 16 <= size:
+        idx, _ref, _res, osize = struct.unpack_from("<HHIQ", blob, pos)
+        if idx == 0:
+          break
+        objs[idx] = blob[pos + 16:pos + 16 + osize]
+        pos += 16 + (osize + 7) // 8 * 8
+      self._heaps[addr] = objs
+    return self._heaps[addr][index]
+
   def _spill(self, dset):
-    """Move a dataset's pending chunks to disk (bounded memory while appending many rows)."""
+    """Move a dataset's pending chunks to disk (bounded memory while appending many rows).  A chunk that is
+    already on disk keeps its address when the new bytes have the same length (always, without a filter)."""
+    c0, tail = dset.chunks[0], (0,) * len(dset.chunks)
     for ci in sorted(dset._mem_chunks):
       raw = np.ascontiguousarray(dset._mem_chunks[ci]).tobytes()
       if dset.compression == "gzip":
         raw = zlib.compress(raw, int(dset.compression_opts))
-      dset._disk_chunks[ci] = (self._append(raw), len(raw))
+      offsets = (ci * c0,) + tail
+      dset._index._right_edge()
+      old = dset._index.find(offsets) if dset._index.last is not None and offsets <= dset._index.last else None
+      if old is not None and old[1] == len(raw):
+        self._write(old[0], raw)
+      else:
+        dset._index.set(offsets, self._append(raw), len(raw))
     dset._mem_chunks.clear()
 
   def flush(self):
@@ -406,8 +744,14 @@ def _message(mtype, body, flags=0):
   return struct.pack("<BHB", mtype, len(body), flags) + body
 
 
-def _object_header(messages):
+def _object_header(messages, capacity=None):
+  """Version-2 object header; with a `capacity` (total bytes) the message area is filled up with a NIL message."""
   body = b"".join(messages)
+  if capacity is not None:
+    pad = capacity - 14 - len(body)          # 10 bytes prefix + 4 bytes checksum
+    assert pad == 0 or pad >= 4
+    if pad:
+      body += _message(MSG_NIL, b"\x00" * (pad - 4))
   # flags: chunk-0 size stored in 4 bytes (bits 0-1 = 2); no times, no attribute phase change
   head = b"OHDR" + bytes([2, 0x02]) + struct.pack("<I", len(body))
   blob = head + body
@@ -415,20 +759,26 @@ def _object_header(messages):
 
 
 class _Writer:
+  """Brings the file up to date with the object tree: pending chunks, then every object whose serialised form
+  changed -- in place when the form still has the size that was allocated for it."""
+
   def __init__(self, file):
     self.f = file
-    self.heap_objects = []     # payloads of the global heap collection of this session
 
   def write(self):
     f = self.f
-    # 1. pending chunk data first (it never moves afterwards)
+    # 1. pending chunk data and the B-tree nodes it touched
     for dset in self._datasets(f):
       if dset.chunks is not None:
-        f._spill(dset)
-    # 2. global heap for variable-length strings: its address must be known before the
-    #    datasets that point into it are serialised
-    strings = [d for d in self._datasets(f) if d.dtype is VLEN_STR]
-    heap_addr = None
+        if dset._mem_chunks:
+          f._spill(dset)
+        dset._index.flush()
+        if dset._index.root_moved:
+          dset._dirty = True
+          dset._index.root_moved = False
+    # 2. global heap for the variable-length strings that changed: its address must be known before the datasets
+    #    that point into it are serialised
+    strings = [d for d in self._datasets(f) if d.dtype is VLEN_STR and d._dirty and d._value is not None]
     if strings:
       payloads = [str(d._value).encode("utf-8") for d in strings]
       heap_addr = f._append(self._global_heap(payloads))
@@ -437,11 +787,9 @@ class _Writer:
     # 3. metadata bottom-up
     root_addr = self._write_group(f)
     # 4. superblock
-    eof = f._eof
-    sb = SIGNATURE + bytes([2, 8, 8, 0]) + struct.pack("<QQQQ", 0, UNDEF, eof, root_addr)
+    sb = SIGNATURE + bytes([2, 8, 8, 0]) + struct.pack("<QQQQ", 0, UNDEF, f._eof, root_addr)
     sb += struct.pack("<I", lookup3(sb))
-    f._fh.seek(0)
-    f._fh.write(sb)
+    f._write(0, sb)
     f._fh.flush()
 
   def _datasets(self, group):
@@ -462,28 +810,48 @@ class _Writer:
     body += struct.pack("<HHIQ", 0, 0, 0, free) + b"\x00" * (free - 16)   # object 0: the free space
     return b"GCOL" + bytes([1, 0, 0, 0]) + struct.pack("<Q", size) + body
 
+  def _place(self, obj, blob):
+    """Write a serialised header over the object's old one when it has the same size, else at the end of file."""
+    f = self.f
+    if obj._addr is not None and len(blob) == obj._cap:
+      f._write(obj._addr, blob)
+    else:
+      obj._addr, obj._cap = f._append(blob), len(blob)
+    obj._dirty = False
+    return obj._addr
+
   def _write_group(self, group):
-    links = []
+    links = {}
     for name, obj in group._members.items():
-      addr = self._write_dataset(obj) if isinstance(obj, Dataset) else self._write_group(obj)
+      links[name] = self._write_dataset(obj) if isinstance(obj, Dataset) else self._write_group(obj)
+    if group._addr is not None and links == group._written_links:
+      return group._addr
+    msgs = [_message(MSG_LINKINFO, bytes([0, 0]) + struct.pack("<QQ", UNDEF, UNDEF)), _message(MSG_GROUPINFO, bytes([0, 0]))]
+    for name, addr in links.items():
       nb = name.encode("utf-8")
       # link message v1: flags = 0x10|size-of-length field (bit 4: character set present -> UTF-8), hard link
       size_code = 0 if len(nb) < 256 else 1
       body = bytes([1, 0x10 | size_code, 1]) + (struct.pack("<B", len(nb)) if size_code == 0 else struct.pack("<H", len(nb)))
-      body += nb + struct.pack("<Q", addr)
-      links.append(_message(MSG_LINK, body))
-    link_info = _message(MSG_LINKINFO, bytes([0, 0]) + struct.pack("<QQ", UNDEF, UNDEF))
-    group_info = _message(MSG_GROUPINFO, bytes([0, 0]))
-    return self.f._append(_object_header([link_info, group_info] + links))
+      msgs.append(_message(MSG_LINK, body + nb + struct.pack("<Q", addr)))
+    need = 14 + sum(len(m) for m in msgs)
+    if group._addr is not None and (need == group._cap or need + 4 <= group._cap):
+      capacity = group._cap
+    else:
+      capacity = (need + GROUP_HEADER_SLACK + 7) // 8 * 8
+      group._addr = None
+    group._written_links = links
+    return self._place(group, _object_header(msgs, capacity))
 
   def _write_dataset(self, d):
+    if d._addr is not None and not d._dirty:
+      return d._addr
     f = self.f
     rank = len(d.shape)
     # dataspace v2
     if rank == 0:
       space = bytes([2, 0, 0, 0])
     else:
-      has_max = d.maxshape != d.shape
+      has_max = d.maxshape != d.shape or d.chunks is not None
       space = bytes([2, rank, 1 if has_max else 0, 1]) + b"".join(struct.pack("<Q", s) for s in d.shape)
       if has_max:
         space += b"".join(struct.pack("<Q", UNLIMITED if m is None else m) for m in d.maxshape)
@@ -493,210 +861,355 @@ class _Writer:
       if d.compression == "gzip":
         filt = struct.pack("<HHHI", 1, 1, 1, int(d.compression_opts))   # deflate, optional, one client value
         msgs.append(_message(MSG_FILTERS, bytes([2, 1]) + filt))
-      btree = self._write_chunk_btree(d)
       itemsize = d.dtype.itemsize
-      layout = bytes([3, 2, rank + 1]) + struct.pack("<Q", btree)
+      layout = bytes([3, 2, rank + 1]) + struct.pack("<Q", d._index.root)
       layout += b"".join(struct.pack("<I", c) for c in d.chunks) + struct.pack("<I", itemsize)
     else:
       msgs.append(_message(MSG_FILLVALUE, bytes([3, 0x0A])))          # late allocation, fill if set
       if d.dtype is VLEN_STR:
         raw = d._heap_ref
-      else:
+      elif d._value is not None:
         raw = np.ascontiguousarray(d._value, dtype=d.dtype).tobytes()
-      addr = f._append(raw) if raw else UNDEF
-      layout = bytes([3, 1]) + struct.pack("<QQ", addr, len(raw))
+      else:
+        raw = None                                                    # untouched since it was loaded
+      if raw is not None:
+        if d._data_addr is not None and len(raw) == d._data_size:
+          f._write(d._data_addr, raw)
+        else:
+          d._data_addr, d._data_size = (f._append(raw) if raw else None), len(raw)
+      layout = bytes([3, 1]) + struct.pack("<QQ", d._data_addr if d._data_addr is not None else UNDEF, d._data_size)
     msgs.append(_message(MSG_LAYOUT, layout))
-    return f._append(_object_header(msgs))
-
-  def _write_chunk_btree(self, d):
-    """Static bulk-loaded v1 B-tree (node type 1) over the chunks along axis 0."""
-    f = self.f
-    rank = len(d.shape)
-    c0 = d.chunks[0]
-    n_chunks = (d.shape[0] + c0 - 1) // c0
-
-    def key(size, row):
-      return struct.pack("<II", size, 0) + struct.pack("<Q", row) + b"\x00" * (8 * rank)
-
-    key_len = 8 + 8 * (rank + 1)
-    node_len = 24 + (2 * BTREE_K + 1) * key_len + 2 * BTREE_K * 8
-    entries = []     # (first row, stored size, child address)
-    for ci in range(n_chunks):
-      if ci in d._disk_chunks:
-        addr, size = d._disk_chunks[ci]
-        entries.append((ci * c0, size, addr))
-    level = 0
-    if not entries:
-      blob = b"TREE" + bytes([1, 0]) + struct.pack("<HQQ", 0, UNDEF, UNDEF)
-      return f._append(blob + b"\x00" * (node_len - len(blob)))
-    end_row = (entries[-1][0] // c0 + 1) * c0
-    while True:
-      groups = [entries[i:i + 2 * BTREE_K] for i in range(0, len(entries), 2 * BTREE_K)]
-      base = (max(f._eof, 48) + 7) // 8 * 8
-      addrs = [base + i * node_len for i in range(len(groups))]
-      parents = []
-      for gi, grp in enumerate(groups):
-        left = addrs[gi - 1] if gi > 0 else UNDEF
-        right = addrs[gi + 1] if gi + 1 < len(groups) else UNDEF
-        blob = b"TREE" + bytes([1, level]) + struct.pack("<HQQ", len(grp), left, right)
-        for row, size, child in grp:
-          blob += key(size, row) + struct.pack("<Q", child)
-        last_row = groups[gi + 1][0][0] if gi + 1 < len(groups) else end_row
-        blob += key(0, last_row)
-        blob += b"\x00" * (node_len - len(blob))
-        got = f._append(blob)
-        assert got == addrs[gi]
-        parents.append((grp[0][0], grp[0][1], got))
-      if len(parents) == 1:
-        return parents[0][2]
-      entries, level = parents, level + 1
+    return self._place(d, _object_header(msgs))
 
 
-# ---- reader (independent walk over the structures above) -------------------------------------------------
+# ---- reader ---------------------------------------------------------------------------------------------
 class _Reader:
+  """Superblock, groups and dataset headers of a file (both generations of each); no raw data, no B-tree node
+  is read before it is asked for."""
+
   def __init__(self, file):
     self.f = file
-    self.heaps = {}
 
   def load(self):
     f = self.f
-    head = f._read(0, 48)
-    if head[:8] != SIGNATURE or head[8] != 2:
-      raise OSError("hdf5_lite can only reopen files with a version-2 superblock (its own output)")
-    if struct.unpack_from("<I", head, 44)[0] != lookup3(head[:44]):
-      raise OSError("superblock checksum mismatch")
-    _base, _ext, eof, root = struct.unpack_from("<QQQQ", head, 12)
-    f._eof = eof
+    size = os.fstat(f._fh.fileno()).st_size
+    offset = 0
+    while True:                                          # the superblock sits at 0, 512, 1024, 2048 ... (user block)
+      if offset + 8 > size:
+        raise OSError(f"hdf5_lite: {f.filename} is not an HDF5 file")
+      if f._read(offset, 8) == SIGNATURE:
+        break
+      offset = 512 if offset == 0 else offset * 2
+    head = f._read(offset, 128)
+    version = head[8]
+    if version in (2, 3):
+      if head[9] != 8 or head[10] != 8:
+        raise OSError("hdf5_lite: only 8-byte offsets and lengths are supported")
+      if struct.unpack_from("<I", head, 44)[0] != lookup3(head[:44]):
+        raise OSError("superblock checksum mismatch")
+      base, _ext, eof, root = struct.unpack_from("<QQQQ", head, 12)
+      f._base = base if base != UNDEF else 0
+      f._eof = f._addr_in(eof)
+      f._own_format = offset == 0 and f._base == 0 and version == 2
+      root = f._addr_in(root)
+    elif version in (0, 1):
+      if head[13] != 8 or head[14] != 8:
+        raise OSError("hdf5_lite: only 8-byte offsets and lengths are supported")
+      pos = 24
+      if version == 1:
+        f._btree_k = struct.unpack_from("<H", head, 24)[0] or BTREE_K
+        pos = 28
+      base, _free, eof, _drv = struct.unpack_from("<QQQQ", head, pos)
+      f._base = base
+      f._eof = f._addr_in(eof)
+      f._own_format = False
+      root = f._addr_in(struct.unpack_from("<Q", head, pos + 32 + 8)[0])     # symbol-table entry: name offset, header address
+    else:
+      raise OSError(f"hdf5_lite: unsupported superblock version {version}")
+    f._addr, f._cap = root, None
     self._load_group(f, root)
 
+  # -- object headers
   def _messages(self, addr):
+    """[(type, body, flags)] of the object header at `addr`, continuation blocks included; also its size when it
+    is a single block (the space an in-place rewrite may use)."""
     f = self.f
     head = f._read(addr, 16)
-    if head[:4] != b"OHDR" or head[4] != 2:
-      raise OSError("unsupported object header")
-    flags = head[5]
-    pos = 6
-    if flags & 0x20:
-      pos += 16
-    if flags & 0x10:
-      pos += 4
-    width = 1 << (flags & 3)
-    size = int.from_bytes(head[pos:pos + width], "little")
-    pos += width
-    blob = f._read(addr, pos + size + 4)
-    if struct.unpack_from("<I", blob, pos + size)[0] != lookup3(blob[:pos + size]):
-      raise OSError("object header checksum mismatch")
-    end = pos + size
     out = []
-    while pos + 4 <= end:
-      mtype, msize, _mflags = struct.unpack_from("<BHB", blob, pos)
-      pos += 4
-      if flags & 0x04:
-        pos += 2
-      out.append((mtype, blob[pos:pos + msize]))
-      pos += msize
+    if head[:4] == b"OHDR":
+      if head[4] != 2:
+        raise OSError("unsupported object header version")
+      flags = head[5]
+      pos = 6
+      if flags & 0x20:
+        pos += 16
+      if flags & 0x10:
+        pos += 4
+      width = 1 << (flags & 3)
+      size = int.from_bytes(head[pos:pos + width] if pos + width <= 16 else f._read(addr + pos, width), "little")
+      pos += width
+      blob = f._read(addr, pos + size + 4)
+      if struct.unpack_from("<I", blob, pos + size)[0] != lookup3(blob[:pos + size]):
+        raise OSError("object header checksum mismatch")
+      blocks = [(blob, pos, pos + size)]
+      total = pos + size + 4
+      while blocks:
+        blob, pos, end = blocks.pop(0)
+        while pos + 4 <= end:
+          mtype, msize, mflags = struct.unpack_from("<BHB", blob, pos)
+          pos += 4
+          if flags & 0x04:
+            pos += 2
+          body = blob[pos:pos + msize]
+          pos += msize
+          if mtype == MSG_CONTINUATION:
+            caddr, clen = struct.unpack_from("<QQ", body)
+            cblob = f._read(f._addr_in(caddr), clen)
+            if cblob[:4] != b"OCHK":
+              raise OSError("bad object header continuation block")
+            blocks.append((cblob, 4, clen - 4))
+            total = None
+          elif mtype != MSG_NIL:
+            out.append((mtype, body, mflags))
+      return out, total
+    if head[0] != 1:
+      raise OSError("unsupported object header")
+    n_msgs = struct.unpack_from("<H", head, 2)[0]
+    size = struct.unpack_from("<I", head, 8)[0]
+    blocks = [(f._read(addr + 16, size), 0, size)]
+    while blocks and len(out) < n_msgs + 64:
+      blob, pos, end = blocks.pop(0)
+      while pos + 8 <= end:
+        mtype, msize, mflags = struct.unpack_from("<HHB", blob, pos)
+        pos += 8
+        body = blob[pos:pos + msize]
+        pos += msize
+        if mtype == MSG_CONTINUATION:
+          caddr, clen = struct.unpack_from("<QQ", body)
+          blocks.append((f._read(f._addr_in(caddr), clen), 0, clen))
+        elif mtype != MSG_NIL:
+          out.append((mtype, body, mflags))
+    return out, None
+
+  # -- groups
+  def _load_group(self, group, addr, messages=None):
+    f = self.f
+    if messages is None:
+      messages, total = self._messages(addr)
+      group._addr, group._cap = addr, total
+    group._dirty = False
+    group._written_links = {}
+    for mtype, body, _ in messages:
+      if mtype == MSG_LINK:
+        name, child = self._link(body)
+        if child is not None:
+          self._attach(group, name, child)
+      elif mtype == MSG_LINKINFO:
+        flags = body[1]
+        pos = 2 + (8 if flags & 1 else 0)
+        heap = struct.unpack_from("<Q", body, pos)[0]
+        if heap != UNDEF:
+          raise OSError("hdf5_lite: groups with dense link storage are not supported")
+      elif mtype == MSG_SYMBOLTABLE:
+        btree, heap = (f._addr_in(a) for a in struct.unpack_from("<QQ", body))
+        for name, child in self._symbol_table(btree, heap):
+          self._attach(group, name, child)
+      elif mtype == MSG_ATTRIBUTE:
+        self._attribute(group, body)
+
+  def _attach(self, group, name, child):
+    messages, total = self._messages(child)
+    kinds = {m for m, _, _ in messages}
+    if MSG_LAYOUT in kinds:
+      obj = self._load_dataset(child, messages)
+    else:
+      obj = Group(self.f)
+      self._load_group(obj, child, messages)
+    obj._addr, obj._cap, obj._dirty = child, total, False
+    group._members[name] = obj
+    group._written_links[name] = child
+
+  def _link(self, body):
+    flags = body[1]
+    pos = 2
+    ltype = 0
+    if flags & 0x08:
+      ltype = body[pos]
+      pos += 1
+    if flags & 0x04:
+      pos += 8
+    if flags & 0x10:
+      pos += 1
+    width = 1 << (flags & 3)
+    nlen = int.from_bytes(body[pos:pos + width], "little")
+    pos += width
+    name = body[pos:pos + nlen].decode("utf-8")
+    if ltype != 0:
+      return name, None                       # soft / external links are not followed
+    return name, self.f._addr_in(struct.unpack_from("<Q", body, pos + nlen)[0])
+
+  def _symbol_table(self, btree, heap):
+    """(name, object header address) of a classic group: group B-tree (node type 0) over symbol-table nodes, names in
+    the local heap."""
+    f = self.f
+    head = f._read(heap, 32)
+    if head[:4] != b"HEAP":
+      raise OSError("bad local heap")
+    seg_size, _free, seg_addr = struct.unpack_from("<QQQ", head, 8)
+    names = f._read(f._addr_in(seg_addr), seg_size)
+    out = []
+
+    def node(addr):
+      raw = f._read(addr, 24)
+      if raw[:4] == b"SNOD":
+        count = struct.unpack_from("<H", raw, 6)[0]
+        body = f._read(addr + 8, count * 40)
+        for i in range(count):
+          name_off, obj = struct.unpack_from("<QQ", body, 40 * i)
+          cache_type = struct.unpack_from("<I", body, 40 * i + 16)[0]
+          if cache_type == 2:
+            continue                            # symbolic link
+          end = names.index(b"\x00", name_off)
+          out.append((names[name_off:end].decode("utf-8"), f._addr_in(obj)))
+        return
+      if raw[:4] != b"TREE" or raw[4] != 0:
+        raise OSError("bad group B-tree node")
+      used = struct.unpack_from("<H", raw, 6)[0]
+      body = f._read(addr + 24, used * 16 + 8)
+      for i in range(used):
+        node(f._addr_in(struct.unpack_from("<Q", body, 8 + 16 * i)[0]))
+
+    if btree != UNDEF:
+      node(btree)
     return out
 
-  def _load_group(self, group, addr):
-    for mtype, body in self._messages(addr):
-      if mtype != MSG_LINK:
-        continue
-      flags = body[1]
-      pos = 2
-      if flags & 0x08:
-        if body[pos] != 0:
-          raise OSError("only hard links are supported")
-        pos += 1
-      if flags & 0x04:
-        pos += 8
-      if flags & 0x10:
-        pos += 1
-      width = 1 << (flags & 3)
-      nlen = int.from_bytes(body[pos:pos + width], "little")
-      pos += width
-      name = body[pos:pos + nlen].decode("utf-8")
-      child = struct.unpack_from("<Q", body, pos + nlen)[0]
-      kinds = {m for m, _ in self._messages(child)}
-      if MSG_LAYOUT in kinds:
-        group._members[name] = self._load_dataset(child)
-      else:
-        sub = Group(self.f)
-        self._load_group(sub, child)
-        group._members[name] = sub
+  # -- datasets
+  @staticmethod
+  def _dataspace(body):
+    version, rank, flags = body[0], body[1], body[2]
+    pos = 8 if version == 1 else 4
+    shape = struct.unpack_from("<%dQ" % rank, body, pos) if rank else ()
+    maxshape = None
+    if flags & 1:
+      mx = struct.unpack_from("<%dQ" % rank, body, pos + 8 * rank)
+      maxshape = tuple(None if m == UNLIMITED else m for m in mx)
+    if version == 2 and body[3] == 2:
+      shape = (0,)                               # null dataspace
+    return tuple(shape), maxshape
 
-  def _load_dataset(self, addr):
+  @staticmethod
+  def _filters(body):
+    version, count = body[0], body[1]
+    pos = 8 if version == 1 else 2
+    out = []
+    for _ in range(count):
+      fid = struct.unpack_from("<H", body, pos)[0]
+      pos += 2
+      nlen = 0
+      if version == 1 or fid >= 256:
+        nlen = struct.unpack_from("<H", body, pos)[0]
+        pos += 2
+      _fflags, ncv = struct.unpack_from("<HH", body, pos)
+      pos += 4
+      pos += (nlen + 7) // 8 * 8 if version == 1 else nlen
+      cdata = struct.unpack_from("<%dI" % ncv, body, pos)
+      pos += 4 * ncv
+      if version == 1 and ncv % 2:
+        pos += 4
+      out.append((fid, cdata))
+    return out
+
+  def _load_dataset(self, addr, messages):
     f = self.f
-    shape, maxshape, dtype, layout, gzip_level = (), None, None, None, None
-    for mtype, body in self._messages(addr):
+    shape, maxshape, dtype, layout, filters = (), None, None, None, []
+    attrs = []
+    for mtype, body, _ in messages:
       if mtype == MSG_DATASPACE:
-        rank, flags = body[1], body[2]
-        shape = struct.unpack_from("<%dQ" % rank, body, 4) if rank else ()
-        if flags & 1:
-          mx = struct.unpack_from("<%dQ" % rank, body, 4 + 8 * rank)
-          maxshape = tuple(None if m == UNLIMITED else m for m in mx)
+        shape, maxshape = self._dataspace(body)
       elif mtype == MSG_DATATYPE:
         dtype = _decode_dtype(body)
       elif mtype == MSG_LAYOUT:
         layout = body
       elif mtype == MSG_FILTERS:
-        if body[0] != 2 or body[1] != 1 or struct.unpack_from("<H", body, 2)[0] != 1:
-          raise OSError("only a single deflate filter is supported")
-        gzip_level = struct.unpack_from("<I", body, 8)[0]
-    if layout[0] != 3:
-      raise OSError("unsupported layout message version")
-    if layout[1] == 2:
-      rank = layout[2] - 1
-      btree = struct.unpack_from("<Q", layout, 3)[0]
-      chunks = struct.unpack_from("<%dI" % rank, layout, 11)
-      d = Dataset(f, shape, dtype, maxshape=maxshape, chunks=chunks, compression="gzip" if gzip_level is not None else None,
-                  compression_opts=gzip_level)
-      self._walk_btree(btree, d)
-      return d
-    if layout[1] != 1:
-      raise OSError("unsupported layout class")
-    caddr, csize = struct.unpack_from("<QQ", layout, 2)
-    d = Dataset(f, shape, dtype, maxshape=maxshape)
-    raw = f._read(caddr, csize) if caddr != UNDEF and csize else b""
-    if dtype is VLEN_STR:
-      length, haddr, index = struct.unpack("<IQI", raw)
-      d._value = self._heap_object(haddr, index)[:length].decode("utf-8")
+        filters = self._filters(body)
+      elif mtype == MSG_ATTRIBUTE:
+        attrs.append(body)
+    version = layout[0]
+    if version == 3:
+      cls = layout[1]
+      if cls == 2:
+        rank = layout[2] - 1
+        btree = struct.unpack_from("<Q", layout, 3)[0]
+        chunks = struct.unpack_from("<%dI" % rank, layout, 11)
+      elif cls == 1:
+        caddr, csize = struct.unpack_from("<QQ", layout, 2)
+      elif cls == 0:
+        csize = struct.unpack_from("<H", layout, 2)[0]
+        compact = layout[4:4 + csize]
+      else:
+        raise OSError("unsupported layout class")
+    elif version in (1, 2):
+      rank, cls = layout[1], layout[2]
+      pos = 8
+      if cls != 0:
+        caddr = btree = struct.unpack_from("<Q", layout, pos)[0]
+        pos += 8
+      dims = struct.unpack_from("<%dI" % rank, layout, pos)
+      pos += 4 * rank
+      if cls == 2:
+        chunks, rank = dims[:-1], rank - 1
+      elif cls == 1:
+        csize = None
+      elif cls == 0:
+        csize = struct.unpack_from("<I", layout, pos)[0]
+        compact = layout[pos + 4:pos + 4 + csize]
     else:
-      d._value = np.frombuffer(raw, dtype=dtype).reshape(shape).copy()
+      raise OSError(f"hdf5_lite: unsupported layout message version {version}")
+    if cls == 2:
+      gzip = next((c[0] if c else 4 for i, c in filters if i == 1), None)
+      d = Dataset(f, shape, dtype, maxshape=maxshape, chunks=chunks, compression="gzip" if gzip is not None else None,
+                  compression_opts=gzip, _loaded=True)
+      d._filters = filters
+      d._index.root = f._addr_in(btree) if btree != UNDEF else None
+    else:
+      d = Dataset(f, shape, dtype, maxshape=maxshape, _loaded=True)
+      if cls == 1:
+        itemsize = 16 if dtype is VLEN_STR else dtype.itemsize
+        d._data_addr = f._addr_in(caddr) if caddr != UNDEF else None
+        d._data_size = csize if csize is not None else int(np.prod(shape, dtype=np.int64)) * itemsize
+        if d._data_addr is None:
+          d._value = "" if dtype is VLEN_STR else np.zeros(shape, dtype=dtype)
+      else:
+        d._value = d._decode(compact, tuple(shape))
+        if dtype is not VLEN_STR:
+          d._value = np.array(d._value)
+    for body in attrs:
+      self._attribute(d, body)
     return d
 
-  def _walk_btree(self, addr, d):
-    f = self.f
-    rank = len(d.shape)
-    key_len = 8 + 8 * (rank + 1)
-    head = f._read(addr, 24)
-    if head[:4] != b"TREE" or head[4] != 1:
-      raise OSError("bad chunk B-tree node")
-    level, used = head[5], struct.unpack_from("<H", head, 6)[0]
-    body = f._read(addr + 24, used * (key_len + 8) + key_len)
-    for i in range(used):
-      off = i * (key_len + 8)
-      size = struct.unpack_from("<I", body, off)[0]
-      row = struct.unpack_from("<Q", body, off + 8)[0]
-      child = struct.unpack_from("<Q", body, off + key_len)[0]
-      if level == 0:
-        d._disk_chunks[row // d.chunks[0]] = (child, size)
-      else:
-        self._walk_btree(child, d)
-
-  def _heap_object(self, addr, index):
-    f = self.f
-    if addr not in self.heaps:
-      head = f._read(addr, 16)
-      if head[:4] != b"GCOL":
-        raise OSError("bad global heap collection")
-      size = struct.unpack_from("<Q", head, 8)[0]
-      blob = f._read(addr, size)
-      objs, pos = {}, 16
-      while pos + 16 <= size:
-        idx, _ref, _res, osize = struct.unpack_from("<HHIQ", blob, pos)
-        if idx == 0:
-          break
-        objs[idx] = blob[pos + 16:pos + 16 + osize]
-        pos += 16 + (osize + 7) // 8 * 8
-      self.heaps[addr] = objs
-    return self.heaps[addr][index]
+  def _attribute(self, obj, body):
+    """Attributes of the simple types; anything else is skipped."""
+    try:
+      version = body[0]
+      name_size, type_size, space_size = struct.unpack_from("<HHH", body, 2)
+      pos = 8 + (1 if version == 3 else 0)
+      pad = (lambda n: (n + 7) // 8 * 8) if version == 1 else (lambda n: n)
+      name = body[pos:pos + name_size].split(b"\x00")[0].decode("utf-8")
+      pos += pad(name_size)
+      type_body = body[pos:pos + type_size]
+      pos += pad(type_size)
+      shape, _ = self._dataspace(body[pos:pos + space_size])
+      pos += pad(space_size)
+      dtype = _decode_dtype(type_body)
+      holder = Dataset(self.f, shape, dtype, _loaded=True)
+      n = int(np.prod(shape, dtype=np.int64))
+      value = holder._decode(body[pos:pos + n * holder._itemsize()], tuple(shape))
+      if dtype is not VLEN_STR:
+        value = np.array(value)
+        if value.dtype.kind == "S":
+          value = value[()] if value.ndim == 0 else value
+        elif value.ndim == 0:
+          value = value[()]
+      obj.attrs[name] = value
+    except Exception:
+      pass

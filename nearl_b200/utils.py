@@ -3,10 +3,15 @@
 ``dump_dict`` (a group of scalar / 1-D datasets, recreated on every call).
 
 Back-end: ``h5py`` when it is importable, otherwise the self-contained writer/reader in
-``nearl_b200.hdf5_lite`` (this image has neither h5py nor libhdf5); both produce files that
-stock h5py opens with the layout of the reference.  While a ``batched_output()`` context is
-active (the featuriser opens one per trajectory) appends are buffered per (file, key) and
-written with one open/close per file, instead of the reference's open/close per result.
+``nearl_b200.hdf5_lite`` (this image has neither h5py nor libhdf5); both produce files with the layout of
+the reference.  The reference opens and closes the file once per result; here
+
+  * inside ``hdf_session()`` (the featuriser holds one for the length of ``run()`` / ``loop_by_residue()``) a file
+    opened for appending stays open until the session ends -- every ``open_hdf(path, "a")`` hands out the same
+    handle -- so its metadata is read once per run, not once per trajectory;
+  * inside ``batched_output()`` (one per trajectory) appends are buffered per (file, key) and written with one
+    resize per dataset; the file's metadata is brought up to date when the context exits, so that what is on
+    disk after every trajectory is a complete, readable file.
 """
 import contextlib
 import sys
@@ -20,20 +25,84 @@ except Exception:          # pragma: no cover - depends on the image
 
 from . import constants, hdf5_lite
 
-__all__ = ["append_hdf_data", "dump_dict", "batched_output", "open_hdf", "hdf_backend", "find_block_single", "find_block_dual", "dual_blocks_by_key"]
+__all__ = ["append_hdf_data", "dump_dict", "batched_output", "hdf_session", "open_hdf", "hdf_backend", "find_block_single",
+           "find_block_dual", "dual_blocks_by_key"]
 
 _pending = None     # {(file, key): {"rows": [...], "dtype":, "maxshape":, "kwargs":}} while batching
+_session = None     # {path: open file} while an hdf_session is active
 
 
 def hdf_backend():
   return "h5py" if _h5py is not None else "hdf5_lite"
 
 
+class _Borrowed:
+  """A file of the active session, handed out by open_hdf: leaving its `with` block (or close()) only flushes."""
+
+  def __init__(self, hdf):
+    self._hdf = hdf
+
+  def __enter__(self):
+    return self._hdf
+
+  def __exit__(self, *exc):
+    self._hdf.flush()
+    return False
+
+  def close(self):
+    self._hdf.flush()
+
+  def __getattr__(self, name):
+    return getattr(self._hdf, name)
+
+  def __contains__(self, key):
+    return key in self._hdf
+
+  def __getitem__(self, key):
+    return self._hdf[key]
+
+  def __setitem__(self, key, value):
+    self._hdf[key] = value
+
+  def __delitem__(self, key):
+    del self._hdf[key]
+
+
+def _open(path, mode):
+  return _h5py.File(path, mode) if _h5py is not None else hdf5_lite.File(path, mode)
+
+
 def open_hdf(path, mode="r"):
   """File object with the subset of the h5py API this package uses."""
-  if _h5py is not None:
-    return _h5py.File(path, mode)
-  return hdf5_lite.File(path, mode)
+  if _session is not None:
+    import os
+    key = os.path.abspath(path)
+    if mode in ("a", "r+"):
+      if key not in _session:
+        _session[key] = _open(path, mode)
+      return _Borrowed(_session[key])
+    if key in _session:
+      if mode == "r":
+        _session[key].flush()                  # a reader sees what the session has written so far
+      else:
+        _session.pop(key).close()              # "w": the file is about to be truncated
+  return _open(path, mode)
+
+
+@contextlib.contextmanager
+def hdf_session():
+  """Keep every file opened for appending open until the context exits (nested sessions join the outer one)."""
+  global _session
+  if _session is not None:
+    yield
+    return
+  _session = {}
+  try:
+    yield
+  finally:
+    session, _session = _session, None
+    for hdf in session.values():
+      hdf.close()
 
 
 def _append_now(hdf, key, data, dtype, maxshape, **kwargs):

@@ -1,0 +1,197 @@
+"""hdf5_lite: appends cost O(log rows) (metadata updated in place, B-tree right edge only), files re-open lazily, and the
+classic-layout reader agrees with a file written by libhdf5 itself."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from nearl_b200 import hdf5_lite, utils
+
+
+def _rows(n, shape=(2, 2, 2), seed=0):
+  return np.random.default_rng(seed).random((n, *shape)).astype(np.float32)
+
+
+def test_append_is_in_place_and_logarithmic(tmp_path):
+  """6 000 one-row chunks: a three-level B-tree (64 children per node).  The file holds the data once plus one node per 64
+  chunks; what an append WRITES does not grow with the number of rows already there."""
+  path = str(tmp_path / "big.h5")
+  rows = _rows(6000)
+  written = []
+  for start in range(0, 6000, 100):
+    with hdf5_lite.File(path, "a") as h:
+      utils._append_now(h, "feat", rows[start:start + 100], np.float32, (None, 2, 2, 2), chunks=(1, 2, 2, 2))
+      if start % 1000 == 0:
+        utils._append_now(h, "gz", rows[start:start + 100], np.float32, (None, 2, 2, 2), chunks=(1, 2, 2, 2), compression="gzip",
+                          compression_opts=4)
+    written.append(h.stats["bytes_written"])
+  plain = [w for i, w in enumerate(written) if i % 10]             # the appends that did not touch "gz" as well
+  assert max(plain[27:]) <= 1.3 * max(plain[:9])                   # bytes per append are flat (a new internal node now and then)
+  with hdf5_lite.File(path, "r") as h:
+    read_at_open = h.stats["bytes_read"]
+    assert h["feat"].shape == (6000, 2, 2, 2) and h["feat"].chunks == (1, 2, 2, 2) and h["feat"].maxshape == (None, 2, 2, 2)
+    assert np.array_equal(h["feat"][4321], rows[4321])
+    assert h.stats["bytes_read"] - read_at_open < 4 * h["feat"]._index.node_len + 64      # one node per level + the chunk
+    assert np.array_equal(h["feat"][:], rows)
+    assert np.array_equal(h["gz"][:], np.concatenate([rows[s:s + 100] for s in range(0, 6000, 1000)]))
+    entries = list(h["feat"]._index.walk())
+    assert [e[0][0] for e in entries] == list(range(6000))
+    assert h["feat"]._index._node(h["feat"]._index.root).level == 2
+  assert read_at_open < 2048                                      # headers only: no B-tree node, no raw data
+  data = 6000 * 32 + 600 * 32
+  nodes = (6000 // 64 + 6000 // 4096 + 4 + 600 // 64 + 2) * h["feat"]._index.node_len
+  assert os.path.getsize(path) < data + nodes + 16384              # data once + one node per 64 chunks
+
+
+def test_overwrite_gap_fill_and_group_growth(tmp_path):
+  path = str(tmp_path / "o.h5")
+  rows = _rows(300, seed=1)
+  with hdf5_lite.File(path, "w") as h:
+    d = h.create_dataset("a", (300, 2, 2, 2), dtype=np.float32, maxshape=(None, 2, 2, 2), chunks=(1, 2, 2, 2))
+    d[200:300] = rows[200:300]          # out of order: the front of the dataset is a gap ...
+    d[0:100] = rows[0:100]              # ... filled afterwards (tree rebuilt around the sorted entries)
+    z = h.create_dataset("z", (10, 2, 2, 2), dtype=np.float32, maxshape=(None, 2, 2, 2), chunks=(4, 2, 2, 2), compression="gzip")
+    z[0:10] = rows[0:10]
+  size0 = os.path.getsize(path)
+  with hdf5_lite.File(path, "a") as h:
+    assert np.array_equal(h["a"][0:100], rows[0:100]) and np.array_equal(h["a"][200:300], rows[200:300])
+    assert not h["a"][100:200].any()                                 # never written: fill value
+    h["a"][10:20] = rows[110:120]                                    # same size, no filter: chunks rewritten where they are
+    h["z"][3:6] = rows[50:53]                                        # partial chunks of a compressed dataset
+  assert os.path.getsize(path) - size0 < 1024
+  with hdf5_lite.File(path, "a") as h:
+    assert np.array_equal(h["a"][10:20], rows[110:120]) and np.array_equal(h["a"][20:100], rows[20:100])
+    expect = rows[0:10].copy()
+    expect[3:6] = rows[50:53]
+    assert np.array_equal(h["z"][:], expect)
+    for i in range(60):                                              # outgrows the slack of the root header: it moves once or twice
+      h.create_dataset(f"extra/long_dataset_name_{i:03d}", data=np.arange(i + 1))
+      h[f"s{i}"] = f"text {i}"
+  with hdf5_lite.File(path, "r") as h:
+    assert len(h.keys()) == 63 and len(h["extra"]) == 60
+    assert np.array_equal(h["extra/long_dataset_name_041"][:], np.arange(42)) and h["s17"][()] == "text 17"
+    assert np.array_equal(h["a"][200:300], rows[200:300])
+    with pytest.raises(OSError):
+      h["a"][0] = 1.0
+
+
+def test_session_keeps_one_handle_and_every_trajectory_leaves_a_complete_file(tmp_path):
+  path = str(tmp_path / "s.h5")
+  rows = _rows(40, seed=2)
+  utils.dump_dict(path, "featurizer_parms", {"cutoff": 5.0, "outfile": path})
+  opened = []
+  real_open = utils._open
+  utils._open = lambda p, m: opened.append((p, m)) or real_open(p, m)
+  try:
+    with utils.hdf_session():
+      for t in range(4):
+        with utils.batched_output():
+          for i in range(10):
+            utils.append_hdf_data(path, "k", rows[t * 10 + i][None], dtype=np.float32, maxshape=(None, 2, 2, 2), chunks=(1, 2, 2, 2))
+        # what is on disk now is a whole file with this trajectory's rows (read through an independent handle)
+        with utils.open_hdf(path, "r") as h:
+          assert h["k"].shape[0] == 10 * (t + 1) and np.array_equal(h["k"][:], rows[:10 * (t + 1)])
+  finally:
+    utils._open = real_open
+  assert [m for _, m in opened].count("a") == 1
+  for i in range(3):                                                 # outside a session: open / append / close per call, as the reference does
+    utils.append_hdf_data(path, "k", rows[i][None], dtype=np.float32, maxshape=(None, 2, 2, 2), chunks=(1, 2, 2, 2))
+  with utils.open_hdf(path, "r") as h:
+    assert h["k"].shape[0] == 43 and h["featurizer_parms/cutoff"][()] == 5.0 and h["featurizer_parms/outfile"][()] == path
+
+
+@pytest.mark.skipif(utils.hdf_backend() != "hdf5_lite", reason="h5py reads its own format")
+def test_classic_layout_written_by_libhdf5():
+  """A MATLAB 7.4 '-v7.3' file (libhdf5 1.6: 512-byte user block, version-0 superblock, symbol-table root group, local
+  heap, version-1 object headers, contiguous float64, a fixed-length string attribute), shipped with scipy's test data,
+  against the same variable in the MAT-5 twin of the file, read by scipy."""
+  import scipy.io
+  data = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data")
+  hits = glob.glob(os.path.join(data, "testhdf5_7.4_GLNX86.mat"))
+  if not hits:
+    pytest.skip("scipy's test data is not installed")
+  with hdf5_lite.File(hits[0], "r") as h:
+    assert h._base == 512 and not h._own_format
+    assert list(h.keys()) == ["testdouble"]
+    d = h["testdouble"]
+    assert d.dtype == np.dtype("<f8") and d.chunks is None
+    assert d.attrs["MATLAB_class"] == b"double"
+    got = d[:]
+    assert np.array_equal(d[2:5], got[2:5]) and d[8, 0] == got[8, 0]
+  twin = scipy.io.loadmat(os.path.join(data, "testdouble_7.4_GLNX86.mat"))["testdouble"]
+  assert np.array_equal(got.reshape(-1), twin.reshape(-1))            # MATLAB stores column-major: (9, 1) here, (1, 9) there
+  with pytest.raises(OSError):
+    hdf5_lite.File(hits[0], "a")
+
+
+def test_classic_layout_chunked_read_path(tmp_path):
+  """The reader's N-D chunk grid, shuffle + deflate + Fletcher-32 pipeline and version-1 messages, on a classic-layout
+  file assembled here byte by byte (no libhdf5 on this image writes one: self-consistency only, the structures are those
+  of the specification sections cited in hdf5_lite)."""
+  import struct
+  import zlib
+  rng = np.random.default_rng(3)
+  data = rng.integers(-1000, 1000, size=(5, 7, 3)).astype(">i4")           # big-endian on purpose
+  chunks = (2, 4, 3)
+  blob = bytearray(b"\x00" * 2048)
+
+  def put(raw, align=8):
+    addr = (len(blob) + align - 1) // align * align
+    blob.extend(b"\x00" * (addr - len(blob)) + raw)
+    return addr
+
+  # chunks: shuffle, deflate, fletcher32 (checksum bytes are not verified by the reader, only stripped)
+  entries = []
+  for i in range(0, 5, 2):
+    for j in range(0, 7, 4):
+      c = np.zeros(chunks, dtype=">i4")
+      part = data[i:i + 2, j:j + 4]
+      c[:part.shape[0], :part.shape[1]] = part
+      raw = c.tobytes()
+      sh = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 4).T.tobytes()
+      z = zlib.compress(sh) + b"\x00\x00\x00\x00"
+      entries.append(((i, j, 0, 0), put(z), len(z)))
+  node = b"TREE" + bytes([1, 0]) + struct.pack("<HQQ", len(entries), hdf5_lite.UNDEF, hdf5_lite.UNDEF)
+  for offs, addr, size in entries:
+    node += struct.pack("<II", size, 0) + struct.pack("<4Q", *offs) + struct.pack("<Q", addr)
+  node += struct.pack("<II", 0, 0) + struct.pack("<4Q", 6, 8, 3, 4)
+  btree = put(node)
+
+  def msg(mtype, body):
+    body += b"\x00" * (-len(body) % 8)
+    return struct.pack("<HHB3x", mtype, len(body), 0) + body
+
+  space = bytes([1, 3, 0, 0, 0, 0, 0, 0]) + struct.pack("<3Q", 5, 7, 3)
+  dtype = bytes([0x10, 0x09, 0x00, 0x00]) + struct.pack("<I", 4) + struct.pack("<HH", 0, 32)
+  layout = bytes([1, 4, 2, 0, 0, 0, 0, 0]) + struct.pack("<Q", btree) + struct.pack("<4I", 2, 4, 3, 4)
+
+  def filt(fid, name, cdata):
+    name += b"\x00" * (8 - len(name) % 8)
+    out = struct.pack("<HHHH", fid, len(name), 1, len(cdata)) + name + b"".join(struct.pack("<I", c) for c in cdata)
+    return out + (b"\x00" * 4 if len(cdata) % 2 else b"")
+
+  pipeline = bytes([1, 3, 0, 0, 0, 0, 0, 0]) + filt(2, b"shuffle", (4,)) + filt(1, b"deflate", (6,)) + filt(3, b"fletcher32", ())
+  body2 = msg(0x0B, pipeline) + msg(0x08, layout)
+  cont = put(body2)
+  body1 = msg(0x01, space) + msg(0x03, dtype) + msg(0x10, struct.pack("<QQ", cont, len(body2)))
+  dset = put(struct.pack("<BBHII4x", 1, 0, 4, 1, len(body1)) + body1)
+  # root group: local heap with the name, one symbol-table node, a one-entry group B-tree
+  names = b"\x00" * 8 + b"values\x00\x00"
+  seg = put(names)
+  heap = put(b"HEAP" + bytes([0, 0, 0, 0]) + struct.pack("<QQQ", len(names), hdf5_lite.UNDEF, seg))
+  snod = put(b"SNOD" + bytes([1, 0]) + struct.pack("<H", 1) + struct.pack("<QQII16x", 8, dset, 0, 0))
+  gtree = put(b"TREE" + bytes([0, 0]) + struct.pack("<HQQ", 1, hdf5_lite.UNDEF, hdf5_lite.UNDEF) + struct.pack("<QQQ", 0, snod, 8))
+  rbody = msg(0x11, struct.pack("<QQ", gtree, heap))
+  root = put(struct.pack("<BBHII4x", 1, 0, 1, 1, len(rbody)) + rbody)
+  sb = hdf5_lite.SIGNATURE + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0)
+  sb += struct.pack("<QQQQ", 0, hdf5_lite.UNDEF, len(blob), hdf5_lite.UNDEF) + struct.pack("<QQII16x", 0, root, 0, 0)
+  blob[0:len(sb)] = sb
+  path = str(tmp_path / "classic.h5")
+  with open(path, "wb") as fh:
+    fh.write(bytes(blob))
+  with hdf5_lite.File(path, "r") as h:
+    d = h["values"]
+    assert d.shape == (5, 7, 3) and d.chunks == chunks and d.dtype == np.dtype(">i4") and d.compression == "gzip"
+    assert np.array_equal(d[:], data) and np.array_equal(d[1:4], data[1:4]) and np.array_equal(d[4], data[4])
+    assert np.array_equal(d[0:3, 2:6, 1], data[0:3, 2:6, 1])
