@@ -73,6 +73,29 @@ def make_workload(name, n_traj, seed_offset=0, pin=True):
   raise SystemExit(f"unknown workload {name}")
 
 
+def atoms_in_focus_box(fz, traj):
+  """Atoms inside the focus box, from the same crop the kernels see (mean over the first three windows)."""
+  from nearl_b200 import features as _features
+  fz.traj = traj
+  fz.parse_focus()
+  f0 = fz.FEATURESPACE[0]
+  f0.cache(traj)
+  return int(np.mean([np.count_nonzero(_features.Feature.query(f0, traj.top, traj.xyz[i * fz.time_window], fz.FOCALPOINTS[i, 0])[0])
+                      for i in range(min(3, fz.SLICENUMBER))]))
+
+
+def workload_config(fz, trajs, workload, n_rot=N_ROTATE):
+  """The `config` object of the JSON line: what is featurised, identical for the native and the reference arm."""
+  traj = trajs[0]
+  n_frames = traj.n_frames
+  total = n_rot * traj.xyz.nbytes
+  return {"workload": workload, "tasks_per_step": fz.FEATURENUMBER * (n_frames // fz.time_window), "frames_per_step": n_frames,
+          "atoms": traj.n_atoms, "atoms_in_focus_box": atoms_in_focus_box(fz, traj), "grid": [int(v) for v in fz.FEATURESPACE[0].dims],
+          "l2": f"inputs larger than L2: {n_rot} trajectories x {traj.xyz.nbytes / 1e6:.1f} MB cycled" if total > 126e6
+                else f"{n_rot} trajectories x {traj.xyz.nbytes / 1e6:.2f} MB cycled (fits L2; extra workload, not the headline)",
+          "sharding": "one process per GPU, trajectories sharded by rank, no collective on the data path"}
+
+
 class ClockSampler:
   """SM clock and throttle reasons sampled DURING a timed region: NVML from a thread every 10 ms
   (the timed regions are tens of milliseconds), `nvidia-smi -lms` as the fallback."""
@@ -291,14 +314,10 @@ def run_native(args):
   kernels = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": v[0] / max(v[1], 1)} for k, v in prof.items()}
   top = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
   roof = None
-  # atoms inside the focus box, from the same crop the kernels saw
-  fz.traj = trajs[0]
-  fz.parse_focus()
+  config = workload_config(fz, trajs, WORKLOAD, n_rot)
+  n_in = config["atoms_in_focus_box"]
   f0 = fz.FEATURESPACE[0]
-  f0.cache(trajs[0])
   from nearl_b200 import features as _features
-  n_in = int(np.mean([np.count_nonzero(_features.Feature.query(f0, trajs[0].top, trajs[0].xyz[i * fz.time_window], fz.FOCALPOINTS[i, 0])[0])
-                      for i in range(min(3, fz.SLICENUMBER))]))
   G = int(np.prod(f0.dims))
   # ncu --set full capture of the same kernels on the same workload (profiles/kernel_table.json, written by
   # scripts/ncu_kernel_table.py from the committed capture): DRAM traffic and warp instructions per launch
@@ -363,11 +382,7 @@ def run_native(args):
     "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
     "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
     "dtype": "f32", "data": "synthetic",
-    "config": {"workload": WORKLOAD, "tasks_per_step": n_tasks, "frames_per_step": n_frames, "atoms": trajs[0].n_atoms,
-               "atoms_in_focus_box": n_in, "grid": [int(v) for v in f0.dims],
-               "l2": f"inputs larger than L2: {n_rot} trajectories x {trajs[0].xyz.nbytes / 1e6:.1f} MB cycled"
-                     if n_rot * trajs[0].xyz.nbytes > 126e6 else f"{n_rot} trajectories x {trajs[0].xyz.nbytes / 1e6:.2f} MB cycled (fits L2; extra workload, not the headline)",
-               "sharding": "one process per GPU, trajectories sharded by rank, no collective on the data path"},
+    "config": config,
     "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
             "h2d_bytes_per_step": int(n_frames * trajs[0].n_atoms * 12 + 4 * trajs[0].n_atoms * 4),
             "d2h_bytes_per_step": int(n_tasks * G * 4),
@@ -416,7 +431,8 @@ def run_reference(args):
   WORKLOAD = WORKLOADS[args.workload]
   # ordinary pageable trajectories, as a Nearl user has them: page-locked host memory in the process makes the
   # reference's per-call cudaMalloc/cudaFree several times slower and would bias the comparison against it
-  fz, trajs = make_workload(args.workload, min(N_ROTATE, max(1, args.steps)), pin=False)
+  # (the same N_ROTATE seeded trajectories as rank 0 of the native arm, so that `config` is the same object)
+  fz, trajs = make_workload(args.workload, N_ROTATE, pin=False)
   kernels, kind, device = None, "port", f"{os.cpu_count()} host cores (CPU oracle port)"
   warm_ctx = False
   if not args.cold_context:
@@ -468,9 +484,11 @@ def run_reference(args):
     "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
     "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": WORKLOAD, "device": device,
-               "note": "the reference has no multi-GPU path: one process (rank 0) on one GPU whatever --gpus says",
-               "cuda_context": "warm (torch allocation alive: cheap cudaMalloc/cudaFree)" if warm_ctx else "bare (as a stand-alone Nearl process)"},
+    "config": workload_config(fz, trajs, WORKLOAD, len(trajs)),
+    "reference_arm": {"device": device,
+                      "note": "the reference has no multi-GPU path: one process (rank 0) on one GPU whatever --gpus says",
+                      "cuda_context": "warm (torch allocation alive: cheap cudaMalloc/cudaFree)" if warm_ctx
+                                      else "bare (as a stand-alone Nearl process)"},
     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1 if kind == "reference" else (os.cpu_count() or 1), "kind": kind,
                      "sample": ("whole trajectory (40 tasks) per step" if max_slices is None else "1 window (4 tasks) per step")},
     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -15,7 +15,11 @@
  * Pointers are HOST pointers unless the function name ends in `_dev`.  Host entry points
  * are synchronous (results are in `out` on return).  `_dev` twins take device pointers
  * and a cudaStream_t (passed as void*; NULL = legacy default stream), enqueue all work
- * on that stream and return without synchronising.
+ * on that stream and return without synchronising.  All entry points of one device share one
+ * workspace per lane; the library orders successive calls that arrive on different streams
+ * with an event wait on the device (a call on stream B does not overwrite buffers the previous
+ * call on stream A is still reading), so `_dev` calls may be issued from any streams, in any
+ * interleaving, from one thread at a time per lane (calls are serialised by a mutex).
  */
 #ifndef NEARL_B200_H
 #define NEARL_B200_H

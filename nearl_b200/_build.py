@@ -38,14 +38,29 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+  """Compile when the library is missing or older than a source.  Safe with one process per GPU: the build runs under an
+  exclusive file lock (the ranks that lose the race wait, then find the library up to date), nvcc writes to a temporary
+  name and the finished file is renamed over the old one, so no process ever maps a half-written library."""
   if not force and not needs_build():
     return LIB_PATH
-  cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "nrl_api.cu")]
-  if verbose:
-    cmd.insert(1, "-Xptxas=-v")
-  res = subprocess.run(cmd, capture_output=True, text=True)
-  if res.returncode != 0:
-    raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-  if verbose:
-    print(res.stderr)
+  import fcntl
+  with open(LIB_PATH + ".lock", "w") as lock:
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+      if not force and not needs_build():          # another process built it while this one waited
+        return LIB_PATH
+      tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+      cmd = [_nvcc()] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "nrl_api.cu")]
+      if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+      res = subprocess.run(cmd, capture_output=True, text=True)
+      if res.returncode != 0:
+        if os.path.exists(tmp):
+          os.remove(tmp)
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+      os.replace(tmp, LIB_PATH)
+      if verbose:
+        print(res.stderr)
+    finally:
+      fcntl.flock(lock, fcntl.LOCK_UN)
   return LIB_PATH

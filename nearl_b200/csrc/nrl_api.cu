@@ -82,6 +82,7 @@ struct Ctx {
   DevBuf sup_idx, sup_ref, sup_rmsd;             // superposition: fitted atom indices, reference set, per-frame RMSD
   DevBuf batoms, bcnt, cstart, grids;            // cell lists: binned frames, cell prefixes, per-frame cell grids | frame list
   bool attr_set[64] = {false};          // "dynamic shared memory opt-in done" per kernel family, indexed by kAttr*
+  bool attr_fused[16] = {false};        // the same for the fused observer sweeps, indexed by their flag set
   cudaStream_t user_stream = nullptr;   // nrl_set_stream: run on the caller's stream instead of our own
   bool use_user_stream = false;
   // side streams: the per-mode tile launches of one batch are independent of each other (and the observers do
@@ -97,6 +98,34 @@ struct Ctx {
   double prof_ms[NRL_PROFILE_CATEGORIES] = {0};
   long long prof_cnt[NRL_PROFILE_CATEGORIES] = {0};
   cudaStream_t work_stream() const { return use_user_stream ? user_stream : stream; }
+  // the workspace above is one set of buffers: a call that runs on another stream than the previous one waits (on
+  // the device) for that call's work before it overwrites them -- see WorkspaceTurn
+  cudaStream_t ws_last = nullptr;
+  cudaEvent_t ws_event = nullptr;
+  bool ws_used = false, ws_recorded = false;
+};
+
+// Orders successive users of a lane's workspace that run on DIFFERENT streams (the stream-ordered `_dev` twins run on the
+// caller's stream and return without a sync; the next call may arrive on another stream, or on the lane's own).  Same
+// stream as the previous call: nothing to do, the stream orders them.  Held under Ctx::mu for the length of the call.
+struct WorkspaceTurn {
+  Ctx &c; cudaStream_t st;
+  WorkspaceTurn(Ctx &c_, cudaStream_t st_) : c(c_), st(st_) {
+    if (c.ws_used && c.ws_last != st) {
+      if (!c.ws_event) cudaEventCreateWithFlags(&c.ws_event, cudaEventDisableTiming);
+      if (!c.ws_recorded) cudaEventRecord(c.ws_event, c.ws_last);      // the lane's own stream: alive as long as the lane
+      cudaStreamWaitEvent(st, c.ws_event, 0);
+    }
+  }
+  ~WorkspaceTurn() {
+    c.ws_used = true;
+    c.ws_last = st;
+    c.ws_recorded = false;
+    if (st != c.stream) {        // a caller's stream may be gone by the next call: take the marker now
+      if (!c.ws_event) cudaEventCreateWithFlags(&c.ws_event, cudaEventDisableTiming);
+      c.ws_recorded = cudaEventRecord(c.ws_event, st) == cudaSuccess;
+    }
+  }
 };
 
 // slots of Ctx::attr_set: 0-9 scan tile kernels by launch slot, kAttrCell + the same for the cell-list kernels
@@ -266,11 +295,11 @@ int launch_cell_tiles_mode(Ctx &c, const NrlCellTileParams &p, int grid, size_t 
 
 template <int FLAGS>
 int launch_cell_fused(Ctx &c, const NrlCellTileParams &p, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_done[64] = {false};
-  if (!attr_done[c.dev]) {
+  static_assert(FLAGS >= 0 && FLAGS < 16, "fused flag set");
+  if (!c.attr_fused[FLAGS]) {        // per lane, touched under Ctx::mu like attr_set
     NRL_CUDA(cudaFuncSetAttribute(nrl_cell_tile_kernel<NRL_OBS_FUSED, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(c.smem_optin - 2048)));
-    attr_done[c.dev] = true;
+    c.attr_fused[FLAGS] = true;
   }
   {
     ScopedProf sp(c, st, CAT_TILE_FUSED);
@@ -644,6 +673,7 @@ int legacy_run(const LegacyArgs &a) {
   Ctx &c = *cp;
   std::lock_guard<std::mutex> lk(c.mu);
   cudaStream_t st = a.on_device ? a.user_stream : c.work_stream();
+  WorkspaceTurn turn(c, st);
   const int nF = std::min(a.F, NRL_MAX_FRAMES);   // gpuutils.cu:88, voxelize.cu:403, marching_observers.cu:490
   const size_t n_atoms = (size_t)nF * (size_t)a.N;
 
@@ -826,6 +856,7 @@ int aggregate_impl(const float *series, int F, long long G, int agg, float *out,
   Ctx &c = *cp;
   std::lock_guard<std::mutex> lk(c.mu);
   cudaStream_t st = on_device ? user : c.work_stream();
+  WorkspaceTurn turn(c, st);
   const int n = std::min(F, NRL_MAX_FRAMES);                 // gpuutils.cu:88
   const float *d_in = series;
   float *d_out = out;
@@ -989,6 +1020,7 @@ int nrl_superpose(void *xyz, int xyz_is_f64, int n_frames, int n_atoms, const in
   Ctx &c = *cp;
   std::lock_guard<std::mutex> lk(c.mu);
   cudaStream_t st = on_device ? (cudaStream_t)stream : c.work_stream();
+  WorkspaceTurn turn(c, st);
   const size_t esz = xyz_is_f64 ? sizeof(double) : sizeof(float);
   const size_t bytes = (size_t)n_frames * n_atoms * 3 * esz;
   void *d_xyz = xyz;
@@ -1178,6 +1210,7 @@ int nrl_summation(const float *arr, long long n, float *out) {
   NRL_TRY(get_ctx(&cp));
   Ctx &c = *cp;
   std::lock_guard<std::mutex> lk(c.mu);
+  WorkspaceTurn turn(c, c.stream);
   const long long nblocks = (n + 255) / 256;
   if (nblocks >= (1ll << 31)) return fail(NRL_ERR_SHAPE, "array too long");
   NRL_TRY(c.series.reserve((size_t)n * sizeof(float)));

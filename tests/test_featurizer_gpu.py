@@ -507,3 +507,59 @@ def test_fused_presence_bit_and_its_exclusions(tmp_path):
     _lib.set_option("no_fuse", 0)
   for key in got:
     assert np.array_equal(got[key].view(np.int32), sep[key].view(np.int32)), key
+
+
+def test_skipped_trajectories_do_not_alias_pipeline_lanes(tmp_path):
+  """A trajectory without focal point is skipped and takes no lane: with three lanes and the second of seven trajectories
+  skipped, the fourth one used to land on the lane of the first while that was still pending (its page-locked result
+  buffer was overwritten: the first trajectory came back with the fourth's grids)."""
+  trajs = [io.synthetic_trajectory(1500 + 50 * i, 4, seed=700 + i, ligand_atoms=(0 if i in (1, 4) else 20)) for i in range(7)]
+
+  def run(depth):
+    fz = featurizer.Featurizer({"dimensions": 12, "lengths": 9, "time_window": 2, "cutoff": 3.0, "sigma": 1.0})
+    fz.pipeline_depth = depth
+    fz.register_features([features.Mass(outkey="mass"), features.MarchingObservers(obs="direct_count", agg="max", outkey="count")])
+    fz.register_focus([":LIG"], "mask")
+    fz.register_trajloader(trajs)
+    seen = []
+    fz.result_sink = lambda outkey, tid, bid, pid, grid: seen.append((outkey, tid, bid, np.array(grid)))
+    stats = fz.run()
+    return seen, stats
+
+  serial, s1 = run(1)
+  piped, s3 = run(3)
+  assert s1["trajectories"] == s3["trajectories"] == 5 and [t for _, t, _, _ in serial] == [t for _, t, _, _ in piped]
+  assert sorted({t for _, t, _, _ in piped}) == [0, 2, 3, 5, 6]
+  for (k1, t1, b1, g1), (k3, t3, b3, g3) in zip(serial, piped):
+    assert (k1, t1, b1) == (k3, t3, b3) and np.array_equal(g1, g3), (k1, t1, b1)
+  assert len({g.tobytes() for k, _, _, g in piped if k == "mass"}) == 10          # ten different grids, none delivered twice
+
+
+def test_static_groups_then_multi_frame_trajectories_stay_pipelined(tmp_path):
+  """Single-frame systems first, multi-frame trajectories after: grouping is switched off at the first multi-frame
+  trajectory and the REST of the list goes through the pipelined loop (it used to run on lane 0, one at a time)."""
+  systems = [io.synthetic_complex(1000 + 31 * i, seed=800 + i) for i in range(6)]
+  systems += [io.synthetic_trajectory(1100 + 17 * i, 3, seed=820 + i, pin=False, ligand_atoms=30) for i in range(5)]
+  lanes = []
+  real = featurizer.LoweredBatch.execute
+
+  def run(group, depth):
+    fz = featurizer.Featurizer({"dimensions": 16, "lengths": 12, "time_window": 1, "cutoff": 3.0, "sigma": 1.2})
+    fz.static_group, fz.pipeline_depth = group, depth
+    fz.register_features([features.Mass(outkey="mass"), features.AtomType(focus_element=6, outkey="carbon")])
+    fz.register_focus([":LIG"], "mask")
+    fz.register_trajloader(systems)
+    fz.keep_results = True
+    stats = fz.run()
+    return {k: np.array(v) for k, v in fz.RESULTS.items()}, stats
+
+  featurizer.LoweredBatch.execute = lambda self, *a, **kw: lanes.append(kw.get("lane")) or real(self, *a, **kw)
+  try:
+    grouped, gs = run(4, 3)
+  finally:
+    featurizer.LoweredBatch.execute = real
+  plain, ps = run(1, 1)
+  assert gs["tasks"] == ps["tasks"] == (6 + 5 * 3) * 2
+  for key in plain:
+    assert np.array_equal(grouped[key], plain[key]), key
+  assert len(set(lanes[-4:])) == 3                                       # the tail of the list uses all three lanes

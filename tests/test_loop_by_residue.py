@@ -89,15 +89,27 @@ def descs_from(fz):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("restype,dtype", [("single", np.float32), ("dual", np.float32), ("single", np.float64)])
-def test_loop_by_residue_vs_reference_loop(tmp_path, restype, dtype):
+@pytest.mark.parametrize("restype,dtype,per_chunk", [("single", np.float32, 10), ("dual", np.float32, 9), ("single", np.float64, 20),
+                                                     ("single", np.float32, 7), ("single", np.float32, 64)])
+def test_loop_by_residue_vs_reference_loop(tmp_path, restype, dtype, per_chunk):
+  """`per_chunk` blocks per native call: 40 blocks x 2 windows make 4 / 2 / 6 / 1 chunks per window (an even count sent the
+  first chunk of a window to the lane still holding the last chunk of the window before)."""
   traj = io.synthetic_peptide(40, 6, seed=11, dtype=dtype, break_every=9)
   out = str(tmp_path / "residues.h5")
   fz = featurizer.Featurizer({**PARMS, "outfile": out})
   fz.register_features(make_features())
   fz.register_trajloader([traj])
   launches = _lib.kernel_launches()
-  stats = fz.loop_by_residue(restype, process_nr=4, chunk_floats=40 * 6 * 16 ** 3)       # several chunks per window
+  calls = []
+  real = featurizer.LoweredBatch.execute
+  featurizer.LoweredBatch.execute = lambda self, *a, **kw: calls.append(kw.get("lane")) or real(self, *a, **kw)
+  try:
+    stats = fz.loop_by_residue(restype, process_nr=4, chunk_floats=per_chunk * 6 * 16 ** 3)
+  finally:
+    featurizer.LoweredBatch.execute = real
+  assert calls == [i % 2 for i in range(len(calls))]                  # one job pending: strictly alternating lanes
+  if restype == "single":
+    assert len(calls) == 2 * -(-40 // per_chunk)
   fz.traj = traj
   blocks = fz._residue_blocks(restype)
   assert stats["tasks"] == 2 * len(blocks) * 6 and stats["native_tasks"] == stats["tasks"]

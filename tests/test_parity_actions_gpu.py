@@ -377,3 +377,45 @@ def test_single_frame_observables_and_reducers_bit_identical_to_the_reference(re
     g = nb.aggregate(series, agg)
     r = ref_actions.aggregate(series, agg)
     assert np.array_equal(g.view(np.int32), r.view(np.int32)), agg
+
+
+@pytest.mark.gpu
+def test_dev_twins_on_different_streams_share_the_workspace_in_order():
+  """The stream-ordered `_dev` twins return without a sync and use one workspace per device: a second call on ANOTHER
+  stream must not repack atoms / tasks while the first call's kernels still read them.  A long call (64 frames, 48^3) on
+  stream A is followed at once by short calls on streams B and C and by a host entry on the library's own stream; every
+  result equals the one computed alone."""
+  import ctypes
+  import torch
+  from nearl_b200 import _lib
+  L = _lib.lib()
+  rng = np.random.default_rng(77)
+  void = ctypes.c_void_p
+
+  def case(F, N, D, obs, agg):
+    coords = (rng.random((F, N, 3)) * (D * 0.5 + 4) - 2).astype(np.float32)
+    weights = rng.integers(1, 9, size=(F, N)).astype(np.float32)
+    dims = np.array([D, D, D], dtype=np.int32)
+    want = np.empty(D ** 3, dtype=np.float32)
+    _lib.check(L.nrl_marching_observer(_lib.ptr(coords), _lib.ptr(weights), F, N, _lib.ptr(dims), 0.5, 4.0, obs, agg, _lib.ptr(want)))
+    return coords, weights, dims, want, (F, N, obs, agg)
+
+  cases = [case(64, 6000, 48, 11, 2), case(3, 400, 16, 2, 1), case(5, 700, 16, 12, 5), case(2, 300, 16, 3, 1)]
+  streams = [torch.cuda.Stream() for _ in cases]
+  dev = [(torch.from_numpy(c).cuda(), torch.from_numpy(w).cuda(), torch.empty(len(want), device="cuda")) for c, w, _, want, _ in cases]
+  torch.cuda.synchronize()
+  for rounds in range(3):
+    for (c, w, out), (_, _, dims, _, (F, N, obs, agg)), st in zip(dev, cases, streams):
+      out.zero_()
+    torch.cuda.synchronize()
+    for (c, w, out), (_, _, dims, _, (F, N, obs, agg)), st in zip(dev, cases, streams):
+      _lib.check(L.nrl_marching_observer_dev(void(c.data_ptr()), void(w.data_ptr()), F, N, _lib.ptr(dims), 0.5, 4.0, obs, agg,
+                                             void(out.data_ptr()), void(st.cuda_stream)))
+    # a host entry right behind them, on the library's own stream
+    coords, weights, dims, want, (F, N, obs, agg) = cases[1]
+    again = np.empty_like(want)
+    _lib.check(L.nrl_marching_observer(_lib.ptr(coords), _lib.ptr(weights), F, N, _lib.ptr(dims), 0.5, 4.0, obs, agg, _lib.ptr(again)))
+    assert np.array_equal(again, want)
+    torch.cuda.synchronize()
+    for (c, w, out), (_, _, _, want, key) in zip(dev, cases):
+      assert np.array_equal(out.cpu().numpy(), want), (rounds, key)
