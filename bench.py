@@ -9,7 +9,9 @@ distinct_count(atomic_number), mean_distance(mass), density_flow(mass); mean ove
 = 40 (feature, window, focus) tasks consuming 100 frames.  metric = featurised frames / s.
 
   value : nrl_featurize_batch with the trajectory already resident in HBM and the results left in
-          HBM (CUDA events on the launching stream, max over ranks).
+          HBM; the K independent steps are issued round-robin over --lanes lanes of the library
+          (stream + workspace each), forked off and joined back into torch's stream between the
+          two CUDA events that time them (max over ranks).
   e2e   : Featurizer.run() on host trajectories in pinned memory -- host lowering, H2D of the
           frames, kernels, D2H of the 40 grids -- nothing cached between steps.
 Eight different trajectories per rank are cycled (8 x 24 MB of coordinates > L2).
@@ -209,7 +211,10 @@ def run_native(args):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
   stream = torch.cuda.current_stream()
   _lib.check(_lib.lib().nrl_set_device(local_rank))
-  _lib.set_stream(stream.cuda_stream, True)
+  L = _lib.lib()
+  import ctypes
+  stream_ptr = ctypes.c_void_p(stream.cuda_stream)
+  n_lanes = max(1, min(int(args.lanes), 8))
 
   # every rank featurises its own trajectories: weak scaling, no data-path collective
   global WORKLOAD
@@ -229,14 +234,26 @@ def run_native(args):
     specs = [f._native_spec() for f in fz.FEATURESPACE]
     lowered.append(fz.lower_batch(list(range(fz.FEATURENUMBER)), specs, traj.n_atoms, False))
     dev_xyz.append(torch.from_numpy(traj.xyz).cuda())
-  dev_out = torch.empty(lowered[0].out_floats, dtype=torch.float32, device="cuda")
+  # The steps are independent trajectories: they are issued round-robin over `n_lanes` lanes of the library (a lane = a
+  # stream + a workspace), so the crop / binning / kernel tails of one step run under the sweeps of another, exactly as
+  # Featurizer.run() pipelines them.  The lanes are forked off torch's stream after the start event and joined back
+  # into it before the stop event: the CUDA events on torch's stream bracket every kernel of the K steps.
+  dev_out = [torch.empty(lowered[0].out_floats, dtype=torch.float32, device="cuda") for _ in range(n_lanes)]
 
   n_rot = len(trajs)
 
   def step_device(i):
-    k = i % n_rot
-    lowered[k].execute(dev_xyz[k].data_ptr(), n_frames, dev_out.data_ptr(), xyz_on_device=True, out_on_device=True,
-                       no_sync=True)
+    k, lane = i % n_rot, i % n_lanes
+    lowered[k].execute(dev_xyz[k].data_ptr(), n_frames, dev_out[lane].data_ptr(), xyz_on_device=True, out_on_device=True,
+                       no_sync=True, lane=lane)
+
+  def lanes_fork():
+    for lane in range(n_lanes):
+      _lib.check(L.nrl_lane_fork(lane, stream_ptr))
+
+  def lanes_join():
+    for lane in range(n_lanes):
+      _lib.check(L.nrl_lane_join(lane, stream_ptr))
 
   # e2e: the public call, Featurizer.run() over a list of host trajectories (it pipelines them over
   # `pipeline_depth` lanes internally); every result grid is read on the host by the sink
@@ -262,6 +279,8 @@ def run_native(args):
       whole(0, max(warmup, min(steps, 128)))
     for i in range(warmup if whole is None else 0):
       step(i)
+    if whole is None:
+      lanes_join()
     barrier()
     if profile:
       _lib.profile(True)
@@ -273,8 +292,11 @@ def run_native(args):
       t_host = time.perf_counter()
       if whole is not None:
         whole(warmup, steps)
-      for i in range(steps if whole is None else 0):
-        step(warmup + i)
+      else:
+        lanes_fork()
+        for i in range(steps):
+          step(warmup + i)
+        lanes_join()
       e1.record(stream)
       barrier()
       t_host = (time.perf_counter() - t_host) * 1e3
@@ -330,8 +352,9 @@ def run_native(args):
     t_launch = kernels[top]["ms_per_launch"] * 1e-3
     windows = n_frames // fz.time_window
     # algorithmic bytes of one (feature, window) task = F*N*16 (packed atoms read) + 4*G (grid written);
-    # one launch of a tile kernel covers the `windows` tasks of its mode
-    alg_bytes = windows * (fz.time_window * n_in * 16 + 4 * G)
+    # one launch of a tile kernel covers the `windows` tasks of its mode -- of every observer it fuses, for the fused sweep
+    n_fused = sum(isinstance(f, _features.MarchingObservers) for f in fz.FEATURESPACE) if top == "tile_fused" else 1
+    alg_bytes = windows * max(n_fused, 1) * (fz.time_window * n_in * 16 + 4 * G)
     achieved = alg_bytes / t_launch / 1e9
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": table.get(top, {}).get("dram_bytes"), "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
@@ -507,6 +530,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
   ap.add_argument("--workload", default="dynamic", choices=sorted(WORKLOADS), help="default: the headline configs[1]")
+  ap.add_argument("--lanes", type=int, default=4, help="native arm, device-resident steps: lanes of the library the steps are spread over")
   ap.add_argument("--cold-context", action="store_true", help="reference arm: do not pre-create a torch CUDA context")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup

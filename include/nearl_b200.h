@@ -166,7 +166,7 @@ typedef struct {
 
 #define NRL_BATCH_NO_SYNC 1      /* enqueue only: results are valid after nrl_lane_synchronize(lane); host buffers
                                     (xyz, out) must be page-locked and stay alive until then */
-#define NRL_MAX_LANES 4
+#define NRL_MAX_LANES 8
 
 int nrl_featurize_batch(const nrl_batch_t *batch);
 
@@ -182,6 +182,13 @@ int nrl_cell_list_fits(const int *dims, float spacing, float cutoff, int *out);
 int nrl_superpose(void *xyz, int xyz_is_f64, int n_frames, int n_atoms, const int *fit_index, int n_fit, int ref_frame,
                   int on_device, float *rmsd, void *stream);
 
+/* Focal points of Featurizer.parse_focus (/root/reference/nearl/featurizer.py:357-372): out[f] = centre of geometry of the
+ * atoms `sel` in trajectory frame frames[f], float32, with the arithmetic of numpy's np.mean(frame[sel], axis=0) (rows added
+ * in order in the trajectory's precision, divided in double).  Plain host code: xyz [n_frames_total, n_atoms, 3] in host
+ * memory, float32 or float64. */
+int nrl_focal_means(const void *xyz, int xyz_is_f64, int n_frames_total, int n_atoms, const int *frames, int n_frames,
+                    const int *sel, int n_sel, float *out);
+
 /* ---- utilities -------------------------------------------------------------------------- */
 /* buff_dim exactly as the device evaluates (cutoff+spacing)/spacing (voxelize.cu:50, div.approx) */
 int nrl_buff_dim(float cutoff, float spacing, int *out);
@@ -191,6 +198,10 @@ int nrl_synchronize(void);
 /* wait for everything enqueued on `lane` (batches submitted with NRL_BATCH_NO_SYNC); batches on
  * different lanes overlap, e.g. the upload of one trajectory under the kernels of the previous one */
 int nrl_lane_synchronize(int lane);
+/* device-side joins between a caller's stream and a lane: nrl_lane_fork makes the lane's future work start after what
+ * `stream` holds now, nrl_lane_join makes `stream` wait for what the lane holds now (no host synchronisation) */
+int nrl_lane_fork(int lane, void *stream);
+int nrl_lane_join(int lane, void *stream);
 /* enable != 0: enqueue all work of the host entry points and of nrl_featurize_batch on `stream`
  * (a cudaStream_t, e.g. torch's current stream) instead of the library's own stream */
 int nrl_set_stream(void *stream, int enable);
@@ -199,7 +210,8 @@ int nrl_set_stream(void *stream, int enable);
  * one focus box do not share a sweep across observables (results are bit-identical either way) */
 int nrl_set_option(const char *name, int value);
 /* per-kernel device timing: CUDA events around every launch of this library, accumulated per
- * category; nrl_profile_read synchronises and copies NRL_PROFILE_CATEGORIES totals (ms, launches) */
+ * category, on every lane of the current device; nrl_profile_read synchronises the lanes and copies
+ * NRL_PROFILE_CATEGORIES totals (ms, launches) summed over them */
 #define NRL_PROFILE_CATEGORIES 19
 int nrl_profile(int enable);
 int nrl_profile_read(double *ms, long long *counts, int reset);

@@ -19,7 +19,7 @@ EXPORTED = [
   "nrl_frame_voxelize", "nrl_frame_observation", "nrl_marching_observer", "nrl_density_flow", "nrl_aggregate",
   "nrl_summation", "nrl_frame_voxelize_dev", "nrl_frame_observation_dev", "nrl_marching_observer_dev",
   "nrl_density_flow_dev", "nrl_aggregate_dev", "nrl_featurize_batch", "nrl_buff_dim", "nrl_device_count",
-  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_set_stream", "nrl_set_option", "nrl_cell_list_fits", "nrl_superpose", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
+  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_lane_fork", "nrl_lane_join", "nrl_focal_means", "nrl_set_stream", "nrl_set_option", "nrl_cell_list_fits", "nrl_superpose", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
   "nrl_last_error", "nrl_version",
 ]
 
@@ -99,6 +99,9 @@ def lib():
   L.nrl_host_unregister.argtypes = [p]
   L.nrl_set_stream.argtypes = [p, c_int]
   L.nrl_lane_synchronize.argtypes = [c_int]
+  L.nrl_lane_fork.argtypes = [c_int, p]
+  L.nrl_lane_join.argtypes = [c_int, p]
+  L.nrl_focal_means.argtypes = [p, c_int, c_int, c_int, p, c_int, p, c_int, p]
   L.nrl_profile.argtypes = [c_int]
   L.nrl_set_option.argtypes = [ctypes.c_char_p, c_int]
   L.nrl_cell_list_fits.argtypes = [p, c_float, c_float, p]
@@ -131,6 +134,12 @@ def check(rc):
 
 def ptr(a):
   return a.ctypes.data_as(c_void_p)
+
+
+def addr(a):
+  """Address of an array the CALLER keeps alive for the length of the native call (several times cheaper than `ptr`, whose
+  ctypes object also holds a reference to the array -- needed for temporaries only)."""
+  return c_void_p(a.__array_interface__["data"][0])
 
 
 def device_count():

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/nearl_b200.h"
@@ -101,7 +102,7 @@ struct Ctx {
   // the workspace above is one set of buffers: a call that runs on another stream than the previous one waits (on
   // the device) for that call's work before it overwrites them -- see WorkspaceTurn
   cudaStream_t ws_last = nullptr;
-  cudaEvent_t ws_event = nullptr;
+  cudaEvent_t ws_event = nullptr, join_event = nullptr;
   bool ws_used = false, ws_recorded = false;
 };
 
@@ -1076,23 +1077,32 @@ int nrl_set_option(const char *name, int value) {
   if (strcmp(name, "agg_pipe_stages") == 0) { g_agg_pipe_stages.store((int)value); return NRL_OK; }
   return fail(NRL_ERR_ARGUMENT, std::string("unknown option ") + name);
 }
+// every lane of the current device (lanes that were never used are created: a context is a stream and empty arenas)
 int nrl_profile(int enable) {
-  Ctx *c = nullptr;
-  NRL_TRY(get_ctx(&c));
-  std::lock_guard<std::mutex> lk(c->mu);
-  c->prof_on = enable != 0;
+  for (int lane = 0; lane < NRL_MAX_LANES; ++lane) {
+    Ctx *c = nullptr;
+    NRL_TRY(get_ctx(&c, lane));
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->prof_on = enable != 0;
+  }
   return NRL_OK;
 }
 int nrl_profile_read(double *ms, long long *counts, int reset) {
-  Ctx *c = nullptr;
-  NRL_TRY(get_ctx(&c));
-  std::lock_guard<std::mutex> lk(c->mu);
-  NRL_CUDA(cudaStreamSynchronize(c->work_stream()));
-  prof_collect(*c);
   for (int i = 0; i < NRL_PROFILE_CATEGORIES; ++i) {
-    if (ms) ms[i] = c->prof_ms[i];
-    if (counts) counts[i] = c->prof_cnt[i];
-    if (reset) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+    if (ms) ms[i] = 0;
+    if (counts) counts[i] = 0;
+  }
+  for (int lane = 0; lane < NRL_MAX_LANES; ++lane) {
+    Ctx *c = nullptr;
+    NRL_TRY(get_ctx(&c, lane));
+    std::lock_guard<std::mutex> lk(c->mu);
+    NRL_CUDA(cudaStreamSynchronize(c->work_stream()));
+    prof_collect(*c);
+    for (int i = 0; i < NRL_PROFILE_CATEGORIES; ++i) {
+      if (ms) ms[i] += c->prof_ms[i];
+      if (counts) counts[i] += c->prof_cnt[i];
+      if (reset) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+    }
   }
   return NRL_OK;
 }
@@ -1105,6 +1115,60 @@ int nrl_host_register(void *ptr, long long bytes) {
   return NRL_OK;
 }
 int nrl_host_unregister(void *ptr) { NRL_CUDA(cudaHostUnregister(ptr)); return NRL_OK; }
+
+// Focal points of Featurizer.parse_focus (/root/reference/nearl/featurizer.py:357-372): the centre of geometry of the atoms
+// `sel` in each of `frames`, with numpy's arithmetic for np.mean(frame[sel], axis=0) -- the selected rows are added one after
+// the other in the array's own precision, the sum is divided by the count in double and rounded to the array's precision --
+// and stored as float32 like FOCALPOINTS.  Host code: the trajectory is still in host memory when the focus boxes are laid out.
+int nrl_focal_means(const void *xyz, int xyz_is_f64, int n_frames_total, int n_atoms, const int *frames, int n_frames, const int *sel,
+                    int n_sel, float *out) {
+  if (!xyz || !frames || !sel || !out) return fail(NRL_ERR_ARGUMENT, "xyz / frames / sel / out is NULL");
+  if (n_sel <= 0 || n_frames < 0 || n_atoms <= 0) return fail(NRL_ERR_SHAPE, "empty selection or trajectory");
+  for (int f = 0; f < n_frames; ++f)
+    if (frames[f] < 0 || frames[f] >= n_frames_total) return fail(NRL_ERR_SHAPE, "frame index outside the trajectory");
+  for (int j = 0; j < n_sel; ++j)
+    if (sel[j] < 0 || sel[j] >= n_atoms) return fail(NRL_ERR_SHAPE, "atom index outside the topology");
+  auto impl = [&](auto *base) {
+    using T = std::remove_cv_t<std::remove_pointer_t<decltype(base)>>;
+    for (int f = 0; f < n_frames; ++f) {
+      const T *frame = base + (size_t)frames[f] * (size_t)n_atoms * 3;
+      T ax = 0, ay = 0, az = 0;
+      for (int j = 0; j < n_sel; ++j) {
+        const T *r = frame + (size_t)sel[j] * 3;
+        ax += r[0]; ay += r[1]; az += r[2];
+      }
+      const double n = (double)n_sel;
+      out[3 * f + 0] = (float)(T)((double)ax / n);
+      out[3 * f + 1] = (float)(T)((double)ay / n);
+      out[3 * f + 2] = (float)(T)((double)az / n);
+    }
+  };
+  if (xyz_is_f64) impl(reinterpret_cast<const double *>(xyz));
+  else impl(reinterpret_cast<const float *>(xyz));
+  return NRL_OK;
+}
+
+// `stream` waits (on the device) for everything enqueued on `lane` so far: a caller that spreads batches over the lanes
+// joins them into its own stream without a host synchronisation (bench.py times the device-resident arm this way).
+int nrl_lane_join(int lane, void *stream) {
+  Ctx *c = nullptr;
+  NRL_TRY(get_ctx(&c, lane));
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->join_event) NRL_CUDA(cudaEventCreateWithFlags(&c->join_event, cudaEventDisableTiming));
+  NRL_CUDA(cudaEventRecord(c->join_event, c->work_stream()));
+  NRL_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->join_event, 0));
+  return NRL_OK;
+}
+// everything enqueued on `lane` from now on starts after what `stream` holds at this point
+int nrl_lane_fork(int lane, void *stream) {
+  Ctx *c = nullptr;
+  NRL_TRY(get_ctx(&c, lane));
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (!c->join_event) NRL_CUDA(cudaEventCreateWithFlags(&c->join_event, cudaEventDisableTiming));
+  NRL_CUDA(cudaEventRecord(c->join_event, (cudaStream_t)stream));
+  NRL_CUDA(cudaStreamWaitEvent(c->work_stream(), c->join_event, 0));
+  return NRL_OK;
+}
 
 int nrl_buff_dim(float cutoff, float spacing, int *out) {
   if (!out) return fail(NRL_ERR_ARGUMENT, "out is NULL");

@@ -212,11 +212,27 @@ class Featurizer:
         self.FOCALPOINTS[:, midx] = item
         continue
       if self.SLICENUMBER:
-        # first frame of every window, one gather: np.mean over axis 1 adds the selected rows in the same
-        # order as the reference's per-frame np.mean(frame[selection], axis=0) -- identical bits
-        firsts = self.traj.xyz[0:self.SLICENUMBER * self.time_window:self.time_window]
-        self.FOCALPOINTS[:, midx] = np.mean(firsts[:, selection], axis=1)
+        self.FOCALPOINTS[:, midx] = self._focal_means(selection)
     return 1
+
+  def _focal_means(self, selection):
+    """Centre of geometry of `selection` in the first frame of every window, [windows, 3]: the reference's per-frame
+    np.mean(frame[selection], axis=0) (featurizer.py:363-365).  For a plain float32 / float64 trajectory array the native
+    library adds the rows with numpy's arithmetic -- same order, same precision, same rounding, so the same bits
+    (tests/test_host_api.py) -- without materialising the gathered copy; anything else takes numpy itself."""
+    xyz = self.traj.xyz
+    selection = np.asarray(selection)
+    if (isinstance(xyz, np.ndarray) and xyz.ndim == 3 and xyz.dtype in (np.float32, np.float64) and xyz.flags.c_contiguous
+        and selection.ndim == 1 and len(selection) > 0 and selection.dtype.kind in "iu" and selection.min() >= 0):
+      frames = np.arange(0, self.SLICENUMBER * self.time_window, self.time_window, dtype=np.int32)
+      sel = np.ascontiguousarray(selection, dtype=np.int32)
+      out = np.empty((len(frames), 3), dtype=np.float32)
+      _lib.check(_lib.lib().nrl_focal_means(_lib.addr(xyz), int(xyz.dtype == np.float64), xyz.shape[0], xyz.shape[1], _lib.addr(frames),
+                                            len(frames), _lib.addr(sel), len(sel), _lib.addr(out)))
+      return out
+    # one gather: np.mean over axis 1 adds the selected rows in the same order as the per-frame np.mean(..., axis=0)
+    firsts = xyz[0:self.SLICENUMBER * self.time_window:self.time_window]
+    return np.mean(firsts[:, selection], axis=1)
 
   # ---- the loop -----------------------------------------------------------------------------
   def run(self, *_ignored, trajectory_indices=None):
@@ -230,7 +246,7 @@ class Featurizer:
     indices = list(range(self.TRAJECTORYNUMBER) if trajectory_indices is None else trajectory_indices)
     stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "frames": 0, "seconds": 0.0}
     t_run = time.perf_counter()
-    depth = max(1, min(int(self.pipeline_depth), 4))        # lanes of the native library (NRL_MAX_LANES)
+    depth = max(1, min(int(self.pipeline_depth), 8))        # lanes of the native library (NRL_MAX_LANES)
     self.__dict__.pop("_fingerprint_memo", None)
     with utils.hdf_session():                                # output files stay open until the run is over
       done = self._run_static_groups(indices, depth, stats) if self._static_groupable() else 0
@@ -449,7 +465,7 @@ class Featurizer:
       if lane not in buffers or buffers[lane].size < batch.out_floats:
         buffers[lane] = pinned_empty((batch.out_floats,), np.float32)     # page-locked, reused across trajectories
       out = buffers[lane][:batch.out_floats]
-      batch.execute(_lib.ptr(xyz), xyz.shape[0], _lib.ptr(out), no_sync=True, lane=lane)
+      batch.execute(_lib.addr(xyz), xyz.shape[0], _lib.addr(out), no_sync=True, lane=lane)      # both live in `job`
       job.update(batch=batch, out=out, xyz=xyz)
     return job
 
@@ -880,12 +896,13 @@ class LoweredBatch:
     b = _lib.BatchStruct()
     b.xyz, b.xyz_is_f64, b.xyz_on_device = xyz_ptr, int(self.is_f64), int(xyz_on_device)
     b.n_frames_total, b.n_atoms = int(n_frames_total), int(self.n_atoms)
-    b.weight_tables, b.n_weight_tables = _lib.ptr(self.weight_tables), len(self.weight_tables)
-    b.selections = _lib.ptr(self.selections) if self.selections is not None else None
+    # (the batch owns these arrays: plain addresses, no ctypes views)
+    b.weight_tables, b.n_weight_tables = _lib.addr(self.weight_tables), len(self.weight_tables)
+    b.selections = _lib.addr(self.selections) if self.selections is not None else None
     b.n_selections = len(self.selections) if self.selections is not None else 0
-    b.residue_index = _lib.ptr(self.residue_index) if self.residue_index is not None else None
+    b.residue_index = _lib.addr(self.residue_index) if self.residue_index is not None else None
     b.n_residues = self.n_residues
-    b.value_orders = _lib.ptr(self.value_orders) if self.value_orders is not None else None
+    b.value_orders = _lib.addr(self.value_orders) if self.value_orders is not None else None
     b.crops, b.n_crops = self.crops, getattr(self, "n_crops", None) or len(self.crops)
     b.tasks, b.n_tasks = self.tasks, getattr(self, "n_tasks", None) or len(self.tasks)
     b.out, b.out_on_device = out_ptr, int(out_on_device)

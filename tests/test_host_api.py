@@ -225,3 +225,38 @@ def test_hdf5_layout_roundtrip(tmp_path):
     from nearl_b200 import hdf5_lite
     assert hdf5_lite.lookup3(b"") == 0xDEADBEEF
     assert hdf5_lite.lookup3(b"Four score and seven years ago") == 0x17770551     # lookup3.c self-test vector
+
+
+def test_focal_means_have_numpy_bits():
+  """nrl_focal_means (host code of the native library) against np.mean(frame[selection], axis=0), the reference's focal point
+  (featurizer.py:363-365): same order of additions, same precision, division in double -> identical float32 bits."""
+  from nearl_b200 import _lib
+  rng = np.random.default_rng(5)
+  for dtype in (np.float32, np.float64):
+    for trial in range(60):
+      F, N = int(rng.integers(1, 9)), int(rng.integers(3, 3000))
+      xyz = (rng.normal(0, 30, size=(F, N, 3)) + rng.normal(0, 100)).astype(dtype)
+      n = int(rng.integers(1, N + 1))
+      sel = np.sort(rng.choice(N, size=n, replace=False)) if trial % 2 else rng.choice(N, size=n, replace=True)
+      W = int(rng.integers(1, F + 1))
+      S = F // W
+      want = np.array([np.mean(xyz[i * W][sel], axis=0) for i in range(S)], dtype=np.float32).reshape(S, 3)
+      frames = np.arange(0, S * W, W, dtype=np.int32)
+      s32 = np.ascontiguousarray(sel, dtype=np.int32)
+      out = np.empty((S, 3), dtype=np.float32)
+      _lib.check(_lib.lib().nrl_focal_means(_lib.ptr(xyz), int(dtype == np.float64), F, N, _lib.ptr(frames), S, _lib.ptr(s32), n, _lib.ptr(out)))
+      assert np.array_equal(out, want), (dtype, trial)
+  # through the featuriser: mask, index lists, float64 trajectory, a non-contiguous trajectory (numpy path)
+  traj = io.synthetic_trajectory(900, 12, seed=4, pin=False)
+  for xyz in (traj.xyz, traj.xyz.astype(np.float64), np.asfortranarray(traj.xyz)):
+    t = io.Trajectory(xyz, traj.top)
+    fz = featurizer.Featurizer({"dimensions": 8, "lengths": 8, "time_window": 5})
+    fz.register_focus([":ARG", ":LYS,GLU"], "mask")
+    fz.traj = t
+    assert fz.parse_focus()
+    for midx, mask in enumerate((":ARG", ":LYS,GLU")):
+      sel = t.top.select(mask)
+      want = np.array([np.mean(xyz[i * 5][sel], axis=0) for i in range(2)], dtype=np.float32)
+      assert np.array_equal(fz.FOCALPOINTS[:, midx], want)
+  with pytest.raises(ValueError):
+    _lib.check(_lib.lib().nrl_focal_means(_lib.ptr(xyz), 0, 12, 900, _lib.ptr(np.array([12], dtype=np.int32)), 1, _lib.ptr(s32[:1]), 1, _lib.ptr(out)))
