@@ -86,7 +86,7 @@ def atoms_in_focus_box(fz, traj):
                       for i in range(min(3, fz.SLICENUMBER))]))
 
 
-def workload_config(fz, trajs, workload, n_rot=N_ROTATE):
+def workload_config(fz, trajs, workload, n_rot=N_ROTATE, by_task=False):
   """The `config` object of the JSON line: what is featurised, identical for the native and the reference arm."""
   traj = trajs[0]
   n_frames = traj.n_frames
@@ -95,7 +95,9 @@ def workload_config(fz, trajs, workload, n_rot=N_ROTATE):
           "atoms": traj.n_atoms, "atoms_in_focus_box": atoms_in_focus_box(fz, traj), "grid": [int(v) for v in fz.FEATURESPACE[0].dims],
           "l2": f"inputs larger than L2: {n_rot} trajectories x {traj.xyz.nbytes / 1e6:.1f} MB cycled" if total > 126e6
                 else f"{n_rot} trajectories x {traj.xyz.nbytes / 1e6:.2f} MB cycled (fits L2; extra workload, not the headline)",
-          "sharding": "one process per GPU, trajectories sharded by rank, no collective on the data path"}
+          "sharding": "one process per GPU, every trajectory split by (window, focal point, grid slab) over the ranks, parts gathered "
+                      "by rank 0; no collective on the data path" if by_task
+                      else "one process per GPU, trajectories sharded by rank, no collective on the data path"}
 
 
 class ClockSampler:
@@ -219,7 +221,11 @@ def run_native(args):
   # every rank featurises its own trajectories: weak scaling, no data-path collective
   global WORKLOAD
   WORKLOAD = WORKLOADS[args.workload]
-  fz, trajs = make_workload(args.workload, N_ROTATE, seed_offset=rank * N_ROTATE)
+  # --shard trajectories (default): every rank featurises its own trajectories, weak scaling, no data-path collective
+  # --shard tasks: every rank holds the SAME trajectories and computes its share of each one's (window, focal point[, grid
+  #                slab]) parts, rank 0 assembles the grids (sharding.run_task_sharded): strong scaling of ONE system
+  by_task = args.shard == "tasks" and world > 1
+  fz, trajs = make_workload(args.workload, N_ROTATE, seed_offset=0 if by_task else rank * N_ROTATE)
   fz.keep_results = True
   n_frames = trajs[0].n_frames
   n_tasks = fz.FEATURENUMBER * (n_frames // fz.time_window)
@@ -232,18 +238,24 @@ def run_native(args):
     for feat in fz.FEATURESPACE:
       feat.cache(traj)
     specs = [f._native_spec() for f in fz.FEATURESPACE]
-    lowered.append(fz.lower_batch(list(range(fz.FEATURENUMBER)), specs, traj.n_atoms, False))
+    task_list = None
+    if by_task:
+      keys, slabs = fz.shard_task_list((rank, world, None), specs)
+      task_list = tuple(k + sl for k, sl in zip(keys, slabs))
+    lowered.append(fz.lower_batch(list(range(fz.FEATURENUMBER)), specs, traj.n_atoms, False, task_list=task_list))
     dev_xyz.append(torch.from_numpy(traj.xyz).cuda())
   # The steps are independent trajectories: they are issued round-robin over `n_lanes` lanes of the library (a lane = a
   # stream + a workspace), so the crop / binning / kernel tails of one step run under the sweeps of another, exactly as
   # Featurizer.run() pipelines them.  The lanes are forked off torch's stream after the start event and joined back
   # into it before the stop event: the CUDA events on torch's stream bracket every kernel of the K steps.
-  dev_out = [torch.empty(lowered[0].out_floats, dtype=torch.float32, device="cuda") for _ in range(n_lanes)]
+  dev_out = [torch.empty(max(max(b.out_floats for b in lowered), 1), dtype=torch.float32, device="cuda") for _ in range(n_lanes)]
 
   n_rot = len(trajs)
 
   def step_device(i):
     k, lane = i % n_rot, i % n_lanes
+    if lowered[k].n_tasks_total == 0:
+      return
     lowered[k].execute(dev_xyz[k].data_ptr(), n_frames, dev_out[lane].data_ptr(), xyz_on_device=True, out_on_device=True,
                        no_sync=True, lane=lane)
 
@@ -265,7 +277,13 @@ def run_native(args):
   fz.result_sink = sink
 
   def run_e2e(first, count):
-    fz.run(trajectory_indices=[(first + i) % n_rot for i in range(count)])
+    indices = [(first + i) % n_rot for i in range(count)]
+    if by_task:
+      from nearl_b200 import sharding
+      for c0 in range(0, count, 16):          # parts are gathered per chunk of trajectories (bounded memory on rank 0)
+        sharding.run_task_sharded(fz, rank=rank, world=world, device=local_rank, trajectory_indices=indices[c0:c0 + 16])
+    else:
+      fz.run(trajectory_indices=indices)
 
   def barrier():
     if world > 1:
@@ -277,9 +295,11 @@ def run_native(args):
       # the public call pipelines / groups its trajectories: warm it up with a run of the timed length, so that the
       # page-locked staging buffers and device arenas it grows on the way exist before the clock starts
       whole(0, max(warmup, min(steps, 128)))
-    for i in range(warmup if whole is None else 0):
-      step(i)
     if whole is None:
+      for i in range(n_lanes):       # every lane grows its workspace before the W warm-up steps (untimed)
+        step(i)
+      for i in range(warmup):
+        step(i)
       lanes_join()
     barrier()
     if profile:
@@ -321,7 +341,7 @@ def run_native(args):
     if world > 1:
       dist.destroy_process_group()
     return
-  frames_total = n_frames * world * args.steps
+  frames_total = n_frames * (1 if by_task else world) * args.steps
   value = frames_total / (ms_dev * 1e-3)
   e2e = frames_total / (ms_e2e * 1e-3)
 
@@ -336,7 +356,7 @@ def run_native(args):
   kernels = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": v[0] / max(v[1], 1)} for k, v in prof.items()}
   top = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
   roof = None
-  config = workload_config(fz, trajs, WORKLOAD, n_rot)
+  config = workload_config(fz, trajs, WORKLOAD, n_rot, by_task)
   n_in = config["atoms_in_focus_box"]
   f0 = fz.FEATURESPACE[0]
   from nearl_b200 import features as _features
@@ -403,7 +423,7 @@ def run_native(args):
 
   line = {
     "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-    "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if by_task else "weak", "vs_baseline": None,
     "dtype": "f32", "data": "synthetic",
     "config": config,
     "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -530,7 +550,10 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="native", choices=["native", "reference"])
   ap.add_argument("--workload", default="dynamic", choices=sorted(WORKLOADS), help="default: the headline configs[1]")
-  ap.add_argument("--lanes", type=int, default=4, help="native arm, device-resident steps: lanes of the library the steps are spread over")
+  ap.add_argument("--lanes", type=int, default=6, help="native arm, device-resident steps: lanes of the library the steps are spread over")
+  ap.add_argument("--shard", default="trajectories", choices=["trajectories", "tasks"],
+                  help="multi-GPU partition: whole trajectories per rank (weak scaling, the headline) or the (window, focal point, "
+                       "grid slab) parts of every trajectory (strong scaling of one system, e.g. --workload stress)")
   ap.add_argument("--cold-context", action="store_true", help="reference arm: do not pre-create a torch CUDA context")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup

@@ -138,6 +138,12 @@ typedef struct {
   int rank_table;        /* distinct_count only: row of `weight_tables` holding, as floats, the rank (0..31) of every
                             atom's value among the distinct values of `weight_table` (-1 for the 99999.0 placeholder,
                             which is never counted); -1 = no ranks: the crop must then be value ordered (sort_table) */
+  /* One task split over several GPUs: only the slab x_begin <= ix < x_begin + x_count of the grid's slowest axis is
+   * computed (focus box, crop and normalisation are those of the whole grid, so the slab has the bits of the same rows
+   * of an unsplit task) and the task's result is that slab alone, x_count * dims[1] * dims[2] floats.  x_count 0 = the
+   * whole grid.  x_begin must be a multiple of 8 (the tile edge), x_count too unless the slab ends with the grid;
+   * cubic grids only. */
+  int x_begin, x_count;
 } nrl_task_t;
 
 typedef struct {

@@ -44,6 +44,7 @@ class TaskStruct(ctypes.Structure):
     ("crop", c_int), ("mode", c_int), ("agg", c_int), ("weight_table", c_int),
     ("dims", c_int * 3), ("spacing", c_float), ("cutoff", c_float), ("sigma", c_float),
     ("rank_table", c_int),
+    ("x_begin", c_int), ("x_count", c_int),
   ]
 
 

@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(NRL_NT, 5) nrl_cell_tile_kernel(const NrlCellT
     const NrlTask &t = p.tasks[lo];
     const int tile = work - t.tile_begin;
     const int nx = t.nx, ny = t.ny, nz = t.nz;
-    const int tzi = tile % t.ntz, tyi = (tile / t.ntz) % t.nty, txi = tile / (t.ntz * t.nty);
+    const int tzi = tile % t.ntz, tyi = (tile / t.ntz) % t.nty, txi = t.tx0 + tile / (t.ntz * t.nty);
     const int x0 = txi * NRL_TX, y0 = tyi * NRL_TY, z0 = tzi * NRL_TZ;
     const float s = t.spacing, c = t.cutoff;
     const float c2 = c * c;

@@ -98,7 +98,9 @@ __device__ __forceinline__ int nrl_buff_dim_device(float cutoff, float spacing) 
 // the plain C layout for the cubic grids every reference config uses.
 struct NrlTask {
   int nx, ny, nz;
-  int ntx, nty, ntz;        // tiles per axis
+  int ntx, nty, ntz;        // tiles per axis (ntx: of the task's slab, see tx0)
+  int tx0;                  // first tile along x: a task may cover only the slab [tx0, tx0 + ntx) of its grid (the grid
+                            // of one task split over several GPUs); ch_out is shifted so that the slab is stored compactly
   int tile_begin;           // first work item of this task in the launch
   int n_frames;             // frames observed (already clamped to NRL_MAX_FRAMES)
   // A work item produces up to NRL_MAX_CH output grids ("channels") from ONE sweep: several reducers

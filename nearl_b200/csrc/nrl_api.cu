@@ -451,11 +451,19 @@ void fill_task_geometry(NrlTask &t, const int *dims, float spacing, float cutoff
   t.ntx = (t.nx + NRL_TX - 1) / NRL_TX;
   t.nty = (t.ny + NRL_TY - 1) / NRL_TY;
   t.ntz = (t.nz + NRL_TZ - 1) / NRL_TZ;
+  t.tx0 = 0;
   t.spacing = spacing;
   t.cutoff = cutoff;
   t.sigma = sigma;
   t.k2 = sigma != 0.0f ? (float)(-0.5 * 1.4426950408889634 / ((double)sigma * (double)sigma)) : 0.0f;
   t.sphere_volume = (4.0 / 3.0) * M_PI * (double)cutoff * (double)cutoff * (double)cutoff;
+}
+
+// restrict a task to the slab [x_begin, x_begin + x_count) of its slowest axis (validated by the caller; x_count 0: no-op)
+void apply_slab(NrlTask &t, int x_begin, int x_count) {
+  if (x_count <= 0) return;
+  t.tx0 = x_begin / NRL_TX;
+  t.ntx = (x_count + NRL_TX - 1) / NRL_TX;
 }
 
 int ensure_aux(Ctx &c) {

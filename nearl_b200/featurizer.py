@@ -88,8 +88,13 @@ class Featurizer:
     # re-used page-locked buffer and must be consumed inside the call
     self.result_sink = None
     self.last_run_stats = {}
-    # nearl_b200: trajectories in flight in run() (upload of i+1 and i+2 under the kernels of i); 1 = no overlap
-    self.pipeline_depth = 3
+    # nearl_b200: a task-sharded run (run(task_shard=...), sharding.run_task_sharded) leaves its parts here
+    self._task_shard = None
+    self.SHARD_RESULTS = {}
+    # nearl_b200: trajectories in flight in run(), one per lane of the native library (the uploads of the next ones and the
+    # crop / binning of the one after run under the sweeps of the current one); 1 = no overlap.  Measured on B200, headline
+    # workload, frames/s end to end: 3 -> 178 k, 4 -> 192 k, 5 -> 205 k, 7 / 8 -> 207 k (the host-to-device link's limit)
+    self.pipeline_depth = 8
     # nearl_b200: single-frame systems featurised per native call when every feature is static (time_window 1);
     # 1 = one system per call
     self.static_group = 32
@@ -235,10 +240,13 @@ class Featurizer:
     return np.mean(firsts[:, selection], axis=1)
 
   # ---- the loop -----------------------------------------------------------------------------
-  def run(self, *_ignored, trajectory_indices=None):
+  def run(self, *_ignored, trajectory_indices=None, task_shard=None):
     """Featurise every registered trajectory (featurizer.py:399-469).  Positional arguments
     (the worker counts some scripts pass) are accepted and ignored.  `trajectory_indices`
-    restricts the loop to a shard (multi-GPU: one process per GPU, see nearl_b200.sharding).
+    restricts the loop to a shard (multi-GPU: one process per GPU, see nearl_b200.sharding).  `task_shard` =
+    (rank, world[, n_slabs]) shards INSIDE every trajectory instead -- this process computes its share of the (window,
+    focal point) units, cut into slabs of the voxel grid when there are fewer units than ranks -- and leaves the parts in
+    `self.SHARD_RESULTS` for `sharding.run_task_sharded` to collect (nothing is dumped by this call).
 
     Trajectories are software-pipelined over `pipeline_depth` lanes of the native library: while
     the kernels of trajectory i run, the host lowers the next ones and their frames upload;
@@ -248,9 +256,17 @@ class Featurizer:
     t_run = time.perf_counter()
     depth = max(1, min(int(self.pipeline_depth), 8))        # lanes of the native library (NRL_MAX_LANES)
     self.__dict__.pop("_fingerprint_memo", None)
+    self._task_shard = None
+    if task_shard is not None:
+      rank, world = int(task_shard[0]), int(task_shard[1])
+      if not 0 <= rank < world:
+        raise ValueError(f"task_shard: rank {rank} outside a world of {world}")
+      self._task_shard = (rank, world, task_shard[2] if len(task_shard) > 2 else None)
+      self.SHARD_RESULTS = {}
     with utils.hdf_session():                                # output files stay open until the run is over
-      done = self._run_static_groups(indices, depth, stats) if self._static_groupable() else 0
+      done = self._run_static_groups(indices, depth, stats) if (self._static_groupable() and self._task_shard is None) else 0
       self._run_pipelined(indices[done:], depth, stats)
+    self._task_shard = None
     stats["seconds"] = time.perf_counter() - t_run
     self.last_run_stats = stats
     printit(f"{self.classname}: All trajectories and tasks are finished. \n")
@@ -447,27 +463,53 @@ class Featurizer:
       feat.cache(self.traj)
     # task list in the reference's order: window -> focal point -> feature
     n_focal = self.FOCALNUMBER if self.FOCALNUMBER > 0 else 1
-    task_keys = [(bid, pid, fidx) for bid in range(self.SLICENUMBER) for pid in range(n_focal)
-                 for fidx in range(self.FEATURENUMBER)]
     specs = [feat._native_spec() if (self.use_native_batch and hasattr(feat, "_native_spec")) else None
              for feat in self.FEATURESPACE]
     native_feats = [f for f in range(self.FEATURENUMBER) if specs[f] is not None]
+    slabs = None
+    if self._task_shard is None:
+      task_keys = [(bid, pid, fidx) for bid in range(self.SLICENUMBER) for pid in range(n_focal)
+                   for fidx in range(self.FEATURENUMBER)]
+    else:
+      task_keys, slabs = self.shard_task_list(self._task_shard, specs)
     native_ids = [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is not None]
-    job = {"tid": tid, "traj": self.traj, "task_keys": task_keys, "native_ids": native_ids, "lane": lane, "start": st,
+    job = {"tid": tid, "traj": self.traj, "task_keys": task_keys, "native_ids": native_ids, "lane": lane, "start": st, "slabs": slabs,
            "generic_ids": [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is None], "batch": None}
     job["generic_results"] = self._run_generic_tasks(job)
     if native_ids:
       xyz = self.traj.xyz
       if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
         xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
-      batch = self.lower_batch(native_feats, specs, xyz.shape[1], xyz.dtype == np.float64, lane=lane)
+      task_list = None if slabs is None else tuple(task_keys[i] + slabs[i] for i in native_ids)
+      batch = self.lower_batch(native_feats, specs, xyz.shape[1], xyz.dtype == np.float64, lane=lane, task_list=task_list)
       buffers = self.__dict__.setdefault("_out_buffers", {})
       if lane not in buffers or buffers[lane].size < batch.out_floats:
-        buffers[lane] = pinned_empty((batch.out_floats,), np.float32)     # page-locked, reused across trajectories
+        buffers[lane] = pinned_empty((max(batch.out_floats, 1),), np.float32)     # page-locked, reused across trajectories
       out = buffers[lane][:batch.out_floats]
       batch.execute(_lib.addr(xyz), xyz.shape[0], _lib.addr(out), no_sync=True, lane=lane)      # both live in `job`
       job.update(batch=batch, out=out, xyz=xyz)
     return job
+
+  def shard_task_list(self, task_shard, specs):
+    """The (window, focal point, feature) tasks of the ACTIVE trajectory that rank `task_shard[0]` of `task_shard[1]`
+    computes, with the grid slab (x_begin, x_count; 0, 0 = whole grid) of each: unit -> slab -> feature order.  A task that
+    cannot be cut (host protocol, non-cubic grid) goes whole to the owner of the unit's first slab."""
+    from . import sharding
+    rank, world, n_slabs = (tuple(task_shard) + (None,))[:3]
+    n_focal = self.FOCALNUMBER if self.FOCALNUMBER > 0 else 1
+    task_keys, slabs = [], []
+    for unit, cuts in sorted(sharding.task_parts(self.SLICENUMBER * n_focal, rank, world, n_slabs).items()):
+      bid, pid = divmod(unit, n_focal)
+      for slab, of in cuts:
+        for fidx, feat in enumerate(self.FEATURESPACE):
+          dims = [int(v) for v in feat.dims] if getattr(feat, "dims", None) is not None else []
+          cuttable = specs[fidx] is not None and of > 1 and len(dims) == 3 and dims[0] == dims[1] == dims[2]
+          xb, xc = sharding.slab_range(dims[0], slab, of) if cuttable else ((0, 0) if slab == 0 else (0, -1))
+          if xc < 0 or (cuttable and xc == 0):
+            continue
+          task_keys.append((bid, pid, fidx))
+          slabs.append((xb, xc))
+    return task_keys, slabs
 
   def _run_generic_tasks(self, job):
     """The host-protocol tasks of `job` (label features, user subclasses that override query / run), evaluated at
@@ -497,6 +539,15 @@ class Featurizer:
     for i, res in job["generic_results"].items():
       results[i] = res
     tid = job["tid"]
+    if job.get("slabs") is not None:
+      # a task-sharded run: the parts wait for sharding.run_task_sharded (copies: the lane's buffer is reused)
+      self.SHARD_RESULTS.setdefault(tid, []).extend(
+        (bid, pid, fidx, xb, np.array(res)) for (bid, pid, fidx), (xb, _), res in zip(task_keys, job["slabs"], results))
+      stats["trajectories"] += 1
+      stats["tasks"] += len(task_keys)
+      stats["native_tasks"] += len(job["native_ids"])
+      stats["frames"] += job["traj"].n_frames // self.time_window * self.time_window
+      return
     printit(f"{self.classname}: Trajectory {tid + 1} yields {len(task_keys)} frame-slices (tasks) for the featurization. ")
     with utils.batched_output():
       for (bid, pid, fidx), result in zip(task_keys, results):
@@ -512,6 +563,27 @@ class Featurizer:
     stats["native_tasks"] += len(job["native_ids"])
     stats["frames"] += job["traj"].n_frames // self.time_window * self.time_window
     printit(f"{self.classname}: Finished the trajectory {tid + 1} / {self.TRAJECTORYNUMBER} with {len(task_keys)} tasks in {time.perf_counter() - job['start']:.6f} seconds")
+
+  def deliver_shard_results(self, parts):
+    """`parts`: {trajectory index: [(window, focal point, feature index, x_begin, array), ...]} from every rank of a
+    task-sharded run.  Slabs are put together along the first axis and the results are handed on in the reference's
+    order (trajectory -> window -> focal point -> feature), as `_finish` does for an unsharded run."""
+    with utils.hdf_session():
+      for tid in sorted(parts):
+        whole = {}
+        for bid, pid, fidx, xb, arr in parts[tid]:
+          whole.setdefault((bid, pid, fidx), []).append((xb, arr))
+        with utils.batched_output():
+          for (bid, pid, fidx) in sorted(whole):
+            pieces = sorted(whole[(bid, pid, fidx)], key=lambda p: p[0])
+            result = pieces[0][1] if len(pieces) == 1 else np.concatenate([a for _, a in pieces], axis=0)
+            feat = self.FEATURESPACE[fidx]
+            if self.result_sink is not None:
+              self.result_sink(feat.outkey, tid, bid, pid, result)
+            if self.keep_results:
+              self.RESULTS.setdefault(feat.outkey, []).append(result)
+            if feat.outfile or (self.result_sink is None and not self.keep_results):
+              feat.dump(result)
 
   # ---- residue-classification data sets ------------------------------------------------------------
   def _residue_blocks(self, restype, tag_limit=0):
@@ -740,7 +812,7 @@ class Featurizer:
     return batch
 
   # ---- lowering to nrl_featurize_batch --------------------------------------------------------
-  def _template(self, native_feats, specs, n_atoms, is_f64):
+  def _template(self, native_feats, specs, n_atoms, is_f64, task_list=None):
     """Crop / task tables for the current (features, windows, focal points) structure.  Only the
     focal points, weights and selections change from one trajectory to the next, so the tables
     are built once and re-used.  Crops are shared by every feature that looks at the same frames
@@ -758,7 +830,7 @@ class Featurizer:
       return fixed + (float(sp["sigma"]), bool(sp.get("selection_folded")), sp["kind"], sp["mode"], sp["agg"],
                       sp["frame_offset"], sp["max_atoms"], sp.get("ranks") is not None, sp.get("weight_sig"))
 
-    key = (tuple(fingerprint(f) for f in native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64))
+    key = (tuple(fingerprint(f) for f in native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64), task_list)
     cache = self.__dict__.setdefault("_template_cache", {})
     if key in cache:
       return cache[key]
@@ -780,49 +852,50 @@ class Featurizer:
     sel_of = {f: i for i, f in enumerate(sel_feats)}
     crops, crop_ids, crop_slots, tasks, shapes = [], {}, [], [], []
     order_feats, any_byres = [], False
-    for bid in range(self.SLICENUMBER):
-      for pid in range(n_focal):
-        for fidx in native_feats:
-          feat, spec = self.FEATURESPACE[fidx], specs[fidx]
-          wid = table_of[fidx]
-          sid = sel_of.get(fidx, -1)
-          sort_table = wid if (spec["mode"] == 3 and fidx not in rank_of) else -1
-          if sort_table >= 0 and fidx not in order_feats:
-            order_feats.append(fidx)
-          start = bid * self.time_window
-          if spec["kind"] == "static":
-            start, n_frames = start + spec["frame_offset"], 1
-          else:
-            n_frames = self.time_window
-          half = feat.spacing / 2
-          lo = 0 - feat.padding - half                                    # python float: numpy compares it as float32 ...
-          lo_cmp = float(np.float32(lo)) if not is_f64 else lo             # ... against float32 coordinates (weak scalar)
-          hi = tuple(float(feat.lengths[k] + feat.padding - half) for k in range(3))   # np.float64: compared in double
-          ckey = (bid, pid, start, n_frames, feat.center.tobytes(), half, lo_cmp, hi, bool(feat.byres), sid,
-                  spec["max_atoms"], sort_table)
-          if ckey not in crop_ids:
-            crop_ids[ckey] = len(crops)
-            c = _lib.CropStruct()
-            c.frame_start, c.n_frames = start, n_frames
-            c.center[:] = [float(v) for v in feat.center]
-            c.half_spacing_f32 = float(np.float32(half))
-            c.half_spacing_f64 = float(half)
-            c.lo[:] = [lo_cmp] * 3
-            c.hi[:] = hi
-            c.byres = 1 if feat.byres else 0
-            c.selection = sid
-            c.max_atoms = spec["max_atoms"]
-            c.sort_table = sort_table
-            any_byres |= bool(feat.byres)
-            crops.append(c)
-            crop_slots.append((bid, pid))
-          t = _lib.TaskStruct()
-          t.crop, t.mode, t.agg, t.weight_table = crop_ids[ckey], spec["mode"], spec["agg"], wid
-          t.rank_table = rank_of.get(fidx, -1)
-          t.dims[:] = [int(v) for v in feat.dims]
-          t.spacing, t.cutoff, t.sigma = float(feat.spacing), float(feat.cutoff), float(spec["sigma"])
-          tasks.append(t)
-          shapes.append(tuple(int(v) for v in feat.dims))
+    if task_list is None:      # every (window, focal point, feature), whole grids
+      task_list = [(bid, pid, fidx, 0, 0) for bid in range(self.SLICENUMBER) for pid in range(n_focal) for fidx in native_feats]
+    for bid, pid, fidx, x_begin, x_count in task_list:
+      feat, spec = self.FEATURESPACE[fidx], specs[fidx]
+      wid = table_of[fidx]
+      sid = sel_of.get(fidx, -1)
+      sort_table = wid if (spec["mode"] == 3 and fidx not in rank_of) else -1
+      if sort_table >= 0 and fidx not in order_feats:
+        order_feats.append(fidx)
+      start = bid * self.time_window
+      if spec["kind"] == "static":
+        start, n_frames = start + spec["frame_offset"], 1
+      else:
+        n_frames = self.time_window
+      half = feat.spacing / 2
+      lo = 0 - feat.padding - half                                    # python float: numpy compares it as float32 ...
+      lo_cmp = float(np.float32(lo)) if not is_f64 else lo             # ... against float32 coordinates (weak scalar)
+      hi = tuple(float(feat.lengths[k] + feat.padding - half) for k in range(3))   # np.float64: compared in double
+      ckey = (bid, pid, start, n_frames, feat.center.tobytes(), half, lo_cmp, hi, bool(feat.byres), sid,
+              spec["max_atoms"], sort_table)
+      if ckey not in crop_ids:
+        crop_ids[ckey] = len(crops)
+        c = _lib.CropStruct()
+        c.frame_start, c.n_frames = start, n_frames
+        c.center[:] = [float(v) for v in feat.center]
+        c.half_spacing_f32 = float(np.float32(half))
+        c.half_spacing_f64 = float(half)
+        c.lo[:] = [lo_cmp] * 3
+        c.hi[:] = hi
+        c.byres = 1 if feat.byres else 0
+        c.selection = sid
+        c.max_atoms = spec["max_atoms"]
+        c.sort_table = sort_table
+        any_byres |= bool(feat.byres)
+        crops.append(c)
+        crop_slots.append((bid, pid))
+      t = _lib.TaskStruct()
+      t.crop, t.mode, t.agg, t.weight_table = crop_ids[ckey], spec["mode"], spec["agg"], wid
+      t.rank_table = rank_of.get(fidx, -1)
+      t.x_begin, t.x_count = int(x_begin), int(x_count)
+      t.dims[:] = [int(v) for v in feat.dims]
+      t.spacing, t.cutoff, t.sigma = float(feat.spacing), float(feat.cutoff), float(spec["sigma"])
+      tasks.append(t)
+      shapes.append((int(x_count) if x_count else int(feat.dims[0]), int(feat.dims[1]), int(feat.dims[2])))
     tpl = {"crops": crops, "crop_slots": crop_slots, "tasks": (_lib.TaskStruct * len(tasks))(*tasks), "shapes": shapes,
            "sel_feats": sel_feats, "order_feats": order_feats, "rank_feats": rank_feats, "table_feats": table_feats,
            "table_of": table_of, "any_byres": any_byres,
@@ -841,12 +914,12 @@ class Featurizer:
       buf = pool[(lane, name)] = pinned_empty((max(need, 1),), dtype)
     return buf[:need].reshape(shape)
 
-  def lower_batch(self, native_feats, specs, n_atoms, is_f64, lane=None):
+  def lower_batch(self, native_feats, specs, n_atoms, is_f64, lane=None, task_list=None):
     """Crop and task tables of the C ABI for the active trajectory (tasks in the reference's
     order window -> focal point -> feature, restricted to `native_feats`).  With a `lane` the
     per-trajectory tables are written into that lane's page-locked buffers, which stay valid until
     the lane's next submission."""
-    tpl = self._template(native_feats, specs, n_atoms, is_f64)
+    tpl = self._template(native_feats, specs, n_atoms, is_f64, task_list)
     batch = LoweredBatch()
     batch.n_atoms, batch.is_f64 = n_atoms, bool(is_f64)
     # the crop table of the template as a numpy record array (a ctypes array costs microseconds per element to copy and
@@ -868,6 +941,7 @@ class Featurizer:
     batch._keep = crops                # the ctypes view below borrows this array
     batch.crops, batch.n_crops = crops.ctypes.data_as(ctypes.POINTER(_lib.CropStruct)), len(crops)
     batch.tasks, batch.shapes, batch.out_floats = tpl["tasks"], tpl["shapes"], tpl["out_floats"]
+    batch.n_tasks_total = len(tpl["shapes"])
     rows = [specs[f]["weights"] for f in tpl["table_feats"]] + [specs[f]["ranks"] for f in tpl["rank_feats"]]
     batch.weight_tables = self._table_buffer(lane, "weights", (len(rows), n_atoms), np.float32)
     for i, row in enumerate(rows):
