@@ -89,7 +89,7 @@ class Featurizer:
     self.result_sink = None
     self.last_run_stats = {}
     # nearl_b200: a task-sharded run (run(task_shard=...), sharding.run_task_sharded) leaves its parts here
-    self._task_shard = None
+    self._task_shard = self._shard_device_out = None
     self.SHARD_RESULTS = {}
     # nearl_b200: trajectories in flight in run(), one per lane of the native library (the uploads of the next ones and the
     # crop / binning of the one after run under the sweeps of the current one); 1 = no overlap.  Measured on B200, headline
@@ -240,13 +240,15 @@ class Featurizer:
     return np.mean(firsts[:, selection], axis=1)
 
   # ---- the loop -----------------------------------------------------------------------------
-  def run(self, *_ignored, trajectory_indices=None, task_shard=None):
+  def run(self, *_ignored, trajectory_indices=None, task_shard=None, shard_device_out=None):
     """Featurise every registered trajectory (featurizer.py:399-469).  Positional arguments
     (the worker counts some scripts pass) are accepted and ignored.  `trajectory_indices`
     restricts the loop to a shard (multi-GPU: one process per GPU, see nearl_b200.sharding).  `task_shard` =
     (rank, world[, n_slabs]) shards INSIDE every trajectory instead -- this process computes its share of the (window,
     focal point) units, cut into slabs of the voxel grid when there are fewer units than ranks -- and leaves the parts in
-    `self.SHARD_RESULTS` for `sharding.run_task_sharded` to collect (nothing is dumped by this call).
+    `self.SHARD_RESULTS` for `sharding.run_task_sharded` to collect (nothing is dumped by this call).  With
+    `shard_device_out` (callable(lane, n_floats) -> device address) the parts stay in device memory, one buffer per lane,
+    to be sent to rank 0 over NVLink; SHARD_RESULTS then describes them instead of holding them.
 
     Trajectories are software-pipelined over `pipeline_depth` lanes of the native library: while
     the kernels of trajectory i run, the host lowers the next ones and their frames upload;
@@ -262,11 +264,12 @@ class Featurizer:
       if not 0 <= rank < world:
         raise ValueError(f"task_shard: rank {rank} outside a world of {world}")
       self._task_shard = (rank, world, task_shard[2] if len(task_shard) > 2 else None)
+      self._shard_device_out = shard_device_out
       self.SHARD_RESULTS = {}
     with utils.hdf_session():                                # output files stay open until the run is over
       done = self._run_static_groups(indices, depth, stats) if (self._static_groupable() and self._task_shard is None) else 0
       self._run_pipelined(indices[done:], depth, stats)
-    self._task_shard = None
+    self._task_shard = self._shard_device_out = None
     stats["seconds"] = time.perf_counter() - t_run
     self.last_run_stats = stats
     printit(f"{self.classname}: All trajectories and tasks are finished. \n")
@@ -476,12 +479,22 @@ class Featurizer:
     job = {"tid": tid, "traj": self.traj, "task_keys": task_keys, "native_ids": native_ids, "lane": lane, "start": st, "slabs": slabs,
            "generic_ids": [i for i, (_, _, fidx) in enumerate(task_keys) if specs[fidx] is None], "batch": None}
     job["generic_results"] = self._run_generic_tasks(job)
+    if slabs is not None and self._shard_device_out is not None and self._task_shard[0] == 0:
+      # rank 0 lays the whole grids out: what every rank sends, in the order it sends it
+      job["all_parts"] = [self.shard_task_list((r,) + self._task_shard[1:], specs) for r in range(self._task_shard[1])]
+      job["native_mask"] = [sp is not None for sp in specs]
+    job["has_generic"] = any(sp is None for sp in specs)
     if native_ids:
       xyz = self.traj.xyz
       if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
         xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
       task_list = None if slabs is None else tuple(task_keys[i] + slabs[i] for i in native_ids)
       batch = self.lower_batch(native_feats, specs, xyz.shape[1], xyz.dtype == np.float64, lane=lane, task_list=task_list)
+      if slabs is not None and self._shard_device_out is not None:
+        # task-sharded run whose parts go to rank 0 over NVLink: results stay on the device, in the caller's buffer of this lane
+        batch.execute(_lib.addr(xyz), xyz.shape[0], self._shard_device_out(lane, batch.out_floats), out_on_device=True, no_sync=True, lane=lane)
+        job.update(batch=batch, out=None, xyz=xyz)
+        return job
       buffers = self.__dict__.setdefault("_out_buffers", {})
       if lane not in buffers or buffers[lane].size < batch.out_floats:
         buffers[lane] = pinned_empty((max(batch.out_floats, 1),), np.float32)     # page-locked, reused across trajectories
@@ -532,13 +545,27 @@ class Featurizer:
     """Wait for the native results of `job`, merge its host-protocol results, dump in order."""
     task_keys = job["task_keys"]
     results = [None] * len(task_keys)
+    on_device = job["batch"] is not None and job.get("out", 0) is None
     if job["batch"] is not None:
       _lib.check(_lib.lib().nrl_lane_synchronize(job["lane"]))
-      for i, arr in zip(job["native_ids"], job["batch"].split(job["out"], copy=self.keep_results)):
-        results[i] = arr
+      if not on_device:
+        for i, arr in zip(job["native_ids"], job["batch"].split(job["out"], copy=self.keep_results)):
+          results[i] = arr
     for i, res in job["generic_results"].items():
       results[i] = res
     tid = job["tid"]
+    if job.get("slabs") is not None and (on_device or self._shard_device_out is not None):
+      # a task-sharded run whose native parts stay in the lane's device buffer: describe them, keep the host-protocol ones
+      self.SHARD_RESULTS[tid] = {
+        "lane": job["lane"], "floats": job["batch"].out_floats if job["batch"] is not None else 0,
+        "generic": [(bid, pid, fidx, 0, np.array(results[i])) for i, (bid, pid, fidx) in enumerate(task_keys) if i in job["generic_results"]],
+        "all_parts": job.get("all_parts"), "native_mask": job.get("native_mask"), "has_generic": job["has_generic"],
+        "dims": [tuple(int(v) for v in f.dims) if getattr(f, "dims", None) is not None else None for f in self.FEATURESPACE]}
+      stats["trajectories"] += 1
+      stats["tasks"] += len(task_keys)
+      stats["native_tasks"] += len(job["native_ids"])
+      stats["frames"] += job["traj"].n_frames // self.time_window * self.time_window
+      return
     if job.get("slabs") is not None:
       # a task-sharded run: the parts wait for sharding.run_task_sharded (copies: the lane's buffer is reused)
       self.SHARD_RESULTS.setdefault(tid, []).extend(

@@ -99,7 +99,10 @@ def slab_range(n, slab, n_slabs):
 def run_task_sharded(featurizer, rank=None, world=None, device=None, group=None, n_slabs=None, trajectory_indices=None):
   """Featurise every trajectory on ALL ranks, each computing its `task_parts`; rank 0 receives the parts of a trajectory,
   puts the grids together and hands them on -- `result_sink`, `keep_results`, `Feature.dump` -- in the reference's order,
-  so the HDF5 file is the one a single GPU writes.  Returns the run's statistics (rank 0: of the assembled results)."""
+  so the HDF5 file is the one a single GPU writes.  Over an NCCL process group the parts never visit the host on the
+  way: every rank leaves them in device memory and sends them to rank 0 point to point (NVLink), rank 0 copies each slab
+  to its place in a page-locked buffer of whole grids.  Otherwise (gloo, tests) the parts travel as host arrays.
+  Returns the run's statistics."""
   import torch.distributed as dist
   from . import _lib
   if rank is None or world is None:
@@ -108,6 +111,8 @@ def run_task_sharded(featurizer, rank=None, world=None, device=None, group=None,
     device = int(os.environ.get("LOCAL_RANK", rank))
   if _lib.device_count() > 0:
     _lib.check(_lib.lib().nrl_set_device(device % _lib.device_count()))
+  if world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
+    return _run_task_sharded_nccl(featurizer, rank, world, group, n_slabs, trajectory_indices)
   stats = featurizer.run(trajectory_indices=trajectory_indices, task_shard=(rank, world, n_slabs))
   local = featurizer.SHARD_RESULTS
   featurizer.SHARD_RESULTS = {}
@@ -124,3 +129,80 @@ def run_task_sharded(featurizer, rank=None, world=None, device=None, group=None,
       merged.setdefault(tid, []).extend(items)
   featurizer.deliver_shard_results(merged)
   return stats
+
+
+def _run_task_sharded_nccl(featurizer, rank, world, group, n_slabs, trajectory_indices):
+  import torch
+  import torch.distributed as dist
+  indices = list(range(featurizer.TRAJECTORYNUMBER) if trajectory_indices is None else trajectory_indices)
+  depth = max(1, min(int(featurizer.pipeline_depth), 8))
+  state = featurizer.__dict__.setdefault("_shard_nccl_state", {"lane": {}, "recv": None, "whole": None})
+  lane_bufs = state["lane"]
+
+  def device_out(lane, n_floats):
+    buf = lane_bufs.get(lane)
+    if buf is None or buf.numel() < n_floats:
+      buf = lane_bufs[lane] = torch.empty(max(int(n_floats * 1.25), 1), dtype=torch.float32, device="cuda")
+    return buf.data_ptr()
+
+  total = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "frames": 0, "seconds": 0.0}
+  for c0 in range(0, len(indices), depth):
+    chunk = indices[c0:c0 + depth]          # one lane (and its device buffer) per trajectory of the chunk
+    stats = featurizer.run(trajectory_indices=chunk, task_shard=(rank, world, n_slabs), shard_device_out=device_out)
+    for key in total:
+      total[key] += stats.get(key, 0)
+    local = featurizer.SHARD_RESULTS
+    featurizer.SHARD_RESULTS = {}
+    generic = {}
+    if any(info["has_generic"] for info in local.values()):      # the same answer on every rank: same trajectories, same features
+      bucket = [None] * world if rank == 0 else None
+      dist.gather_object({tid: info["generic"] for tid, info in local.items()}, bucket, dst=0, group=group)
+      for part in bucket or []:
+        for tid, items in part.items():
+          generic.setdefault(tid, []).extend(items)
+    parts = {}
+    for tid in chunk:
+      info = local.get(tid)
+      if info is None:
+        continue                              # skipped (no focal point): on every rank alike
+      if rank != 0:
+        if info["floats"]:
+          dist.send(lane_bufs[info["lane"]][:info["floats"]], dst=0, group=group)
+        continue
+      # rank 0: whole grids of this trajectory in a page-locked buffer, every slab copied to its rows
+      dims, native = info["dims"], info["native_mask"]
+      offsets, n_whole = {}, 0
+      for r in range(world):
+        for (bid, pid, fidx) in info["all_parts"][r][0]:
+          if native[fidx] and (bid, pid, fidx) not in offsets:
+            offsets[(bid, pid, fidx)] = n_whole
+            n_whole += int(np.prod(dims[fidx]))
+      if state["whole"] is None or state["whole"].numel() < n_whole:
+        state["whole"] = torch.empty(max(n_whole, 1), dtype=torch.float32).pin_memory()
+      whole = state["whole"]
+      for r in range(world):
+        keys, slabs = info["all_parts"][r]
+        sizes = [(xc or dims[fidx][0]) * dims[fidx][1] * dims[fidx][2] if native[fidx] else 0 for (_, _, fidx), (_, xc) in zip(keys, slabs)]
+        n_r = int(sum(sizes))
+        if n_r == 0:
+          continue
+        if r == 0:
+          src = lane_bufs[info["lane"]]
+        else:
+          if state["recv"] is None or state["recv"].numel() < n_r:
+            state["recv"] = torch.empty(int(n_r * 1.25), dtype=torch.float32, device="cuda")
+          src = state["recv"]
+          dist.recv(src[:n_r], src=r, group=group)
+        pos = 0
+        for (bid, pid, fidx), (xb, _), size in zip(keys, slabs, sizes):
+          if size == 0:
+            continue
+          at = offsets[(bid, pid, fidx)] + xb * dims[fidx][1] * dims[fidx][2]
+          whole[at:at + size].copy_(src[pos:pos + size], non_blocking=True)
+          pos += size
+        torch.cuda.current_stream().synchronize()       # `recv` is reused for the next rank
+      host = whole.numpy()
+      items = [(bid, pid, fidx, 0, host[at:at + int(np.prod(dims[fidx]))].reshape(dims[fidx])) for (bid, pid, fidx), at in offsets.items()]
+      featurizer.deliver_shard_results({tid: items + generic.get(tid, [])})
+    torch.cuda.synchronize()                  # the lanes' device buffers are written again by the next chunk
+  return total

@@ -48,6 +48,43 @@ if rank == 0:
       ok &= same
       print(key, x.shape, "identical to the single-GPU file:", same)
   print("shards:", [sharding.shard_indices(7, r, world) for r in range(world)])
+
+# ---- one trajectory over all GPUs: (window, focal point) units and grid slabs, parts sent to rank 0 over NCCL ----------
+class Custom(features.Mass):                 # a user subclass: host protocol, goes whole to the owner of the unit's first slab
+  def run(self, coords, weights):
+    return features.Mass.run(self, coords, weights) * 2.0
+
+def make_big(outfile=None):
+  trajs = [io.synthetic_trajectory(6000, 12, seed=600 + i, pin=False) for i in range(3)]
+  fz = featurizer.Featurizer({"dimensions": 48, "lengths": 24, "time_window": 6, "cutoff": 4.0, "sigma": 1.3,
+                              **({"outfile": outfile} if outfile else {})})
+  fz.register_features([features.Mass(outkey="mass"),
+                        features.MarchingObservers(obs="existence", agg="mean", outkey="exist"),
+                        features.MarchingObservers(obs="mean_distance", agg="standard_deviation", weight_type="mass", outkey="meandist"),
+                        features.DensityFlow(agg="mean", weight_type="mass", outkey="flow"),
+                        Custom(outkey="custom", dimensions=16, lengths=8.0)])
+  fz.register_focus([":ARG"], "mask")
+  fz.register_trajloader(trajs)
+  return fz
+
+tmp = [tempfile.mkdtemp() if rank == 0 else None]
+dist.broadcast_object_list(tmp, src=0)
+shard_file = os.path.join(tmp[0], "task_sharded.h5")
+fzs = make_big(outfile=shard_file if rank == 0 else None)
+for feat in fzs.FEATURESPACE:
+  feat.outfile = shard_file if rank == 0 else None
+sstats = sharding.run_task_sharded(fzs, rank, world, device=local_rank)
+if rank == 0:
+  ref_file = os.path.join(tmp[0], "task_single.h5")
+  single = make_big(outfile=ref_file)
+  single.run()
+  with utils.open_hdf(shard_file, "r") as a, utils.open_hdf(ref_file, "r") as b:
+    for key in ("mass", "exist", "meandist", "flow", "custom"):
+      x, y = a[key][:], b[key][:]
+      same = x.shape == y.shape and np.array_equal(x, y)
+      ok &= same
+      print("task-sharded", key, x.shape, "identical to the single-GPU file:", same)
+  print("parts of rank 0..:", [sharding.task_parts(2, r, world) for r in range(world)])
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 dist.destroy_process_group()
