@@ -34,6 +34,7 @@ std::atomic<int> g_force_scan{0};    // nrl_set_option("force_scan", 1): never u
 std::atomic<int> g_agg_pipe_w{0};    // nrl_set_option("agg_pipe_w" / "agg_pipe_stages"): tile width / ring depth of the pipelined K3
 std::atomic<int> g_agg_pipe_stages{0};
 std::atomic<int> g_agg_entropy_legacy{0};   // nrl_set_option("agg_entropy_legacy"): former histogram form in the staged / pipelined K3 (tests)  // (0 = chosen from the series length; -1 stages = staged one-shot kernel instead)
+std::atomic<int> g_crop_legacy{0};   // nrl_set_option("crop_legacy", 1): never use the streaming crop kernel (tests / A-B timing)
 std::atomic<int> g_no_fuse{0};       // nrl_set_option("no_fuse", 1): one sweep per observable (tests / A-B timing)
 
 int fail(int code, const std::string &msg) {
@@ -81,6 +82,7 @@ struct Ctx {
   DevBuf crops;                                  // descriptor blob of a batch: crops | frame offsets | frame -> crop | frame -> source frame
   DevBuf pbase;                                  // per crop frame: payload base
   DevBuf sup_idx, sup_ref, sup_rmsd;             // superposition: fitted atom indices, reference set, per-frame RMSD
+  DevBuf runcnt;                                 // streaming crop: kept atoms per (frame, run)
   DevBuf batoms, bcnt, cstart, grids;            // cell lists: binned frames, cell prefixes, per-frame cell grids | frame list
   bool attr_set[64] = {false};          // "dynamic shared memory opt-in done" per kernel family, indexed by kAttr*
   bool attr_fused[16] = {false};        // the same for the fused observer sweeps, indexed by their flag set
@@ -1080,6 +1082,7 @@ int nrl_set_option(const char *name, int value) {
   if (!name) return fail(NRL_ERR_ARGUMENT, "option name is NULL");
   if (strcmp(name, "force_scan") == 0) { g_force_scan.store(value != 0); return NRL_OK; }
   if (strcmp(name, "no_fuse") == 0) { g_no_fuse.store(value != 0); return NRL_OK; }
+  if (strcmp(name, "crop_legacy") == 0) { g_crop_legacy.store(value != 0); return NRL_OK; }
   if (strcmp(name, "agg_entropy_legacy") == 0) { g_agg_entropy_legacy.store(value != 0); return NRL_OK; }
   if (strcmp(name, "agg_pipe_w") == 0) { g_agg_pipe_w.store((int)value); return NRL_OK; }
   if (strcmp(name, "agg_pipe_stages") == 0) { g_agg_pipe_stages.store((int)value); return NRL_OK; }

@@ -563,3 +563,43 @@ def test_static_groups_then_multi_frame_trajectories_stay_pipelined(tmp_path):
   for key in plain:
     assert np.array_equal(grouped[key], plain[key]), key
   assert len(set(lanes[-4:])) == 3                                       # the tail of the list uses all three lanes
+
+
+@pytest.mark.parametrize("dtype,n_atoms", [(np.float32, 9000), (np.float64, 9000), (np.float32, 2051), (np.float32, 30001)])
+def test_streaming_crop_keeps_the_same_atoms_in_the_same_order(tmp_path, dtype, n_atoms):
+  """Whole frames in topology order without by-residue expansion go through the streaming crop kernel (every warp a
+  contiguous run, 16-byte loads, kept atoms compacted on the way): selections, the atom cap, float64 coordinates, atom
+  counts that are no multiple of 4 (unaligned frames: scalar loads) and of 128 -- results and per-frame atom counts are
+  those of the first crop kernel, bit for bit, and the host pipeline's."""
+  traj = io.synthetic_trajectory(n_atoms, 6, seed=93, dtype=dtype)
+  parms = {"dimensions": 20, "lengths": 14, "time_window": 3, "cutoff": 3.5, "sigma": 1.2}
+
+  def feats():
+    capped = features.MarchingObservers(obs="direct_count", agg="max", weight_type="mass", outkey="count_capped")
+    capped.MAX_ALLOWED_ATOMS = 300                         # the first 300 in-box atoms in topology order
+    return [features.Mass(outkey="mass", padding=2.0),
+            features.Selection(selection=":ARG,LYS,GLU", outkey="sel"),
+            features.MarchingObservers(obs="mean_distance", agg="mean", weight_type="mass", outkey="mean_distance"),
+            features.MarchingObservers(obs="direct_count", agg="mean", weight_type="mass", outkey="count", selection=":ALA,GLY,SER,THR"),
+            features.DensityFlow(agg="standard_deviation", weight_type="mass", outkey="flow", frame_offset=1),
+            capped]
+
+  out = {}
+  for legacy in (0, 1):
+    _lib.set_option("crop_legacy", legacy)
+    try:
+      sub = tmp_path / f"legacy{legacy}"
+      sub.mkdir()
+      out[legacy], fz = build(traj, sub, feats, parms)
+    finally:
+      _lib.set_option("crop_legacy", 0)
+  for key in out[0]:
+    assert np.array_equal(out[0][key], out[1][key]), key
+  host, _ = build(traj, tmp_path, feats, parms, native=False)
+  for key in out[0]:
+    if key in ("count", "count_capped"):
+      assert np.array_equal(out[0][key], host[key]), key
+    else:
+      scale = max(float(np.abs(host[key]).max()), 1e-30)
+      assert rel_bad(out[0][key], host[key], atol=1e-5 * scale if key == "flow" else 0.0) == 0, (key, np.abs(out[0][key] - host[key]).max())
+  assert out[0]["count_capped"].max() <= 300 and out[0]["count"].max() > 0 and out[0]["sel"].sum() > 0
