@@ -81,6 +81,7 @@ struct Ctx {
   DevBuf xyz, wtabs, sels, resid, orders, resflags;
   DevBuf crops;                                  // descriptor blob of a batch: crops | frame offsets | frame -> crop | frame -> source frame
   DevBuf pbase;                                  // per crop frame: payload base
+  DevBuf sup_xform;                              // superposition: per frame rotation (9) + centroid (3), double
   DevBuf sup_idx, sup_ref, sup_rmsd;             // superposition: fitted atom indices, reference set, per-frame RMSD
   DevBuf runcnt;                                 // streaming crop: kept atoms per (frame, run)
   DevBuf batoms, bcnt, cstart, grids;            // cell lists: binned frames, cell prefixes, per-frame cell grids | frame list
@@ -1041,20 +1042,26 @@ int nrl_superpose(void *xyz, int xyz_is_f64, int n_frames, int n_atoms, const in
     d_xyz = c.xyz.p;
   }
   NRL_TRY(c.sup_idx.reserve((size_t)n_fit * sizeof(int)));
-  NRL_TRY(c.sup_ref.reserve((size_t)(3 + 3 * (size_t)n_fit) * sizeof(double)));
+  NRL_TRY(c.sup_ref.reserve((size_t)(4 + 3 * (size_t)n_fit) * sizeof(double)));
   NRL_TRY(c.sup_rmsd.reserve((size_t)n_frames * sizeof(float)));
   NRL_CUDA(cudaMemcpyAsync(c.sup_idx.p, fit_index, (size_t)n_fit * sizeof(int), cudaMemcpyHostToDevice, st));
   {
     ScopedProf sp(c, st, CAT_SUPERPOSE);
+    NRL_TRY(c.sup_xform.reserve((size_t)n_frames * 12 * sizeof(double)));
+    // apply: enough CTAs per frame for ~8 resident CTAs per SM over all frames, at most one per 1024 atoms
+    const int per_frame = std::max(1, std::min((n_atoms / 4 + NRL_SUPA_NT - 1) / NRL_SUPA_NT, std::max(1, (c.sms * 8 + n_frames - 1) / n_frames)));
+    const dim3 agrid((unsigned)per_frame, (unsigned)n_frames);
     if (xyz_is_f64) {
       nrl_superpose_ref_kernel<double><<<1, NRL_SUP_NT, 0, st>>>((const double *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, ref_frame, c.sup_ref.as<double>());
-      nrl_superpose_kernel<double><<<n_frames, NRL_SUP_NT, 0, st>>>((double *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, c.sup_ref.as<double>(), ref_frame, c.sup_rmsd.as<float>());
+      nrl_superpose_kernel<double><<<n_frames, NRL_SUP_NT, 0, st>>>((double *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, c.sup_ref.as<double>(), ref_frame, c.sup_rmsd.as<float>(), c.sup_xform.as<double>());
+      nrl_superpose_apply_kernel<double><<<agrid, NRL_SUPA_NT, 0, st>>>((double *)d_xyz, n_atoms, c.sup_xform.as<double>(), c.sup_ref.as<double>(), ref_frame);
     } else {
       nrl_superpose_ref_kernel<float><<<1, NRL_SUP_NT, 0, st>>>((const float *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, ref_frame, c.sup_ref.as<double>());
-      nrl_superpose_kernel<float><<<n_frames, NRL_SUP_NT, 0, st>>>((float *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, c.sup_ref.as<double>(), ref_frame, c.sup_rmsd.as<float>());
+      nrl_superpose_kernel<float><<<n_frames, NRL_SUP_NT, 0, st>>>((float *)d_xyz, n_atoms, c.sup_idx.as<int>(), n_fit, c.sup_ref.as<double>(), ref_frame, c.sup_rmsd.as<float>(), c.sup_xform.as<double>());
+      nrl_superpose_apply_kernel<float><<<agrid, NRL_SUPA_NT, 0, st>>>((float *)d_xyz, n_atoms, c.sup_xform.as<double>(), c.sup_ref.as<double>(), ref_frame);
     }
   }
-  g_launches.fetch_add(2);
+  g_launches.fetch_add(3);
   NRL_CUDA(cudaGetLastError());
   if (rmsd) {
     if (on_device) NRL_CUDA(cudaMemcpyAsync(rmsd, c.sup_rmsd.p, (size_t)n_frames * sizeof(float), cudaMemcpyDeviceToDevice, st));
