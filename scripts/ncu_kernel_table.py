@@ -12,7 +12,7 @@ def category(name):
   m = re.search(r"nrl_(cell_)?tile_kernel<\(?(?:int\))?(\d+)", name)
   if m:
     return CATEGORY.get(int(m.group(2)), "tile_?")
-  for key, cat in (("crop_pack", "crop_pack"), ("bin_kernel", "cell_bin"), ("atom_norm", "atom_norm"), ("pack_legacy", "pack_legacy"),
+  for key, cat in (("crop_pack", "crop_pack"), ("crop_stream", "crop_pack"), ("crop_place", "crop_pack"), ("bin_kernel", "cell_bin"), ("atom_norm", "atom_norm"), ("pack_legacy", "pack_legacy"),
                    ("aggregate", "aggregate")):
     if key in name:
       return cat
@@ -33,9 +33,19 @@ def to_bytes(r, key):
     return None
   return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[ix[key]], 1)
 out = {}
+seen_kernels = set()
 for r in rows[2:]:
   cat = category(r[ix["Kernel Name"]])
-  if cat is None or cat in out:
+  if cat is None or r[ix["Kernel Name"]] in seen_kernels:
+    continue
+  seen_kernels.add(r[ix["Kernel Name"]])
+  if cat in out:
+    # a category served by two kernels of one step (the streaming crop and its placement pass): add them up
+    dur = val(r, "gpu__time_duration.sum") * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[ix["gpu__time_duration.sum"]], 1.0)
+    out[cat]["kernel"] += " + " + r[ix["Kernel Name"]]
+    out[cat]["duration_us"] += dur
+    out[cat]["dram_bytes"] += (to_bytes(r, "dram__bytes_read.sum") or 0) + (to_bytes(r, "dram__bytes_write.sum") or 0)
+    out[cat]["warp_instructions"] += val(r, "smsp__inst_executed.sum") or 0
     continue
   dur = val(r, "gpu__time_duration.sum")
   dur_us = dur * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[ix["gpu__time_duration.sum"]], 1.0)
