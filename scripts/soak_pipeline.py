@@ -1,4 +1,4 @@
-"""Soak: many trajectories of ragged sizes through Featurizer.run with three lanes in flight, every result compared bit for
+"""Soak: many trajectories of ragged sizes through Featurizer.run with eight (then five) lanes in flight, every result compared bit for
 bit with a serial single-lane run (buffer re-use, lane hand-over, arena growth).  python scripts/soak_pipeline.py [n_traj]"""
 import os, sys, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,7 +13,7 @@ trajs = [io.synthetic_trajectory(int(rng.integers(200, 9000)), int(rng.choice([4
 def run(depth):
   fz = featurizer.Featurizer({"dimensions": 16, "lengths": 12, "time_window": 4, "cutoff": 3.5, "sigma": 1.2})
   fz.register_features([
-    features.Mass(outkey="mass"), features.HeavyAtom(outkey="heavy", byres=True, selection="!@H="),
+    features.Mass(outkey="mass"), features.HeavyAtom(outkey="heavy", byres=BYRES, selection="!@H="),
     features.MarchingObservers(obs="existence", agg="mean", outkey="e"),
     features.MarchingObservers(obs="distinct_count", agg="max", weight_type="atomic_number", outkey="d"),
     features.MarchingObservers(obs="mean_distance", agg="standard_deviation", weight_type="mass", outkey="m"),
@@ -27,6 +27,12 @@ def run(depth):
   fz.result_sink = lambda key, tid, bid, pid, grid: sums.append((key, tid, bid, pid, zlib.crc32(np.ascontiguousarray(grid).tobytes())))
   fz.run()
   return sums
-a = run(3); b = run(1); c = run(3)
-print("results", len(a), "pipelined == serial:", a == b, "; pipelined twice:", a == c)
-sys.exit(0 if (a == b and a == c) else 1)
+ok = True
+for BYRES in (True, False):        # without a by-residue crop the batches take the streaming crop kernel (first crop kernel: crop_legacy)
+  a = run(8); b = run(1); c = run(5)
+  from nearl_b200 import _lib
+  _lib.set_option("crop_legacy", 1); d = run(8); _lib.set_option("crop_legacy", 0)
+  print("by-residue" if BYRES else "streaming crop", "results", len(a), "pipelined == serial:", a == b, "; pipelined twice:", a == c,
+        "; first crop kernel gives the same:", a == d)
+  ok &= a == b and a == c and a == d
+sys.exit(0 if ok else 1)

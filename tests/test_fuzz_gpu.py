@@ -130,10 +130,13 @@ def test_random_configuration_against_the_oracle(seed):
   fz.keep_results = True
   if seed % 5 == 0:
     _lib.set_option("force_scan", 1)             # every fifth case on the full-frame scan kernels
+  if seed % 2 == 1:
+    _lib.set_option("crop_stream_min", 1)        # every other case: the streaming crop whatever the size of the system
   try:
     fz.run()
   finally:
     _lib.set_option("force_scan", 0)
+    _lib.set_option("crop_stream_min", 0)
   got = {k: np.array(v) for k, v in fz.RESULTS.items()}
   ref = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs_from(fz), fz.FOCALPOINTS, fz.time_window, buff_dim=_lib.buff_dim)
   for f in fz.FEATURESPACE:
@@ -213,9 +216,13 @@ def test_random_single_frame_systems_grouped(seed):
   fz.register_focus([":LIG", ":ARG"][: int(rng.integers(1, 3))], "mask")
   fz.register_trajloader(systems)
   fz.static_group = int(rng.choice([2, 3, 32]))
+  _lib.set_option("crop_stream_min", 1 if seed % 2 else 0)      # odd seeds: member slices (unaligned starts) on the streaming crop
   rows = {}
   fz.result_sink = lambda outkey, tid, bid, pid, grid: rows.setdefault((tid, outkey), []).append(np.array(grid))
-  fz.run()
+  try:
+    fz.run()
+  finally:
+    _lib.set_option("crop_stream_min", 0)
   for tid, traj in enumerate(systems):
     one = featurizer.Featurizer(parms)
     one.register_features([cls(**k) for cls, k in specs])
