@@ -89,7 +89,7 @@ class Featurizer:
     self.result_sink = None
     self.last_run_stats = {}
     # nearl_b200: a task-sharded run (run(task_shard=...), sharding.run_task_sharded) leaves its parts here
-    self._task_shard = self._shard_device_out = None
+    self._task_shard = self._shard_device_out = self._shard_device_xyz = None
     self.SHARD_RESULTS = {}
     # nearl_b200: trajectories in flight in run(), one per lane of the native library (the uploads of the next ones and the
     # crop / binning of the one after run under the sweeps of the current one); 1 = no overlap.  Measured on B200, headline
@@ -240,7 +240,7 @@ class Featurizer:
     return np.mean(firsts[:, selection], axis=1)
 
   # ---- the loop -----------------------------------------------------------------------------
-  def run(self, *_ignored, trajectory_indices=None, task_shard=None, shard_device_out=None):
+  def run(self, *_ignored, trajectory_indices=None, task_shard=None, shard_device_out=None, shard_device_xyz=None):
     """Featurise every registered trajectory (featurizer.py:399-469).  Positional arguments
     (the worker counts some scripts pass) are accepted and ignored.  `trajectory_indices`
     restricts the loop to a shard (multi-GPU: one process per GPU, see nearl_b200.sharding).  `task_shard` =
@@ -248,7 +248,9 @@ class Featurizer:
     focal point) units, cut into slabs of the voxel grid when there are fewer units than ranks -- and leaves the parts in
     `self.SHARD_RESULTS` for `sharding.run_task_sharded` to collect (nothing is dumped by this call).  With
     `shard_device_out` (callable(lane, n_floats) -> device address) the parts stay in device memory, one buffer per lane,
-    to be sent to rank 0 over NVLink; SHARD_RESULTS then describes them instead of holding them.
+    to be sent to rank 0 over NVLink; SHARD_RESULTS then describes them instead of holding them.  `shard_device_xyz`
+    (callable(lane, xyz) -> device address of the whole trajectory) lets the caller bring the coordinates to the device
+    itself (every rank uploads a share of the frames, an all-gather over NVLink does the rest).
 
     Trajectories are software-pipelined over `pipeline_depth` lanes of the native library: while
     the kernels of trajectory i run, the host lowers the next ones and their frames upload;
@@ -265,11 +267,12 @@ class Featurizer:
         raise ValueError(f"task_shard: rank {rank} outside a world of {world}")
       self._task_shard = (rank, world, task_shard[2] if len(task_shard) > 2 else None)
       self._shard_device_out = shard_device_out
+      self._shard_device_xyz = shard_device_xyz
       self.SHARD_RESULTS = {}
     with utils.hdf_session():                                # output files stay open until the run is over
       done = self._run_static_groups(indices, depth, stats) if (self._static_groupable() and self._task_shard is None) else 0
       self._run_pipelined(indices[done:], depth, stats)
-    self._task_shard = self._shard_device_out = None
+    self._task_shard = self._shard_device_out = self._shard_device_xyz = None
     stats["seconds"] = time.perf_counter() - t_run
     self.last_run_stats = stats
     printit(f"{self.classname}: All trajectories and tasks are finished. \n")
@@ -484,6 +487,18 @@ class Featurizer:
       job["all_parts"] = [self.shard_task_list((r,) + self._task_shard[1:], specs) for r in range(self._task_shard[1])]
       job["native_mask"] = [sp is not None for sp in specs]
     job["has_generic"] = any(sp is None for sp in specs)
+    xyz_dev = None
+    if slabs is not None and self._shard_device_xyz is not None and native_feats:
+      # Grid slabs: several ranks read the same frames, so the coordinates go up split over the ranks and an all-gather
+      # completes them on every device.  A collective: EVERY rank takes part for this trajectory, whether or not it has a
+      # task of its own (the decision depends on the trajectory and the world only, never on the rank).
+      units, world = self.SLICENUMBER * n_focal, self._task_shard[1]
+      n_slabs = self._task_shard[2] or (1 if units >= world or units == 0 else -(-world // units))
+      if n_slabs > 1:
+        xyz = self.traj.xyz
+        if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
+          xyz = np.ascontiguousarray(xyz, dtype=np.float64 if np.asarray(xyz).dtype == np.float64 else np.float32)
+        xyz_dev = self._shard_device_xyz(lane, xyz)
     if native_ids:
       xyz = self.traj.xyz
       if not isinstance(xyz, np.ndarray) or xyz.dtype not in (np.float32, np.float64) or not xyz.flags.c_contiguous:
@@ -492,7 +507,11 @@ class Featurizer:
       batch = self.lower_batch(native_feats, specs, xyz.shape[1], xyz.dtype == np.float64, lane=lane, task_list=task_list)
       if slabs is not None and self._shard_device_out is not None:
         # task-sharded run whose parts go to rank 0 over NVLink: results stay on the device, in the caller's buffer of this lane
-        batch.execute(_lib.addr(xyz), xyz.shape[0], self._shard_device_out(lane, batch.out_floats), out_on_device=True, no_sync=True, lane=lane)
+        if xyz_dev is not None:
+          batch.execute(xyz_dev, xyz.shape[0], self._shard_device_out(lane, batch.out_floats), xyz_on_device=True,
+                        out_on_device=True, no_sync=True, lane=lane)
+        else:
+          batch.execute(_lib.addr(xyz), xyz.shape[0], self._shard_device_out(lane, batch.out_floats), out_on_device=True, no_sync=True, lane=lane)
         job.update(batch=batch, out=None, xyz=xyz)
         return job
       buffers = self.__dict__.setdefault("_out_buffers", {})
