@@ -419,7 +419,7 @@ def run_native(args):
     cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
            "sample": "skipped: one window of this workload is ~2e12 brute-force pair tests per feature on the CPU oracle (hours)"}
   else:
-    cpu = cpu_baseline_sample(fz, trajs[0])
+    cpu = cpu_baseline_sample(fz, trajs) if world == 1 else None      # rank 0 at N = 1 only
 
   line = {
     "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -441,25 +441,30 @@ def run_native(args):
     dist.destroy_process_group()
 
 
-def cpu_baseline_sample(fz, traj, max_slices=1):
-  """Oracle port (CPU restatement of the reference kernels + numpy host pipeline) on the host
-  cores for `max_slices` windows of the workload."""
+def cpu_baseline_sample(fz, trajs, budget_s=10.0):
+  """Oracle port (CPU restatement of the reference kernels + numpy host pipeline) on the host cores: whole trajectories of
+  the workload, one after the other, until about `budget_s` seconds of CPU work are spent (at least one, at most all)."""
   from nearl_b200 import workloads
   from oracle import host_ref
   cores = os.cpu_count() or 1
   os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-  fz.traj = traj
-  fz.parse_focus()
-  for f in fz.FEATURESPACE:
-    f.cache(traj)
-  descs = workloads.describe(fz)
-  t0 = time.perf_counter()
-  host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs, fz.FOCALPOINTS, fz.time_window, max_slices=max_slices)
-  dt = time.perf_counter() - t0
-  frames = max_slices * fz.time_window
+  frames, dt, n_done = 0, 0.0, 0
+  for traj in trajs:
+    fz.traj = traj
+    fz.parse_focus()
+    for f in fz.FEATURESPACE:
+      f.cache(traj)
+    descs = workloads.describe(fz)
+    t0 = time.perf_counter()
+    host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, descs, fz.FOCALPOINTS, fz.time_window)
+    dt += time.perf_counter() - t0
+    frames += fz.SLICENUMBER * fz.time_window
+    n_done += 1
+    if dt >= budget_s:
+      break
   return {"value": frames / dt, "unit": UNIT, "cores": cores, "kind": "port",
-          "sample": f"{max_slices} window(s) x {fz.FEATURENUMBER} features ({frames} frames) of the same workload, "
-                    f"brute-force oracle (oracle/nearl_oracle.c, OpenMP over voxels) in {dt:.2f} s"}
+          "sample": f"{n_done} whole trajector{'y' if n_done == 1 else 'ies'} ({frames} frames, {fz.FEATURENUMBER} features each) of the same "
+                    f"workload, brute-force oracle (oracle/nearl_oracle.c, OpenMP over voxels) in {dt:.2f} s"}
 
 
 def run_reference(args):
