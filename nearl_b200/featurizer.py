@@ -260,6 +260,8 @@ class Featurizer:
     t_run = time.perf_counter()
     depth = max(1, min(int(self.pipeline_depth), 8))        # lanes of the native library (NRL_MAX_LANES)
     self.__dict__.pop("_fingerprint_memo", None)
+    self.__dict__.pop("_spec_memo", None)
+    self.__dict__.pop("_template_quick", None)
     self._task_shard = None
     if task_shard is not None:
       rank, world = int(task_shard[0]), int(task_shard[1])
@@ -469,8 +471,7 @@ class Featurizer:
       feat.cache(self.traj)
     # task list in the reference's order: window -> focal point -> feature
     n_focal = self.FOCALNUMBER if self.FOCALNUMBER > 0 else 1
-    specs = [feat._native_spec() if (self.use_native_batch and hasattr(feat, "_native_spec")) else None
-             for feat in self.FEATURESPACE]
+    specs = self._native_specs()
     native_feats = [f for f in range(self.FEATURENUMBER) if specs[f] is not None]
     slabs = None
     if self._task_shard is None:
@@ -521,6 +522,28 @@ class Featurizer:
       batch.execute(_lib.addr(xyz), xyz.shape[0], _lib.addr(out), no_sync=True, lane=lane)      # both live in `job`
       job.update(batch=batch, out=out, xyz=xyz)
     return job
+
+  def _native_specs(self):
+    """`_native_spec()` of every feature for the active trajectory (None: host protocol).  A spec is a function of the
+    feature's parameters -- fixed inside a run -- and of the per-atom arrays `cache` derived from the topology, which are
+    memoised per topology object: the spec of a (feature, arrays) pair is built once per run (run() clears the memo)."""
+    memo = self.__dict__.setdefault("_spec_memo", {})
+    specs = []
+    for fidx, feat in enumerate(self.FEATURESPACE):
+      if not (self.use_native_batch and hasattr(feat, "_native_spec")):
+        specs.append(None)
+        continue
+      arr, sel = getattr(feat, "cached_array", None), getattr(feat, "selected", None)
+      key = (fidx, id(arr), id(sel), _lib.OPTION_EPOCH)
+      hit = memo.get(key)
+      if hit is None or hit[0] is not arr or hit[1] is not sel or arr is None:
+        if len(memo) > 1024 or hit is not None:
+          # spec objects are about to be released: the identities `_template` keys its shortcut on may come back
+          memo.clear()
+          self.__dict__.pop("_template_quick", None)
+        hit = memo[key] = (arr, sel, feat._native_spec())
+      specs.append(hit[2])
+    return specs
 
   def shard_task_list(self, task_shard, specs):
     """The (window, focal point, feature) tasks of the ACTIVE trajectory that rank `task_shard[0]` of `task_shard[1]`
@@ -876,9 +899,17 @@ class Featurizer:
       return fixed + (float(sp["sigma"]), bool(sp.get("selection_folded")), sp["kind"], sp["mode"], sp["agg"],
                       sp["frame_offset"], sp["max_atoms"], sp.get("ranks") is not None, sp.get("weight_sig"))
 
+    # inside a run the spec OBJECTS are memoised (`_native_specs`): their identities name the template without rebuilding
+    # the fingerprints (run() clears this shortcut together with the spec memo, which keeps the objects alive)
+    quick = self.__dict__.setdefault("_template_quick", {})
+    qkey = (tuple(id(specs[f]) for f in native_feats), tuple(native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64), task_list)
+    if "_spec_memo" in self.__dict__ and qkey in quick:
+      return quick[qkey]
     key = (tuple(fingerprint(f) for f in native_feats), self.SLICENUMBER, n_focal, self.time_window, bool(is_f64), task_list)
     cache = self.__dict__.setdefault("_template_cache", {})
     if key in cache:
+      if "_spec_memo" in self.__dict__:
+        quick[qkey] = cache[key]
       return cache[key]
     # one weight-table row per distinct weight signature (features without one get their own row)
     table_feats, table_of, sig_row = [], {}, {}
@@ -1035,6 +1066,8 @@ class LoweredBatch:
     """Per-task views of the flat result buffer (copied out of the re-used pinned buffer when the
     caller keeps them)."""
     flat = np.array(out[:self.out_floats]) if copy else out[:self.out_floats]
+    if len(self.shapes) > 1 and self.shapes.count(self.shapes[0]) == len(self.shapes):
+      return list(flat.reshape((len(self.shapes),) + tuple(self.shapes[0])))      # equal shapes: rows of one block
     results, pos = [], 0
     for shape in self.shapes:
       size = shape[0] * shape[1] * shape[2]
