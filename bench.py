@@ -337,6 +337,32 @@ def run_native(args):
   ms_dev, launches, prof, clocks = timed(step_device, args.steps, args.warmup, profile=True)
   ms_e2e, _, _, clocks_e2e = timed(None, args.steps, args.warmup, whole=run_e2e)
 
+  # untimed extra pass: the same steps one after the other on ONE lane with the per-mode launches not forked onto side
+  # streams, so that the event span of a launch is the kernel alone (in the timed region the spans of concurrent launches
+  # overlap: they add up to more than the step)
+  prof_alone, ms_alone = {}, None
+  if rank == 0:
+    _lib.set_option("no_fork", 1)
+    try:
+      def serial_steps(count):
+        for i in range(count):
+          k = i % n_rot
+          if lowered[k].n_tasks_total:
+            lowered[k].execute(dev_xyz[k].data_ptr(), n_frames, dev_out[0].data_ptr(), xyz_on_device=True, out_on_device=True,
+                               no_sync=True, lane=0)
+        _lib.check(L.nrl_lane_synchronize(0))
+      serial_steps(3)
+      _lib.profile(True)
+      _lib.profile_read(reset=True)
+      n_alone = min(args.steps, 16)
+      t0 = time.perf_counter()
+      serial_steps(n_alone)
+      ms_alone = (time.perf_counter() - t0) * 1e3 / n_alone
+      prof_alone = _lib.profile_read(reset=True)
+      _lib.profile(False)
+    finally:
+      _lib.set_option("no_fork", 0)
+
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -376,9 +402,16 @@ def run_native(args):
     n_fused = sum(isinstance(f, _features.MarchingObservers) for f in fz.FEATURESPACE) if top == "tile_fused" else 1
     alg_bytes = windows * max(n_fused, 1) * (fz.time_window * n_in * 16 + 4 * G)
     achieved = alg_bytes / t_launch / 1e9
+    alone = prof_alone.get(top)
+    alone_ms = alone[0] / max(alone[1], 1) if alone else None
+    alone_sum = sum(v[0] / max(v[1], 1) for v in prof_alone.values()) if prof_alone else None
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
             "traffic": table.get(top, {}).get("dram_bytes"), "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
             "launch_ms": kernels[top]["ms_per_launch"],
+            # the same kernel alone (untimed extra pass: one lane, launches not forked): its span, its share of the sum of the
+            # spans of a step's kernels -- the figure the ncu launch list (profiles/*_launches.csv) shows --, the bytes over it
+            "launch_ms_alone": alone_ms, "share_of_step_alone": (alone_ms / alone_sum) if alone_ms and alone_sum else None,
+            "achieved_alone": (alg_bytes / (alone_ms * 1e-3) / 1e9) if alone_ms else None, "ms_per_step_alone": ms_alone,
             "note": "the gather kernels are FP32-issue bound, not HBM bound (see roofline_compute); the per-mode launches of a "
                     "step run concurrently on side streams, so a launch's event span includes the time it shares the SMs"}
     # compute side: voxel x candidate pair tests per second against the FP32 issue rate
@@ -434,6 +467,7 @@ def run_native(args):
     "gpu_launches": int(launches),
     "clocks": clocks, "clocks_e2e": clocks_e2e,
     "roofline": roof, "roofline_compute": roof_c, "kernels": kernels,
+    "kernels_alone": {k: {"ms_per_launch": v[0] / max(v[1], 1), "launches": v[1]} for k, v in prof_alone.items()},
     "cpu_baseline": cpu,
   }
   print(json.dumps(line))

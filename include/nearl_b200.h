@@ -214,7 +214,8 @@ int nrl_set_stream(void *stream, int enable);
 /* tuning / test switches.  "force_scan" != 0: never use the cell-list kernels (every task runs on the
  * full-frame scan kernels; results are identical up to float summation order).  "no_fuse" != 0: observers of
  * one focus box do not share a sweep across observables (results are bit-identical either way) */
-/* "crop_legacy" != 0: whole-frame crops never take the streaming kernel; "crop_stream_min" = n: the shortest topology
+/* "no_fork" != 0: the per-mode launches of a batch are not forked onto side streams (they run one after the other: per-kernel
+ * event times are then those of the kernels alone); "crop_legacy" != 0: whole-frame crops never take the streaming kernel; "crop_stream_min" = n: the shortest topology
  * slice that does (default 2048; the forms select the same atoms in the same order) */
 int nrl_set_option(const char *name, int value);
 /* per-kernel device timing: CUDA events around every launch of this library, accumulated per

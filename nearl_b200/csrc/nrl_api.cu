@@ -36,6 +36,7 @@ std::atomic<int> g_agg_pipe_stages{0};
 std::atomic<int> g_agg_entropy_legacy{0};   // nrl_set_option("agg_entropy_legacy"): former histogram form in the staged / pipelined K3 (tests)  // (0 = chosen from the series length; -1 stages = staged one-shot kernel instead)
 std::atomic<int> g_crop_stream_min{2048};   // nrl_set_option("crop_stream_min", n): shortest slice that takes the streaming crop (tests: 1)
 std::atomic<int> g_crop_legacy{0};   // nrl_set_option("crop_legacy", 1): never use the streaming crop kernel (tests / A-B timing)
+std::atomic<int> g_no_fork{0};       // nrl_set_option("no_fork", 1): the launches of a batch run one after the other on its stream (A-B timing)
 std::atomic<int> g_no_fuse{0};       // nrl_set_option("no_fuse", 1): one sweep per observable (tests / A-B timing)
 
 int fail(int code, const std::string &msg) {
@@ -563,7 +564,7 @@ int run_tasks(Ctx &c, std::vector<NrlTask> &tasks, const std::vector<char> &use_
   NRL_TRY(c.cand_scr.reserve(cand_total));
   NRL_TRY(c.ser_scr.reserve(ser_total));
 
-  const bool fork = ranges.size() > 1;
+  const bool fork = ranges.size() > 1 && !g_no_fork;
   if (fork) {
     NRL_TRY(ensure_aux(c));
     NRL_CUDA(cudaEventRecord(c.ev_fork, st));
@@ -1091,6 +1092,7 @@ int nrl_set_option(const char *name, int value) {
   if (strcmp(name, "force_scan") == 0) { g_force_scan.store(value != 0); return NRL_OK; }
   if (strcmp(name, "no_fuse") == 0) { g_no_fuse.store(value != 0); return NRL_OK; }
   if (strcmp(name, "crop_legacy") == 0) { g_crop_legacy.store(value != 0); return NRL_OK; }
+  if (strcmp(name, "no_fork") == 0) { g_no_fork.store(value != 0); return NRL_OK; }
   if (strcmp(name, "crop_stream_min") == 0) { g_crop_stream_min.store(value > 0 ? value : 2048); return NRL_OK; }
   if (strcmp(name, "agg_entropy_legacy") == 0) { g_agg_entropy_legacy.store(value != 0); return NRL_OK; }
   if (strcmp(name, "agg_pipe_w") == 0) { g_agg_pipe_w.store((int)value); return NRL_OK; }
