@@ -10,13 +10,15 @@ reference's trajectory back-end, /root/reference/nearl/io/traj.py:17) is not par
 path and not installed.  Any sequence of such objects is a valid "trajloader"
 (featurizer.py:295,405 only use ``len`` and ``[]``).
 """
+import os
 import re
 
 import numpy as np
 
 from . import constants
 
-__all__ = ["Atom", "Residue", "Topology", "Trajectory", "TrajectoryLoader", "MisatoTraj", "load_amber_topology", "superpose",
+__all__ = ["Atom", "Residue", "Topology", "Trajectory", "TrajectoryLoader", "MisatoTraj", "load_amber_topology", "load_pdb",
+           "write_pdb", "load_coordinates", "load_topology", "superpose",
            "synthetic_trajectory", "synthetic_complex", "synthetic_peptide", "pinned_empty"]
 
 
@@ -231,16 +233,69 @@ class Frame:
 
 
 class Trajectory:
-  """Coordinates ``xyz [F, N, 3]`` (float32 or float64) + topology + identity."""
+  """Coordinates ``xyz [F, N, 3]`` (float32 or float64) + topology + identity
+  (/root/reference/nearl/io/traj.py:17-155, which wraps ``pytraj.load``).  Three ways in, as in the reference:
 
-  def __init__(self, xyz, top, identity="traj"):
-    xyz = np.asarray(xyz)
+  * arrays -- ``Trajectory(xyz, top[, identity])`` (what this package and its tests build);
+  * file names -- ``Trajectory("traj.nc", "top.parm7")``, ``Trajectory("traj.nc", "top.pdb")``,
+    ``Trajectory("complex.pdb")`` (a PDB file is its own topology; one frame per MODEL); read here without pytraj:
+    PDB by columns, Amber NetCDF trajectories / restarts through ``scipy.io.netcdf_file``, parm7 as `load_amber_topology`;
+  * another trajectory -- ``Trajectory(traj, mask=":LIG")``.
+
+  Keyword arguments of the reference: ``stride`` (wins over) ``frame_indices``, ``mask``, ``identity`` (default: the
+  trajectory file name), ``superpose`` (fit onto the first frame over ``@CA`` on the device); ``dtype`` (default
+  float64, what pytraj hands out; ``np.float32`` keeps the precision of a NetCDF trajectory and halves the upload)."""
+
+  def __init__(self, traj_src=None, pdb_src=None, identity=None, **kwarg):
+    stride, frame_indices, mask = kwarg.get("stride"), kwarg.get("frame_indices"), kwarg.get("mask")
+    self.top_filename = self.traj_filename = None
+    if isinstance(traj_src, (str, os.PathLike)):
+      traj_src = os.fspath(traj_src)
+      dtype = np.dtype(kwarg.get("dtype", np.float64))
+      if pdb_src is None:
+        xyz, top = load_pdb(traj_src)
+      else:
+        pdb_src = os.fspath(pdb_src)
+        top = load_topology(pdb_src)
+        xyz = load_coordinates(traj_src)
+      self.top_filename, self.traj_filename = pdb_src, traj_src
+      xyz = np.ascontiguousarray(xyz, dtype=dtype)
+    elif isinstance(traj_src, Trajectory):
+      xyz, top = traj_src.xyz, traj_src.top
+      self.top_filename, self.traj_filename = traj_src.top_filename, traj_src.traj_filename
+      identity = identity if identity is not None else traj_src.identity_
+    elif traj_src is None and pdb_src is None:
+      raise ValueError("Trajectory needs coordinates: arrays, file names or another trajectory")
+    else:
+      xyz, top = np.asarray(traj_src), pdb_src
     if xyz.ndim == 2:
       xyz = xyz[None]
-    assert xyz.ndim == 3 and xyz.shape[2] == 3 and xyz.shape[1] == top.n_atoms
+    if not (xyz.ndim == 3 and xyz.shape[2] == 3 and xyz.shape[1] == top.n_atoms):
+      raise ValueError(f"The number of atoms in the topology and the coordinates should be the same, rather than {top.n_atoms} and {xyz.shape}")
+    if stride is not None:
+      xyz = np.ascontiguousarray(xyz[::int(stride)])
+    elif frame_indices is not None:
+      xyz = np.ascontiguousarray(xyz[np.asarray(frame_indices, dtype=int)])
+    if mask is not None:
+      sel = top.select(mask)
+      xyz, top = np.ascontiguousarray(xyz[:, sel, :]), top[sel]
     self.xyz = xyz
     self.top = top
-    self.identity = identity
+    self.mask = mask
+    self.identity_ = identity
+    if kwarg.get("superpose", False):
+      superpose(self, mask="@CA")
+
+  @property
+  def identity(self):
+    """What meta-data is looked up under (traj.py:160-174): the given identity, else the trajectory file name."""
+    if self.identity_ is not None:
+      return self.identity_
+    return self.traj_filename if self.traj_filename is not None else "traj"
+
+  @identity.setter
+  def identity(self, value):
+    self.identity_ = value
 
   @property
   def n_frames(self):
@@ -250,15 +305,150 @@ class Trajectory:
   def n_atoms(self):
     return self.xyz.shape[1]
 
+  @property
+  def atoms(self):
+    return np.array(self.top.atoms, dtype=object)            # traj.py:192-193 (make_index)
+
+  @property
+  def residues(self):
+    return np.array(list(self.top.residues), dtype=object)
+
   def __len__(self):
     return self.n_frames
 
   def __getitem__(self, index):
-    """`traj[i]` -> Frame (copy), `traj[slice]` -> Trajectory of those frames (pytraj's indexing, as far as the
-    label features and scripts use it)."""
+    """`traj[i]` -> Frame (copy), `traj[slice]` -> Trajectory of those frames, `traj[":LIG"]` -> Trajectory of those
+    atoms (pytraj's indexing, as far as the label features and scripts use it)."""
     if isinstance(index, (int, np.integer)):
       return Frame(np.array(self.xyz[int(index)]))
-    return Trajectory(np.ascontiguousarray(self.xyz[index]), self.top, identity=self.identity)
+    if isinstance(index, str):
+      return Trajectory(self, mask=index)
+    out = Trajectory(np.ascontiguousarray(self.xyz[index]), self.top, identity=self.identity_)
+    out.top_filename, out.traj_filename = self.top_filename, self.traj_filename
+    return out
+
+  def copy_traj(self):
+    out = Trajectory(self.xyz.copy(), self.top[:], identity=self.identity_)
+    out.top_filename, out.traj_filename = self.top_filename, self.traj_filename
+    return out
+
+  def write_frame(self, frames, outfile="", mask="", **_ignored):
+    """Save frames (an index, a list, a slice) of the atoms of `mask` as a PDB file, one MODEL per frame
+    (traj.py:195-236)."""
+    if isinstance(frames, (int, np.integer)):
+      coords = self.xyz[[int(frames)]]
+    else:
+      coords = self.xyz[np.arange(self.n_frames)[frames] if isinstance(frames, (slice, np.ndarray)) else np.asarray(frames, dtype=int)]
+    top = self.top
+    if len(mask) > 0:
+      sel = self.top.select(mask)
+      coords, top = coords[:, sel, :], self.top[sel]
+    if len(outfile) > 0:
+      write_pdb(outfile, coords, top)
+
+
+# ---- file formats (what pt.load reads for the reference: traj.py:97-106) -------------------------------------------
+def _guess_atomic_number(name_field, resname):
+  """Element of a PDB atom without an element column, from the atom-name columns 13-16: two-letter symbols are
+  right-justified into columns 13-14 ('FE  ', 'CL  ', 'CA  ' = calcium), everything else starts in column 14
+  (' CA ' = C-alpha)."""
+  two = name_field[:2].strip().capitalize()
+  if name_field[0].isalpha() and len(two) == 2 and two in constants.SYMBOL2ATOMICNR and (two.upper() == resname.strip().upper()[:2] or two not in ("Ca", "Cd", "Ce", "Cf", "Cm", "Co", "Cr", "Cs", "Cu", "Hf", "Hg", "Ho", "Hs", "Nb", "Nd", "Ne", "Ni", "No", "Np", "Os", "Sb", "Sc", "Se", "Sg", "Si", "Sm", "Sn", "Sr")):
+    return constants.SYMBOL2ATOMICNR[two]
+  core = name_field.strip().lstrip("0123456789")
+  return constants.SYMBOL2ATOMICNR.get(core[:1].upper(), 0) if core else 0
+
+
+def load_pdb(path):
+  """(xyz [frames, atoms, 3] float64, Topology) of a PDB file: ATOM / HETATM records by column (name 13-16, residue name
+  18-21, chain 22, residue number 23-26, insertion code 27, x / y / z 31-54, element 77-78), one frame per MODEL (every
+  model must list the same atoms; the topology is the first model's).  Residues are maximal runs of one (chain, number,
+  insertion code, name); `resids` count them from 0 like pytraj's ``atom.resid``.  Alternate locations are all kept."""
+  import gzip
+  opener = gzip.open if str(path).endswith(".gz") else open
+  names, resnames, reskeys, zs = [], [], [], []
+  frames, coords = [], []
+  first = True
+  with opener(path, "rt") as fh:
+    for line in fh:
+      rec = line[:6]
+      if rec in ("ATOM  ", "HETATM"):
+        coords.append((float(line[30:38]), float(line[38:46]), float(line[46:54])))
+        if first:
+          name_field = line[12:16]
+          resname = line[17:21].strip()
+          names.append(name_field.strip())
+          resnames.append(resname)
+          reskeys.append((line[21], line[22:27], resname))
+          sym = line[76:78].strip().capitalize() if len(line) >= 78 else ""
+          zs.append(constants.SYMBOL2ATOMICNR[sym] if sym in constants.SYMBOL2ATOMICNR else _guess_atomic_number(name_field, resname))
+      elif rec == "ENDMDL" or (rec.startswith("END") and coords):
+        if coords:
+          frames.append(coords)
+          coords, first = [], False
+  if coords:
+    frames.append(coords)
+  if not frames:
+    raise ValueError(f"{path}: no ATOM / HETATM record")
+  n = len(names)
+  if any(len(f) != n for f in frames):
+    raise ValueError(f"{path}: the models do not list the same number of atoms")
+  change = np.ones(n, dtype=bool)
+  change[1:] = [reskeys[i] != reskeys[i - 1] for i in range(1, n)]
+  resids = np.cumsum(change) - 1
+  return np.array(frames, dtype=np.float64), Topology(names, resids, resnames, zs)
+
+
+def write_pdb(path, xyz, top):
+  """Minimal PDB writer (one MODEL per frame) for `Trajectory.write_frame`."""
+  xyz = np.asarray(xyz)
+  if xyz.ndim == 2:
+    xyz = xyz[None]
+  with open(path, "w") as fh:
+    for f, frame in enumerate(xyz):
+      if len(xyz) > 1:
+        fh.write(f"MODEL     {f + 1:4d}\n")
+      for i in range(top.n_atoms):
+        name = str(top.names[i])
+        sym = constants.ATOMICNR2SYMBOL.get(int(top.atomic_numbers[i]), "")
+        field = name.ljust(4) if (len(name) >= 4 or len(sym) == 2) else (" " + name).ljust(4)
+        fh.write("ATOM  %5d %4s %-4s%1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f          %2s\n" % (
+          (i + 1) % 100000, field[:4], str(top.resnames[i])[:4], "A", (int(top.resids[i]) + 1) % 10000,
+          frame[i, 0], frame[i, 1], frame[i, 2], 1.0, 0.0, sym.upper().rjust(2)))
+      fh.write("ENDMDL\n" if len(xyz) > 1 else "END\n")
+
+
+def load_coordinates(path):
+  """Coordinates [frames, atoms, 3] of a trajectory file: Amber NetCDF trajectory (.nc / .ncdf / .netcdf: variable
+  ``coordinates`` [frame, atom, spatial]) or restart (.ncrst / .rst7 in NetCDF form: [atom, spatial]) -- NetCDF-3, read
+  through scipy --, or a PDB file (.pdb)."""
+  lower = str(path).lower()
+  if lower.endswith((".pdb", ".pdb.gz")):
+    return load_pdb(path)[0]
+  with open(path, "rb") as fh:
+    magic = fh.read(4)
+  if magic[:3] != b"CDF":
+    raise ValueError(f"{path}: only NetCDF-3 (Amber .nc / .ncrst) and PDB trajectories are read without pytraj")
+  from scipy.io import netcdf_file
+  with netcdf_file(path, "r", mmap=False) as nc:
+    if "coordinates" not in nc.variables:
+      raise ValueError(f"{path}: no `coordinates` variable (not an Amber NetCDF file)")
+    var = nc.variables["coordinates"]
+    xyz = np.array(var[:])
+    scale = getattr(var, "scale_factor", None)
+    if scale is not None:
+      xyz = xyz * scale
+  if xyz.ndim == 2:
+    xyz = xyz[None]
+  return xyz
+
+
+def load_topology(path):
+  """Topology of a topology file: Amber parm7 (.parm7 / .prmtop / .top, optionally .gz) or PDB."""
+  lower = str(path).lower()
+  if lower.endswith((".pdb", ".pdb.gz")):
+    return load_pdb(path)[1]
+  return load_amber_topology(path)
 
 
 _ELEMENTS = np.array([1, 6, 7, 8, 16])

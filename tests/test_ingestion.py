@@ -139,3 +139,104 @@ def test_misato_trajectory_through_the_featurizer(tmp_path):
   stats = fz.run()
   assert stats["native_tasks"] == 4 and np.array(fz.RESULTS["mass"]).shape == (2, 16, 16, 16)
   assert np.array(fz.RESULTS["mass"]).sum() > 0
+
+
+PDB_TEXT = """\
+HEADER    TEST
+MODEL        1
+ATOM      1  N   ALA A   1      11.104   6.134  -6.504  1.00  0.00           N
+ATOM      2  CA  ALA A   1      11.639   6.071  -5.147  1.00  0.00           C
+ATOM      3  C   ALA A   1      10.573   5.700  -4.127  1.00  0.00           C
+ATOM      4  HA AALA A   1      12.400   5.300  -5.100  0.50  0.00
+ATOM      5  HA BALA A   1      12.410   5.310  -5.110  0.50  0.00
+ATOM      6  N   GLY A   2       9.300   5.900  -4.500  1.00  0.00           N
+ATOM      7  CA  GLY A   2       8.200   5.600  -3.600  1.00  0.00           C
+ATOM      8  N   GLY A   2A      7.100   5.000  -3.000  1.00  0.00           N
+TER       9      GLY A   2A
+ATOM     10  N   SER B   2       1.000   2.000   3.000  1.00  0.00           N
+HETATM   11 CA    CA B 101       0.500   0.250  -0.125  1.00  0.00
+HETATM   12 CL    CL B 102       4.000   4.000   4.000  1.00  0.00          CL
+HETATM   13  O   HOH B 201       5.000   5.000   5.000  1.00  0.00           O
+HETATM   14 1H   HOH B 201       5.500   5.500   5.500  1.00  0.00
+ENDMDL
+MODEL        2
+ATOM      1  N   ALA A   1      12.104   6.134  -6.504  1.00  0.00           N
+ATOM      2  CA  ALA A   1      12.639   6.071  -5.147  1.00  0.00           C
+ATOM      3  C   ALA A   1      11.573   5.700  -4.127  1.00  0.00           C
+ATOM      4  HA AALA A   1      13.400   5.300  -5.100  0.50  0.00
+ATOM      5  HA BALA A   1      13.410   5.310  -5.110  0.50  0.00
+ATOM      6  N   GLY A   2      10.300   5.900  -4.500  1.00  0.00           N
+ATOM      7  CA  GLY A   2       9.200   5.600  -3.600  1.00  0.00           C
+ATOM      8  N   GLY A   2A      8.100   5.000  -3.000  1.00  0.00           N
+TER       9      GLY A   2A
+ATOM     10  N   SER B   2       2.000   2.000   3.000  1.00  0.00           N
+HETATM   11 CA    CA B 101       1.500   0.250  -0.125  1.00  0.00
+HETATM   12 CL    CL B 102       5.000   4.000   4.000  1.00  0.00          CL
+HETATM   13  O   HOH B 201       6.000   5.000   5.000  1.00  0.00           O
+HETATM   14 1H   HOH B 201       6.500   5.500   5.500  1.00  0.00
+ENDMDL
+END
+"""
+
+
+def test_pdb_and_netcdf_files_without_pytraj(tmp_path):
+  """Trajectory("traj.nc", "top.parm7" | "top.pdb") and Trajectory("complex.pdb") (/root/reference/nearl/io/traj.py:97-106 hands
+  these to pt.load): PDB by columns -- residues from (chain, number, insertion code, name), elements from columns 77-78
+  or the name columns (' CA ' is a C-alpha, 'CA  ' in residue CA is calcium), one frame per MODEL --, Amber NetCDF through
+  scipy.  stride wins over frame_indices, masks apply to coordinates and topology, the identity defaults to the
+  trajectory file name."""
+  from scipy.io import netcdf_file
+  pdb = tmp_path / "multi.pdb"
+  pdb.write_text(PDB_TEXT)
+  traj = io.Trajectory(str(pdb))
+  assert traj.n_frames == 2 and traj.n_atoms == 13 and traj.xyz.dtype == np.float64
+  assert traj.identity == str(pdb) and traj.top_filename is None
+  assert list(traj.top.names) == ["N", "CA", "C", "HA", "HA", "N", "CA", "N", "N", "CA", "CL", "O", "1H"]
+  assert list(traj.top.resids) == [0, 0, 0, 0, 0, 1, 1, 2, 3, 4, 5, 6, 6]               # insertion code and chain start new residues
+  assert list(traj.top.resnames[[0, 5, 8, 9, 10, 12]]) == ["ALA", "GLY", "SER", "CA", "CL", "HOH"]
+  assert list(traj.top.atomic_numbers) == [7, 6, 6, 1, 1, 7, 6, 7, 7, 20, 17, 8, 1]
+  assert np.array_equal(traj.xyz[0, 1], [11.639, 6.071, -5.147]) and np.array_equal(traj.xyz[1, 9], [1.5, 0.25, -0.125])
+  assert np.array_equal(traj.xyz[1, :, 0] - traj.xyz[0, :, 0], np.ones(13))
+  assert list(traj.top.select(":ALA@CA")) == [1] and list(traj.top.select(":HOH")) == [11, 12]
+  assert len(traj.atoms) == 13 and len(traj.residues) == 7 and traj.residues[0].name == "ALA"
+  lig = traj[":CA,CL"]
+  assert lig.n_atoms == 2 and lig.n_frames == 2 and list(lig.top.resnames) == ["CA", "CL"]
+  # NetCDF trajectory (float32, as sander / pmemd write it) + PDB topology, then + parm7 topology
+  pep = io.synthetic_peptide(9, 7, seed=3)
+  nc_path = str(tmp_path / "traj.nc")
+  with netcdf_file(nc_path, "w") as nc:
+    nc.Conventions = "AMBER"
+    nc.createDimension("frame", pep.n_frames); nc.createDimension("atom", pep.n_atoms); nc.createDimension("spatial", 3)
+    var = nc.createVariable("coordinates", "f", ("frame", "atom", "spatial"))
+    var[:] = pep.xyz.astype(np.float32)
+  top_pdb = str(tmp_path / "top.pdb")
+  io.write_pdb(top_pdb, pep.xyz[0], pep.top)
+  a = io.Trajectory(nc_path, top_pdb)
+  assert a.xyz.dtype == np.float64 and a.xyz.shape == pep.xyz.shape and np.array_equal(a.xyz, pep.xyz.astype(np.float32).astype(np.float64))
+  assert list(a.top.names) == [str(n) for n in pep.top.names] and np.array_equal(a.top.atomic_numbers, pep.top.atomic_numbers)
+  assert np.array_equal(a.top.resids, pep.top.resids - pep.top.resids.min()) and list(a.top.resnames) == list(pep.top.resnames)
+  assert a.identity == nc_path and a.top_filename == top_pdb and a.traj_filename == nc_path
+  parm = str(tmp_path / "top.parm7")
+  write_parm7(parm, pep.top)
+  b = io.Trajectory(nc_path, parm, stride=3, frame_indices=[0, 1], dtype=np.float32, identity="pep")
+  assert b.xyz.dtype == np.float32 and b.n_frames == 3 and np.array_equal(b.xyz, pep.xyz.astype(np.float32)[::3]) and b.identity == "pep"
+  c = io.Trajectory(nc_path, parm, frame_indices=[5, 2], mask="@CA")
+  sel = pep.top.select("@CA")
+  assert c.n_frames == 2 and np.array_equal(c.xyz, pep.xyz.astype(np.float32).astype(np.float64)[[5, 2]][:, sel]) and list(c.top.names) == ["CA"] * len(sel)
+  # restart-style file: one frame of doubles
+  rst = str(tmp_path / "last.ncrst")
+  with netcdf_file(rst, "w") as nc:
+    nc.createDimension("atom", pep.n_atoms); nc.createDimension("spatial", 3)
+    nc.createVariable("coordinates", "d", ("atom", "spatial"))[:] = pep.xyz[3].astype(np.float64)
+  d = io.Trajectory(rst, parm)
+  assert d.n_frames == 1 and np.array_equal(d.xyz[0], pep.xyz[3].astype(np.float64))
+  # round trip through the PDB writer, frames and masks
+  out = str(tmp_path / "frames.pdb")
+  a.write_frame([0, 4], out, mask="@CA,C,N")
+  e = io.Trajectory(out)
+  keep = pep.top.select("@CA,C,N")
+  assert e.n_frames == 2 and np.allclose(e.xyz, a.xyz[[0, 4]][:, keep], atol=5e-4) and list(e.top.names) == [str(n) for n in pep.top.names[keep]]
+  with pytest.raises(ValueError):
+    io.Trajectory(nc_path, str(pdb))                                # 13-atom topology, other coordinates
+  with pytest.raises(ValueError):
+    io.load_coordinates(str(tmp_path / "top.parm7"))
