@@ -95,6 +95,8 @@ class Featurizer:
     # crop / binning of the one after run under the sweeps of the current one); 1 = no overlap.  Measured on B200, headline
     # workload, frames/s end to end: 3 -> 178 k, 4 -> 192 k, 5 -> 205 k, 7 / 8 -> 207 k (the host-to-device link's limit)
     self.pipeline_depth = 8
+    # nearl_b200: coordinates in flight, in bytes: trajectories larger than pipeline_bytes / pipeline_depth use fewer lanes
+    self.pipeline_bytes = 8 << 30
     # nearl_b200: single-frame systems featurised per native call when every feature is static (time_window 1);
     # 1 = one system per call
     self.static_group = 32
@@ -281,23 +283,29 @@ class Featurizer:
     return stats
 
   def _run_pipelined(self, indices, depth, stats, loaded=None):
-    """One native call per trajectory, `depth` of them in flight.  A lane (its page-locked result buffer and table
-    buffers) belongs to a job from submission until `_finish`: the lane number advances with the jobs actually
-    submitted -- a skipped trajectory takes none -- and the job `depth` submissions back, the lane's previous owner,
-    is finished before the lane is handed out again."""
+    """One native call per trajectory, up to `depth` of them in flight.  A lane (its page-locked result buffer, its
+    table buffers, its device workspace) belongs to a job from submission until `_finish`: a job takes the lowest lane
+    that no pending job holds -- a skipped trajectory takes none -- and the oldest job is finished first when none is
+    free.  Large trajectories narrow the pipeline: only `pipeline_bytes // trajectory bytes` lanes are used for them, so
+    that the lanes' workspaces (a few times the trajectory each, grow-only) stay bounded."""
     pending = []                                             # submitted, not yet finished, oldest first
-    submitted = 0
     multi_frame = False
     for tid in indices:
-      if len(pending) >= depth:
-        self._finish(pending.pop(0), stats)                  # frees the lane (and its buffers) about to be reused
-      lane = submitted % depth
-      assert all(job["lane"] != lane for job in pending), "pipeline lane handed out while its job is pending"
-      job = self._submit(tid, lane=lane, traj=None if loaded is None else loaded.get(tid))
+      traj = loaded.get(tid) if loaded is not None else None
+      if traj is None:
+        traj = self.TRAJLOADER[tid]
+      nbytes = int(getattr(getattr(traj, "xyz", None), "nbytes", 0) or 0)
+      lanes = max(1, min(depth, int(self.pipeline_bytes) // max(nbytes, 1)))
+      lane = None
+      while lane is None:
+        busy = {job["lane"] for job in pending}
+        lane = next((k for k in range(lanes) if k not in busy), None)
+        if lane is None:
+          self._finish(pending.pop(0), stats)                # frees a lane (and its buffers)
+      job = self._submit(tid, lane=lane, traj=traj)
       multi_frame |= self.traj.n_frames != 1
       if job is None:
         continue                                             # skipped (no focal point): the lane stays free
-      submitted += 1
       pending.append(job)              # host-protocol tasks were evaluated inside _submit
     while pending:
       self._finish(pending.pop(0), stats)

@@ -185,8 +185,12 @@ def _run_task_sharded_nccl(featurizer, rank, world, group, n_slabs, trajectory_i
   total = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "frames": 0, "seconds": 0.0}
   for c0 in range(0, len(indices), depth):
     chunk = indices[c0:c0 + depth]          # one lane (and its device buffer) per trajectory of the chunk
+    # (a lane's device buffer holds a trajectory's parts until they were sent: no lane may be used twice inside a chunk,
+    #  so the byte budget that narrows the pipeline for large trajectories is lifted for this run)
+    budget, featurizer.pipeline_bytes = featurizer.pipeline_bytes, 1 << 62
     stats = featurizer.run(trajectory_indices=chunk, task_shard=(rank, world, n_slabs), shard_device_out=device_out,
                            shard_device_xyz=device_xyz if gather_uploads else None)
+    featurizer.pipeline_bytes = budget
     for key in total:
       total[key] += stats.get(key, 0)
     local = featurizer.SHARD_RESULTS

@@ -1,5 +1,5 @@
 set -x
-D=gpurun_out/${1:-r2c}; mkdir -p $D
+D=gpurun_out/${1:-r2f}; mkdir -p $D
 timeout 900 python -m pytest tests -m gpu -x -q > $D/pytest.log 2>&1; tail -2 $D/pytest.log
 python bench.py > $D/bench_n1.json 2> $D/bench_n1.err
 python bench.py --impl reference > $D/bench_ref.json 2> $D/bench_ref.err

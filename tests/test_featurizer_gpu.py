@@ -515,19 +515,33 @@ def test_skipped_trajectories_do_not_alias_pipeline_lanes(tmp_path):
   buffer was overwritten: the first trajectory came back with the fourth's grids)."""
   trajs = [io.synthetic_trajectory(1500 + 50 * i, 4, seed=700 + i, ligand_atoms=(0 if i in (1, 4) else 20)) for i in range(7)]
 
-  def run(depth):
+  def run(depth, budget=None):
     fz = featurizer.Featurizer({"dimensions": 12, "lengths": 9, "time_window": 2, "cutoff": 3.0, "sigma": 1.0})
     fz.pipeline_depth = depth
+    if budget is not None:
+      fz.pipeline_bytes = budget
     fz.register_features([features.Mass(outkey="mass"), features.MarchingObservers(obs="direct_count", agg="max", outkey="count")])
     fz.register_focus([":LIG"], "mask")
     fz.register_trajloader(trajs)
-    seen = []
+    seen, lanes = [], []
+    real = featurizer.LoweredBatch.execute
+    featurizer.LoweredBatch.execute = lambda self, *a, **kw: lanes.append(kw.get("lane")) or real(self, *a, **kw)
     fz.result_sink = lambda outkey, tid, bid, pid, grid: seen.append((outkey, tid, bid, np.array(grid)))
-    stats = fz.run()
+    try:
+      stats = fz.run()
+    finally:
+      featurizer.LoweredBatch.execute = real
+    stats["lanes"] = lanes
     return seen, stats
 
   serial, s1 = run(1)
   piped, s3 = run(3)
+  # a byte budget of two of the largest trajectories narrows the pipeline to two lanes, of less than one to a single lane
+  two, s2 = run(8, budget=2 * max(t.xyz.nbytes for t in trajs))
+  one, s0 = run(8, budget=1000)
+  assert set(s2["lanes"]) == {0, 1} and set(s0["lanes"]) == {0} and set(s3["lanes"]) == {0, 1, 2}
+  for a, b, c in zip(serial, two, one):
+    assert a[:3] == b[:3] == c[:3] and np.array_equal(a[3], b[3]) and np.array_equal(a[3], c[3])
   assert s1["trajectories"] == s3["trajectories"] == 5 and [t for _, t, _, _ in serial] == [t for _, t, _, _ in piped]
   assert sorted({t for _, t, _, _ in piped}) == [0, 2, 3, 5, 6]
   for (k1, t1, b1, g1), (k3, t3, b3, g3) in zip(serial, piped):
