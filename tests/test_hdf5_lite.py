@@ -119,6 +119,12 @@ def test_classic_layout_written_by_libhdf5():
     assert d.attrs["MATLAB_class"] == b"double"
     got = d[:]
     assert np.array_equal(d[2:5], got[2:5]) and d[8, 0] == got[8, 0]
+    # the WRITER's datatype message for float64 is, byte for byte, the one libhdf5 put into this file (the version-1
+    # object header pads the message to a multiple of eight)
+    messages, _ = hdf5_lite._Reader(h)._messages(d._addr)
+    body = next(b for t, b, _ in messages if t == hdf5_lite.MSG_DATATYPE)
+    mine = hdf5_lite._encode_dtype("<f8")
+    assert bytes(body[:len(mine)]) == mine and not any(body[len(mine):])
   twin = scipy.io.loadmat(os.path.join(data, "testdouble_7.4_GLNX86.mat"))["testdouble"]
   assert np.array_equal(got.reshape(-1), twin.reshape(-1))            # MATLAB stores column-major: (9, 1) here, (1, 9) there
   with pytest.raises(OSError):
