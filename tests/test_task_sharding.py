@@ -144,3 +144,38 @@ def test_sharded_run_has_the_bits_of_the_unsharded_run(tmp_path, world, n_slabs)
       assert a[key].shape == b[key].shape and a[key].shape[0] == 2 * 2 * 2
       assert np.array_equal(a[key][:], b[key][:]), key
     assert a["mass"][:].sum() > 0 and a["rog"][:].sum() > 0
+
+
+@pytest.mark.gpu
+def test_sharded_run_skips_what_the_unsharded_run_skips(tmp_path):
+  """A trajectory without focal point is skipped by every rank alike; one window (a single unit) over 5 ranks is cut into 5
+  slabs of a 40^3 grid = 5 tiles, rank by rank; results kept in memory (keep_results) and sunk arrive in the same order."""
+  trajs = [io.synthetic_trajectory(2000 + 100 * i, 3, seed=950 + i, pin=False, ligand_atoms=(0 if i == 1 else 16)) for i in range(3)]
+
+  def make():
+    fz = featurizer.Featurizer({"dimensions": 40, "lengths": 20.0, "time_window": 3, "cutoff": 3.0, "sigma": 1.2})
+    fz.register_features([features.Mass(outkey="mass"), features.MarchingObservers(obs="direct_count", agg="mean", outkey="count")])
+    fz.register_focus([":LIG"], "mask")
+    fz.register_trajloader(trajs)
+    fz.keep_results = True
+    return fz
+
+  ref = make()
+  ref.run()
+  fz = make()
+  order = []
+  fz.result_sink = lambda outkey, tid, bid, pid, grid: order.append((outkey, tid, bid, pid))
+  merged = {}
+  for rank in range(5):
+    stats = fz.run(task_shard=(rank, 5))
+    assert stats["trajectories"] == 2
+    assert all(arr.shape == (8, 40, 40) for items in fz.SHARD_RESULTS.values() for *_, arr in items)
+    for tid, items in fz.SHARD_RESULTS.items():
+      merged.setdefault(tid, []).extend(items)
+  assert sorted(merged) == [0, 2]
+  fz.deliver_shard_results(merged)
+  assert order == [(k, t, 0, 0) for t in (0, 2) for k in ("mass", "count")]
+  for key in ("mass", "count"):
+    assert len(fz.RESULTS[key]) == 2 and all(np.array_equal(a, b) for a, b in zip(fz.RESULTS[key], ref.RESULTS[key])), key
+  with pytest.raises(ValueError):
+    fz.run(task_shard=(5, 5))
