@@ -25,7 +25,7 @@ except Exception:          # pragma: no cover - depends on the image
 
 from . import constants, hdf5_lite
 
-__all__ = ["append_hdf_data", "dump_dict", "batched_output", "hdf_session", "open_hdf", "hdf_backend", "find_block_single",
+__all__ = ["append_hdf_data", "update_hdf_data", "dump_dict", "batched_output", "hdf_session", "open_hdf", "hdf_backend", "find_block_single",
            "find_block_dual", "dual_blocks_by_key"]
 
 _pending = None     # {(file, key): {"rows": [...], "dtype":, "maxshape":, "kwargs":}} while batching
@@ -147,6 +147,23 @@ def batched_output():
       with open_hdf(path, "a") as hdf:
         for key, slot in items:
           _append_now(hdf, key, np.concatenate(slot["rows"], axis=0), slot["dtype"], slot["maxshape"], **slot["kwargs"])
+
+
+def update_hdf_data(hdffile, dataset_name, data, hdf_slice, **kwargs):
+  """Write `data` into the rows `hdf_slice` of a dataset, growing it along axis 0 when the slice ends beyond it; the
+  dataset is created from `data` (with `kwargs`: dtype, maxshape ...) when it does not exist yet (utils.py:524-559).
+  `hdffile`: a path or an open file."""
+  if isinstance(hdffile, (str, bytes)) or hasattr(hdffile, "__fspath__"):
+    with open_hdf(hdffile, "a") as hdf:
+      return update_hdf_data(hdf, dataset_name, data, hdf_slice, **kwargs)
+  data = np.asarray(data)
+  if dataset_name not in hdffile:
+    hdffile.create_dataset(dataset_name, data=data, **kwargs)
+    return
+  dset = hdffile[dataset_name]
+  if hdf_slice.stop is not None and hdf_slice.stop > dset.shape[0]:
+    dset.resize(hdf_slice.stop, axis=0)
+  dset[hdf_slice] = data
 
 
 def dump_dict(outfile, groupname, dic):

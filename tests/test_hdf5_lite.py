@@ -101,6 +101,22 @@ def test_session_keeps_one_handle_and_every_trajectory_leaves_a_complete_file(tm
     assert h["k"].shape[0] == 43 and h["featurizer_parms/cutoff"][()] == 5.0 and h["featurizer_parms/outfile"][()] == path
 
 
+def test_update_hdf_data_grows_and_overwrites(tmp_path):
+  """utils.update_hdf_data (/root/reference/nearl/utils.py:524-559): created from the first slice, grown when a slice ends
+  beyond the dataset, overwritten in place otherwise -- by path and on an open file."""
+  path = str(tmp_path / "u.h5")
+  for epoch in range(5):
+    utils.update_hdf_data(path, "loss", np.array([epoch * 1.5], dtype=np.float64), np.s_[epoch:epoch + 1], dtype=np.float64, maxshape=(None,))
+  utils.update_hdf_data(path, "loss", np.array([-1.0, -2.0]), np.s_[1:3])
+  with utils.open_hdf(path, "a") as h:
+    utils.update_hdf_data(h, "grid", np.ones((2, 3, 3), dtype=np.float32), np.s_[0:2], dtype=np.float32, maxshape=(None, 3, 3))
+    utils.update_hdf_data(h, "grid", np.full((2, 3, 3), 7, dtype=np.float32), np.s_[3:5])
+  with utils.open_hdf(path, "r") as h:
+    assert np.array_equal(h["loss"][:], [0.0, -1.0, -2.0, 4.5, 6.0]) and h["loss"].dtype == np.float64
+    assert h["grid"].shape == (5, 3, 3) and np.array_equal(h["grid"][0:2], np.ones((2, 3, 3))) and not h["grid"][2].any()
+    assert np.array_equal(h["grid"][3:5], np.full((2, 3, 3), 7))
+
+
 @pytest.mark.skipif(utils.hdf_backend() != "hdf5_lite", reason="h5py reads its own format")
 def test_classic_layout_written_by_libhdf5():
   """A MATLAB 7.4 '-v7.3' file (libhdf5 1.6: 512-byte user block, version-0 superblock, symbol-table root group, local
