@@ -667,27 +667,107 @@ class MisatoTraj(Trajectory):
 
 
 class TrajectoryLoader:
-  """Lazy list of trajectories (/root/reference/nearl/io/trajloader.py:165-200): every entry is a tuple of
-  constructor arguments (or an object that already is a trajectory); `trajtype` builds it on access."""
+  """Lazy list of trajectories (/root/reference/nearl/io/trajloader.py:12-247): every entry is a tuple of constructor
+  arguments -- or an object that already is a trajectory -- and the entry's trajectory type builds it on access with the
+  loading options (``stride``, ``frame_indices``, ``mask``, ``superpose``; per-trajectory ``strides`` / ``masks`` win
+  over the common ones) and its identity (``trajids``).  ``loader[i]``, ``loader[[i, j]]``, ``loader[a:b]``, iteration,
+  ``len`` and ``append`` as in the reference.  (The reference reads ``self.strides`` / ``self.masks`` before it assigns
+  them when ``strides=`` / ``masks=`` are given, trajloader.py:92-104; here the lengths are checked on the arguments.)"""
 
-  def __init__(self, trajs=None, trajtype=None, **kwarg):
-    self.trajs = list(trajs or [])
-    self.trajtype = trajtype
-    self.kwargs = kwarg
+  def __init__(self, trajs=None, trajtype=None, trajids=None, **kwarg):
+    self.trajs = []
+    if trajs is not None:
+      if not hasattr(trajs, "__iter__") or isinstance(trajs, (str, bytes)):
+        raise ValueError(f"The input should be a list or tuple of trajectory arguments rather than {type(trajs)}")
+      for item in trajs:
+        self.trajs.append(item if (hasattr(item, "xyz") and hasattr(item, "top")) else (tuple(item) if isinstance(item, (list, tuple)) else (item,)))
+    n = len(self.trajs)
+    self.OUTPUT_TYPE = [trajtype or Trajectory] * n
+    if trajids is not None and len(trajids) != n:
+      raise ValueError(f"The number of trajectory ids {len(trajids)} does not match the number of trajectories {n}")
+    self.trajids = list(trajids) if trajids is not None else [None] * n
+    self.i_ = 0
+    self._loading_options = {"stride": None, "frame_indices": None, "mask": None, "superpose": False}
+    strides, masks = kwarg.pop("strides", None), kwarg.pop("masks", None)
+    self.loading_options = kwarg
+    if strides is not None and len(strides) != n:
+      raise ValueError(f"The manually defined number of strides {len(strides)} does not match the number of trajectories {n}")
+    if masks is not None and len(masks) != n:
+      raise ValueError(f"The manually defined number of masks {len(masks)} does not match the number of trajectories {n}")
+    self.strides = [int(v) if v is not None else None for v in strides] if strides is not None else [None] * n
+    self.masks = list(masks) if masks is not None else [None] * n
+
+  # kept for callers of the first version of this class
+  @property
+  def trajtype(self):
+    return self.OUTPUT_TYPE[0] if self.OUTPUT_TYPE else Trajectory
+
+  @property
+  def kwargs(self):
+    return {k: v for k, v in self._loading_options.items() if v is not None and v is not False}
+
+  @property
+  def loading_options(self):
+    """The common loading options that are set, plus the identity of the trajectory being processed."""
+    options = {k: v for k, v in self._loading_options.items() if v is not None}
+    if self.trajids and self.i_ < len(self.trajids):
+      options["identity"] = self.trajids[self.i_]
+    return options
+
+  @loading_options.setter
+  def loading_options(self, kwargs):
+    self._loading_options.update(kwargs)
+
+  def get_loading_options(self, index):
+    """Constructor keywords of trajectory `index`: the common options, its own stride / mask, its identity."""
+    options = {k: v for k, v in self._loading_options.items() if v is not None and v is not False}
+    if self.strides[index] is not None:
+      options["stride"] = self.strides[index]
+    if self.masks[index] is not None:
+      options["mask"] = self.masks[index]
+    if self.trajids[index] is not None:
+      options["identity"] = self.trajids[index]
+    return options
+
+  def _load(self, index):
+    index = int(index)
+    self.i_ = index
+    item = self.trajs[index]
+    if hasattr(item, "xyz") and hasattr(item, "top"):
+      return item
+    return self.OUTPUT_TYPE[index](*item, **self.get_loading_options(index))
 
   def __len__(self):
     return len(self.trajs)
 
   def __getitem__(self, index):
-    item = self.trajs[index]
-    if hasattr(item, "xyz") and hasattr(item, "top"):
-      return item
-    args = item if isinstance(item, (tuple, list)) else (item,)
-    builder = self.trajtype or Trajectory
-    return builder(*args, **self.kwargs)
+    if isinstance(index, (int, np.integer)):
+      return self._load(index + len(self) if index < 0 else index)
+    if isinstance(index, (list, tuple, np.ndarray)):
+      return [self._load(i) for i in np.array(index, dtype=int)]
+    if isinstance(index, slice):
+      return [self._load(i) for i in np.arange(len(self))[index]]
+    raise IndexError("Index must be either an integer or a slice")
 
   def __iter__(self):
-    return (self[i] for i in range(len(self)))
+    return (self._load(i) for i in range(len(self)))
+
+  def __str__(self):
+    return "\n".join(str(t) for t in self).strip("\n")
+
+  def append(self, trajs=None, trajtype=None, **kwarg):
+    """Append trajectories (a list of constructor-argument tuples) of type `trajtype`, with optional ``trajids``,
+    ``strides`` and ``masks`` lists of the same length (trajloader.py:213-247)."""
+    if not isinstance(trajs, (list, tuple)):
+      raise ValueError(f"The input should be a list or tuple of trajectory arguments rather than {type(trajs)}")
+    if len(trajs) == 0:
+      raise ValueError("No trajectory detected in the input")
+    for idx, item in enumerate(trajs):
+      self.trajs.append(item if (hasattr(item, "xyz") and hasattr(item, "top")) else (tuple(item) if isinstance(item, (list, tuple)) else (item,)))
+      self.OUTPUT_TYPE.append(trajtype or Trajectory)
+      self.trajids.append(kwarg["trajids"][idx] if kwarg.get("trajids") is not None else None)
+      self.strides.append(kwarg["strides"][idx] if kwarg.get("strides") is not None else None)
+      self.masks.append(kwarg["masks"][idx] if kwarg.get("masks") is not None else None)
 
   def push(self, item):
-    self.trajs.append(item)
+    self.append([item])

@@ -240,3 +240,28 @@ def test_pdb_and_netcdf_files_without_pytraj(tmp_path):
     io.Trajectory(nc_path, str(pdb))                                # 13-atom topology, other coordinates
   with pytest.raises(ValueError):
     io.load_coordinates(str(tmp_path / "top.parm7"))
+
+
+def test_trajectory_loader_options(tmp_path):
+  """TrajectoryLoader (/root/reference/nearl/io/trajloader.py:12-247): lazy construction with the common loading options,
+  per-trajectory strides / masks / identities, integer / list / slice indexing, append, ready-made trajectory objects."""
+  pep = io.synthetic_peptide(8, 6, seed=9)
+  pdb = str(tmp_path / "p.pdb")
+  io.write_pdb(pdb, pep.xyz, pep.top)
+  loader = io.TrajectoryLoader([(pdb,), (pdb,), [pdb]], trajids=["a", "b", None], stride=2, strides=[None, 3, None], masks=[None, None, "@CA"])
+  assert len(loader) == 3 and loader.get_loading_options(1) == {"stride": 3, "identity": "b"}
+  t0, t1, t2 = loader[0], loader[1], loader[-1]
+  assert (t0.n_frames, t1.n_frames, t2.n_frames) == (3, 2, 3) and (t0.identity, t1.identity, t2.identity) == ("a", "b", pdb)
+  assert t2.n_atoms == len(pep.top.select("@CA")) and t0.n_atoms == pep.n_atoms and loader.i_ == 2
+  assert [t.identity for t in loader[[0, 1]]] == ["a", "b"] and [t.n_frames for t in loader[1:]] == [2, 3]
+  assert [t.n_frames for t in loader] == [3, 2, 3]
+  loader.append([(pdb,)], trajids=["late"], masks=["@N"])
+  loader.push(pep)                                          # an object that already is a trajectory is handed out as it is
+  assert len(loader) == 5 and loader[3].identity == "late" and loader[3].n_atoms == len(pep.top.select("@N")) and loader[4] is pep
+  assert loader.loading_options["stride"] == 2 and loader.trajtype is io.Trajectory
+  with pytest.raises(ValueError):
+    io.TrajectoryLoader([(pdb,)], trajids=["a", "b"])
+  with pytest.raises(ValueError):
+    io.TrajectoryLoader([(pdb,)], strides=[1, 2])
+  with pytest.raises(IndexError):
+    loader["x"]
