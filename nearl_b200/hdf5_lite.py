@@ -513,10 +513,41 @@ class Dataset(_Object):
       self._file._spill(self)
 
 
+class _LazyRef:
+  """A group member that was not read yet: the address of its object header."""
+  __slots__ = ("addr",)
+
+  def __init__(self, addr):
+    self.addr = addr
+
+
+class _Members(dict):
+  """name -> object; members of a group of a foreign file are read when they are asked for (MISATO's MD.hdf5 has one
+  group per PDB code, ~17 000 in the root group: opening the file reads their names, not their headers)."""
+
+  loader = None
+
+  def __getitem__(self, key):
+    obj = dict.__getitem__(self, key)
+    if type(obj) is _LazyRef:
+      obj = self.loader(obj.addr)
+      dict.__setitem__(self, key, obj)
+    return obj
+
+  def get(self, key, default=None):
+    return self[key] if key in self else default
+
+  def values(self):
+    return [self[k] for k in list(self.keys())]
+
+  def items(self):
+    return [(k, self[k]) for k in list(self.keys())]
+
+
 class Group(_Object):
   def __init__(self, file):
     _Object.__init__(self, file)
-    self._members = {}
+    self._members = _Members()
     self._written_links = None    # {name: address} as serialised in the header on disk
 
   def _resolve(self, path, create=False):
@@ -1018,6 +1049,16 @@ class _Reader:
         self._attribute(group, body)
 
   def _attach(self, group, name, child):
+    if not self.f._own_format:
+      # a foreign (read-only) file: the member's header is read when the member is asked for
+      group._members.loader = self._materialise
+      dict.__setitem__(group._members, name, _LazyRef(child))
+      return
+    obj = self._materialise(child)
+    group._members[name] = obj
+    group._written_links[name] = child
+
+  def _materialise(self, child):
     messages, total = self._messages(child)
     kinds = {m for m, _, _ in messages}
     if MSG_LAYOUT in kinds:
@@ -1026,8 +1067,7 @@ class _Reader:
       obj = Group(self.f)
       self._load_group(obj, child, messages)
     obj._addr, obj._cap, obj._dirty = child, total, False
-    group._members[name] = obj
-    group._written_links[name] = child
+    return obj
 
   def _link(self, body):
     flags = body[1]
@@ -1123,10 +1163,15 @@ class _Reader:
     f = self.f
     shape, maxshape, dtype, layout, filters = (), None, None, None, []
     attrs = []
-    for mtype, body, _ in messages:
+    for mtype, body, mflags in messages:
       if mtype == MSG_DATASPACE:
         shape, maxshape = self._dataspace(body)
       elif mtype == MSG_DATATYPE:
+        if mflags & 0x02:
+          # a shared message: the datatype is committed in an object header of its own (version 1 / 2: the address sits
+          # behind two / eight bytes; version 3 with type 2 likewise behind two)
+          ref = struct.unpack_from("<Q", body, 8 if body[0] == 1 else 2)[0]
+          body = next(b for t, b, _f in self._messages(f._addr_in(ref))[0] if t == MSG_DATATYPE)
         dtype = _decode_dtype(body)
       elif mtype == MSG_LAYOUT:
         layout = body

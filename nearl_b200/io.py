@@ -647,8 +647,8 @@ class MisatoTraj(Trajectory):
     for solvent in ("WAT", "Cl-", "Na+"):          # keep the coordinates aligned with the topology (traj.py:362-369)
       if solvent in present:
         top.strip(f":{solvent}")
-    with utils.open_hdf(self.trajfile, "r") as hdf:
-      if pdbcode.upper() not in hdf.keys():
+    with utils.shared_reader(self.trajfile) as hdf:          # kept open between trajectories
+      if pdbcode.upper() not in hdf:
         raise ValueError(f"Not found the key for PDB code {pdbcode.upper()} in the HDF5 trajectory file.")
       coord = hdf[f"{pdbcode.upper()}/trajectory_coordinates"][:]
     if kwarg.get("stride", None) is not None:

@@ -25,7 +25,7 @@ except Exception:          # pragma: no cover - depends on the image
 
 from . import constants, hdf5_lite
 
-__all__ = ["append_hdf_data", "update_hdf_data", "dump_dict", "batched_output", "hdf_session", "open_hdf", "hdf_backend", "find_block_single",
+__all__ = ["append_hdf_data", "update_hdf_data", "shared_reader", "dump_dict", "batched_output", "hdf_session", "open_hdf", "hdf_backend", "find_block_single",
            "find_block_dual", "dual_blocks_by_key"]
 
 _pending = None     # {(file, key): {"rows": [...], "dtype":, "maxshape":, "kwargs":}} while batching
@@ -87,6 +87,54 @@ def open_hdf(path, mode="r"):
       else:
         _session.pop(key).close()              # "w": the file is about to be truncated
   return _open(path, mode)
+
+
+_readers = {}       # (path, mtime, size) -> open read-only file, for inputs that are opened once per trajectory
+
+
+class _SharedReader:
+  """A read-only file kept open between uses (`shared_reader`): leaving its `with` block does not close it."""
+
+  def __init__(self, hdf):
+    self._hdf = hdf
+
+  def __enter__(self):
+    return self._hdf
+
+  def __exit__(self, *exc):
+    return False
+
+  def close(self):
+    pass
+
+  def __getattr__(self, name):
+    return getattr(self._hdf, name)
+
+  def __contains__(self, key):
+    return key in self._hdf
+
+  def __getitem__(self, key):
+    return self._hdf[key]
+
+
+def shared_reader(path):
+  """`open_hdf(path, "r")` for a file that is read again and again (MISATO's MD.hdf5: one open per trajectory in the
+  reference, /root/reference/nearl/io/traj.py:375): the handle -- and what it has learnt about the file, e.g. the names in
+  the root group -- is kept until the file changes on disk.  At most four files are kept."""
+  import os
+  st = os.stat(path)
+  key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+  hdf = _readers.get(key)
+  if hdf is None:
+    for old in [k for k in _readers if k[0] == key[0]] + (list(_readers)[:1] if len(_readers) >= 4 else []):
+      stale = _readers.pop(old, None)
+      if stale is not None:
+        try:
+          stale.close()
+        except Exception:
+          pass
+    hdf = _readers[key] = _open(path, "r")
+  return _SharedReader(hdf)
 
 
 @contextlib.contextmanager

@@ -217,3 +217,83 @@ def test_classic_layout_chunked_read_path(tmp_path):
     assert d.shape == (5, 7, 3) and d.chunks == chunks and d.dtype == np.dtype(">i4") and d.compression == "gzip"
     assert np.array_equal(d[:], data) and np.array_equal(d[1:4], data[1:4]) and np.array_equal(d[4], data[4])
     assert np.array_equal(d[0:3, 2:6, 1], data[0:3, 2:6, 1])
+
+
+def test_classic_layout_many_groups_are_read_lazily(tmp_path):
+  """MISATO's MD.hdf5 is one group per PDB code (~17 000 in the root group).  A classic-layout file with 40 groups under a
+  two-level group B-tree (5 symbol-table nodes), each holding a contiguous dataset: opening the file reads the names only,
+  looking one group up reads that group only (self-assembled file: structures per the specification)."""
+  import struct
+  U = hdf5_lite.UNDEF
+  blob = bytearray(b"\x00" * 1024)
+
+  def put(raw, align=8):
+    addr = (len(blob) + align - 1) // align * align
+    blob.extend(b"\x00" * (addr - len(blob)) + raw)
+    return addr
+
+  def msg(mtype, body):
+    body += b"\x00" * (-len(body) % 8)
+    return struct.pack("<HHB3x", mtype, len(body), 0) + body
+
+  def header(messages):
+    body = b"".join(messages)
+    return put(struct.pack("<BBHII4x", 1, 0, len(messages), 1, len(body)) + body)
+
+  def group(children):
+    """children: sorted [(name, object header address)] -> object header address of a group holding them."""
+    names = b"\x00" * 8
+    offs = []
+    for name, _ in children:
+      offs.append(len(names))
+      names += name.encode() + b"\x00"
+      names += b"\x00" * (-len(names) % 8)
+    seg = put(names)
+    heap = put(b"HEAP" + bytes([0, 0, 0, 0]) + struct.pack("<QQQ", len(names), U, seg))
+    snods = []
+    for i in range(0, len(children), 8):
+      part = list(zip(offs[i:i + 8], children[i:i + 8]))
+      body = b"SNOD" + bytes([1, 0]) + struct.pack("<H", len(part))
+      for off, (_, addr) in part:
+        body += struct.pack("<QQII16x", off, addr, 0, 0)
+      snods.append((put(body), part[0][0], part[-1][0]))
+
+    def tree(level, kids):            # kids: [(address, first key, last key)]
+      body = b"TREE" + bytes([0, level]) + struct.pack("<HQQ", len(kids), U, U) + struct.pack("<Q", 0)
+      for addr, _, last in kids:
+        body += struct.pack("<QQ", addr, last)
+      return put(body), kids[0][1], kids[-1][2]
+
+    leaves = [tree(0, snods[i:i + 3]) for i in range(0, len(snods), 3)]
+    root = leaves[0] if len(leaves) == 1 else tree(1, leaves)
+    return header([msg(0x11, struct.pack("<QQ", root[0], heap))])
+
+  def dataset(arr):
+    raw = put(arr.tobytes())
+    space = bytes([1, arr.ndim, 0, 0, 0, 0, 0, 0]) + struct.pack("<%dQ" % arr.ndim, *arr.shape)
+    dtype = bytes([0x11, 0x20, 31, 0]) + struct.pack("<I", 4) + struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127)
+    layout = bytes([3, 1]) + struct.pack("<QQ", raw, arr.nbytes)
+    return header([msg(0x01, space), msg(0x03, dtype), msg(0x08, layout)])
+
+  rng = np.random.default_rng(4)
+  codes = sorted(f"{i:03d}X" for i in range(40))
+  data = {c: rng.random((3, 5, 3)).astype(np.float32) for c in codes}
+  members = [(c, group([("trajectory_coordinates", dataset(data[c]))])) for c in codes]
+  root = group(members)
+  sb = hdf5_lite.SIGNATURE + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", 4, 16, 0)
+  sb += struct.pack("<QQQQ", 0, U, len(blob), U) + struct.pack("<QQII16x", 0, root, 0, 0)
+  blob[0:len(sb)] = sb
+  path = str(tmp_path / "many.h5")
+  with open(path, "wb") as fh:
+    fh.write(bytes(blob))
+  with hdf5_lite.File(path, "r") as h:
+    at_open = h.stats["bytes_read"]
+    assert sorted(h.keys()) == codes and len(h) == 40 and "017X" in h and "999X" not in h
+    assert h.stats["bytes_read"] == at_open < 4096                       # names only: no member header was read
+    got = h["017X/trajectory_coordinates"][:]
+    assert np.array_equal(got, data["017X"])
+    one = h.stats["bytes_read"] - at_open
+    assert one < 1200                                                    # that group, its dataset header, its 180 bytes
+    assert np.array_equal(h["031X"]["trajectory_coordinates"][1:3], data["031X"][1:3])
+    assert sum(1 for v in dict.values(h._members) if isinstance(v, hdf5_lite._LazyRef)) == 38
+    assert all(np.array_equal(g["trajectory_coordinates"][:], data[c]) for c, g in h.items())
