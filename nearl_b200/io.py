@@ -660,7 +660,7 @@ class MisatoTraj(Trajectory):
       coord, top = coord[:, sel, :], top[sel]
     xyz = pinned_empty(coord.shape, coord.dtype if coord.dtype in (np.float32, np.float64) else np.float32)
     xyz[...] = coord
-    super().__init__(xyz, top, identity=str(pdbcode).lower())
+    super().__init__(xyz, top, identity=utils.get_pdbcode(str(pdbcode)))       # traj.py:411-421: lower case, superseded codes replaced
     assert self.xyz.ndim == 3, f"Fatal: The shape of the trajectory {self.identity} is {self.xyz.shape}!!! It should be (n_frames, n_atoms, 3). "
     if kwarg.get("superpose", False):
       superpose(self, mask="@CA")
