@@ -167,9 +167,27 @@ __device__ __forceinline__ float nrl_agg_voxel(float *fb, const int W, const int
   float r = 0.0f;
   if (n > 1) {
     const float *col = fb + v;
+    // (minimum and maximum are exact whatever the order: sixteen loads in flight, two chains each)
     float mn = col[0], mx = col[0];
-#pragma unroll 8
-    for (int i = 1; i < n; ++i) { const float x = col[i * W]; if (x < mn) mn = x; if (x > mx) mx = x; }
+    {
+      float mn2 = mn, mx2 = mx;
+      int i = 1;
+      for (; i + 16 <= n; i += 16) {
+        float x[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) x[u] = col[(i + u) * W];
+#pragma unroll
+        for (int u = 0; u < 16; u += 2) {
+          if (x[u] < mn) mn = x[u];
+          if (x[u] > mx) mx = x[u];
+          if (x[u + 1] < mn2) mn2 = x[u + 1];
+          if (x[u + 1] > mx2) mx2 = x[u + 1];
+        }
+      }
+      for (; i < n; ++i) { const float x = col[i * W]; if (x < mn) mn = x; if (x > mx) mx = x; }
+      if (mn2 < mn) mn = mn2;
+      if (mx2 > mx) mx = mx2;
+    }
     const float range = mx - mn;
     unsigned long long h0 = 0ull, h1 = 0ull, h2 = 0ull, h3 = 0ull;      // 16 counters of 16 bits
     if (legacy) {
@@ -187,15 +205,29 @@ __device__ __forceinline__ float nrl_agg_voxel(float *fb, const int W, const int
     } else {
       const unsigned long long lanes = 0x000F000F000F000Full;
       for (int i0 = 0; i0 < n; i0 += 15) {
+        // fifteen samples per spill; the full groups are unrolled completely: fifteen independent load -> bin chains in
+        // flight per thread (a CTA of the pipelined kernel is alone on its SM: eight warps have to hide the latency of the
+        // shared-memory loads and of the float -> int conversions themselves), three partial sums of the shifted ones
         unsigned long long acc = 0ull;
-        const int i1 = min(i0 + 15, n);
-#pragma unroll 5
-        for (int i = i0; i < i1; ++i) {
-          const float sc = nrl_div_approx(col[i * W] - mn, range) * 16.0f;
-          int bin;
-          asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
-          bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
-          acc += 1ull << (4 * bin);
+        if (i0 + 15 <= n) {
+          unsigned long long part[3] = {0ull, 0ull, 0ull};
+#pragma unroll
+          for (int u = 0; u < 15; ++u) {
+            const float sc = nrl_div_approx(col[(i0 + u) * W] - mn, range) * 16.0f;
+            int bin;
+            asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
+            bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
+            part[u % 3] += 1ull << (4 * bin);
+          }
+          acc = part[0] + part[1] + part[2];
+        } else {
+          for (int i = i0; i < n; ++i) {
+            const float sc = nrl_div_approx(col[i * W] - mn, range) * 16.0f;
+            int bin;
+            asm("cvt.rzi.ftz.s32.f32 %0, %1;" : "=r"(bin) : "f"(sc));
+            bin = max(0, min(bin, NRL_ENTROPY_BINS - 1));
+            acc += 1ull << (4 * bin);
+          }
         }
         h0 += acc & lanes; h1 += (acc >> 4) & lanes; h2 += (acc >> 8) & lanes; h3 += (acc >> 12) & lanes;
       }
