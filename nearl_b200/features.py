@@ -26,7 +26,7 @@ logger = logging.getLogger(__name__)
 
 __all__ = [
   "Feature", "AtomicNumber", "Mass", "HeavyAtom", "Selection", "Backbone", "AtomType", "Electronegativity",
-  "Hydrophobicity", "DynamicFeature", "DensityFlow", "MarchingObservers", "cache_properties", "crop",
+  "Hydrophobicity", "PartialCharge", "DynamicFeature", "DensityFlow", "MarchingObservers", "cache_properties", "crop",
   "LabelIdentity", "LabelAffinity", "LabelStepping", "LabelRMSD", "LabelPCDT",
   "SUPPORTED_FEATURES", "SUPPORTED_AGGREGATION", "SUPPORTED_OBSERVATION",
 ]
@@ -492,6 +492,50 @@ class Hydrophobicity(_PerAtomWeight):
   def _weights(self, trajectory):
     en = _lookup(_ELECNEG_LUT, constants.ELECNEG, self.atomic_numbers)
     return np.abs(en - constants.ELECNEG[6])
+
+
+class PartialCharge(_PerAtomWeight):
+  """Partial charge of every atom (features.py:895-1031): ``charge_type`` "topology" (the charges of the topology, an error
+  when they are all zero), "manual" (``charge_parm``: {trajectory identity: charges}) or "external" (``charge_parm``: a
+  function of the trajectory); ``keep_sign`` "positive" / "p" keeps max(q, 0), "negative" / "n" min(q, 0), "both" / "b"
+  everything.  "chargefw" needs ChargeFW2, which is outside this path.  Negative weights deposit negative density; atoms
+  of charge exactly 0 are skipped by the voxeliser like any zero weight (voxelize.cu:63)."""
+
+  def __init__(self, charge_type="topology", charge_parm=None, keep_sign="both", **kwargs):
+    super().__init__(**kwargs)
+    if charge_type not in ("topology", "manual", "chargefw", "external"):
+      raise ValueError(f"{self.classname}: The charge type should be either 'topology', 'manual', 'chargefw' or 'external' rather than {charge_type}")
+    if keep_sign not in ("positive", "negative", "both", "p", "n", "b"):
+      raise ValueError(f"{self.classname}: The keep_sign parameter should be either positive/p, negative/n or both/b rather than {keep_sign}")
+    self.charge_type, self.charge_parm = charge_type, charge_parm
+    self.keep_sign = {"p": "positive", "n": "negative", "b": "both"}.get(keep_sign, keep_sign)
+
+  def __str__(self):
+    return f"{self.classname} <type:{self.charge_type}|sign:{self.keep_sign}>"
+
+  def cache(self, trajectory):
+    if self.charge_type != "topology":
+      self.force_recache = True            # the charges belong to the trajectory (its identity, a user function), not to the topology object
+    super().cache(trajectory)
+
+  def _weights(self, trajectory):
+    if self.charge_type == "topology":
+      q = np.asarray(getattr(trajectory.top, "charge", np.zeros(trajectory.top.n_atoms)), dtype=np.float64)
+      if np.allclose(q, 0):
+        raise ValueError(f"{self.classname}: The charge values in the topology are all zero meaning the topology of the trajectory does not contain necessary charge information. ")
+    elif self.charge_type == "manual":
+      q = np.array(self.charge_parm[trajectory.identity], dtype=np.float32)
+    elif self.charge_type == "external":
+      q = np.asarray(self.charge_parm(trajectory))
+    else:
+      raise NotImplementedError(f"{self.classname}: charge_type 'chargefw' needs ChargeFW2 (chargefw2_python), which is outside this path")
+    if len(q) != trajectory.top.n_atoms:
+      raise AssertionError(f"{self.classname}: The number of charge values does not match the number of atoms in the trajectory. ")
+    if self.keep_sign == "positive":
+      q = np.maximum(q, 0)
+    elif self.keep_sign == "negative":
+      q = np.minimum(q, 0)
+    return q
 
 
 def cache_properties(trajectory, property_type, **kwargs):

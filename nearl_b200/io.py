@@ -64,13 +64,16 @@ class Residue:
 class Topology:
   """Column-store topology with an Amber-mask subset (``select``)."""
 
-  def __init__(self, names, resids, resnames, atomic_numbers):
+  def __init__(self, names, resids, resnames, atomic_numbers, charges=None):
     self.names = np.asarray(names, dtype=object)
     self.resids = np.asarray(resids, dtype=np.int64)
     self.resnames = np.asarray(resnames, dtype=object)
     self.atomic_numbers = np.asarray(atomic_numbers, dtype=np.int64)
     n = len(self.names)
     assert len(self.resids) == n and len(self.resnames) == n and len(self.atomic_numbers) == n
+    # partial charges in units of the electron charge (pytraj's Topology.charge; zero when the source has none)
+    self.charge = np.zeros(n, dtype=np.float64) if charges is None else np.asarray(charges, dtype=np.float64)
+    assert len(self.charge) == n
     self._atoms = None
 
   @property
@@ -103,7 +106,7 @@ class Topology:
 
   def __getitem__(self, key):
     idx = np.arange(self.n_atoms)[key]
-    return Topology(self.names[idx], self.resids[idx], self.resnames[idx], self.atomic_numbers[idx])
+    return Topology(self.names[idx], self.resids[idx], self.resnames[idx], self.atomic_numbers[idx], self.charge[idx])
 
   def set_reference(self, frame):
     """pytraj's Topology.set_reference (the frame distance-based masks refer to; /root/reference/nearl/utils.py:97-100
@@ -117,6 +120,7 @@ class Topology:
     keep[self.select(mask)] = False
     self.names, self.resids = self.names[keep], self.resids[keep]
     self.resnames, self.atomic_numbers = self.resnames[keep], self.atomic_numbers[keep]
+    self.charge = self.charge[keep]
     self._atoms = None
     for key in ("_select_cache", "_residue_blocks", "_dual_blocks_memo"):
       self.__dict__.pop(key, None)
@@ -606,7 +610,11 @@ def load_amber_topology(path):
     masses = np.array(_parm7_values(sec["MASS"])[:n_atoms], dtype=float)
     table = np.array([constants.ATOMICMASS.get(i, 1e9) for i in range(1, 119)])
     z = np.abs(masses[:, None] - table[None, :]).argmin(axis=1) + 1
-  return Topology(names, resids, resnames, z)
+  charges = None
+  if "CHARGE" in sec:
+    # parm7 stores charges multiplied by 18.2223 (the square root of the electrostatic constant in kcal/mol units)
+    charges = np.array(_parm7_values(sec["CHARGE"])[:n_atoms], dtype=np.float64) / 18.2223
+  return Topology(names, resids, resnames, z, charges)
 
 
 def superpose(traj, mask="@CA", ref=0):

@@ -617,3 +617,30 @@ def test_streaming_crop_keeps_the_same_atoms_in_the_same_order(tmp_path, dtype, 
       scale = max(float(np.abs(host[key]).max()), 1e-30)
       assert rel_bad(out[0][key], host[key], atol=1e-5 * scale if key == "flow" else 0.0) == 0, (key, np.abs(out[0][key] - host[key]).max())
   assert out[0]["count_capped"].max() <= 300 and out[0]["count"].max() > 0 and out[0]["sel"].sum() > 0
+
+
+def test_partial_charge_channels_on_the_device_path(tmp_path):
+  """PartialCharge deposits signed weights: the batched device path against the per-task host protocol, and
+  q == max(q, 0) + min(q, 0) voxel by voxel (the channels share one focus box and one sweep)."""
+  traj = io.synthetic_trajectory(3000, 4, seed=77, pin=False, ligand_atoms=24)
+  traj.top.charge = np.round(np.random.default_rng(7).normal(0.0, 0.35, size=traj.n_atoms), 4)
+  traj.top.charge[::9] = 0.0                                       # exactly neutral atoms are skipped like any zero weight
+  parms = {"dimensions": 24, "lengths": 14, "time_window": 2, "cutoff": 3.5, "sigma": 1.3}
+
+  def feats():
+    return [features.PartialCharge(outkey="q"), features.PartialCharge(keep_sign="p", outkey="qp"),
+            features.PartialCharge(keep_sign="n", outkey="qn", selection="!:LIG"),
+            features.PartialCharge(charge_type="external", charge_parm=lambda t: np.abs(t.top.charge), outkey="qa")]
+
+  got, fz = build(traj, tmp_path, feats, parms, focus=(":LIG",))
+  assert fz.last_run_stats["native_tasks"] == fz.last_run_stats["tasks"] == 2 * 4
+  host, _ = build(traj, tmp_path, feats, parms, focus=(":LIG",), native=False)
+  for key in ("q", "qp", "qn", "qa"):
+    scale = max(float(np.abs(host[key]).max()), 1e-30)
+    assert np.abs(got[key] - host[key]).max() <= 2e-5 * scale, (key, np.abs(got[key] - host[key]).max())
+  assert got["qn"].max() <= 0.0 and got["qp"].min() >= 0.0 and got["q"].min() < 0 < got["q"].max()
+  ref = descs_from(fz)
+  want = host_ref.featurize(traj.xyz, fz.FEATURESPACE[0].resids, ref, fz.FOCALPOINTS, 2, buff_dim=_lib.buff_dim)
+  for key in ("q", "qp", "qa"):
+    scale = max(float(np.abs(want[key]).max()), 1e-30)
+    assert np.abs(got[key] - want[key]).max() <= 2e-5 * scale, key

@@ -30,6 +30,7 @@ def write_parm7(path, top, with_atomic_number=True):
   lines = ["%VERSION  VERSION_STAMP = V0001.000  DATE = 01/01/24  00:00:00", "%FLAG TITLE", "%FORMAT(20a4)", "synthetic"]
   lines += sec("POINTERS", "10I8", pointers, 10, 8, "i")
   lines += sec("ATOM_NAME", "20a4", [str(x)[:4] for x in top.names], 20, 4, "a")
+  lines += sec("CHARGE", "5E16.8", [float(q) * 18.2223 for q in top.charge], 5, 16, "e")
   lines += sec("MASS", "5E16.8", [float(constants.ATOMICMASS[int(z)]) for z in top.atomic_numbers], 5, 16, "e")
   if with_atomic_number:
     lines += sec("ATOMIC_NUMBER", "10I8", [int(z) for z in top.atomic_numbers], 10, 8, "i")
@@ -265,3 +266,42 @@ def test_trajectory_loader_options(tmp_path):
     io.TrajectoryLoader([(pdb,)], strides=[1, 2])
   with pytest.raises(IndexError):
     loader["x"]
+
+
+def test_partial_charge_weights(tmp_path):
+  """PartialCharge (/root/reference/nearl/features.py:895-1031): charges of the topology (parm7 CHARGE / 18.2223), of a
+  table keyed by the trajectory's identity, of a user function; keep_sign; the reference's errors."""
+  from nearl_b200 import features, featurizer
+  pep = io.synthetic_peptide(7, 2, seed=21)
+  rng = np.random.default_rng(2)
+  pep.top.charge = np.round(rng.normal(0, 0.4, size=pep.n_atoms), 4)
+  parm = str(tmp_path / "q.parm7")
+  write_parm7(parm, pep.top)
+  top = io.load_amber_topology(parm)
+  assert np.allclose(top.charge, pep.top.charge, atol=1e-6) and np.array_equal(top[3:9].charge, top.charge[3:9])
+  traj = io.Trajectory(pep.xyz, top, identity="pep")
+  fz = featurizer.Featurizer({"dimensions": 8, "lengths": 8, "time_window": 1, "cutoff": 2.0, "sigma": 1.0})
+  feats = {"both": features.PartialCharge(outkey="q"), "pos": features.PartialCharge(keep_sign="p", outkey="qp"),
+           "neg": features.PartialCharge(keep_sign="negative", outkey="qn"),
+           "manual": features.PartialCharge(charge_type="manual", charge_parm={"pep": list(range(pep.n_atoms))}, outkey="qm"),
+           "ext": features.PartialCharge(charge_type="external", charge_parm=lambda t: np.full(t.top.n_atoms, -0.5), keep_sign="p", outkey="qe")}
+  fz.register_features(feats)
+  for f in feats.values():
+    f.cache(traj)
+  q = top.charge.astype(np.float32)
+  assert np.array_equal(feats["both"].cached_array, q) and feats["both"].cached_array.dtype == np.float32
+  assert np.array_equal(feats["pos"].cached_array, np.maximum(q, 0)) and np.array_equal(feats["neg"].cached_array, np.minimum(q, 0))
+  assert np.array_equal(feats["manual"].cached_array, np.arange(pep.n_atoms, dtype=np.float32)) and not feats["ext"].cached_array.any()
+  assert str(feats["neg"]) == "PartialCharge <type:topology|sign:negative>"
+  coords, weights = feats["both"].query(top, pep.xyz[0], np.asarray(pep.xyz[0].mean(axis=0), dtype=np.float32))
+  assert len(coords) == len(weights) > 0 and set(np.round(weights, 4)) <= set(np.round(q, 4))
+  with pytest.raises(ValueError):
+    features.PartialCharge(outkey="z", **{}).cache(io.Trajectory(pep.xyz, io.Topology(top.names, top.resids, top.resnames, top.atomic_numbers)))
+  with pytest.raises(ValueError):
+    features.PartialCharge(charge_type="mulliken")
+  with pytest.raises(ValueError):
+    features.PartialCharge(keep_sign="x")
+  cf = features.PartialCharge(charge_type="chargefw", charge_parm="eem", outkey="c")
+  fz.register_feature(cf)
+  with pytest.raises(NotImplementedError):
+    cf.cache(traj)
