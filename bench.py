@@ -363,6 +363,33 @@ def run_native(args):
     finally:
       _lib.set_option("no_fork", 0)
 
+  # untimed probe of the host link with this step's own transfers (rank 0): one trajectory up from its page-locked array,
+  # one step's result grids down -- the floor the copies alone put under an end-to-end step
+  link = None
+  if rank == 0:
+    try:
+      host_xyz = torch.from_numpy(trajs[0].xyz)
+      host_out = torch.empty(max(n_tasks * int(np.prod(fz.FEATURESPACE[0].dims)), 1), dtype=torch.float32).pin_memory()
+      dev_res = torch.empty_like(host_out, device="cuda")
+      def copy_ms(dst, src, reps=10):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(reps):
+          dst.copy_(src, non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize()
+        return c0.elapsed_time(c1) / reps
+      up_ms, down_ms = copy_ms(dev_xyz[0], host_xyz), copy_ms(host_out, dev_res)
+      link = {"h2d_gbs": host_xyz.numel() * host_xyz.element_size() / up_ms / 1e6, "h2d_ms_per_step": up_ms,
+              "d2h_gbs": host_out.numel() * 4 / down_ms / 1e6, "d2h_ms_per_step": down_ms, "page_locked_source": bool(host_xyz.is_pinned()),
+              "note": "untimed probe after the runs: cudaMemcpyAsync of one trajectory / one step's grids alone on the link; "
+                      "the two directions overlap in the pipelined run, so the larger one is the floor of an end-to-end step"}
+      del host_out, dev_res
+    except Exception as exc:      # the probe is evidence, not part of the measurement
+      link = {"error": str(exc)}
+
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -463,7 +490,8 @@ def run_native(args):
             "h2d_bytes_per_step": int(n_frames * trajs[0].n_atoms * 12 + 4 * trajs[0].n_atoms * 4),
             "d2h_bytes_per_step": int(n_tasks * G * 4),
             "api": "nearl_b200.featurizer.Featurizer.run() over K pinned host trajectories -> host result grids (read by a sink)",
-            "timer": "host wall clock around the K-step call, barrier + synchronize on both sides, max over ranks"},
+            "timer": "host wall clock around the K-step call, barrier + synchronize on both sides, max over ranks",
+            "link": link},
     "gpu_launches": int(launches),
     "clocks": clocks, "clocks_e2e": clocks_e2e,
     "roofline": roof, "roofline_compute": roof_c, "kernels": kernels,
