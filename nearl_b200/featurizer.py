@@ -100,6 +100,8 @@ class Featurizer:
     # nearl_b200: single-frame systems featurised per native call when every feature is static (time_window 1);
     # 1 = one system per call
     self.static_group = 32
+    # nearl_b200: loader threads that read the files of the next trajectories ahead (io.TrajectoryLoader.prefetched; 0: none)
+    self.prefetch_workers = 4
     if config.verbose():
       printit(f"{self.classname}: Featurizer is initialized successfully with dimensions: {self.dims} and lengths: {self.lengths}")
     if "outfile" in parms:
@@ -290,10 +292,7 @@ class Featurizer:
     that the lanes' workspaces (a few times the trajectory each, grow-only) stay bounded."""
     pending = []                                             # submitted, not yet finished, oldest first
     multi_frame = False
-    for tid in indices:
-      traj = loaded.get(tid) if loaded is not None else None
-      if traj is None:
-        traj = self.TRAJLOADER[tid]
+    for tid, traj in self._trajectories(indices, loaded):
       nbytes = int(getattr(getattr(traj, "xyz", None), "nbytes", 0) or 0)
       lanes = max(1, min(depth, int(self.pipeline_bytes) // max(nbytes, 1)))
       lane = None
@@ -310,6 +309,17 @@ class Featurizer:
     while pending:
       self._finish(pending.pop(0), stats)
     return multi_frame
+
+  def _trajectories(self, indices, loaded=None):
+    """(index, trajectory) in order: through the loader's read-ahead threads where it has them (file-backed trajectory
+    types that split their constructor), else built one by one on this thread as `self.TRAJLOADER[tid]`."""
+    loader, workers = self.TRAJLOADER, int(self.prefetch_workers or 0)
+    if loaded is None and workers > 0 and hasattr(loader, "prefetched"):
+      yield from loader.prefetched(indices, workers=workers)
+      return
+    for tid in indices:
+      traj = loaded.get(tid) if loaded is not None else None
+      yield tid, (traj if traj is not None else loader[tid])
 
   # ---- single-frame systems (PDBBind-style): many systems per native call ------------------------------
   def _static_groupable(self):

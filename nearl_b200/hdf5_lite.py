@@ -702,8 +702,17 @@ class File(Group):
     return addr if addr == UNDEF else addr - self._base
 
   def _read(self, addr, size):
-    self._fh.seek(addr)
     self.stats["bytes_read"] += size
+    if self.mode == "r":
+      # positional read: no shared file position, so several threads may read one open file (io.TrajectoryLoader.prefetched)
+      blob = os.pread(self._fh.fileno(), size, addr)
+      while len(blob) < size:
+        more = os.pread(self._fh.fileno(), size - len(blob), addr + len(blob))
+        if not more:
+          break
+        blob += more
+      return blob
+    self._fh.seek(addr)
     return self._fh.read(size)
 
   def _write(self, addr, blob):

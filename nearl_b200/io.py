@@ -586,34 +586,145 @@ def _parm7_values(section):
   return out
 
 
+_PARM7_REQUIRED = ("POINTERS", "ATOM_NAME", "RESIDUE_LABEL", "RESIDUE_POINTER")
+_PARM7_WANTED = _PARM7_REQUIRED + ("CHARGE", "MASS", "ATOMIC_NUMBER")
+
+
+def _parm7_complete(buf, flags):
+  """True when every section of `flags` lies in `buf` whole (a later %FLAG follows it)."""
+  for flag in flags:
+    at = buf.find(b"%FLAG " + flag.encode())
+    if at < 0 or buf.find(b"%FLAG", at + 6) < 0:
+      return False
+  return True
+
+
+def _parm7_head(path):
+  """Bytes of a parm7 file up to the end of the last section the topology needs.  The per-atom and per-residue tables
+  stand at the head of the file (tleap / parmed order); the bonded terms and exclusion lists that follow are four fifths
+  of a solvated system's file, so a gzip member is inflated only as far as needed (the whole file when a wanted
+  section has not shown up by then -- files that predate ATOMIC_NUMBER, unusual orders)."""
+  import zlib
+  with open(path, "rb") as fh:
+    if not str(path).endswith(".gz"):
+      return fh.read()
+    inflate = zlib.decompressobj(16 + zlib.MAX_WBITS)
+    buf = bytearray()
+    while True:
+      chunk = fh.read(1 << 18)
+      if not chunk:
+        break
+      buf += inflate.decompress(chunk)
+      if inflate.eof:
+        if not inflate.unused_data.strip(b"\0"):
+          break
+        raise ValueError("multi-member gzip")        # rare: the caller falls back to the gzip module
+      if _parm7_complete(buf, _PARM7_WANTED):
+        break
+    return bytes(buf)
+
+
+def _parm7_sections_bytes(buf, wanted):
+  """{flag: [format, body bytes]} of the wanted sections that are whole in `buf`."""
+  marks, at = [], buf.find(b"%FLAG")
+  while at >= 0:
+    marks.append(at)
+    at = buf.find(b"%FLAG", at + 5)
+  marks.append(len(buf))
+  sections = {}
+  for at, end in zip(marks[:-1], marks[1:]):
+    p = buf.find(b"\n", at, end) + 1
+    if p <= 0:
+      continue
+    words = buf[at + 5:p].split()
+    flag = words[0].decode() if words else ""
+    if flag not in wanted or flag in sections:
+      continue
+    fmt = None
+    while p < end and buf[p:p + 1] == b"%":                # %FORMAT(...), %COMMENT lines
+      e = buf.find(b"\n", p, end)
+      e = end if e < 0 else e
+      line = buf[p:e]
+      if line.startswith(b"%FORMAT"):
+        fmt = line[line.index(b"(") + 1:line.rindex(b")")].decode()
+      p = e + 1
+    if fmt is not None:
+      sections[flag] = [fmt, buf[p:end]]
+  return sections
+
+
+def _parm7_array(section):
+  """The fields of one section as an array, parsed in one piece: every line but the last holds its full count of
+  fixed-width fields (else None: the caller takes the line-by-line parser)."""
+  fmt, body = section
+  m = re.fullmatch(r"(\d+)([aAiIeEfF])(\d+)(?:\.\d+)?", fmt.strip())
+  if not m:
+    return None
+  per, kind, width = int(m.group(1)), m.group(2).lower(), int(m.group(3))
+  body = body.replace(b"\r", b"")
+  if body.endswith(b"\n"):
+    body = body[:-1]
+  full = per * width
+  breaks = np.flatnonzero(np.frombuffer(body, dtype=np.uint8) == 10)
+  if len(breaks) and not np.array_equal(breaks, (np.arange(len(breaks)) + 1) * (full + 1) - 1):
+    return None
+  flat = body.replace(b"\n", b"")
+  if kind != "a":
+    flat = flat.rstrip()
+  flat += b" " * (-len(flat) % width)
+  fields = np.frombuffer(flat, dtype=f"S{width}")
+  try:
+    if kind == "a":
+      # names and labels repeat: strip and decode the distinct ones only
+      distinct, inverse = np.unique(fields, return_inverse=True)
+      return np.array([d.decode().strip() for d in distinct.tolist()], dtype=object)[inverse]
+    return fields.astype(np.int64 if kind == "i" else np.float64)
+  except ValueError:
+    return None
+
+
 def load_amber_topology(path):
   """Topology from an Amber parm7 / prmtop file, optionally gzip-compressed (what pt.load_topology gives
   MisatoTraj for production.top.gz, /root/reference/nearl/io/traj.py:361): atom names, residue labels and
-  pointers, atomic numbers (from the masses when the file predates the ATOMIC_NUMBER section)."""
-  import gzip
-  opener = gzip.open if str(path).endswith(".gz") else open
-  with opener(path, "rt") as fh:
-    sec = _parm7_sections(fh.read())
-  for need in ("POINTERS", "ATOM_NAME", "RESIDUE_LABEL", "RESIDUE_POINTER"):
+  pointers, atomic numbers (from the masses when the file predates the ATOMIC_NUMBER section), charges."""
+  sec = None
+  try:
+    sec = _parm7_sections_bytes(_parm7_head(path), _PARM7_WANTED)
+  except (OSError, ValueError, EOFError, __import__("zlib").error):
+    pass
+  if sec is None or any(need not in sec for need in _PARM7_REQUIRED):
+    import gzip
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rt") as fh:
+      sec = _parm7_sections(fh.read())
+  for need in _PARM7_REQUIRED:
     if need not in sec:
       raise ValueError(f"{path}: parm7 section {need} is missing")
-  pointers = _parm7_values(sec["POINTERS"])
-  n_atoms, n_res = pointers[0], pointers[11]
-  names = _parm7_values(sec["ATOM_NAME"])[:n_atoms]
-  labels = _parm7_values(sec["RESIDUE_LABEL"])[:n_res]
-  first = np.array(_parm7_values(sec["RESIDUE_POINTER"])[:n_res], dtype=np.int64) - 1
+
+  def values(flag):
+    arr = _parm7_array(sec[flag]) if isinstance(sec[flag][1], bytes) else None
+    if arr is None:
+      fmt, body = sec[flag]
+      arr = _parm7_values([fmt, body.decode().splitlines() if isinstance(body, bytes) else body])
+    return arr
+
+  pointers = values("POINTERS")
+  n_atoms, n_res = int(pointers[0]), int(pointers[11])
+  names = values("ATOM_NAME")[:n_atoms]
+  labels = values("RESIDUE_LABEL")[:n_res]
+  first = np.array(values("RESIDUE_POINTER")[:n_res], dtype=np.int64) - 1
   resids = np.repeat(np.arange(n_res), np.diff(np.r_[first, n_atoms]))
   resnames = np.array(labels, dtype=object)[resids]
   if "ATOMIC_NUMBER" in sec:
-    z = np.array(_parm7_values(sec["ATOMIC_NUMBER"])[:n_atoms], dtype=np.int64)
+    z = np.array(values("ATOMIC_NUMBER")[:n_atoms], dtype=np.int64)
   else:
-    masses = np.array(_parm7_values(sec["MASS"])[:n_atoms], dtype=float)
+    masses = np.array(values("MASS")[:n_atoms], dtype=float)
     table = np.array([constants.ATOMICMASS.get(i, 1e9) for i in range(1, 119)])
     z = np.abs(masses[:, None] - table[None, :]).argmin(axis=1) + 1
   charges = None
   if "CHARGE" in sec:
     # parm7 stores charges multiplied by 18.2223 (the square root of the electrostatic constant in kcal/mol units)
-    charges = np.array(_parm7_values(sec["CHARGE"])[:n_atoms], dtype=np.float64) / 18.2223
+    charges = np.array(values("CHARGE")[:n_atoms], dtype=np.float64) / 18.2223
   return Topology(names, resids, resnames, z, charges)
 
 
@@ -640,22 +751,37 @@ class MisatoTraj(Trajectory):
   in the reference: ``stride`` or ``frame_indices``, ``mask``, ``superpose`` (fit onto the first frame over
   ``@CA``, done on the device)."""
 
-  def __init__(self, pdbcode, misatodir, **kwarg):
+  def __init__(self, pdbcode, misatodir, _raw=None, **kwarg):
+    raw = _raw if _raw is not None else self.read_raw(pdbcode, misatodir, **kwarg)
+    self.topfile, self.trajfile, self.pdbcode = raw["topfile"], raw["trajfile"], pdbcode
+    coord, top = raw["coord"], raw["top"]
+    xyz = pinned_empty(coord.shape, coord.dtype if coord.dtype in (np.float32, np.float64) else np.float32)
+    xyz[...] = coord
+    from . import utils
+    super().__init__(xyz, top, identity=utils.get_pdbcode(str(pdbcode)))       # traj.py:411-421: lower case, superseded codes replaced
+    assert self.xyz.ndim == 3, f"Fatal: The shape of the trajectory {self.identity} is {self.xyz.shape}!!! It should be (n_frames, n_atoms, 3). "
+    if kwarg.get("superpose", False):
+      superpose(self, mask="@CA")
+
+  @staticmethod
+  def read_raw(pdbcode, misatodir, **kwarg):
+    """The file half of the constructor -- topology parsed and stripped, coordinates read, strided and masked -- with no
+    use of the device or of the native library: `TrajectoryLoader.prefetched` runs it on loader threads (inflating the
+    files is most of it and releases the interpreter lock) and hands the result to the constructor as `_raw`."""
     import os
     from . import utils
-    self.topfile = f"{misatodir}/parameter_restart_files_MD/{pdbcode.lower()}/production.top.gz"
-    if not os.path.exists(self.topfile):
-      raise FileNotFoundError(f"The topology file of PDB {pdbcode} is not found ({self.topfile})")
-    self.trajfile = os.path.join(misatodir, "MD.hdf5")
-    if not os.path.exists(self.trajfile):
-      raise FileNotFoundError(f"The trajectory file is not found ({self.trajfile})")
-    self.pdbcode = pdbcode
-    top = load_amber_topology(self.topfile)
+    topfile = f"{misatodir}/parameter_restart_files_MD/{pdbcode.lower()}/production.top.gz"
+    if not os.path.exists(topfile):
+      raise FileNotFoundError(f"The topology file of PDB {pdbcode} is not found ({topfile})")
+    trajfile = os.path.join(misatodir, "MD.hdf5")
+    if not os.path.exists(trajfile):
+      raise FileNotFoundError(f"The trajectory file is not found ({trajfile})")
+    top = load_amber_topology(topfile)
     present = set(top.resnames.tolist())
     for solvent in ("WAT", "Cl-", "Na+"):          # keep the coordinates aligned with the topology (traj.py:362-369)
       if solvent in present:
         top.strip(f":{solvent}")
-    with utils.shared_reader(self.trajfile) as hdf:          # kept open between trajectories
+    with utils.shared_reader(trajfile) as hdf:          # kept open between trajectories
       if pdbcode.upper() not in hdf:
         raise ValueError(f"Not found the key for PDB code {pdbcode.upper()} in the HDF5 trajectory file.")
       coord = hdf[f"{pdbcode.upper()}/trajectory_coordinates"][:]
@@ -666,12 +792,7 @@ class MisatoTraj(Trajectory):
     if kwarg.get("mask", None) is not None:
       sel = top.select(kwarg["mask"])
       coord, top = coord[:, sel, :], top[sel]
-    xyz = pinned_empty(coord.shape, coord.dtype if coord.dtype in (np.float32, np.float64) else np.float32)
-    xyz[...] = coord
-    super().__init__(xyz, top, identity=utils.get_pdbcode(str(pdbcode)))       # traj.py:411-421: lower case, superseded codes replaced
-    assert self.xyz.ndim == 3, f"Fatal: The shape of the trajectory {self.identity} is {self.xyz.shape}!!! It should be (n_frames, n_atoms, 3). "
-    if kwarg.get("superpose", False):
-      superpose(self, mask="@CA")
+    return {"coord": coord, "top": top, "topfile": topfile, "trajfile": trajfile}
 
 
 class TrajectoryLoader:
@@ -744,6 +865,43 @@ class TrajectoryLoader:
     if hasattr(item, "xyz") and hasattr(item, "top"):
       return item
     return self.OUTPUT_TYPE[index](*item, **self.get_loading_options(index))
+
+  def prefetched(self, indices, workers=4, ahead=None):
+    """(index, trajectory) for every index of `indices`, in order, with the FILE half of the next trajectories read ahead
+    on `workers` threads: for trajectory types that split their constructor (`read_raw(*args, **options)` -> what the
+    constructor takes as `_raw`; `MisatoTraj` does) up to `ahead` (default 2 x workers) reads are in flight while the
+    caller works on the current trajectory.  Everything that touches the device -- page-locking, superposition -- stays on
+    the calling thread, inside the constructor.  Other entries are built on access, as `loader[i]` does; an exception of a
+    read is raised when its trajectory's turn comes, as the unthreaded loop would."""
+    indices = [int(i) for i in indices]
+    can = lambda i: workers > 0 and not (hasattr(self.trajs[i], "xyz") and hasattr(self.trajs[i], "top")) and hasattr(self.OUTPUT_TYPE[i], "read_raw")
+    if not any(can(i) for i in indices):
+      for i in indices:
+        yield i, self._load(i)
+      return
+    from concurrent.futures import ThreadPoolExecutor
+    ahead = max(1, int(ahead) if ahead is not None else 2 * int(workers))
+    with ThreadPoolExecutor(max_workers=int(workers), thread_name_prefix="nearl-loader") as pool:
+      futures, submitted = {}, 0
+      try:
+        for k, i in enumerate(indices):
+          while submitted < len(indices) and submitted <= k + ahead:
+            j = indices[submitted]
+            if can(j) and submitted not in futures:
+              options = self.get_loading_options(j)
+              futures[submitted] = pool.submit(self.OUTPUT_TYPE[j].read_raw, *self.trajs[j],
+                                               **{o: v for o, v in options.items() if o != "identity"})
+            submitted += 1
+          fut = futures.pop(k, None)
+          if fut is None:
+            yield i, self._load(i)
+            continue
+          raw = fut.result()
+          self.i_ = i
+          yield i, self.OUTPUT_TYPE[i](*self.trajs[i], _raw=raw, **self.get_loading_options(i))
+      finally:
+        for fut in futures.values():
+          fut.cancel()
 
   def __len__(self):
     return len(self.trajs)

@@ -90,6 +90,7 @@ def open_hdf(path, mode="r"):
 
 
 _readers = {}       # (path, mtime, size) -> open read-only file, for inputs that are opened once per trajectory
+_readers_lock = __import__("threading").Lock()
 
 
 class _SharedReader:
@@ -124,16 +125,17 @@ def shared_reader(path):
   import os
   st = os.stat(path)
   key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
-  hdf = _readers.get(key)
-  if hdf is None:
-    for old in [k for k in _readers if k[0] == key[0]] + (list(_readers)[:1] if len(_readers) >= 4 else []):
-      stale = _readers.pop(old, None)
-      if stale is not None:
-        try:
-          stale.close()
-        except Exception:
-          pass
-    hdf = _readers[key] = _open(path, "r")
+  with _readers_lock:                     # loader threads share the handle (hdf5_lite reads by position)
+    hdf = _readers.get(key)
+    if hdf is None:
+      for old in [k for k in _readers if k[0] == key[0]] + (list(_readers)[:1] if len(_readers) >= 4 else []):
+        stale = _readers.pop(old, None)
+        if stale is not None:
+          try:
+            stale.close()
+          except Exception:
+            pass
+      hdf = _readers[key] = _open(path, "r")
   return _SharedReader(hdf)
 
 

@@ -73,6 +73,80 @@ def test_parm7_topology(tmp_path):
   assert top.n_atoms == n - np.count_nonzero(traj.top.resnames == "LEU") and "LEU" not in set(top.resnames)
 
 
+def test_parm7_fast_parser_matches_the_line_parser(tmp_path):
+  """The one-piece parser (sections found by position, fields through numpy, a gzip member inflated only as far as the
+  last wanted section) against the line-by-line one, on the shapes of file it has to cope with."""
+  traj = io.synthetic_peptide(57, 1, seed=6)
+  path = str(tmp_path / "full.parm7")
+  write_parm7(path, traj.top)
+  text = open(path).read()
+  # a long tail of sections the topology does not need, a %COMMENT line, CRLF line ends, a ragged section
+  tail = "\n".join(["%FLAG BONDS_INC_HYDROGEN", "%FORMAT(10I8)"] + ["".join(f"{v:8d}" for v in range(k, k + 10)) for k in range(0, 200000, 10)]) + "\n"
+  commented = text.replace("%FLAG CHARGE\n", "%FLAG CHARGE\n%COMMENT  Atomic charge in internal units\n")
+  ragged = text.replace("%FLAG RESIDUE_POINTER\n%FORMAT(10I8)\n", "%FLAG RESIDUE_POINTER\n%FORMAT(10I8)\n       1\n", 1)
+  assert ragged != text
+  ragged = ragged.replace("%FLAG RESIDUE_POINTER\n%FORMAT(10I8)\n       1\n       1", "%FLAG RESIDUE_POINTER\n%FORMAT(10I8)\n       1\n        ", 1)
+  variants = {"plain.parm7": text, "tail.top.gz": text + tail, "comment.parm7": commented, "crlf.parm7": text.replace("\n", "\r\n")}
+  want = io.load_amber_topology(path)
+  sec = io._parm7_sections(text)
+  assert list(want.names) == io._parm7_values(sec["ATOM_NAME"])[:want.n_atoms]
+  assert np.array_equal(want.charge, np.array(io._parm7_values(sec["CHARGE"])) / 18.2223)
+  assert np.array_equal(want.atomic_numbers, np.array(io._parm7_values(sec["ATOMIC_NUMBER"])))
+  assert all(type(n) is str for n in want.names[:3]) and all(type(n) is str for n in want.resnames[:3])
+  for name, body in variants.items():
+    opener = gzip.open if name.endswith(".gz") else open
+    with opener(str(tmp_path / name), "wt", newline="") as fh:
+      fh.write(body)
+    got = io.load_amber_topology(str(tmp_path / name))
+    assert list(got.names) == list(want.names) and list(got.resnames) == list(want.resnames), name
+    assert np.array_equal(got.resids, want.resids) and np.array_equal(got.atomic_numbers, want.atomic_numbers), name
+    assert np.array_equal(got.charge, want.charge), name
+  head = io._parm7_head(str(tmp_path / "tail.top.gz"))
+  assert len(head) < len(text + tail) and b"RESIDUE_POINTER" in head            # the tail was not inflated to its end
+  # a section whose lines are not all full falls back to the line parser, section by section
+  assert io._parm7_array(io._parm7_sections_bytes(ragged.encode(), ("RESIDUE_POINTER",))["RESIDUE_POINTER"]) is None
+  open(str(tmp_path / "ragged.parm7"), "w").write(ragged)
+  got = io.load_amber_topology(str(tmp_path / "ragged.parm7"))
+  assert np.array_equal(got.resids, want.resids)
+
+
+def test_loader_prefetch_reads_ahead_in_order(tmp_path):
+  """TrajectoryLoader.prefetched: file halves of the constructors on loader threads, trajectories handed out in order,
+  identical to the unthreaded loads; an unreadable entry raises when its turn comes; in-memory entries pass through."""
+  root = str(tmp_path / "misato")
+  codes = ["1abc", "2xyz", "3pqr", "4stu", "5vwx"]
+  trajs = {code: io.synthetic_peptide(9 + i, 6, seed=40 + i) for i, code in enumerate(codes)}
+  for code, traj in trajs.items():
+    make_misato_dir(root, code, traj)
+  memory = io.synthetic_peptide(7, 3, seed=50)
+  loader = io.TrajectoryLoader([(c, root) for c in codes], trajtype=io.MisatoTraj, strides=[None, 2, None, None, 3], masks=[None, None, "@CA,C,N", None, None])
+  loader.append([memory])
+  order = [4, 0, 5, 2, 1, 3, 0]
+  plain = [loader[i] for i in order]
+  for workers in (0, 1, 3):
+    got = list(loader.prefetched(order, workers=workers, ahead=2))
+    assert [i for i, _ in got] == order
+    for (_, a), b in zip(got, plain):
+      assert a.identity == b.identity and a.xyz.dtype == b.xyz.dtype and np.array_equal(a.xyz, b.xyz)
+      assert list(a.top.names) == list(b.top.names)
+  assert got[2][1] is memory
+  # several threads reading one open file at once give what one thread reads
+  from concurrent.futures import ThreadPoolExecutor
+  with ThreadPoolExecutor(6) as pool:
+    raws = list(pool.map(lambda c: io.MisatoTraj.read_raw(c, root)["coord"], codes * 6))
+  for code, coord in zip(codes * 6, raws):
+    assert np.array_equal(coord, trajs[code].xyz.astype(np.float32))
+  # the failure of a read surfaces at its own position, after the trajectories in front of it were delivered
+  os.makedirs(os.path.join(root, "parameter_restart_files_MD", "9bad"))
+  write_parm7(os.path.join(root, "parameter_restart_files_MD", "9bad", "production.top.gz"), trajs["1abc"].top)
+  broken = io.TrajectoryLoader([("1abc", root), ("9bad", root), ("2xyz", root)], trajtype=io.MisatoTraj)
+  seen = []
+  with pytest.raises(ValueError, match="9BAD"):
+    for i, t in broken.prefetched([0, 1, 2], workers=2):
+      seen.append(i)
+  assert seen == [0]
+
+
 def test_misato_layout_and_loader(tmp_path):
   root = str(tmp_path / "misato")
   trajs = {code: io.synthetic_peptide(10 + i, 8, seed=20 + i) for i, code in enumerate(("1abc", "2XYZ"))}
@@ -140,6 +214,31 @@ def test_misato_trajectory_through_the_featurizer(tmp_path):
   stats = fz.run()
   assert stats["native_tasks"] == 4 and np.array(fz.RESULTS["mass"]).shape == (2, 16, 16, 16)
   assert np.array(fz.RESULTS["mass"]).sum() > 0
+
+
+@pytest.mark.gpu
+def test_misato_run_with_and_without_loader_threads(tmp_path):
+  """Featurizer.run() over file-backed MISATO trajectories (superposed on the device by their constructor, on the calling
+  thread): the read-ahead threads change nothing in the results, whatever their number."""
+  root = str(tmp_path / "misato")
+  codes = [f"{i}abc" for i in range(1, 8)]
+  for i, code in enumerate(codes):
+    make_misato_dir(root, code, io.synthetic_peptide(40 + 3 * i, 20, seed=60 + i))
+  outs = []
+  for workers in (0, 1, 4):
+    loader = io.TrajectoryLoader([(c, root) for c in codes], trajtype=io.MisatoTraj, superpose=True)
+    fz = featurizer.Featurizer({"dimensions": 16, "lengths": 12, "time_window": 10, "cutoff": 3.0, "sigma": 1.0})
+    fz.register_features([features.Mass(outkey="mass"), features.MarchingObservers(obs="mean_distance", agg="standard_deviation", outkey="md")])
+    fz.register_focus([":ARG,LYS,GLU"], "mask")
+    fz.register_trajloader(loader)
+    fz.keep_results = True
+    fz.prefetch_workers = workers
+    stats = fz.run()
+    assert stats["trajectories"] == len(codes)
+    outs.append({k: np.array(v) for k, v in fz.RESULTS.items()})
+  for other in outs[1:]:
+    for key in outs[0]:
+      assert np.array_equal(outs[0][key], other[key]), key
 
 
 PDB_TEXT = """\
