@@ -590,15 +590,6 @@ _PARM7_REQUIRED = ("POINTERS", "ATOM_NAME", "RESIDUE_LABEL", "RESIDUE_POINTER")
 _PARM7_WANTED = _PARM7_REQUIRED + ("CHARGE", "MASS", "ATOMIC_NUMBER")
 
 
-def _parm7_complete(buf, flags):
-  """True when every section of `flags` lies in `buf` whole (a later %FLAG follows it)."""
-  for flag in flags:
-    at = buf.find(b"%FLAG " + flag.encode())
-    if at < 0 or buf.find(b"%FLAG", at + 6) < 0:
-      return False
-  return True
-
-
 def _parm7_head(path):
   """Bytes of a parm7 file up to the end of the last section the topology needs.  The per-atom and per-residue tables
   stand at the head of the file (tleap / parmed order); the bonded terms and exclusion lists that follow are four fifths
@@ -610,8 +601,10 @@ def _parm7_head(path):
       return fh.read()
     inflate = zlib.decompressobj(16 + zlib.MAX_WBITS)
     buf = bytearray()
+    whole, scan = set(), 0          # sections with a later %FLAG behind them; where the search for the next marker resumes
+    last = None
     while True:
-      chunk = fh.read(1 << 18)
+      chunk = fh.read(1 << 16)
       if not chunk:
         break
       buf += inflate.decompress(chunk)
@@ -619,7 +612,18 @@ def _parm7_head(path):
         if not inflate.unused_data.strip(b"\0"):
           break
         raise ValueError("multi-member gzip")        # rare: the caller falls back to the gzip module
-      if _parm7_complete(buf, _PARM7_WANTED):
+      while True:
+        at = buf.find(b"%FLAG", scan)
+        nl = buf.find(b"\n", at) if at >= 0 else -1
+        if nl < 0:
+          scan = at if at >= 0 else max(len(buf) - 4, scan)
+          break
+        if last is not None:
+          whole.add(last)
+        words = bytes(buf[at + 5:nl]).split()
+        last = words[0].decode("ascii", "replace") if words else ""
+        scan = nl
+      if whole.issuperset(_PARM7_WANTED):
         break
     return bytes(buf)
 
@@ -653,9 +657,11 @@ def _parm7_sections_bytes(buf, wanted):
   return sections
 
 
-def _parm7_array(section):
+def _parm7_array(section, count=None, take=None):
   """The fields of one section as an array, parsed in one piece: every line but the last holds its full count of
-  fixed-width fields (else None: the caller takes the line-by-line parser)."""
+  fixed-width fields (else None: the caller takes the line-by-line parser).  `count` / `take`: only the first `count`
+  fields, and of those only the ones a boolean mask picks, are converted (the per-atom tables of a solvated system are
+  nine tenths water that the caller drops)."""
   fmt, body = section
   m = re.fullmatch(r"(\d+)([aAiIeEfF])(\d+)(?:\.\d+)?", fmt.strip())
   if not m:
@@ -673,6 +679,12 @@ def _parm7_array(section):
     flat = flat.rstrip()
   flat += b" " * (-len(flat) % width)
   fields = np.frombuffer(flat, dtype=f"S{width}")
+  if count is not None:
+    fields = fields[:count]
+  if take is not None:
+    if len(take) != len(fields):
+      return None
+    fields = fields[take]
   try:
     if kind == "a":
       # names and labels repeat: strip and decode the distinct ones only
@@ -683,10 +695,12 @@ def _parm7_array(section):
     return None
 
 
-def load_amber_topology(path):
+def load_amber_topology(path, drop_residues=()):
   """Topology from an Amber parm7 / prmtop file, optionally gzip-compressed (what pt.load_topology gives
   MisatoTraj for production.top.gz, /root/reference/nearl/io/traj.py:361): atom names, residue labels and
-  pointers, atomic numbers (from the masses when the file predates the ATOMIC_NUMBER section), charges."""
+  pointers, atomic numbers (from the masses when the file predates the ATOMIC_NUMBER section), charges.
+  `drop_residues`: residue names whose atoms are left out -- the topology `strip(":NAME")` of each would leave, without
+  converting the fields of the dropped atoms."""
   sec = None
   try:
     sec = _parm7_sections_bytes(_parm7_head(path), _PARM7_WANTED)
@@ -701,30 +715,40 @@ def load_amber_topology(path):
     if need not in sec:
       raise ValueError(f"{path}: parm7 section {need} is missing")
 
-  def values(flag):
-    arr = _parm7_array(sec[flag]) if isinstance(sec[flag][1], bytes) else None
+  def values(flag, count, take=None):
+    arr = _parm7_array(sec[flag], count, take) if isinstance(sec[flag][1], bytes) else None
     if arr is None:
       fmt, body = sec[flag]
-      arr = _parm7_values([fmt, body.decode().splitlines() if isinstance(body, bytes) else body])
+      arr = np.array(_parm7_values([fmt, body.decode().splitlines() if isinstance(body, bytes) else body])[:count],
+                     dtype=object if "a" in fmt.lower() else None)
+      if take is not None:
+        arr = arr[take]
     return arr
 
-  pointers = values("POINTERS")
+  pointers = values("POINTERS", None)
   n_atoms, n_res = int(pointers[0]), int(pointers[11])
-  names = values("ATOM_NAME")[:n_atoms]
-  labels = values("RESIDUE_LABEL")[:n_res]
-  first = np.array(values("RESIDUE_POINTER")[:n_res], dtype=np.int64) - 1
-  resids = np.repeat(np.arange(n_res), np.diff(np.r_[first, n_atoms]))
-  resnames = np.array(labels, dtype=object)[resids]
+  labels = values("RESIDUE_LABEL", n_res)
+  first = np.asarray(values("RESIDUE_POINTER", n_res), dtype=np.int64) - 1
+  sizes = np.diff(np.r_[first, n_atoms])
+  resids = np.repeat(np.arange(n_res), sizes)
+  take = None
+  if len(drop_residues):
+    keep_res = ~np.isin(np.asarray(labels, dtype=object).astype(str), [str(r) for r in drop_residues])
+    if not keep_res.all():
+      take = np.repeat(keep_res, sizes)
+      resids = resids[take]
+  names = values("ATOM_NAME", n_atoms, take)
+  resnames = np.asarray(labels, dtype=object)[resids]
   if "ATOMIC_NUMBER" in sec:
-    z = np.array(values("ATOMIC_NUMBER")[:n_atoms], dtype=np.int64)
+    z = np.asarray(values("ATOMIC_NUMBER", n_atoms, take), dtype=np.int64)
   else:
-    masses = np.array(values("MASS")[:n_atoms], dtype=float)
+    masses = np.asarray(values("MASS", n_atoms, take), dtype=float)
     table = np.array([constants.ATOMICMASS.get(i, 1e9) for i in range(1, 119)])
     z = np.abs(masses[:, None] - table[None, :]).argmin(axis=1) + 1
   charges = None
   if "CHARGE" in sec:
     # parm7 stores charges multiplied by 18.2223 (the square root of the electrostatic constant in kcal/mol units)
-    charges = np.array(values("CHARGE")[:n_atoms], dtype=np.float64) / 18.2223
+    charges = np.asarray(values("CHARGE", n_atoms, take), dtype=np.float64) / 18.2223
   return Topology(names, resids, resnames, z, charges)
 
 
@@ -776,11 +800,7 @@ class MisatoTraj(Trajectory):
     trajfile = os.path.join(misatodir, "MD.hdf5")
     if not os.path.exists(trajfile):
       raise FileNotFoundError(f"The trajectory file is not found ({trajfile})")
-    top = load_amber_topology(topfile)
-    present = set(top.resnames.tolist())
-    for solvent in ("WAT", "Cl-", "Na+"):          # keep the coordinates aligned with the topology (traj.py:362-369)
-      if solvent in present:
-        top.strip(f":{solvent}")
+    top = load_amber_topology(topfile, drop_residues=("WAT", "Cl-", "Na+"))   # keep the coordinates aligned with the topology (traj.py:362-369)
     with utils.shared_reader(trajfile) as hdf:          # kept open between trajectories
       if pdbcode.upper() not in hdf:
         raise ValueError(f"Not found the key for PDB code {pdbcode.upper()} in the HDF5 trajectory file.")

@@ -101,6 +101,19 @@ def test_parm7_fast_parser_matches_the_line_parser(tmp_path):
     assert list(got.names) == list(want.names) and list(got.resnames) == list(want.resnames), name
     assert np.array_equal(got.resids, want.resids) and np.array_equal(got.atomic_numbers, want.atomic_numbers), name
     assert np.array_equal(got.charge, want.charge), name
+  # residues dropped while parsing = the topology strip() of each would leave (MisatoTraj: water and ions)
+  solvated = str(tmp_path / "misato")
+  make_misato_dir(solvated, "1abc", traj, solvent_atoms=12)
+  topfile = os.path.join(solvated, "parameter_restart_files_MD", "1abc", "production.top.gz")
+  stripped = io.load_amber_topology(topfile)
+  assert stripped.n_atoms == want.n_atoms + 14
+  for name in ("WAT", "Cl-", "Na+"):
+    stripped.strip(f":{name}")
+  dropped = io.load_amber_topology(topfile, drop_residues=("WAT", "Cl-", "Na+"))
+  assert dropped.n_atoms == want.n_atoms and list(dropped.names) == list(stripped.names) and list(dropped.resnames) == list(stripped.resnames)
+  assert np.array_equal(dropped.resids, stripped.resids) and np.array_equal(dropped.atomic_numbers, stripped.atomic_numbers)
+  assert np.array_equal(dropped.charge, stripped.charge)
+  assert io.load_amber_topology(topfile, drop_residues=("XYZ",)).n_atoms == want.n_atoms + 14
   head = io._parm7_head(str(tmp_path / "tail.top.gz"))
   assert len(head) < len(text + tail) and b"RESIDUE_POINTER" in head            # the tail was not inflated to its end
   # a section whose lines are not all full falls back to the line parser, section by section
