@@ -752,10 +752,24 @@ class File(Group):
     """Move a dataset's pending chunks to disk (bounded memory while appending many rows).  A chunk that is
     already on disk keeps its address when the new bytes have the same length (always, without a filter)."""
     c0, tail = dset.chunks[0], (0,) * len(dset.chunks)
-    for ci in sorted(dset._mem_chunks):
-      raw = np.ascontiguousarray(dset._mem_chunks[ci]).tobytes()
-      if dset.compression == "gzip":
-        raw = zlib.compress(raw, int(dset.compression_opts))
+    order = sorted(dset._mem_chunks)
+    deflate = dset.compression == "gzip"
+    level = int(dset.compression_opts) if deflate else 0
+    packed = {}
+    if deflate and level > 0 and len(order) > 3:
+      # deflating is most of the cost of a compressed sink and releases the interpreter lock: the pending chunks of a
+      # spill are independent, a few threads take them side by side (blocks of 64 chunks bound the copies in flight)
+      pool = _deflate_pool()
+      for b0 in range(0, len(order), 64):
+        block = order[b0:b0 + 64]
+        for ci, raw in zip(block, pool.map(lambda ci: zlib.compress(np.ascontiguousarray(dset._mem_chunks[ci]).tobytes(), level), block)):
+          packed[ci] = raw
+    for ci in order:
+      raw = packed.pop(ci, None)
+      if raw is None:
+        raw = np.ascontiguousarray(dset._mem_chunks[ci]).tobytes()
+        if deflate:
+          raw = zlib.compress(raw, level)
       offsets = (ci * c0,) + tail
       dset._index._right_edge()
       old = dset._index.find(offsets) if dset._index.last is not None and offsets <= dset._index.last else None
@@ -777,6 +791,17 @@ class File(Group):
     self.flush()
     self._fh.close()
     self._fh = None
+
+
+_DEFLATE_POOL = None
+
+
+def _deflate_pool():
+  global _DEFLATE_POOL
+  if _DEFLATE_POOL is None:
+    from concurrent.futures import ThreadPoolExecutor
+    _DEFLATE_POOL = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) // 2)), thread_name_prefix="hdf5-deflate")
+  return _DEFLATE_POOL
 
 
 # ---- writer -------------------------------------------------------------------------------------------

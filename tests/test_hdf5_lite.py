@@ -297,3 +297,25 @@ def test_classic_layout_many_groups_are_read_lazily(tmp_path):
     assert np.array_equal(h["031X"]["trajectory_coordinates"][1:3], data["031X"][1:3])
     assert sum(1 for v in dict.values(h._members) if isinstance(v, hdf5_lite._LazyRef)) == 38
     assert all(np.array_equal(g["trajectory_coordinates"][:], data[c]) for c, g in h.items())
+
+
+def test_compressed_chunks_deflated_side_by_side_give_the_same_file(tmp_path, monkeypatch):
+  """A spill of many pending chunks of a gzip dataset deflates them on a few threads: the file is the one a single
+  thread writes, byte for byte, and reads back."""
+  rows = _rows(300, shape=(8, 8, 8), seed=3) * (_rows(300, shape=(8, 8, 8), seed=4) > 0.7)
+
+  def write(path):
+    with hdf5_lite.File(path, "w") as h:
+      for start in range(0, 300, 75):
+        utils._append_now(h, "gz", rows[start:start + 75], np.float32, (None, 8, 8, 8), chunks=(1, 8, 8, 8), compression="gzip", compression_opts=4)
+  write(str(tmp_path / "threads.h5"))
+
+  class Serial:
+    def map(self, fn, items):
+      return map(fn, items)
+  monkeypatch.setattr(hdf5_lite, "_deflate_pool", lambda: Serial())
+  write(str(tmp_path / "serial.h5"))
+  assert open(str(tmp_path / "threads.h5"), "rb").read() == open(str(tmp_path / "serial.h5"), "rb").read()
+  with hdf5_lite.File(str(tmp_path / "threads.h5"), "r") as h:
+    assert np.array_equal(h["gz"][:], rows)
+    assert os.path.getsize(str(tmp_path / "threads.h5")) < rows.nbytes // 2
