@@ -100,8 +100,9 @@ class Featurizer:
     # nearl_b200: single-frame systems featurised per native call when every feature is static (time_window 1);
     # 1 = one system per call
     self.static_group = 32
-    # nearl_b200: loader threads that read the files of the next trajectories ahead (io.TrajectoryLoader.prefetched; 0: none)
-    self.prefetch_workers = 4
+    # nearl_b200: loader threads that read the files of the next trajectories ahead (io.TrajectoryLoader.prefetched; 0: none;
+    # None: half of this process's share of the host cores, between 2 and 8)
+    self.prefetch_workers = None
     if config.verbose():
       printit(f"{self.classname}: Featurizer is initialized successfully with dimensions: {self.dims} and lengths: {self.lengths}")
     if "outfile" in parms:
@@ -313,7 +314,12 @@ class Featurizer:
   def _trajectories(self, indices, loaded=None):
     """(index, trajectory) in order: through the loader's read-ahead threads where it has them (file-backed trajectory
     types that split their constructor), else built one by one on this thread as `self.TRAJLOADER[tid]`."""
-    loader, workers = self.TRAJLOADER, int(self.prefetch_workers or 0)
+    loader, workers = self.TRAJLOADER, self.prefetch_workers
+    if workers is None:
+      import os
+      ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+      workers = max(2, min(8, (os.cpu_count() or 4) // (2 * ranks_here)))
+    workers = int(workers)
     if loaded is None and workers > 0 and hasattr(loader, "prefetched"):
       yield from loader.prefetched(indices, workers=workers)
       return
