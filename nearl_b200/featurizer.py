@@ -722,8 +722,8 @@ class Featurizer:
   def _loop_by_residue(self, restype, tag_limit, chunk_floats):
     stats = {"trajectories": 0, "tasks": 0, "native_tasks": 0, "blocks": 0, "seconds": 0.0}
     t_run = time.perf_counter()
-    for tid in range(self.TRAJECTORYNUMBER):
-      self.traj = self.TRAJLOADER[tid]
+    for tid, traj in self._trajectories(range(self.TRAJECTORYNUMBER)):       # file-backed trajectories are read ahead
+      self.traj = traj
       printit(f"{self.classname}: Start processing the trajectory {tid + 1} with {self.SLICENUMBER} frames")
       for feat in self.FEATURESPACE:
         feat.cache(self.traj)

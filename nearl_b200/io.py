@@ -250,20 +250,31 @@ class Trajectory:
   trajectory file name), ``superpose`` (fit onto the first frame over ``@CA`` on the device); ``dtype`` (default
   float64, what pytraj hands out; ``np.float32`` keeps the precision of a NetCDF trajectory and halves the upload)."""
 
+  @staticmethod
+  def read_raw(traj_src=None, pdb_src=None, identity=None, **kwarg):
+    """The file half of the constructor for a trajectory given by file names (None otherwise): coordinates and topology as
+    read, in the requested dtype.  `TrajectoryLoader.prefetched` runs it on loader threads and hands the result to the
+    constructor as `_raw`; nothing here touches the device."""
+    import os
+    if not isinstance(traj_src, (str, os.PathLike)):
+      return None
+    traj_src = os.fspath(traj_src)
+    dtype = np.dtype(kwarg.get("dtype", np.float64))
+    if pdb_src is None:
+      xyz, top = load_pdb(traj_src)
+    else:
+      pdb_src = os.fspath(pdb_src)
+      top = load_topology(pdb_src)
+      xyz = load_coordinates(traj_src)
+    return {"xyz": np.ascontiguousarray(xyz, dtype=dtype), "top": top, "top_filename": pdb_src, "traj_filename": traj_src}
+
   def __init__(self, traj_src=None, pdb_src=None, identity=None, **kwarg):
     stride, frame_indices, mask = kwarg.get("stride"), kwarg.get("frame_indices"), kwarg.get("mask")
     self.top_filename = self.traj_filename = None
     if isinstance(traj_src, (str, os.PathLike)):
-      traj_src = os.fspath(traj_src)
-      dtype = np.dtype(kwarg.get("dtype", np.float64))
-      if pdb_src is None:
-        xyz, top = load_pdb(traj_src)
-      else:
-        pdb_src = os.fspath(pdb_src)
-        top = load_topology(pdb_src)
-        xyz = load_coordinates(traj_src)
-      self.top_filename, self.traj_filename = pdb_src, traj_src
-      xyz = np.ascontiguousarray(xyz, dtype=dtype)
+      raw = kwarg.pop("_raw", None) or self.read_raw(traj_src, pdb_src, **kwarg)
+      xyz, top = raw["xyz"], raw["top"]
+      self.top_filename, self.traj_filename = raw["top_filename"], raw["traj_filename"]
     elif isinstance(traj_src, Trajectory):
       xyz, top = traj_src.xyz, traj_src.top
       self.top_filename, self.traj_filename = traj_src.top_filename, traj_src.traj_filename
@@ -894,7 +905,9 @@ class TrajectoryLoader:
     the calling thread, inside the constructor.  Other entries are built on access, as `loader[i]` does; an exception of a
     read is raised when its trajectory's turn comes, as the unthreaded loop would."""
     indices = [int(i) for i in indices]
-    can = lambda i: workers > 0 and not (hasattr(self.trajs[i], "xyz") and hasattr(self.trajs[i], "top")) and hasattr(self.OUTPUT_TYPE[i], "read_raw")
+    # (a type takes part when it defines `read_raw` ITSELF: a subclass with a constructor of its own does not inherit it)
+    can = lambda i: (workers > 0 and not (hasattr(self.trajs[i], "xyz") and hasattr(self.trajs[i], "top"))
+                     and "read_raw" in vars(self.OUTPUT_TYPE[i]))
     if not any(can(i) for i in indices):
       for i in indices:
         yield i, self._load(i)
@@ -917,6 +930,9 @@ class TrajectoryLoader:
             yield i, self._load(i)
             continue
           raw = fut.result()
+          if raw is None:                       # not file-backed after all
+            yield i, self._load(i)
+            continue
           self.i_ = i
           yield i, self.OUTPUT_TYPE[i](*self.trajs[i], _raw=raw, **self.get_loading_options(i))
       finally:

@@ -378,6 +378,21 @@ def test_trajectory_loader_options(tmp_path):
     io.TrajectoryLoader([(pdb,)], strides=[1, 2])
   with pytest.raises(IndexError):
     loader["x"]
+  # read ahead on loader threads: the same trajectories, identities and options; a subclass with a constructor of its own
+  # does not take part (it is built on access, on the calling thread)
+  ahead = list(loader.prefetched(range(len(loader)), workers=2))
+  for i, t in ahead:
+    same = loader[i]
+    assert t.identity == same.identity and t.n_frames == same.n_frames and np.array_equal(t.xyz, same.xyz) and t.xyz.dtype == same.xyz.dtype
+    assert t.traj_filename == same.traj_filename and list(t.top.names) == list(same.top.names)
+  assert ahead[4][1] is pep
+
+  class Own(io.Trajectory):
+    def __init__(self, path, scale):
+      super().__init__(path)
+      self.xyz = self.xyz * scale
+  own = io.TrajectoryLoader([(pdb, 2.0)], trajtype=Own)
+  assert np.array_equal(next(iter(own.prefetched([0], workers=2)))[1].xyz, io.Trajectory(pdb).xyz * 2.0)
 
 
 def test_partial_charge_weights(tmp_path):
