@@ -45,6 +45,17 @@ def _normalise(ret_data, normalize):
   return ret_data
 
 
+_READ_POOLS = {}
+
+
+def _read_pool(workers):
+  pool = _READ_POOLS.get(workers)
+  if pool is None:
+    from concurrent.futures import ThreadPoolExecutor
+    pool = _READ_POOLS[workers] = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="nearl-dataset-read")
+  return pool
+
+
 def readdata(input_file, keyword, theslice, normalize=False):
   """One sample (or slice) of dataset `keyword` (dataset.py:51-88)."""
   with utils.open_hdf(input_file, "r") as h5file:
@@ -173,16 +184,46 @@ class Dataset:
     files = self.file_map[batch]
     for fidx in np.unique(files):
       rows = np.flatnonzero(files == fidx)
-      with utils.open_hdf(self.FILELIST[fidx], "r") as hdf:
-        for c, key in enumerate(self.feature_keys):
-          dset = hdf[key]
-          for r in rows:
+      hdf = self._reader(int(fidx))
+      dsets = [hdf[key] for key in self.feature_keys]
+
+      def read_rows(part):
+        for r in part:
+          for c, dset in enumerate(dsets):
             data[r, c] = _normalise(np.asarray(dset[self.position(batch[r])], dtype=np.float32), self.normalize)
-        if self.label_key is not None:
-          dset = hdf[self.label_key]
-          for r in rows:
-            labels[r, 0] = dset[self.position(batch[r])]
+      workers = max(1, int(getattr(self, "read_workers", 4)))
+      if workers > 1 and len(rows) >= 2 * workers:
+        # samples are independent chunks: reading one (file read, inflate) releases the interpreter lock
+        list(_read_pool(workers).map(read_rows, np.array_split(rows, workers)))
+      else:
+        read_rows(rows)
+      if self.label_key is not None:
+        dset = hdf[self.label_key]
+        for r in rows:
+          labels[r, 0] = dset[self.position(batch[r])]
     return data, labels
+
+  def _reader(self, fidx):
+    """The file of index `fidx`, kept open between batches (what a reader has learnt about a file -- chunk index nodes,
+    member headers -- serves every later batch); at most `max_open_files` handles, the least recently used one goes."""
+    pool = self.__dict__.setdefault("_open_files", {})
+    hdf = pool.pop(fidx, None)
+    if hdf is None:
+      while len(pool) >= max(1, int(getattr(self, "max_open_files", 64))):
+        pool.pop(next(iter(pool))).close()
+      hdf = utils.open_hdf(self.FILELIST[fidx], "r")
+    pool[fidx] = hdf                       # most recently used last
+    return hdf
+
+  def close(self):
+    for hdf in self.__dict__.pop("_open_files", {}).values():
+      try:
+        hdf.close()
+      except Exception:
+        pass
+
+  def __del__(self):
+    self.close()
 
   def mini_batches(self, batch_nr=None, batch_size=None, shuffle=True, process_nr=None, augment=False, augment_translation=0,
                    augment_add_noise=False, device=None, **kwargs):
@@ -201,11 +242,21 @@ class Dataset:
       raise ValueError("Either batch_nr or batch_size should be specified")
     if config.verbose():
       printit(f"Iterating the dataset: {len(batches)} batches with batch size {batch_size}.")
-    for batch in batches:
-      data_numpy, labels_numpy = self._read_batch(batch)
-      data, label = torch.from_numpy(data_numpy), torch.from_numpy(labels_numpy)
-      if device is not None:
-        data, label = data.to(device, non_blocking=True), label.to(device, non_blocking=True)
-      if augment:
-        data = data_augment(data, trans=augment_translation, add_noise=augment_add_noise)
-      yield data, label
+    # the next batch is read on one reader thread while the caller works on the current one (reading a chunk -- the file
+    # read, the inflate -- releases the interpreter lock); the random draws of shuffle and augmentation stay where they were
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=1, thread_name_prefix="nearl-dataset") as pool:
+      ahead = pool.submit(self._read_batch, batches[0]) if len(batches) else None
+      for k in range(len(batches)):
+        data_numpy, labels_numpy = ahead.result()
+        ahead = pool.submit(self._read_batch, batches[k + 1]) if k + 1 < len(batches) else None
+        yield self._deliver(data_numpy, labels_numpy, device, augment, augment_translation, augment_add_noise)
+
+  def _deliver(self, data_numpy, labels_numpy, device, augment, augment_translation, augment_add_noise):
+    import torch
+    data, label = torch.from_numpy(data_numpy), torch.from_numpy(labels_numpy)
+    if device is not None:
+      data, label = data.to(device, non_blocking=True), label.to(device, non_blocking=True)
+    if augment:
+      data = data_augment(data, trans=augment_translation, add_noise=augment_add_noise)
+    return data, label

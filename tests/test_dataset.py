@@ -78,3 +78,33 @@ def test_augmentation_invariants():
   assert len(kept) <= x.numel() and set(np.round(kept.numpy(), 6)).issubset(set(np.round(x.numpy().reshape(-1), 6)))
   y = dataset.data_augment(x.clone(), add_noise=True)
   assert y.shape == x.shape and not torch.equal(torch.sort(y.reshape(-1)).values, torch.sort(x.reshape(-1)).values)
+
+
+def test_batches_read_on_threads_are_the_batches_read_on_one(tmp_path):
+  """A batch is read by a few threads (samples are independent chunks), the next batch while the caller works on the
+  current one, the files stay open between batches: the same batches in the same order, whatever the number of threads
+  and of open handles."""
+  files, arrays = [], []
+  for k in range(3):
+    path = str(tmp_path / f"f{k}.h5")
+    a, b, labels = make_file(path, 21 + k, 6, 10 + k)
+    files.append(path)
+    arrays.append((a, b, labels))
+  want = None
+  for workers, handles in ((1, 64), (4, 64), (3, 1)):
+    ds = dataset.Dataset(files, feature_keys=["mass", "flow"], normalize="zscore")
+    ds.read_workers, ds.max_open_files = workers, handles
+    np.random.seed(5)
+    got = [(d.numpy().copy(), l.numpy().copy()) for d, l in ds.mini_batches(batch_size=16, shuffle=True)]
+    assert sum(len(d) for d, _ in got) == len(ds) == 66
+    if want is None:
+      want = got
+    for (d0, l0), (d1, l1) in zip(want, got):
+      assert np.array_equal(d0, d1) and np.array_equal(l0, l1)
+    assert len(ds.__dict__.get("_open_files", {})) <= handles
+    ds.close()
+    assert not ds.__dict__.get("_open_files")
+  # unshuffled, unnormalised: the rows of the files in order
+  ds = dataset.Dataset(files, feature_keys=["mass", "flow"])
+  flat = np.concatenate([d.numpy() for d, _ in ds.mini_batches(batch_size=25, shuffle=False)])
+  assert np.array_equal(flat[:, 0], np.concatenate([a for a, _, _ in arrays])) and np.array_equal(flat[:, 1], np.concatenate([b for _, b, _ in arrays]))
