@@ -762,12 +762,12 @@ class File(Group):
       pool = _deflate_pool()
       for b0 in range(0, len(order), 64):
         block = order[b0:b0 + 64]
-        for ci, raw in zip(block, pool.map(lambda ci: zlib.compress(np.ascontiguousarray(dset._mem_chunks[ci]).tobytes(), level), block)):
+        for ci, raw in zip(block, pool.map(lambda ci: zlib.compress(_chunk_bytes(dset._mem_chunks[ci]), level), block)):
           packed[ci] = raw
     for ci in order:
       raw = packed.pop(ci, None)
       if raw is None:
-        raw = np.ascontiguousarray(dset._mem_chunks[ci]).tobytes()
+        raw = _chunk_bytes(dset._mem_chunks[ci])
         if deflate:
           raw = zlib.compress(raw, level)
       offsets = (ci * c0,) + tail
@@ -791,6 +791,12 @@ class File(Group):
     self.flush()
     self._fh.close()
     self._fh = None
+
+
+def _chunk_bytes(chunk):
+  """The bytes of a pending chunk without a copy (a view of the array's own memory where it has one)."""
+  arr = np.ascontiguousarray(chunk)
+  return arr.tobytes() if arr.dtype.hasobject else memoryview(arr.reshape(-1)).cast("B")
 
 
 _DEFLATE_POOL = None
