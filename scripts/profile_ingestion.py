@@ -62,22 +62,27 @@ t = time.perf_counter()
 for code in codes[:8]:
   io.MisatoTraj.read_raw(code, root)
 rows["read_raw_ms"] = (time.perf_counter() - t) / 8 * 1e3
-for workers in (0, 2, 4, 8, 0, 4):
+for workers, to_file in ((0, False), (2, False), (4, False), (8, False), (0, False), (4, False), (0, True), (8, True)):
   loader = io.TrajectoryLoader([(c, root) for c in codes], trajtype=io.MisatoTraj, superpose=True)
-  fz = featurizer.Featurizer({"dimensions": 32, "lengths": 16, "time_window": 10, "cutoff": 5.0, "sigma": 1.5})
+  out = os.path.join(root, f"out_{workers}.h5")
+  fz = featurizer.Featurizer({"dimensions": 32, "lengths": 16, "time_window": 10, "cutoff": 5.0, "sigma": 1.5, "outfile": out} if to_file else
+                             {"dimensions": 32, "lengths": 16, "time_window": 10, "cutoff": 5.0, "sigma": 1.5})
   fz.register_features([features.MarchingObservers(obs="existence", agg="mean", outkey="e"),
                         features.MarchingObservers(obs="distinct_count", agg="mean", outkey="d"),
                         features.MarchingObservers(obs="mean_distance", agg="mean", outkey="m"),
                         features.DensityFlow(agg="mean", outkey="f")])
   fz.register_focus([":ARG"], "mask")
   fz.register_trajloader(loader)
-  fz.result_sink = lambda *a: None
+  if not to_file:
+    fz.result_sink = lambda *a: None
   fz.prefetch_workers = workers
   t = time.perf_counter()
   stats = fz.run()
   dt = time.perf_counter() - t
-  rows.setdefault("runs", []).append({"loader_threads": workers, "ms_per_trajectory": dt / n * 1e3, "frames_per_s": stats["frames"] / dt,
-                                      "trajectories": stats["trajectories"], "tasks": stats["tasks"]})
+  rows.setdefault("runs", []).append({"loader_threads": workers, "sink": "HDF5 file (gzip level 0, the default)" if to_file else "none",
+                                      "ms_per_trajectory": dt / n * 1e3, "frames_per_s": stats["frames"] / dt,
+                                      "trajectories": stats["trajectories"], "tasks": stats["tasks"],
+                                      "out_mb": os.path.getsize(out) / 1e6 if to_file else None})
   print(rows["runs"][-1], file=sys.stderr, flush=True)
 shutil.rmtree(root, ignore_errors=True)
 print(json.dumps(rows, indent=1))
