@@ -84,5 +84,6 @@ for workers, to_file in ((0, False), (2, False), (4, False), (8, False), (0, Fal
                                       "trajectories": stats["trajectories"], "tasks": stats["tasks"],
                                       "out_mb": os.path.getsize(out) / 1e6 if to_file else None})
   print(rows["runs"][-1], file=sys.stderr, flush=True)
-shutil.rmtree(root, ignore_errors=True)
+if not os.environ.get("NRL_INGEST_KEEP"):
+  shutil.rmtree(root, ignore_errors=True)
 print(json.dumps(rows, indent=1))
