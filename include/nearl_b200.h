@@ -35,6 +35,7 @@ extern "C" {
 #define NRL_ERR_SHAPE 4        /* inconsistent / non-positive sizes        actions_py.cpp:58-61,132 */
 #define NRL_ERR_ARGUMENT 5     /* null pointer or invalid parameter */
 #define NRL_ERR_NO_DEVICE 6    /* no usable CUDA device: there is NO CPU fallback */
+#define NRL_ERR_PARSE 7        /* nrl_pdb_parse: the text is not plain enough for the column parser (the caller reads it line by line) */
 #define NRL_ERR_CUDA 100       /* 100 + cudaError_t */
 
 #define NRL_MAX_FRAME_NUMBER 512   /* /root/reference/src/constants.h:11 */
@@ -194,6 +195,17 @@ int nrl_superpose(void *xyz, int xyz_is_f64, int n_frames, int n_atoms, const in
  * memory, float32 or float64. */
 int nrl_focal_means(const void *xyz, int xyz_is_f64, int n_frames_total, int n_atoms, const int *frames, int n_frames,
                     const int *sel, int n_sel, float *out);
+
+/* Ingestion (host code, no device): the ATOM / HETATM records of a PDB text -- what pt.load hands
+ * Trajectory for "complex.pdb" (/root/reference/nearl/io/traj.py:97-106).  Two calls: with xyz == NULL and columns == NULL the
+ * counts only (records in the file, records of the first model, models), then the fill: xyz [n_records, 3] float64 in file
+ * order, columns [n_first, 16] bytes per record of the first model: atom name (PDB columns 13-16), residue name (18-21),
+ * chain (22), residue number + insertion code (23-27), element (77-78, blank when the line ends before them).  A frame ends at
+ * a line that starts with END (ENDMDL included) and has records in front of it.  NRL_ERR_PARSE: the text is not plain enough
+ * (non-ASCII bytes, a bare carriage return, a record shorter than 54 columns, a coordinate field that is not
+ * [blank][sign]digits[.digits][blank], models of different sizes, no record): the caller parses it line by line. */
+int nrl_pdb_parse(const char *text, long long n_bytes, long long *n_records, long long *n_first, long long *n_frames, double *xyz,
+                  char *columns);
 
 /* ---- utilities -------------------------------------------------------------------------- */
 /* buff_dim exactly as the device evaluates (cutoff+spacing)/spacing (voxelize.cu:50, div.approx) */

@@ -19,12 +19,12 @@ EXPORTED = [
   "nrl_frame_voxelize", "nrl_frame_observation", "nrl_marching_observer", "nrl_density_flow", "nrl_aggregate",
   "nrl_summation", "nrl_frame_voxelize_dev", "nrl_frame_observation_dev", "nrl_marching_observer_dev",
   "nrl_density_flow_dev", "nrl_aggregate_dev", "nrl_featurize_batch", "nrl_buff_dim", "nrl_device_count",
-  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_lane_fork", "nrl_lane_join", "nrl_focal_means", "nrl_set_stream", "nrl_set_option", "nrl_cell_list_fits", "nrl_superpose", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
+  "nrl_set_device", "nrl_synchronize", "nrl_lane_synchronize", "nrl_lane_fork", "nrl_lane_join", "nrl_focal_means", "nrl_pdb_parse", "nrl_set_stream", "nrl_set_option", "nrl_cell_list_fits", "nrl_superpose", "nrl_profile", "nrl_profile_read", "nrl_profile_name", "nrl_host_register", "nrl_host_unregister", "nrl_kernel_launches",
   "nrl_last_error", "nrl_version",
 ]
 
 NRL_OK = 0
-ERR_OBSERVABLE, ERR_AGGREGATION, ERR_FRAMES, ERR_SHAPE, ERR_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA = 1, 2, 3, 4, 5, 6, 100
+ERR_OBSERVABLE, ERR_AGGREGATION, ERR_FRAMES, ERR_SHAPE, ERR_ARGUMENT, ERR_NO_DEVICE, ERR_PARSE, ERR_CUDA = 1, 2, 3, 4, 5, 6, 7, 100
 
 
 class CropStruct(ctypes.Structure):
@@ -103,6 +103,7 @@ def lib():
   L.nrl_lane_fork.argtypes = [c_int, p]
   L.nrl_lane_join.argtypes = [c_int, p]
   L.nrl_focal_means.argtypes = [p, c_int, c_int, c_int, p, c_int, p, c_int, p]
+  L.nrl_pdb_parse.argtypes = [ctypes.c_char_p, ctypes.c_longlong, p, p, p, p, p]
   L.nrl_profile.argtypes = [c_int]
   L.nrl_set_option.argtypes = [ctypes.c_char_p, c_int]
   L.nrl_cell_list_fits.argtypes = [p, c_float, c_float, p]

@@ -1170,6 +1170,90 @@ int nrl_focal_means(const void *xyz, int xyz_is_f64, int n_frames_total, int n_a
   return NRL_OK;
 }
 
+// PDB text -> coordinates of every ATOM / HETATM record and the fixed-width columns of the first model's records (what
+// pt.load hands /root/reference/nearl/io/traj.py:97-106 for a PDB file; nearl_b200.io.load_pdb words the semantics and is the
+// fallback).  Plain host code, two passes by the caller: counts first (xyz == NULL), then the fill.  Anything that is not
+// plain -- bytes outside ASCII, a bare carriage return, a record shorter than its coordinate columns, a coordinate that is not
+// [blank][sign]digits[.digits][blank], models of different sizes -- returns NRL_ERR_PARSE and leaves the file to the caller.
+//   columns: 16 bytes per record of the first model: atom name (cols 13-16), residue name (18-21), chain (22), residue number
+//   and insertion code (23-27), element (77-78; blanks when the line ends before them).
+static bool pdb_field(const char *p, double *out) {
+  int i = 0;
+  while (i < 8 && p[i] == ' ') ++i;
+  bool neg = false;
+  if (i < 8 && (p[i] == '+' || p[i] == '-')) { neg = p[i] == '-'; ++i; }
+  unsigned long long mant = 0;
+  int digits = 0, frac = 0;
+  bool point = false;
+  for (; i < 8; ++i) {
+    const char ch = p[i];
+    if (ch >= '0' && ch <= '9') { mant = mant * 10 + (unsigned)(ch - '0'); ++digits; if (point) ++frac; }
+    else if (ch == '.' && !point) point = true;
+    else break;
+  }
+  while (i < 8 && p[i] == ' ') ++i;
+  if (i != 8 || digits == 0) return false;
+  // at most 8 digits and 10^frac <= 10^7: both exact in double, one correctly rounded division = what strtod / float() give
+  static const double pow10[9] = {1.0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8};
+  const double v = (double)mant / pow10[frac];
+  *out = neg ? -v : v;
+  return true;
+}
+
+int nrl_pdb_parse(const char *text, long long n_bytes, long long *n_records, long long *n_first, long long *n_frames, double *xyz,
+                  char *columns) {
+  if (!text || !n_records || !n_first || !n_frames || n_bytes < 0) return fail(NRL_ERR_ARGUMENT, "text / counters is NULL");
+  long long records = 0, first = 0, frames = 0, in_frame = 0;
+  bool first_model = true;
+  long long pos = 0;
+  while (pos < n_bytes) {
+    const char *line = text + pos;
+    const char *nl = static_cast<const char *>(memchr(line, '\n', (size_t)(n_bytes - pos)));
+    const bool has_nl = nl != nullptr;
+    long long len = has_nl ? (long long)(nl - line) : n_bytes - pos;
+    pos += len + (has_nl ? 1 : 0);
+    if (len > 0 && line[len - 1] == '\r') --len;               // CRLF (text mode hands Python the line without it)
+    for (long long k = 0; k < len; ++k)
+      if ((unsigned char)line[k] >= 0x80 || line[k] == '\r') return fail(NRL_ERR_PARSE, "PDB text is not plain ASCII lines");
+    if (len >= 6 && (memcmp(line, "ATOM  ", 6) == 0 || memcmp(line, "HETATM", 6) == 0)) {
+      if (len < 54) return fail(NRL_ERR_PARSE, "PDB record shorter than its coordinate columns");
+      double v[3];
+      for (int a = 0; a < 3; ++a)
+        if (!pdb_field(line + 30 + 8 * a, &v[a])) return fail(NRL_ERR_PARSE, "PDB coordinate field is not a plain decimal");
+      if (xyz) { xyz[3 * records] = v[0]; xyz[3 * records + 1] = v[1]; xyz[3 * records + 2] = v[2]; }
+      if (first_model) {
+        if (columns) {
+          char *c = columns + 16 * first;
+          memcpy(c, line + 12, 4);
+          memcpy(c + 4, line + 17, 4);
+          memcpy(c + 8, line + 21, 6);
+          // Python reads line[76:78] when len(line) >= 78, the newline counted: a column beyond the text is blank
+          const bool has_elem = len + (has_nl ? 1 : 0) >= 78;
+          c[14] = (has_elem && len > 76) ? line[76] : ' ';
+          c[15] = (has_elem && len > 77) ? line[77] : ' ';
+        }
+        ++first;
+      }
+      ++records;
+      ++in_frame;
+    } else if (len >= 3 && memcmp(line, "END", 3) == 0 && in_frame > 0) {
+      if (in_frame != first) return fail(NRL_ERR_PARSE, "PDB models do not list the same number of atoms");
+      ++frames;
+      in_frame = 0;
+      first_model = false;
+    }
+  }
+  if (in_frame > 0) {
+    if (in_frame != first) return fail(NRL_ERR_PARSE, "PDB models do not list the same number of atoms");
+    ++frames;
+  }
+  if (frames == 0) return fail(NRL_ERR_PARSE, "no ATOM / HETATM record");
+  *n_records = records;
+  *n_first = first;
+  *n_frames = frames;
+  return NRL_OK;
+}
+
 // `stream` waits (on the device) for everything enqueued on `lane` so far: a caller that spreads batches over the lanes
 // joins them into its own stream without a host synchronisation (bench.py times the device-resident arm this way).
 int nrl_lane_join(int lane, void *stream) {

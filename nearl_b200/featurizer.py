@@ -353,11 +353,15 @@ class Featurizer:
     group = max(2, int(self.static_group))
     pending = []
     submitted = 0
+    source = self._trajectories(indices)                     # file-backed systems are read ahead on the loader threads
     for g0 in range(0, len(indices), group):
       tids = indices[g0:g0 + group]
       if len(pending) >= depth:
         self._finish_static_group(pending.pop(0), stats)
       loaded = {}
+      for _ in tids:
+        tid, traj = next(source)
+        loaded[tid] = traj
       lane = submitted % depth
       assert all(job["lane"] != lane for job in pending), "pipeline lane handed out while its job is pending"
       job = self._submit_static_group(tids, lane=lane, loaded=loaded)
@@ -367,6 +371,7 @@ class Featurizer:
         while pending:
           self._finish_static_group(pending.pop(0), stats)
         if self._run_pipelined(tids, depth, stats, loaded=loaded):
+          source.close()                                     # the rest of the list goes through the pipelined loop's own source
           return g0 + len(tids)
         continue
       if job["batch"] is None:
@@ -381,10 +386,12 @@ class Featurizer:
     members = []
     n_focal = None
     for tid in tids:
-      self.traj = self.TRAJLOADER[tid]
-      traj = self.traj
-      if loaded is not None:
-        loaded[tid] = traj
+      traj = loaded.get(tid) if loaded is not None else None
+      if traj is None:
+        traj = self.TRAJLOADER[tid]
+        if loaded is not None:
+          loaded[tid] = traj
+      self.traj = traj
       if traj.n_frames != 1:
         return None
       if self.FOCALPOINTS_PROTOTYPE is not None:

@@ -374,11 +374,79 @@ def _guess_atomic_number(name_field, resname):
   return constants.SYMBOL2ATOMICNR.get(core[:1].upper(), 0) if core else 0
 
 
+def _load_pdb_native(data):
+  """`load_pdb` on the column parser of the native library (`nrl_pdb_parse`: host code, one pass over the text for the
+  coordinates and the fixed-width columns of the first model), names / residues / elements resolved once per DISTINCT
+  value.  None when the library is not there or finds the text not plain enough: the caller reads it line by line, which
+  also words the errors."""
+  import ctypes
+  try:
+    from . import _lib
+    lib = _lib.lib()
+  except Exception:
+    return None
+  counts = (ctypes.c_longlong * 3)()
+  ref = lambda k: ctypes.byref(counts, 8 * k)
+  if lib.nrl_pdb_parse(data, len(data), ref(0), ref(1), ref(2), None, None) != 0:
+    return None
+  n_records, n, n_frames = int(counts[0]), int(counts[1]), int(counts[2])
+  xyz = np.empty((n_frames, n, 3), dtype=np.float64)
+  cols = np.empty((n, 16), dtype=np.uint8)
+  if n_records != n_frames * n or lib.nrl_pdb_parse(data, len(data), ref(0), ref(1), ref(2), xyz.ctypes.data_as(ctypes.c_void_p),
+                                                     cols.ctypes.data_as(ctypes.c_void_p)) != 0:
+    return None
+
+  # every column group as an integer per record: sorting integers is what np.unique is fast at
+  def codes(lo, hi):
+    width = hi - lo
+    raw = np.zeros((n, 8), dtype=np.uint8)
+    raw[:, :width] = cols[:, lo:hi]
+    values, inverse = np.unique(raw.view("<u8").ravel(), return_inverse=True)
+    texts = [int(v).to_bytes(8, "little")[:width].decode() for v in values.tolist()]
+    return texts, inverse
+  name_texts, name_code = codes(0, 4)
+  res_texts, res_raw_code = codes(4, 8)
+  elem_texts, elem_code = codes(14, 16)
+  names = np.array([t.strip() for t in name_texts], dtype=object)[name_code]
+  res_stripped = [t.strip() for t in res_texts]
+  resnames = np.array(res_stripped, dtype=object)[res_raw_code]
+  # element: from columns 77-78, else guessed from the name columns and the residue name -- once per distinct combination
+  combo = (elem_code.astype(np.int64) * len(name_texts) + name_code) * len(res_texts) + res_raw_code
+  combos, combo_inverse = np.unique(combo, return_inverse=True)
+  z_of = np.empty(len(combos), dtype=np.int64)
+  for k, c in enumerate(combos.tolist()):
+    c, r = divmod(c, len(res_texts))
+    e, a = divmod(c, len(name_texts))
+    sym = elem_texts[e].strip().capitalize()
+    z_of[k] = constants.SYMBOL2ATOMICNR[sym] if sym in constants.SYMBOL2ATOMICNR else _guess_atomic_number(name_texts[a], res_stripped[r])
+  zs = z_of[combo_inverse]
+  # residues: maximal runs of one (chain, number + insertion code, stripped name)
+  stripped_id = {t: k for k, t in enumerate(dict.fromkeys(res_stripped))}
+  res_code = np.array([stripped_id[t] for t in res_stripped], dtype=np.int64)[res_raw_code]
+  change = np.ones(n, dtype=bool)
+  change[1:] = np.any(cols[1:, 8:14] != cols[:-1, 8:14], axis=1) | (res_code[1:] != res_code[:-1])
+  return xyz, Topology(names, np.cumsum(change) - 1, resnames, zs)
+
+
 def load_pdb(path):
   """(xyz [frames, atoms, 3] float64, Topology) of a PDB file: ATOM / HETATM records by column (name 13-16, residue name
   18-21, chain 22, residue number 23-26, insertion code 27, x / y / z 31-54, element 77-78), one frame per MODEL (every
   model must list the same atoms; the topology is the first model's).  Residues are maximal runs of one (chain, number,
-  insertion code, name); `resids` count them from 0 like pytraj's ``atom.resid``.  Alternate locations are all kept."""
+  insertion code, name); `resids` count them from 0 like pytraj's ``atom.resid``.  Alternate locations are all kept.
+  The text goes through the native library's column parser (`nrl_pdb_parse`) when it is plain; this loop is the definition
+  and the fallback."""
+  import gzip
+  with open(path, "rb") as fh:
+    data = fh.read()
+  if str(path).endswith(".gz"):
+    data = gzip.decompress(data)
+  fast = _load_pdb_native(data)
+  if fast is not None:
+    return fast
+  return _load_pdb_lines(path)
+
+
+def _load_pdb_lines(path):
   import gzip
   opener = gzip.open if str(path).endswith(".gz") else open
   names, resnames, reskeys, zs = [], [], [], []

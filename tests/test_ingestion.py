@@ -355,6 +355,55 @@ def test_pdb_and_netcdf_files_without_pytraj(tmp_path):
     io.load_coordinates(str(tmp_path / "top.parm7"))
 
 
+def test_pdb_column_parser_of_the_library_matches_the_line_parser(tmp_path):
+  """nrl_pdb_parse (host code of the native library) + the per-distinct-value topology against io._load_pdb_lines, the
+  definition: same coordinates to the bit, same names / residues / elements -- and the texts it declines (None) are left
+  to the line parser."""
+  def same(text, name="t.pdb"):
+    path = str(tmp_path / name)
+    with open(path, "wb") as fh:
+      fh.write(text if isinstance(text, bytes) else text.encode())
+    fast = io._load_pdb_native(open(path, "rb").read())
+    assert fast is not None, name
+    xyz, top = io._load_pdb_lines(path)
+    assert fast[0].dtype == np.float64 and np.array_equal(fast[0], xyz), name
+    assert list(fast[1].names) == list(top.names) and list(fast[1].resnames) == list(top.resnames), name
+    assert np.array_equal(fast[1].resids, top.resids) and np.array_equal(fast[1].atomic_numbers, top.atomic_numbers), name
+    assert all(type(v) is str for v in fast[1].names[:2])
+    got = io.load_pdb(path)
+    assert np.array_equal(got[0], xyz) and list(got[1].names) == list(top.names)
+    return xyz, top
+  xyz, top = same(PDB_TEXT)
+  assert xyz.shape == (2, 13, 3)
+  same(PDB_TEXT.replace("\n", "\r\n"), "crlf.pdb")
+  same(PDB_TEXT.rstrip("\n"), "no_final_newline.pdb")
+  same(PDB_TEXT.replace("ENDMDL\n", "").replace("END\n", "").split("MODEL        2")[0], "no_end.pdb")
+  # lines cut inside / in front of the element columns, negative and unsigned-plus coordinates, no decimals
+  atom = "ATOM      1 FE   HEM A   1     -11.104  +6.134      -6  1.00  0.00          FE"
+  for cut in (54, 60, 66, 76, 77, 78, 79):
+    same("\n".join(line[:cut] for line in (atom, atom.replace("FE   HEM", " CA  ALA"), atom.replace("FE   HEM", "CA    CA"))) + "\n", f"cut{cut}.pdb")
+    same("\n".join(line[:cut] for line in (atom, atom.replace(" 1 FE", " 2 FE"))), f"cut{cut}_open.pdb")
+  pep = io.synthetic_peptide(30, 3, seed=8, break_every=7)
+  io.write_pdb(str(tmp_path / "pep.pdb"), pep.xyz, pep.top)
+  same(open(str(tmp_path / "pep.pdb"), "rb").read(), "pep_again.pdb")
+  # declined: the line parser decides (and words the error where there is one)
+  for text in (atom.replace("-11.104", "-1.1e+01"), atom[:50], atom.replace("HEM", "H\u00c9M"), atom.replace("-11.104", "        "),
+               atom + "\r" + atom):
+    assert io._load_pdb_native(text.encode()) is None, text[:40]
+  lopsided = PDB_TEXT.split("\n")
+  del lopsided[[i for i, l in enumerate(lopsided) if l.startswith("HETATM   14")][1]]
+  assert io._load_pdb_native("\n".join(lopsided).encode()) is None
+  open(str(tmp_path / "lopsided.pdb"), "w").write("\n".join(lopsided))
+  with pytest.raises(ValueError, match="same number of atoms"):
+    io.load_pdb(str(tmp_path / "lopsided.pdb"))
+  open(str(tmp_path / "empty.pdb"), "w").write("HEADER\nEND\n")
+  with pytest.raises(ValueError, match="no ATOM"):
+    io.load_pdb(str(tmp_path / "empty.pdb"))
+  with gzip.open(str(tmp_path / "z.pdb.gz"), "wt") as fh:
+    fh.write(PDB_TEXT)
+  assert np.array_equal(io.load_pdb(str(tmp_path / "z.pdb.gz"))[0], xyz)
+
+
 def test_trajectory_loader_options(tmp_path):
   """TrajectoryLoader (/root/reference/nearl/io/trajloader.py:12-247): lazy construction with the common loading options,
   per-trajectory strides / masks / identities, integer / list / slice indexing, append, ready-made trajectory objects."""
