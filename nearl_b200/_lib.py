@@ -64,8 +64,18 @@ class BatchStruct(ctypes.Structure):
   ]
 
 
+_load_lock = __import__("threading").Lock()
+
+
 def lib():
   """Load (building first if needed) the native library."""
+  if _lib is not None:
+    return _lib
+  with _load_lock:                  # loader threads (io.TrajectoryLoader.prefetched) may be the first to ask
+    return _load()
+
+
+def _load():
   global _lib
   if _lib is not None:
     return _lib
