@@ -481,3 +481,34 @@ def test_partial_charge_weights(tmp_path):
   fz.register_feature(cf)
   with pytest.raises(NotImplementedError):
     cf.cache(traj)
+
+
+@pytest.mark.gpu
+def test_static_groups_from_pdb_files_with_and_without_loader_threads(tmp_path):
+  """PDBBind-style run from PDB files (single-frame systems grouped per native call): the loader threads and the column
+  parser of the library leave the results what the line parser and no threads give."""
+  paths = []
+  for i in range(37):
+    c = io.synthetic_complex(300 + 7 * i, seed=70 + i)
+    paths.append(str(tmp_path / f"c{i}.pdb"))
+    io.write_pdb(paths[-1], c.xyz, c.top)
+  outs = []
+  for workers, parser in ((0, "lines"), (0, "native"), (4, "native")):
+    if parser == "lines":
+      trajs = [io.Trajectory(*io._load_pdb_lines(p), identity=p) for p in paths]
+      loader = io.TrajectoryLoader(trajs)
+    else:
+      loader = io.TrajectoryLoader([(p,) for p in paths])
+    fz = featurizer.Featurizer({"dimensions": 16, "lengths": 12, "time_window": 1, "cutoff": 2.5, "sigma": 1.5})
+    fz.register_features([features.Mass(outkey="mass"), features.HeavyAtom(outkey="heavy"), features.AtomType(focus_element=7, outkey="n")])
+    fz.register_focus([":LIG"], "mask")
+    fz.register_trajloader(loader)
+    fz.keep_results = True
+    fz.prefetch_workers = workers
+    fz.static_group = 8
+    stats = fz.run()
+    assert stats["trajectories"] == len(paths)
+    outs.append({k: np.array(v) for k, v in fz.RESULTS.items()})
+  for other in outs[1:]:
+    for key in outs[0]:
+      assert outs[0][key].shape[0] == len(paths) and np.array_equal(outs[0][key], other[key]), key
